@@ -1,0 +1,213 @@
+/*
+ * plagnn.h — C ABI of libplagnn.so: the B200 (sm_100a) kernels behind the PLA-GNN
+ * message-passing hot path.
+ *
+ * The reference (quinlanW/PLA-GNN) has no FFI of its own: its hot path is Python calling
+ * third-party DGL / PyTorch binaries.  Each entry point below therefore names the reference
+ * call site (path relative to the reference checkout, file:line) whose work it replaces.
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name says host;
+ *   - matrices are row-major fp32 with an explicit row pitch ("ld", in elements);
+ *   - graph structure is int32 (E' < 2^31 also for the 100M-edge synthetic graph);
+ *   - the caller owns every buffer, chooses the device (cudaSetDevice) and the stream;
+ *   - calls enqueue work on `stream` and return without synchronising it, except the two
+ *     *_build functions, which are set-up calls and say so;
+ *   - return value 0 = PLAGNN_OK, negative = error; plagnn_last_error() gives the text
+ *     (thread-local).  Nothing throws, nothing allocates or frees caller memory.
+ *   - re-entrant across streams and devices.
+ */
+#ifndef PLAGNN_H_
+#define PLAGNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* plagnn_stream_t; /* a cudaStream_t */
+
+enum {
+    PLAGNN_OK = 0,
+    PLAGNN_ERR_ARG = -1,       /* bad argument (null pointer, negative size, unknown enum) */
+    PLAGNN_ERR_ALIGN = -2,     /* pointer / pitch alignment requirement not met */
+    PLAGNN_ERR_WORKSPACE = -3, /* workspace too small */
+    PLAGNN_ERR_CUDA = -4,      /* CUDA runtime error at launch */
+    PLAGNN_ERR_UNSUPPORTED = -5
+};
+
+enum { PLAGNN_ACT_NONE = 0, PLAGNN_ACT_RELU = 1, PLAGNN_ACT_LEAKY = 2, PLAGNN_ACT_SIGMOID = 3 };
+enum { PLAGNN_GEMM_AUTO = 0, PLAGNN_GEMM_SIMT = 1, PLAGNN_GEMM_TCGEN05 = 2 };
+enum { PLAGNN_REDUCE_SUM = 0, PLAGNN_REDUCE_MAX = 1 };
+
+int plagnn_version(void);
+const char* plagnn_last_error(void);
+/* 1 if the current device is compute capability 10.x (the only target), else 0. */
+int plagnn_device_supported(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  graph construction — replaces the lazy COO->CSR/CSC that DGL runs for
+ *     code/utils.py:44-45  (dgl.graph((start,end)) + dgl.add_self_loop).
+ *
+ * Stable counting/radix sort of edge ids by `key` (key = destination gives the in-edge CSR
+ * "CSC" that update_all(copy_u, reduce) walks; key = source gives the out-edge CSR used by the
+ * transposed aggregation).  With add_self_loop != 0, N edges (i,i) with ids E..E+N-1 are
+ * appended first, exactly like dgl.add_self_loop, so each row's self-loop is its last entry.
+ *   indptr[N+1], indices[E'] = other endpoint, eids[E'] = original edge id, E' = E (+N).
+ * Set-up call: synchronises `stream` before returning (host reads nothing back otherwise).
+ * ---------------------------------------------------------------------------------------- */
+size_t plagnn_csr_build_workspace_bytes(int64_t num_nodes, int64_t num_edges, int add_self_loop);
+int plagnn_csr_build(const int32_t* key, const int32_t* other, int64_t num_edges, int64_t num_nodes,
+                     int64_t num_other_nodes /* id range of `other`; 0 = num_nodes (row-partitioned slices differ) */,
+                     int add_self_loop, int32_t* indptr, int32_t* indices, int32_t* eids,
+                     void* workspace, size_t workspace_bytes, plagnn_stream_t stream);
+
+/* Aggregation plan: splits every row's neighbour list into chunks of <= `chunk` edges so that one
+ * warp owns one chunk (power-law hubs no longer serialise on one warp).
+ *   plan layout (int32): see csrc/spmm.cu; sized by plagnn_spmm_plan_bytes.
+ *   host_counts[0] = work items, [1] = rows split over several chunks, [2] = partial slots.
+ * Set-up call: synchronises `stream`. */
+size_t plagnn_spmm_plan_bytes(int64_t num_rows, int64_t num_edges, int32_t chunk);
+int plagnn_spmm_plan_build(const int32_t* indptr, int64_t num_rows, int64_t num_edges, int32_t chunk,
+                           void* plan, size_t plan_bytes, int64_t* host_counts, plagnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  aggregation — replaces DGL's gspmm for
+ *     code/model.py:20,22,24  SAGEConv('pool'): update_all(copy_u, max)   and its autograd
+ *     backward at code/train.py:204.
+ *
+ * max, forward:  out[v,f] = max_{u in in(v)} x[u,f]  (0 when in(v) is empty);
+ *                arg[v,f] = source id of the FIRST maximum in in-edge order, -1 if none.
+ * partial: scratch of plagnn_spmm_partial_bytes(plan counts, feat) bytes (may be NULL when the
+ *          plan has no split rows).
+ * ---------------------------------------------------------------------------------------- */
+size_t plagnn_spmm_partial_bytes(int64_t partial_slots, int64_t feat, int reduce);
+int plagnn_spmm_max_fwd(const int32_t* indptr, const int32_t* indices, const void* plan,
+                        const int64_t* plan_counts /* host[3], from plagnn_spmm_plan_build */,
+                        int64_t num_rows, const float* x, int64_t ldx, int64_t feat,
+                        float* out, int32_t* arg, int64_t ldo,
+                        void* partial, size_t partial_bytes, plagnn_stream_t stream);
+
+/* max, backward: dx[arg[v,f], f] += dz[v,f] * (z ? (z[v,f] > 0) : 1).
+ * `z` is the saved forward output; passing it folds the ReLU that precedes the aggregation in
+ * SAGEConv-pool into the scatter (x[arg] == z, so relu'(x[arg]) == (z > 0)).
+ * dx (n_src x feat, pitch lddx) is zeroed by the call.  Accumulation uses fp32 red.global.add,
+ * like DGL's own backward (order not fixed; see plagnn_spmm_max_bwd_gather for the ordered twin). */
+int plagnn_spmm_max_bwd(const float* dz, const int32_t* arg, const float* z, int64_t num_rows,
+                        int64_t feat, int64_t ldz, float* dx, int64_t n_src, int64_t lddx,
+                        plagnn_stream_t stream);
+
+/* Ordered (run-to-run bit-stable) twin of the above: per SOURCE row u, walk the out-edge CSR and
+ * add dz[v,f] for the edges whose arg[v,f] == u, in out-edge order.  Costs a full pass over E'. */
+int plagnn_spmm_max_bwd_gather(const int32_t* out_indptr, const int32_t* out_indices, const void* out_plan,
+                               const int64_t* out_plan_counts /* host[3] */, int64_t n_src, const float* dz, const int32_t* arg, const float* z,
+                               int64_t ldz, int64_t feat, float* dx, int64_t lddx,
+                               void* partial, size_t partial_bytes, plagnn_stream_t stream);
+
+/* sum family (copy_u / u_mul_e + sum, optional per-destination scale = mean / right norm):
+ *   out[v,:] = act( scale[v] * sum_{e in in(v)} w[eids[e]] * x[src(e),:] + bias ) [* dropout mask]
+ * eids/w/scale/bias may be NULL.  dropout_p == 0 disables dropout (the reference never applies
+ * any: code/model.py:11 accepts and ignores `dropout`).  The same call on the out-edge CSR is the
+ * exact transpose used by backward. */
+int plagnn_spmm_sum(const int32_t* indptr, const int32_t* indices, const int32_t* eids, const void* plan,
+                    const int64_t* plan_counts /* host[3] */,
+                    int64_t num_rows, const float* w, const float* scale,
+                    const float* x, int64_t ldx, int64_t feat,
+                    const float* bias, int act, float slope, float dropout_p, uint64_t dropout_seed,
+                    float* out, int64_t ldo, void* partial, size_t partial_bytes, plagnn_stream_t stream);
+/* backward companion of the dropout epilogue: grad[r,c] *= keep(r,c)/(1-p) with the same counter-based mask */
+int plagnn_dropout_scale(float* grad, int64_t rows, int64_t feat, int64_t ld, float dropout_p,
+                         uint64_t dropout_seed, plagnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  dense contraction — replaces the cuBLAS SGEMMs behind nn.Linear in
+ *     code/model.py:16-17,20-28 (fc_pool / fc_self / fc_neigh inside SAGEConv, liner1, liner2)
+ *     and their autograd backward.
+ *
+ *   C[m x n] = epilogue( sum_p  op(A_p)[m x k_p] * op(B_p)[k_p x n] )
+ *   a_trans = 0: A_p stored [m x k_p] (k contiguous);  1: stored [k_p x m] (m contiguous)
+ *   b_trans = 0: B_p stored [n x k_p] (k contiguous, an nn.Linear weight: C = A*W^T);
+ *             1: stored [k_p x n] (n contiguous)
+ *   epilogue: v = acc (+ bias[n]);  v = act(v);  if gate: v *= act'(gate[m,n]) with the derivative
+ *   written in terms of the saved forward OUTPUT (relu/leaky: sign test, sigmoid: y(1-y)).
+ *   Up to PLAGNN_GEMM_MAX_PAIRS pairs accumulate into one tile (fc_self + fc_neigh in one pass).
+ *   backend: AUTO picks tcgen05 (3xTF32 split, fp32-level accuracy) when shapes allow.
+ * ---------------------------------------------------------------------------------------- */
+#define PLAGNN_GEMM_MAX_PAIRS 2
+typedef struct {
+    const float* a; int64_t lda; int32_t a_trans;
+    const float* b; int64_t ldb; int32_t b_trans;
+    int64_t k;
+} plagnn_gemm_pair;
+
+size_t plagnn_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k_total);
+int plagnn_gemm(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs /* host */,
+                const float* bias, int act, float slope,
+                const float* gate, int64_t ldg, int gate_act,
+                float* c, int64_t ldc, void* workspace, size_t workspace_bytes,
+                int backend, plagnn_stream_t stream);
+
+/* column sums: out[j] = sum_i x[i,j]   (bias gradients). workspace >= plagnn_colsum_workspace_bytes. */
+size_t plagnn_colsum_workspace_bytes(int64_t rows, int64_t cols);
+int plagnn_colsum(const float* x, int64_t rows, int64_t cols, int64_t ldx, float* out,
+                  void* workspace, size_t workspace_bytes, plagnn_stream_t stream);
+
+/* dz = dy * act'(y) * row_scale[r], the derivative written through the saved forward output y
+ * (torch.sigmoid after liner2, code/model.py:29, is the one activation not folded into a GEMM epilogue).
+ * y == NULL skips the activation factor, row_scale == NULL the per-row factor. */
+int plagnn_act_backward(const float* dy, int64_t lddy, const float* y, int64_t ldy, int64_t rows, int64_t cols,
+                        int act, float slope, const float* row_scale, float* dz, int64_t lddz,
+                        plagnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  loss and optimiser — replace
+ *     code/train.py:89-108,203  multi_loss(logits[train_index], labels[train_index], i_weight)
+ *     code/train.py:180,205     torch.optim.Adam(model.parameters(), lr).step()
+ *
+ * bce: p = probabilities (the model output is already sigmoid, code/model.py:29), rows selected by
+ *   `index` (int64, NULL = all rows).  Computes the reference's class-weighted, clamp(1e-9,10)
+ *   BCE exactly in fp32 (p, 1-p, clamp, log) and writes
+ *     loss[0]            = sum_i -(1/R) sum_r [...]            (fp32)
+ *     dprob[N x C]       = d loss / d p  on the selected rows, 0 elsewhere (if dprob != NULL)
+ *   grad_scale multiplies dprob (upstream gradient of the scalar loss).
+ * ---------------------------------------------------------------------------------------- */
+size_t plagnn_bce_workspace_bytes(int64_t num_index, int64_t classes);
+int plagnn_bce_weighted(const float* prob, int64_t ldp, const float* target, int64_t ldt,
+                        const int64_t* index, int64_t num_index, int64_t num_rows, int64_t classes,
+                        const float* class_weight       /* device fp32[classes]: (float) w_i        */,
+                        const float* class_weight_plus1 /* device fp32[classes]: (float)(w_i + 1.0) */,
+                        float grad_scale, float* loss, float* dprob, int64_t lddp,
+                        void* workspace, size_t workspace_bytes, plagnn_stream_t stream);
+
+/* multi-tensor Adam (betas, eps, no weight decay, no amsgrad — torch.optim.Adam defaults).
+ * tensors: DEVICE array of `count` descriptors.  bias_correction1 = 1-beta1^t and
+ * bias_correction2_sqrt = sqrt(1-beta2^t) are computed by the host in double, as torch does. */
+typedef struct {
+    float* param; const float* grad; float* exp_avg; float* exp_avg_sq; int64_t numel;
+} plagnn_adam_tensor;
+int plagnn_adam_multi(const plagnn_adam_tensor* tensors /* device */, int32_t count, int64_t max_numel,
+                      float lr, float beta1, float beta2, float eps,
+                      double bias_correction1, double bias_correction2_sqrt, plagnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * next-1: label decision on device — replaces the Python row loop of
+ *     code/train.py:19-40  protein_loc_correction(loc_proba, alpha)
+ * pred[N x C] (fp32 0/1). */
+size_t plagnn_loc_correction_workspace_bytes(int64_t classes);
+int plagnn_loc_correction(const float* prob, int64_t ldp, int64_t num_rows, int64_t classes, float alpha,
+                          float* pred, int64_t ldpred, void* workspace, size_t workspace_bytes,
+                          plagnn_stream_t stream);
+
+/* small utilities used by the host layer */
+int plagnn_pad_copy(const float* src, int64_t rows, int64_t cols, int64_t lds, float* dst, int64_t ldd,
+                    plagnn_stream_t stream); /* dst[:, :cols] = src; dst[:, cols:ldd] = 0 */
+int plagnn_transpose(const float* src, int64_t rows, int64_t cols, int64_t lds, float* dst, int64_t ldd,
+                     plagnn_stream_t stream); /* dst[cols x rows] = src^T */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLAGNN_H_ */

@@ -1,0 +1,23 @@
+"""plagnn_b200 — B200-native (sm_100a) implementation of PLA-GNN's message-passing hot path.
+
+Public surface (mirrors what the reference's train loop touches):
+    GNN32, SAGEConv            model.py drop-ins (nn.py)
+    create_graph, Graph, graph, add_self_loop    utils.py / dgl drop-ins (utils.py, graph.py)
+    multi_loss, multi_loss_indexed, weight_cal   fused loss (loss.py)
+    FusedAdam                  fused optimiser (optim.py)
+    protein_loc_correction     on-device label decision (metrics.py)
+The kernels live in libplagnn.so (csrc/, C ABI in include/plagnn.h); importing this package does not
+need a GPU, calling any kernel does.
+"""
+from . import _lib
+from ._lib import PlagnnError, LIB_PATH
+from .graph import Graph, Csr, graph, add_self_loop, build_csr
+from .nn import GNN32, SAGEConv, GraphConvSum, GCN
+from .loss import multi_loss, multi_loss_indexed, weight_cal
+from .optim import FusedAdam
+from .metrics import protein_loc_correction, performances_record
+from .utils import create_graph
+
+__all__ = ["GNN32", "SAGEConv", "GraphConvSum", "GCN", "Graph", "Csr", "graph", "add_self_loop", "build_csr",
+           "create_graph", "multi_loss", "multi_loss_indexed", "weight_cal", "FusedAdam", "protein_loc_correction",
+           "performances_record", "PlagnnError", "LIB_PATH"]

@@ -1,0 +1,346 @@
+// K4 — loss, optimiser and the small HBM-bound helpers around the aggregation / GEMM kernels.
+//
+//   plagnn_bce_weighted   <- code/train.py:89-108,203   multi_loss(logits[train_index], labels[train_index], i_weight)
+//   plagnn_adam_multi     <- code/train.py:180,205      torch.optim.Adam(model.parameters(), lr).step()
+//   plagnn_loc_correction <- code/train.py:19-40        protein_loc_correction (label decision)
+//   plagnn_colsum         <- bias gradients of nn.Linear / SAGEConv.bias (autograd at code/train.py:204)
+//
+// The loss keeps the reference's fp32 operator order (p, 1-p, clamp(1e-9,10), log, *w, /(w+1), *2) and the
+// closed-interval clamp gradient, because saturated sigmoid outputs make the "nicer" with-logits form differ.
+#include "common.cuh"
+
+namespace plagnn {
+
+constexpr int BCE_THREADS = 256;
+constexpr int BCE_MAX_CLASSES = 64;
+
+__global__ void __launch_bounds__(BCE_THREADS)
+bce_kernel(const float* __restrict__ prob, int64_t ldp, const float* __restrict__ target, int64_t ldt,
+           const int64_t* __restrict__ index, int64_t num_index, int64_t num_rows, int classes,
+           const float* __restrict__ cw, const float* __restrict__ cwp1, float grad_scale,
+           double* __restrict__ block_part, float* __restrict__ dprob, int64_t lddp, int* __restrict__ bad) {
+    __shared__ double red[BCE_THREADS / 32][BCE_MAX_CLASSES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * BCE_THREADS + threadIdx.x;
+    int64_t row = -1;
+    if (i < num_index) {
+        row = index ? index[i] : i;
+        if (row < 0) row += num_rows;            // python-style negative index
+        if (row < 0 || row >= num_rows) { atomicOr(bad, 1); row = -1; }
+    }
+    const float inv_r = -1.0f / (float)num_index;   // grad of  -(sum)/R  w.r.t. sum
+    for (int c = 0; c < classes; ++c) {
+        double term = 0.0;
+        if (row >= 0) {
+            const float p = prob[row * ldp + c];
+            const float t = target[row * ldt + c];
+            const float w = cw[c], wp1 = cwp1[c];
+            const float q = 1.0f - p;
+            const float pc = fminf(fmaxf(p, 1e-9f), 10.0f);
+            const float qc = fminf(fmaxf(q, 1e-9f), 10.0f);
+            const float pos = t * logf(pc) * w;
+            const float neg = (1.0f - t) * logf(qc);
+            term = (double)((pos + neg) / wp1 * 2.0f);
+            if (dprob) {
+                const float g2 = (inv_r * grad_scale * 2.0f) / wp1;
+                float g = 0.f;
+                if (p >= 1e-9f && p <= 10.0f) g += ((g2 * w) * t) / pc;
+                if (q >= 1e-9f && q <= 10.0f) g -= (g2 * (1.0f - t)) / qc;
+                atomicAdd(dprob + row * lddp + c, g);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) term += __shfl_xor_sync(0xffffffffu, term, d);
+        if (lane == 0) red[warp][c] = term;
+    }
+    __syncthreads();
+    if (threadIdx.x < classes) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < BCE_THREADS / 32; ++w) s += red[w][threadIdx.x];
+        block_part[(int64_t)blockIdx.x * classes + threadIdx.x] = s;
+    }
+}
+
+__global__ void bce_finalize_kernel(const double* __restrict__ block_part, int num_blocks, int classes,
+                                    int64_t num_index, float* __restrict__ loss) {
+    __shared__ float per_class[BCE_MAX_CLASSES];
+    if (threadIdx.x < classes) {
+        double s = 0.0;
+        for (int b = 0; b < num_blocks; ++b) s += block_part[(int64_t)b * classes + threadIdx.x];
+        // reference: scl_loss = -scl_loss.sum() / len(input)   (fp32 sum, fp32 divide)
+        per_class[threadIdx.x] = -((float)s) / (float)num_index;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float l = 0.f;
+        for (int c = 0; c < classes; ++c) l += per_class[c];   // loss += scl_loss, in class order
+        loss[0] = l;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(const plagnn_adam_tensor* __restrict__ tensors, float lerp_w, float beta2, float one_minus_beta2,
+            float eps, float step_size, float bc2_sqrt) {
+    const plagnn_adam_tensor T = tensors[blockIdx.y];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T.numel; i += (int64_t)gridDim.x * blockDim.x) {
+        const float g = T.grad[i];
+        float m = T.exp_avg[i];
+        float v = T.exp_avg_sq[i];
+        m = m + lerp_w * (g - m);                     // exp_avg.lerp_(grad, 1 - beta1)
+        v = v * beta2;                                // exp_avg_sq.mul_(beta2)
+        v = v + one_minus_beta2 * (g * g);            //   .addcmul_(grad, grad, value=1 - beta2)
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        T.param[i] = T.param[i] - (step_size * m) / denom;   // param.addcdiv_(exp_avg, denom, value=-step_size)
+        T.exp_avg[i] = m;
+        T.exp_avg_sq[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int CS_ROWS_PER_CHUNK = 512;
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ldx, float* __restrict__ part) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS_PER_CHUNK;
+    const int64_t r1 = r0 + CS_ROWS_PER_CHUNK < rows ? r0 + CS_ROWS_PER_CHUNK : rows;
+    float s = 0.f;
+    if (c < cols)
+        for (int64_t r = r0 + ty; r < r1; r += 8) s += __ldg(x + r * ldx + c);
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][tx];
+        part[(int64_t)blockIdx.y * cols + c] = t;
+    }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int chunks, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int k = 0; k < chunks; ++k) s += part[(int64_t)k * cols + c];
+    out[c] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// label decision: column min/max, then per-row normalise + threshold
+__global__ void __launch_bounds__(256)
+colminmax_partial_kernel(const float* __restrict__ p, int64_t ldp, int64_t rows, int classes, float* __restrict__ part) {
+    // part[block][2*classes] : mins then maxs
+    __shared__ float smin[256], smax[256];
+    for (int c = 0; c < classes; ++c) {
+        float mn = INFINITY, mx = -INFINITY;
+        for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+            const float v = p[r * ldp + c];
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+        }
+        smin[threadIdx.x] = mn;
+        smax[threadIdx.x] = mx;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                smin[threadIdx.x] = fminf(smin[threadIdx.x], smin[threadIdx.x + s]);
+                smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + s]);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            part[(int64_t)blockIdx.x * 2 * classes + c] = smin[0];
+            part[(int64_t)blockIdx.x * 2 * classes + classes + c] = smax[0];
+        }
+        __syncthreads();
+    }
+}
+__global__ void loc_decide_kernel(const float* __restrict__ p, int64_t ldp, int64_t rows, int classes, float alpha,
+                                  const float* __restrict__ part, int nparts, float* __restrict__ pred, int64_t ldpred) {
+    __shared__ float cmin[BCE_MAX_CLASSES], cmax[BCE_MAX_CLASSES];
+    if (threadIdx.x < classes) {
+        float mn = INFINITY, mx = -INFINITY;
+        for (int b = 0; b < nparts; ++b) {
+            mn = fminf(mn, part[(int64_t)b * 2 * classes + threadIdx.x]);
+            mx = fmaxf(mx, part[(int64_t)b * 2 * classes + classes + threadIdx.x]);
+        }
+        cmin[threadIdx.x] = mn;
+        cmax[threadIdx.x] = mx;
+    }
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float v[BCE_MAX_CLASSES];
+    float s = 0.f;
+    for (int c = 0; c < classes; ++c) {
+        v[c] = (p[r * ldp + c] - cmin[c]) / (cmax[c] - cmin[c]);
+        s += v[c];
+    }
+    float rmax = -INFINITY, rmin = INFINITY;
+    for (int c = 0; c < classes; ++c) {
+        v[c] = v[c] / s;
+        rmax = fmaxf(rmax, v[c]);
+        rmin = fminf(rmin, v[c]);
+    }
+    const float thr = rmax - (rmax - rmin) * alpha;
+    for (int c = 0; c < classes; ++c) pred[r * ldpred + c] = v[c] > thr ? 1.f : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pad_copy_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t lds, float* __restrict__ dst, int64_t ldd) {
+    const int64_t total = rows * ldd;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / ldd;
+        const int c = (int)(i - r * ldd);
+        dst[i] = c < cols ? __ldg(src + r * lds + c) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t lds, float* __restrict__ dst, int64_t ldd) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    for (int i = ty; i < 32; i += 8)
+        tile[i][tx] = (r0 + i < rows && c0 + tx < cols) ? __ldg(src + (r0 + i) * lds + c0 + tx) : 0.f;
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < cols && r0 + tx < rows) dst[(c0 + i) * ldd + r0 + tx] = tile[tx][i];
+}
+
+static inline int capped_grid(int64_t work_items, int threads, int waves) {
+    const int64_t want = ceil_div(work_items, threads);
+    const int64_t cap = (int64_t)sm_count() * waves;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace plagnn
+
+using namespace plagnn;
+
+extern "C" {
+
+size_t plagnn_bce_workspace_bytes(int64_t num_index, int64_t classes) {
+    const int64_t blocks = ceil_div(num_index > 0 ? num_index : 1, BCE_THREADS);
+    return align_up((size_t)blocks * classes * sizeof(double), 256) + 256;
+}
+
+int plagnn_bce_weighted(const float* prob, int64_t ldp, const float* target, int64_t ldt, const int64_t* index,
+                        int64_t num_index, int64_t num_rows, int64_t classes, const float* class_weight,
+                        const float* class_weight_plus1, float grad_scale, float* loss, float* dprob, int64_t lddp,
+                        void* workspace, size_t workspace_bytes, plagnn_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!prob || !target || !class_weight || !class_weight_plus1 || !loss || num_index <= 0 || num_rows <= 0 ||
+        classes <= 0 || classes > BCE_MAX_CLASSES || ldp < classes || ldt < classes || (dprob && lddp < classes))
+        return fail(PLAGNN_ERR_ARG, "bce_weighted", "bad arguments");
+    const size_t need = plagnn_bce_workspace_bytes(num_index, classes);
+    if (!workspace || workspace_bytes < need) return fail(PLAGNN_ERR_WORKSPACE, "bce_weighted", "workspace too small");
+    const int blocks = (int)ceil_div(num_index, BCE_THREADS);
+    double* part = (double*)workspace;
+    int* bad = (int*)((char*)workspace + need - 256);
+    PLAGNN_CUDA_TRY(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    if (dprob) PLAGNN_CUDA_TRY(cudaMemset2DAsync(dprob, lddp * sizeof(float), 0, classes * sizeof(float), num_rows, st));
+    bce_kernel<<<blocks, BCE_THREADS, 0, st>>>(prob, ldp, target, ldt, index, num_index, num_rows, (int)classes,
+                                                class_weight, class_weight_plus1, grad_scale, part, dprob, lddp, bad);
+    bce_finalize_kernel<<<1, BCE_MAX_CLASSES, 0, st>>>(part, blocks, (int)classes, num_index, loss);
+    return check_launch("bce_weighted");
+}
+
+int plagnn_adam_multi(const plagnn_adam_tensor* tensors, int32_t count, int64_t max_numel, float lr, float beta1,
+                      float beta2, float eps, double bias_correction1, double bias_correction2_sqrt,
+                      plagnn_stream_t stream) {
+    if (!tensors || count <= 0 || max_numel <= 0 || bias_correction1 <= 0.0 || bias_correction2_sqrt <= 0.0)
+        return fail(PLAGNN_ERR_ARG, "adam_multi", "bad arguments");
+    const float step_size = (float)((double)lr / bias_correction1);
+    const float lerp_w = (float)(1.0 - (double)beta1);
+    const float omb2 = (float)(1.0 - (double)beta2);
+    dim3 grid((unsigned)capped_grid(max_numel, 256, 4), (unsigned)count);
+    adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tensors, lerp_w, beta2, omb2, eps, step_size,
+                                                        (float)bias_correction2_sqrt);
+    return check_launch("adam_multi");
+}
+
+size_t plagnn_colsum_workspace_bytes(int64_t rows, int64_t cols) {
+    return align_up((size_t)ceil_div(rows > 0 ? rows : 1, CS_ROWS_PER_CHUNK) * (size_t)cols * sizeof(float), 256);
+}
+
+int plagnn_colsum(const float* x, int64_t rows, int64_t cols, int64_t ldx, float* out, void* workspace,
+                  size_t workspace_bytes, plagnn_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!x || !out || rows <= 0 || cols <= 0 || ldx < cols) return fail(PLAGNN_ERR_ARG, "colsum", "bad arguments");
+    if (!workspace || workspace_bytes < plagnn_colsum_workspace_bytes(rows, cols))
+        return fail(PLAGNN_ERR_WORKSPACE, "colsum", "workspace too small");
+    const int chunks = (int)ceil_div(rows, CS_ROWS_PER_CHUNK);
+    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)chunks);
+    colsum_partial_kernel<<<grid, 256, 0, st>>>(x, rows, (int)cols, ldx, (float*)workspace);
+    colsum_final_kernel<<<(unsigned)ceil_div(cols, 128), 128, 0, st>>>((const float*)workspace, chunks, (int)cols, out);
+    return check_launch("colsum");
+}
+
+size_t plagnn_loc_correction_workspace_bytes(int64_t classes) {
+    return align_up((size_t)sm_count() * 2 * (size_t)(classes > 0 ? classes : 1) * sizeof(float), 256);
+}
+
+int plagnn_loc_correction(const float* prob, int64_t ldp, int64_t num_rows, int64_t classes, float alpha, float* pred,
+                          int64_t ldpred, void* workspace, size_t workspace_bytes, plagnn_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!prob || !pred || num_rows <= 0 || classes <= 0 || classes > BCE_MAX_CLASSES || ldp < classes || ldpred < classes)
+        return fail(PLAGNN_ERR_ARG, "loc_correction", "bad arguments");
+    const int nparts = capped_grid(num_rows, 256, 1);
+    if (!workspace || workspace_bytes < (size_t)nparts * 2 * classes * sizeof(float))
+        return fail(PLAGNN_ERR_WORKSPACE, "loc_correction", "workspace too small (need 2*classes*sm_count floats)");
+    colminmax_partial_kernel<<<nparts, 256, 0, st>>>(prob, ldp, num_rows, (int)classes, (float*)workspace);
+    loc_decide_kernel<<<(unsigned)ceil_div(num_rows, 128), 128, 0, st>>>(prob, ldp, num_rows, (int)classes, alpha,
+                                                                          (const float*)workspace, nparts, pred, ldpred);
+    return check_launch("loc_correction");
+}
+
+int plagnn_pad_copy(const float* src, int64_t rows, int64_t cols, int64_t lds, float* dst, int64_t ldd,
+                    plagnn_stream_t stream) {
+    if (!src || !dst || rows <= 0 || cols <= 0 || lds < cols || ldd < cols) return fail(PLAGNN_ERR_ARG, "pad_copy", "bad arguments");
+    pad_copy_kernel<<<capped_grid(rows * ldd, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, rows, (int)cols, lds, dst, ldd);
+    return check_launch("pad_copy");
+}
+
+int plagnn_transpose(const float* src, int64_t rows, int64_t cols, int64_t lds, float* dst, int64_t ldd,
+                     plagnn_stream_t stream) {
+    if (!src || !dst || rows <= 0 || cols <= 0 || lds < cols || ldd < rows) return fail(PLAGNN_ERR_ARG, "transpose", "bad arguments");
+    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+    transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, rows, cols, lds, dst, ldd);
+    return check_launch("transpose");
+}
+
+}  // extern "C"
+
+// dz = dy * act'(y), derivative written through the saved forward output y (sigmoid after liner2,
+// code/model.py:29, is the one activation whose gradient is not folded into a GEMM epilogue)
+namespace plagnn {
+__global__ void __launch_bounds__(256)
+act_backward_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ y, int64_t ldy, int64_t rows,
+                    int cols, int act, float slope, const float* __restrict__ row_scale, float* __restrict__ dz,
+                    int64_t lddz) {
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols;
+        const int c = (int)(i - r * cols);
+        float v = dy[r * lddy + c];
+        if (y) v *= act_grad_from_output(y[r * ldy + c], act, slope);
+        if (row_scale) v *= __ldg(row_scale + r);
+        dz[r * lddz + c] = v;
+    }
+}
+}  // namespace plagnn
+
+extern "C" int plagnn_act_backward(const float* dy, int64_t lddy, const float* y, int64_t ldy, int64_t rows, int64_t cols,
+                                   int act, float slope, const float* row_scale, float* dz, int64_t lddz,
+                                   plagnn_stream_t stream) {
+    using namespace plagnn;
+    if (!dy || !dz || rows <= 0 || cols <= 0 || lddy < cols || (y && ldy < cols) || lddz < cols)
+        return fail(PLAGNN_ERR_ARG, "act_backward", "bad arguments");
+    act_backward_kernel<<<capped_grid(rows * cols, 256, 8), 256, 0, (cudaStream_t)stream>>>(dy, lddy, y, ldy, rows,
+                                                                                          (int)cols, act, slope, row_scale, dz, lddz);
+    return check_launch("act_backward");
+}

@@ -1,0 +1,70 @@
+// K3 — C-ABI front end of the dense contraction: argument checks and backend choice.
+// (reference call sites: code/model.py:16-17,20-28 nn.Linear / SAGEConv fc_* and their backward.)
+#include "common.cuh"
+#include <cstdlib>
+
+namespace plagnn {
+struct GemmParams;
+// gemm_simt.cu
+int gemm_simt_entry(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs, const float* bias, int act,
+                    float slope, const float* gate, int64_t ldg, int gate_act, float* c, int64_t ldc, void* workspace,
+                    size_t workspace_bytes, cudaStream_t st);
+// gemm_tc.cu
+bool gemm_tc_eligible(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs);
+int gemm_tc_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs, const float* bias, int act,
+                   float slope, const float* gate, int64_t ldg, int gate_act, float* c, int64_t ldc, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st);
+}  // namespace plagnn
+
+using namespace plagnn;
+
+extern "C" {
+
+size_t plagnn_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k_total) {
+    // split-K partials: at most 64 splits, only used when the output has fewer tiles than SMs
+    const int64_t tiles = ceil_div(m, 128) * ceil_div(n, 128);
+    if (tiles >= 148 * 2 || k_total < 128) return 0;
+    int64_t s = ceil_div((int64_t)2 * 148, tiles);
+    if (s > 64) s = 64;
+    return align_up((size_t)s * (size_t)m * (size_t)n * sizeof(float), 256);
+}
+
+int plagnn_gemm(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs, const float* bias, int act,
+                float slope, const float* gate, int64_t ldg, int gate_act, float* c, int64_t ldc, void* workspace,
+                size_t workspace_bytes, int backend, plagnn_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m <= 0 || n <= 0 || npairs < 1 || npairs > PLAGNN_GEMM_MAX_PAIRS || !pairs || !c)
+        return fail(PLAGNN_ERR_ARG, "gemm", "bad sizes or null pointers");
+    if (act < PLAGNN_ACT_NONE || act > PLAGNN_ACT_SIGMOID || gate_act < PLAGNN_ACT_NONE || gate_act > PLAGNN_ACT_SIGMOID)
+        return fail(PLAGNN_ERR_ARG, "gemm", "unknown activation");
+    if (ldc < n || (gate && ldg < n)) return fail(PLAGNN_ERR_ARG, "gemm", "output/gate pitch smaller than n");
+    for (int p = 0; p < npairs; ++p) {
+        const plagnn_gemm_pair& q = pairs[p];
+        if (!q.a || !q.b || q.k <= 0) return fail(PLAGNN_ERR_ARG, "gemm", "null operand or k <= 0");
+        if (q.lda < (q.a_trans ? m : q.k) || q.ldb < (q.b_trans ? n : q.k))
+            return fail(PLAGNN_ERR_ARG, "gemm", "operand pitch too small");
+    }
+    if (backend == PLAGNN_GEMM_AUTO) {
+        static const int forced = [] {
+            const char* e = getenv("PLAGNN_GEMM");
+            if (!e) return (int)PLAGNN_GEMM_AUTO;
+            if (e[0] == 's' || e[0] == 'S') return (int)PLAGNN_GEMM_SIMT;
+            if (e[0] == 't' || e[0] == 'T') return (int)PLAGNN_GEMM_TCGEN05;
+            return (int)PLAGNN_GEMM_AUTO;
+        }();
+        backend = forced;
+    }
+    const bool tc_ok = gemm_tc_eligible(m, n, npairs, pairs);
+    if (backend == PLAGNN_GEMM_TCGEN05 && !tc_ok)
+        return fail(PLAGNN_ERR_UNSUPPORTED, "gemm", "tcgen05 backend needs n >= 16 and k >= 8");
+    if (backend == PLAGNN_GEMM_AUTO) backend = tc_ok ? PLAGNN_GEMM_TCGEN05 : PLAGNN_GEMM_SIMT;
+    if (backend == PLAGNN_GEMM_TCGEN05)
+        return gemm_tc_launch(m, n, npairs, pairs, bias, act, slope, gate, ldg, gate_act, c, ldc, workspace,
+                              workspace_bytes, st);
+    if (backend == PLAGNN_GEMM_SIMT)
+        return gemm_simt_entry(m, n, npairs, pairs, bias, act, slope, gate, ldg, gate_act, c, ldc, workspace,
+                               workspace_bytes, st);
+    return fail(PLAGNN_ERR_ARG, "gemm", "unknown backend");
+}
+
+}  // extern "C"

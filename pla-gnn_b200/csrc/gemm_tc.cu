@@ -1,0 +1,425 @@
+// K3 — dense feature x weight contraction on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Replaces the cuBLAS SGEMMs behind nn.Linear in code/model.py:16-17,20-28 (fc_pool / fc_self / fc_neigh
+// inside SAGEConv, liner1, liner2) and their autograd backward.
+//
+// fp32-level accuracy on TF32 tensor cores: every fp32 operand x is split in registers into
+//   hi = tf32(x)   and   lo = tf32(x - hi)
+// and the product is accumulated in fp32 in tensor memory as  hi*hi + hi*lo + lo*hi  (3xTF32).
+// Because the split has to pass through registers anyway, operands are NOT brought in by TMA: eight
+// loader warps read the fp32 tiles with coalesced 16-byte loads, split them and write the four tf32
+// tiles (A_hi, A_lo, B_hi, B_lo) straight into the 128-byte-swizzled K-major layout that the UMMA
+// shared-memory descriptors expect, transposing on the way when the operand is stored MN-contiguous.
+//
+// CTA = 9 warps:  warps 0-7 loaders (then epilogue: TMEM -> registers -> global),  warp 8 = TMEM
+// allocator + single-thread tcgen05.mma issuer.  3-stage shared-memory ring (64 KB per stage) handed
+// over with mbarriers: loaders -> full[s] -> MMA -> tcgen05.commit -> empty[s]; accumulator hand-off
+// to the epilogue through a third mbarrier.  One 128 x 128 output tile per CTA, optional split-K.
+#include "common.cuh"
+
+namespace plagnn {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
+constexpr int TC_LOAD_WARPS = 8;
+constexpr int TC_THREADS = (TC_LOAD_WARPS + 1) * 32;
+constexpr int TC_PART_BYTES = TC_BM * TC_BK * 4;          // 16 KB: one tf32 tile (128 rows x 128 bytes)
+constexpr int TC_STAGE_BYTES = 4 * TC_PART_BYTES;         // A_hi, A_lo, B_hi, B_lo
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_TMEM_COLS = 128;
+
+struct TcParams {
+    int64_t m, n;
+    int npairs;
+    const float* a[PLAGNN_GEMM_MAX_PAIRS];
+    const float* b[PLAGNN_GEMM_MAX_PAIRS];
+    int64_t lda[PLAGNN_GEMM_MAX_PAIRS], ldb[PLAGNN_GEMM_MAX_PAIRS];
+    int a_trans[PLAGNN_GEMM_MAX_PAIRS], b_trans[PLAGNN_GEMM_MAX_PAIRS];
+    int a_vec[PLAGNN_GEMM_MAX_PAIRS], b_vec[PLAGNN_GEMM_MAX_PAIRS];
+    int64_t k[PLAGNN_GEMM_MAX_PAIRS];
+    int kblocks[PLAGNN_GEMM_MAX_PAIRS];
+    int total_kblocks, kblocks_per_split, splits;
+    const float* bias;
+    int act;
+    float slope;
+    const float* gate;
+    int64_t ldg;
+    int gate_act;
+    float* c;
+    int64_t ldc;
+    float* partial;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), descriptor version 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// kind::tf32, D = f32, A/B K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
+
+// ---- operand tile: global fp32 -> registers ------------------------------------------------------
+// Tile = 128 (mn) x 32 (k).  Each of the 256 loader threads owns 4 float4.
+//   trans == 0 (k contiguous):  i-th float4 = row (t>>3)+32i, k-chunk c = t&7         (elements k = 4c..4c+3)
+//   trans == 1 (mn contiguous): i-th float4 = k-row 8*(w&3)+(lane&7), mn-quad 16*(w>>2)+4i+(lane>>3)
+__device__ __forceinline__ void tile_load(const float* __restrict__ p, int64_t ld, int trans, int vec, int64_t rows,
+                                          int64_t kdim, int64_t r0, int64_t k0, float4 (&v)[4]) {
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!trans) {
+            const int64_t r = r0 + (t >> 3) + 32 * i;
+            const int64_t kk = k0 + (t & 7) * 4;
+            if (r < rows && kk < kdim) {
+                const float* q = p + r * ld + kk;
+                if (vec && kk + 3 < kdim) {
+                    x = ldg_f4(q);
+                } else {
+                    x.x = __ldg(q);
+                    if (kk + 1 < kdim) x.y = __ldg(q + 1);
+                    if (kk + 2 < kdim) x.z = __ldg(q + 2);
+                    if (kk + 3 < kdim) x.w = __ldg(q + 3);
+                }
+            }
+        } else {
+            const int64_t kk = k0 + 8 * (w & 3) + (lane & 7);
+            const int64_t r = r0 + 4 * (16 * (w >> 2) + 4 * i + (lane >> 3));
+            if (kk < kdim && r < rows) {
+                const float* q = p + kk * ld + r;
+                if (vec && r + 3 < rows) {
+                    x = ldg_f4(q);
+                } else {
+                    x.x = __ldg(q);
+                    if (r + 1 < rows) x.y = __ldg(q + 1);
+                    if (r + 2 < rows) x.z = __ldg(q + 2);
+                    if (r + 3 < rows) x.w = __ldg(q + 3);
+                }
+            }
+        }
+        v[i] = x;
+    }
+}
+
+// ---- registers -> split -> swizzled K-major shared tiles -----------------------------------------
+// byte offset of (row, 16-byte chunk c) inside a tile: row*128 + ((c ^ (row & 7)) << 4)
+__device__ __forceinline__ void tile_store(uint32_t s_hi, uint32_t s_lo, int trans, const float4 (&v)[4]) {
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_tf32(x[e], hi[e], lo[e]);
+        if (!trans) {
+            const int row = (t >> 3) + 32 * i;
+            const int c = t & 7;
+            const uint32_t off = (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4));
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+        } else {
+            const int kk = 8 * (w & 3) + (lane & 7);
+            const int jq = lane >> 3;
+            const int rbase = 4 * (16 * (w >> 2) + 4 * i + jq);
+            const int chunk = kk >> 2, el = kk & 3;
+            // rotate the element order per lane group so the 32 lanes of one store hit 32 different banks
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int e = (s + jq) & 3;
+                const uint32_t h = e == 0 ? hi[0] : e == 1 ? hi[1] : e == 2 ? hi[2] : hi[3];
+                const uint32_t l = e == 0 ? lo[0] : e == 1 ? lo[1] : e == 2 ? lo[2] : lo[3];
+                const int row = rbase + e;
+                const uint32_t off = (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4) + el * 4);
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(s_hi + off), "r"(h) : "memory");
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(s_lo + off), "r"(l) : "memory");
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float tc_epilogue_one(const TcParams& P, float v, int64_t r, int64_t c) {
+    if (P.bias) v += __ldg(P.bias + c);
+    v = apply_act(v, P.act, P.slope);
+    if (P.gate) v *= act_grad_from_output(__ldg(P.gate + r * P.ldg + c), P.gate_act, P.slope);
+    return v;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles = (raw + 1023u) & ~1023u;                 // 1024-byte aligned (swizzle atom)
+    const uint32_t bars = tiles + TC_STAGES * TC_STAGE_BYTES;       // full[3], empty[3], acc, tmem slot
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * TC_STAGES, bar_acc = bars + 16 * TC_STAGES;
+    const uint32_t tmem_slot = bar_acc + 8;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int64_t m0 = (int64_t)blockIdx.y * TC_BM, n0 = (int64_t)blockIdx.x * TC_BN;
+    const int split = blockIdx.z;
+    const int kb_beg = split * P.kblocks_per_split;
+    const int kb_end = min(P.total_kblocks, kb_beg + P.kblocks_per_split);
+    const int nkb = kb_end - kb_beg;
+
+    if (t == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, TC_LOAD_WARPS * 32);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        fence_mbar_init();
+    }
+    if (warp == TC_LOAD_WARPS) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp < TC_LOAD_WARPS) {
+        // ================= loaders =================
+        float4 ca[4], cb[4], na[4], nb[4];
+        auto issue = [&](int kb, float4 (&va)[4], float4 (&vb)[4]) {
+            int p = 0, local = kb;
+            if (P.npairs > 1 && local >= P.kblocks[0]) { local -= P.kblocks[0]; p = 1; }
+            const int64_t k0 = (int64_t)local * TC_BK;
+            tile_load(P.a[p], P.lda[p], P.a_trans[p], P.a_vec[p], P.m, P.k[p], m0, k0, va);
+            tile_load(P.b[p], P.ldb[p], P.b_trans[p], P.b_vec[p], P.n, P.k[p], n0, k0, vb);
+            return p;
+        };
+        int pcur = 0;
+        if (nkb > 0) pcur = issue(kb_beg, ca, cb);
+        for (int it = 0; it < nkb; ++it) {
+            const int s = it % TC_STAGES;
+            const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
+            int pnext = 0;
+            if (it + 1 < nkb) pnext = issue(kb_beg + it + 1, na, nb);
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            const uint32_t st = tiles + s * TC_STAGE_BYTES;
+            tile_store(st, st + TC_PART_BYTES, P.a_trans[pcur], ca);
+            tile_store(st + 2 * TC_PART_BYTES, st + 3 * TC_PART_BYTES, P.b_trans[pcur], cb);
+            fence_proxy_async_smem();
+            mbar_arrive(bar_full + 8 * s);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
+            pcur = pnext;
+        }
+
+        // ================= epilogue =================
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        const int lg = warp & 3, ch = warp >> 2;
+        const int64_t r = m0 + lg * 32 + lane;
+        const bool direct = P.splits == 1;
+        float* dst = direct ? P.c : P.partial + (int64_t)split * P.m * P.n;
+        const int64_t ldd = direct ? P.ldc : P.n;
+        const bool vec_out = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const int cbase = 64 * ch + 16 * j;
+            if (n0 + cbase >= P.n) break;   // warp-uniform
+            uint32_t acc[16];
+            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)cbase, acc);
+            tmem_ld_wait();
+            if (r < P.m) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int64_t c = n0 + cbase + 4 * q;
+                    if (c >= P.n) break;
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        v[e] = __uint_as_float(acc[4 * q + e]);
+                        if (direct && c + e < P.n) v[e] = tc_epilogue_one(P, v[e], r, c + e);
+                    }
+                    if (vec_out && c + 3 < P.n) {
+                        *reinterpret_cast<float4*>(dst + r * ldd + c) = make_float4(v[0], v[1], v[2], v[3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (c + e < P.n) dst[r * ldd + c + e] = v[e];
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ================= MMA issuer (one elected lane) =================
+        if (lane == 0) {
+            const int64_t nrem = P.n - n0;
+            const uint32_t n_eff = nrem >= TC_BN ? TC_BN : (uint32_t)((nrem + 15) / 16 * 16);
+            const uint32_t idesc = make_idesc(n_eff);
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
+                mbar_wait(bar_full + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t st = tiles + s * TC_STAGE_BYTES;
+                const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + TC_PART_BYTES);
+                const uint64_t b_hi = make_smem_desc(st + 2 * TC_PART_BYTES), b_lo = make_smem_desc(st + 3 * TC_PART_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                    const uint64_t adv = (uint64_t)(kk * 2);   // 8 tf32 = 32 bytes = 2 x 16-byte units
+                    // small terms first, the hi*hi term last
+                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (it | kk) ? 1u : 0u);
+                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+                }
+                umma_commit(bar_empty + 8 * s);     // frees the stage when these MMAs have read it
+            }
+            umma_commit(bar_acc);                   // accumulator complete
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == TC_LOAD_WARPS) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    }
+}
+
+// ordered reduction of split-K partials + epilogue
+__global__ void __launch_bounds__(256) gemm_tc_reduce_kernel(const TcParams P) {
+    const int64_t total = P.m * P.n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int z = 0; z < P.splits; ++z) s += P.partial[(int64_t)z * total + i];
+        const int64_t r = i / P.n, c = i - r * P.n;
+        P.c[r * P.ldc + c] = tc_epilogue_one(P, s, r, c);
+    }
+}
+
+static int tc_choose_splits(int64_t m, int64_t n, int total_kblocks) {
+    const int64_t tiles = ceil_div(m, TC_BM) * ceil_div(n, TC_BN);
+    const int sms = sm_count();
+    if (tiles >= sms || total_kblocks < 8) return 1;
+    int64_t s = sms / tiles;   // one wave: tiles * splits <= SM count (1 CTA per SM)
+    if (s > total_kblocks / 4) s = total_kblocks / 4;
+    if (s > 64) s = 64;
+    return s < 1 ? 1 : (int)s;
+}
+
+bool gemm_tc_eligible(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs) {
+    if (n < 16 || m < 1) return false;
+    for (int p = 0; p < npairs; ++p)
+        if (pairs[p].k < 8) return false;
+    return true;
+}
+
+int gemm_tc_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs, const float* bias, int act,
+                   float slope, const float* gate, int64_t ldg, int gate_act, float* c, int64_t ldc, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st) {
+    TcParams P;
+    P.m = m; P.n = n; P.npairs = npairs;
+    P.total_kblocks = 0;
+    for (int p = 0; p < PLAGNN_GEMM_MAX_PAIRS; ++p) {
+        const plagnn_gemm_pair& q = pairs[p < npairs ? p : 0];
+        P.a[p] = q.a; P.b[p] = q.b; P.lda[p] = q.lda; P.ldb[p] = q.ldb;
+        P.a_trans[p] = q.a_trans ? 1 : 0; P.b_trans[p] = q.b_trans ? 1 : 0;
+        P.a_vec[p] = ((q.lda & 3) == 0 && aligned16(q.a)) ? 1 : 0;
+        P.b_vec[p] = ((q.ldb & 3) == 0 && aligned16(q.b)) ? 1 : 0;
+        P.k[p] = p < npairs ? q.k : 0;
+        P.kblocks[p] = p < npairs ? (int)ceil_div(q.k, TC_BK) : 0;
+        P.total_kblocks += P.kblocks[p];
+    }
+    P.bias = bias; P.act = act; P.slope = slope; P.gate = gate; P.ldg = ldg; P.gate_act = gate_act;
+    P.c = c; P.ldc = ldc;
+    int splits = tc_choose_splits(m, n, P.total_kblocks);
+    if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * m * n * sizeof(float))) splits = 1;
+    P.kblocks_per_split = (int)ceil_div(P.total_kblocks, splits);
+    P.splits = (int)ceil_div(P.total_kblocks, P.kblocks_per_split);
+    P.partial = P.splits > 1 ? (float*)workspace : nullptr;
+
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return PLAGNN_ERR_CUDA;
+        }
+        attr_dev = dev;
+    }
+    dim3 grid((unsigned)ceil_div(n, TC_BN), (unsigned)ceil_div(m, TC_BM), (unsigned)P.splits);
+    gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(P);
+    if (P.splits > 1) {
+        const int64_t total = m * n;
+        const int g = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 8 ? ceil_div(total, 256) : (int64_t)sm_count() * 8);
+        gemm_tc_reduce_kernel<<<g, 256, 0, st>>>(P);
+    }
+    return check_launch("gemm_tc");
+}
+
+}  // namespace plagnn

@@ -1,0 +1,404 @@
+// K2 — neighbourhood aggregation (SpMM with a pluggable reducer) for sm_100a.
+//
+// Replaces DGL's gspmm behind  code/model.py:20,22,24  (SAGEConv 'pool': update_all(copy_u, max))
+// and its autograd backward at  code/train.py:204;  the sum / u_mul_e / mean members of the same
+// kernel family serve BASELINE.json configs[3] (weighted synthetic graph).
+//
+// Shape of the kernel (HBM / L2 bound, no tensor cores):
+//   * one warp owns one work item = (destination row, chunk of <= `chunk` in-edges) from the plan
+//     built in graph_build.cu, so power-law hubs are spread over many warps;
+//   * a lane owns VEC float4 column groups (lane, lane+32, ...): every neighbour row is read with
+//     fully coalesced 512-byte LDG.128 requests; NB neighbour rows are in flight per lane;
+//   * neighbour ids are read 32 at a time (one coalesced load) and broadcast with shuffles;
+//   * rows split over several chunks write (value,arg) partials that a second small kernel folds
+//     in chunk order, which keeps "first maximum wins" and makes sums order-stable.
+#include "common.cuh"
+#include <math.h>
+
+namespace plagnn {
+
+void plan_pointers(const void* plan, int64_t n_rows, const int32_t** item_ptr, const int32_t** slot_ptr,
+                   const int32_t** item_row, const int32_t** hub_rows);
+
+enum { MODE_MAX = 0, MODE_SUM = 1, MODE_MATCH = 2 };
+constexpr int SPMM_WARPS = 8;
+
+struct SpmmEpilogue {
+    const float* scale;   // per destination row, nullable
+    const float* bias;    // per column, nullable
+    int act;
+    float slope;
+    float dropout_p;
+    unsigned long long seed;
+};
+
+__device__ __forceinline__ unsigned hash_u32(unsigned long long seed, unsigned long long idx) {
+    unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return (unsigned)((z ^ (z >> 31)) >> 32);
+}
+__device__ __forceinline__ float dropout_keep_scale(unsigned long long seed, long long row, int col, int64_t feat,
+                                                    float p) {
+    const float u = hash_u32(seed, (unsigned long long)row * (unsigned long long)feat + col) * (1.0f / 4294967296.0f);
+    return u >= p ? 1.0f / (1.0f - p) : 0.0f;
+}
+
+__device__ __forceinline__ float4 sum_epilogue(float4 a, const SpmmEpilogue& ep, long long row, int col, int64_t feat) {
+    float v[4] = {a.x, a.y, a.z, a.w};
+    const float s = ep.scale ? __ldg(ep.scale + row) : 1.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float t = ep.scale ? v[i] * s : v[i];
+        if (ep.bias && col + i < feat) t += __ldg(ep.bias + col + i);
+        t = apply_act(t, ep.act, ep.slope);
+        if (ep.dropout_p > 0.f) t *= dropout_keep_scale(ep.seed, row, col + i, feat, ep.dropout_p);
+        v[i] = t;
+    }
+    return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+template <int MODE>
+__device__ __forceinline__ void reduce_one(float4& acc, int4& arg, const float4 v, const int u) {
+    if (MODE == MODE_MAX) {
+        if (v.x > acc.x) { acc.x = v.x; arg.x = u; }
+        if (v.y > acc.y) { acc.y = v.y; arg.y = u; }
+        if (v.z > acc.z) { acc.z = v.z; arg.z = u; }
+        if (v.w > acc.w) { acc.w = v.w; arg.w = u; }
+    } else {
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+}
+
+// MODE_MAX  : x = features,  out/arg written
+// MODE_SUM  : x = features,  optional edge weights, epilogue
+// MODE_MATCH: x = dz (rows = destinations v of the out-edge u->v), argm = arg[v,:], zfwd = z[v,:] (nullable);
+//             acc[u,f] += (argm[v,f]==u && z>0) ? dz[v,f] : 0
+template <int MODE, int VEC, int NB>
+__global__ void __launch_bounds__(SPMM_WARPS * 32)
+spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int32_t* __restrict__ eids,
+            const float* __restrict__ ew, const int32_t* __restrict__ plan_hdr, const int32_t* __restrict__ item_ptr,
+            const int32_t* __restrict__ slot_ptr, const int32_t* __restrict__ item_row, int n_items,
+            const float* __restrict__ x, int64_t ldx, int feat, const int32_t* __restrict__ argm,
+            const float* __restrict__ zfwd, float* __restrict__ out, int32_t* __restrict__ arg_out, int64_t ldo,
+            float* __restrict__ part_val, int32_t* __restrict__ part_arg, int part_ld, SpmmEpilogue ep) {
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+    if (item >= n_items) return;
+    const int chunk = __ldg(plan_hdr);
+    const int row = __ldg(item_row + item);
+    const int first = __ldg(item_ptr + row);
+    const int nch = __ldg(item_ptr + row + 1) - first;
+    const int k = item - first;
+    const int rbeg = __ldg(indptr + row), rend = __ldg(indptr + row + 1);
+    const int beg = rbeg + k * chunk;
+    const int end = min(rend, beg + chunk);
+
+    const int col0 = blockIdx.y * (128 * VEC);   // first column of this block's slab
+    int col[VEC];
+    bool cok[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+        col[q] = col0 + 4 * (lane + 32 * q);
+        cok[q] = col[q] < feat;
+    }
+
+    float4 acc[VEC];
+    int4 arg[VEC];
+    const float init = MODE == MODE_MAX ? -INFINITY : 0.f;
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+        acc[q] = make_float4(init, init, init, init);
+        arg[q] = make_int4(-1, -1, -1, -1);
+    }
+
+    for (int base = beg; base < end; base += 32) {
+        const int cnt = min(32, end - base);
+        int my_u = 0;
+        float my_w = 1.f;
+        if (lane < cnt) {
+            my_u = __ldg(indices + base + lane);
+            if (MODE == MODE_SUM && ew) my_w = __ldg(ew + (eids ? __ldg(eids + base + lane) : base + lane));
+        }
+        for (int j = 0; j < cnt; j += NB) {
+            int u[NB];
+            float w[NB];
+            float4 v[NB][VEC];
+            int4 am[NB][VEC];
+            float4 zz[NB][VEC];
+#pragma unroll
+            for (int t = 0; t < NB; ++t) {
+                const int src_lane = min(j + t, 31);
+                u[t] = __shfl_sync(0xffffffffu, my_u, src_lane);
+                w[t] = __shfl_sync(0xffffffffu, my_w, src_lane);
+                const bool live = (j + t) < cnt;
+                const float* xr = x + (int64_t)u[t] * ldx;
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    if (live && cok[q]) {
+                        v[t][q] = ldg_f4(xr + col[q]);
+                        if (MODE == MODE_MATCH) {
+                            am[t][q] = __ldg(reinterpret_cast<const int4*>(argm + (int64_t)u[t] * ldx + col[q]));
+                            if (zfwd) zz[t][q] = ldg_f4(zfwd + (int64_t)u[t] * ldx + col[q]);
+                        }
+                    } else {
+                        v[t][q] = make_float4(init, init, init, init);
+                        if (MODE == MODE_MATCH) am[t][q] = make_int4(-2, -2, -2, -2);
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < NB; ++t) {
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    float4 val = v[t][q];
+                    if (MODE == MODE_SUM && ew) {
+                        val.x *= w[t]; val.y *= w[t]; val.z *= w[t]; val.w *= w[t];
+                    }
+                    if (MODE == MODE_MATCH) {
+                        const int4 a = am[t][q];
+                        float4 g = val;
+                        if (zfwd && (j + t) < cnt && cok[q]) {
+                            const float4 z4 = zz[t][q];
+                            g.x = z4.x > 0.f ? g.x : 0.f; g.y = z4.y > 0.f ? g.y : 0.f;
+                            g.z = z4.z > 0.f ? g.z : 0.f; g.w = z4.w > 0.f ? g.w : 0.f;
+                        }
+                        val.x = a.x == row ? g.x : 0.f; val.y = a.y == row ? g.y : 0.f;
+                        val.z = a.z == row ? g.z : 0.f; val.w = a.w == row ? g.w : 0.f;
+                    }
+                    reduce_one<MODE>(acc[q], arg[q], val, u[t]);
+                }
+            }
+        }
+    }
+
+    // ---- write: final result for unsplit rows, ordered partial otherwise --------------------
+    if (nch == 1) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            if (!cok[q]) continue;
+            float4 r = acc[q];
+            if (MODE == MODE_MAX) {
+                const int4 a = arg[q];
+                r.x = a.x < 0 ? 0.f : r.x; r.y = a.y < 0 ? 0.f : r.y;
+                r.z = a.z < 0 ? 0.f : r.z; r.w = a.w < 0 ? 0.f : r.w;
+                *reinterpret_cast<int4*>(arg_out + (int64_t)row * ldo + col[q]) = a;
+            } else if (MODE == MODE_SUM) {
+                r = sum_epilogue(r, ep, row, col[q], feat);
+            }
+            *reinterpret_cast<float4*>(out + (int64_t)row * ldo + col[q]) = r;
+        }
+    } else {
+        const int64_t slot = (int64_t)__ldg(slot_ptr + row) + k;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            if (!cok[q]) continue;
+            *reinterpret_cast<float4*>(part_val + slot * part_ld + col[q]) = acc[q];
+            if (MODE == MODE_MAX) *reinterpret_cast<int4*>(part_arg + slot * part_ld + col[q]) = arg[q];
+        }
+    }
+}
+
+// folds the partials of split rows in chunk order: one warp per (split row, 128-column group)
+template <int MODE>
+__global__ void __launch_bounds__(SPMM_WARPS * 32)
+spmm_combine_kernel(const int32_t* __restrict__ item_ptr, const int32_t* __restrict__ slot_ptr,
+                    const int32_t* __restrict__ hub_rows, int n_hubs, int feat, const float* __restrict__ part_val,
+                    const int32_t* __restrict__ part_arg, int part_ld, float* __restrict__ out,
+                    int32_t* __restrict__ arg_out, int64_t ldo, SpmmEpilogue ep) {
+    const int lane = threadIdx.x & 31;
+    const int h = blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+    if (h >= n_hubs) return;
+    const int col = blockIdx.y * 128 + lane * 4;
+    if (col >= feat) return;
+    const int row = __ldg(hub_rows + h);
+    const int nch = __ldg(item_ptr + row + 1) - __ldg(item_ptr + row);
+    const int64_t slot0 = __ldg(slot_ptr + row);
+    const float init = MODE == MODE_MAX ? -INFINITY : 0.f;
+    float4 acc = make_float4(init, init, init, init);
+    int4 arg = make_int4(-1, -1, -1, -1);
+    for (int k = 0; k < nch; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(part_val + (slot0 + k) * part_ld + col);
+        if (MODE == MODE_MAX) {
+            const int4 a = *reinterpret_cast<const int4*>(part_arg + (slot0 + k) * part_ld + col);
+            if (v.x > acc.x) { acc.x = v.x; arg.x = a.x; }
+            if (v.y > acc.y) { acc.y = v.y; arg.y = a.y; }
+            if (v.z > acc.z) { acc.z = v.z; arg.z = a.z; }
+            if (v.w > acc.w) { acc.w = v.w; arg.w = a.w; }
+        } else {
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    if (MODE == MODE_MAX) {
+        acc.x = arg.x < 0 ? 0.f : acc.x; acc.y = arg.y < 0 ? 0.f : acc.y;
+        acc.z = arg.z < 0 ? 0.f : acc.z; acc.w = arg.w < 0 ? 0.f : acc.w;
+        *reinterpret_cast<int4*>(arg_out + (int64_t)row * ldo + col) = arg;
+    } else if (MODE == MODE_SUM) {
+        acc = sum_epilogue(acc, ep, row, col, feat);
+    }
+    *reinterpret_cast<float4*>(out + (int64_t)row * ldo + col) = acc;
+}
+
+// reverse of the max reducer with fp32 reductions to global memory (RED.E.ADD.F32)
+__global__ void __launch_bounds__(256)
+spmm_max_scatter_kernel(const float* __restrict__ dz, const int32_t* __restrict__ arg, const float* __restrict__ z,
+                        int64_t n_rows, int feat, int64_t ldz, float* __restrict__ dx, int64_t lddx) {
+    const int f4 = (feat + 3) >> 2;
+    const int64_t total = n_rows * f4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = i / f4;
+        const int c = (int)(i - v * f4) * 4;
+        const float4 g = ldg_f4(dz + v * ldz + c);
+        const int4 a = __ldg(reinterpret_cast<const int4*>(arg + v * ldz + c));
+        float4 zz = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (z) zz = ldg_f4(z + v * ldz + c);
+        if (a.x >= 0 && g.x != 0.f && zz.x > 0.f && c + 0 < feat) atomicAdd(dx + (int64_t)a.x * lddx + c + 0, g.x);
+        if (a.y >= 0 && g.y != 0.f && zz.y > 0.f && c + 1 < feat) atomicAdd(dx + (int64_t)a.y * lddx + c + 1, g.y);
+        if (a.z >= 0 && g.z != 0.f && zz.z > 0.f && c + 2 < feat) atomicAdd(dx + (int64_t)a.z * lddx + c + 2, g.z);
+        if (a.w >= 0 && g.w != 0.f && zz.w > 0.f && c + 3 < feat) atomicAdd(dx + (int64_t)a.w * lddx + c + 3, g.w);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dropout_scale_kernel(float* __restrict__ g, int64_t rows, int feat, int64_t ld, float p, unsigned long long seed) {
+    const int64_t total = rows * feat;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / feat;
+        const int c = (int)(i - r * feat);
+        g[r * ld + c] *= dropout_keep_scale(seed, r, c, feat, p);
+    }
+}
+
+struct SpmmArgs {
+    const int32_t *indptr, *indices, *eids;
+    const float* ew;
+    const void* plan;
+    const int64_t* counts;
+    int64_t n_rows;
+    const float* x;
+    int64_t ldx;
+    int64_t feat;
+    const int32_t* argm;
+    const float* zfwd;
+    float* out;
+    int32_t* arg_out;
+    int64_t ldo;
+    void* partial;
+    size_t partial_bytes;
+    SpmmEpilogue ep;
+};
+
+static inline int part_ld_of(int64_t feat) { return (int)((feat + 3) / 4 * 4); }
+
+template <int MODE, int VEC, int NB>
+static void launch_main(const SpmmArgs& a, const int32_t* item_ptr, const int32_t* slot_ptr, const int32_t* item_row,
+                        float* pv, int32_t* pa, cudaStream_t st) {
+    const int n_items = (int)a.counts[0];
+    dim3 grid((unsigned)ceil_div(n_items, SPMM_WARPS), (unsigned)ceil_div((a.feat + 3) / 4, 32 * VEC));
+    spmm_kernel<MODE, VEC, NB><<<grid, SPMM_WARPS * 32, 0, st>>>(
+        a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, n_items, a.x, a.ldx,
+        (int)a.feat, a.argm, a.zfwd, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep);
+}
+
+template <int MODE>
+static int spmm_dispatch(const SpmmArgs& a, const char* name, cudaStream_t st) {
+    if (!a.indptr || !a.indices || !a.plan || !a.counts || !a.x || !a.out) return fail(PLAGNN_ERR_ARG, name, "null pointer");
+    if (a.n_rows <= 0 || a.feat <= 0) return fail(PLAGNN_ERR_ARG, name, "bad sizes");
+    const int64_t f4 = (a.feat + 3) / 4 * 4;
+    if (a.ldx < f4 || a.ldo < f4 || (a.ldx & 3) || (a.ldo & 3) || !aligned16(a.x) || !aligned16(a.out) ||
+        (a.arg_out && !aligned16(a.arg_out)))
+        return fail(PLAGNN_ERR_ALIGN, name, "feature matrices need 16-byte aligned rows (pitch % 4 == 0, pitch >= roundup4(feat))");
+    if (MODE == MODE_MATCH && (!a.argm || !aligned16(a.argm))) return fail(PLAGNN_ERR_ARG, name, "arg matrix missing/unaligned");
+    const int64_t n_items = a.counts[0], n_hubs = a.counts[1], n_slots = a.counts[2];
+    if (n_items <= 0 || n_items >= ((int64_t)1 << 31)) return fail(PLAGNN_ERR_ARG, name, "bad plan counts");
+    const int pld = part_ld_of(a.feat);
+    const size_t need_val = align_up((size_t)n_slots * pld * sizeof(float), 256);
+    const size_t need = n_slots ? need_val * (MODE == MODE_MAX ? 2 : 1) : 0;
+    if (need && (!a.partial || a.partial_bytes < need)) return fail(PLAGNN_ERR_WORKSPACE, name, "partial buffer too small");
+    float* pv = (float*)a.partial;
+    int32_t* pa = (int32_t*)((char*)a.partial + need_val);
+    const int32_t *item_ptr, *slot_ptr, *item_row, *hub_rows;
+    plan_pointers(a.plan, a.n_rows, &item_ptr, &slot_ptr, &item_row, &hub_rows);
+
+    const int64_t groups = (a.feat + 3) / 4;   // float4 column groups
+    if (groups <= 32) launch_main<MODE, 1, 8>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
+    else if (groups <= 64) launch_main<MODE, 2, 4>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
+    else if (groups <= 96) launch_main<MODE, 3, 2>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
+    else launch_main<MODE, 4, 2>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
+    if (n_hubs > 0) {
+        dim3 grid((unsigned)ceil_div(n_hubs, SPMM_WARPS), (unsigned)ceil_div(a.feat, 128));
+        spmm_combine_kernel<MODE><<<grid, SPMM_WARPS * 32, 0, st>>>(item_ptr, slot_ptr, hub_rows, (int)n_hubs, (int)a.feat,
+                                                                     pv, pa, pld, a.out, a.arg_out, a.ldo, a.ep);
+    }
+    return check_launch(name);
+}
+
+}  // namespace plagnn
+
+using namespace plagnn;
+
+extern "C" {
+
+size_t plagnn_spmm_partial_bytes(int64_t partial_slots, int64_t feat, int reduce) {
+    if (partial_slots <= 0) return 0;
+    const size_t one = align_up((size_t)partial_slots * part_ld_of(feat) * sizeof(float), 256);
+    return one * (reduce == PLAGNN_REDUCE_MAX ? 2 : 1);
+}
+
+int plagnn_spmm_max_fwd(const int32_t* indptr, const int32_t* indices, const void* plan, const int64_t* plan_counts,
+                        int64_t num_rows, const float* x, int64_t ldx, int64_t feat, float* out, int32_t* arg,
+                        int64_t ldo, void* partial, size_t partial_bytes, plagnn_stream_t stream) {
+    if (!arg) return fail(PLAGNN_ERR_ARG, "spmm_max_fwd", "arg output is required");
+    SpmmArgs a{indptr, indices, nullptr, nullptr, plan, plan_counts, num_rows, x, ldx, feat, nullptr, nullptr,
+               out, arg, ldo, partial, partial_bytes, SpmmEpilogue{nullptr, nullptr, 0, 0.f, 0.f, 0ull}};
+    return spmm_dispatch<MODE_MAX>(a, "spmm_max_fwd", (cudaStream_t)stream);
+}
+
+int plagnn_spmm_max_bwd(const float* dz, const int32_t* arg, const float* z, int64_t num_rows, int64_t feat,
+                        int64_t ldz, float* dx, int64_t n_src, int64_t lddx, plagnn_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!dz || !arg || !dx || num_rows <= 0 || feat <= 0 || n_src <= 0) return fail(PLAGNN_ERR_ARG, "spmm_max_bwd", "bad arguments");
+    const int64_t f4 = (feat + 3) / 4 * 4;
+    if (ldz < f4 || (ldz & 3) || lddx < feat || !aligned16(dz) || !aligned16(arg) || (z && !aligned16(z)))
+        return fail(PLAGNN_ERR_ALIGN, "spmm_max_bwd", "dz/arg/z need 16-byte aligned rows");
+    PLAGNN_CUDA_TRY(cudaMemset2DAsync(dx, lddx * sizeof(float), 0, (size_t)(lddx < f4 ? feat : f4) * sizeof(float), n_src, st));
+    const int64_t total = num_rows * (f4 / 4);
+    const int grid = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 16 ? ceil_div(total, 256) : (int64_t)sm_count() * 16);
+    spmm_max_scatter_kernel<<<grid, 256, 0, st>>>(dz, arg, z, num_rows, (int)feat, ldz, dx, lddx);
+    return check_launch("spmm_max_bwd");
+}
+
+int plagnn_spmm_max_bwd_gather(const int32_t* out_indptr, const int32_t* out_indices, const void* out_plan,
+                               const int64_t* out_plan_counts, int64_t n_src, const float* dz, const int32_t* arg,
+                               const float* z, int64_t ldz, int64_t feat, float* dx, int64_t lddx, void* partial,
+                               size_t partial_bytes, plagnn_stream_t stream) {
+    if (z && !aligned16(z)) return fail(PLAGNN_ERR_ALIGN, "spmm_max_bwd_gather", "z unaligned");
+    SpmmArgs a{out_indptr, out_indices, nullptr, nullptr, out_plan, out_plan_counts, n_src, dz, ldz, feat, arg, z,
+               dx, nullptr, lddx, partial, partial_bytes, SpmmEpilogue{nullptr, nullptr, 0, 0.f, 0.f, 0ull}};
+    return spmm_dispatch<MODE_MATCH>(a, "spmm_max_bwd_gather", (cudaStream_t)stream);
+}
+
+int plagnn_spmm_sum(const int32_t* indptr, const int32_t* indices, const int32_t* eids, const void* plan,
+                    const int64_t* plan_counts, int64_t num_rows, const float* w, const float* scale, const float* x,
+                    int64_t ldx, int64_t feat, const float* bias, int act, float slope, float dropout_p,
+                    uint64_t dropout_seed, float* out, int64_t ldo, void* partial, size_t partial_bytes,
+                    plagnn_stream_t stream) {
+    if (act < PLAGNN_ACT_NONE || act > PLAGNN_ACT_SIGMOID) return fail(PLAGNN_ERR_ARG, "spmm_sum", "unknown activation");
+    if (dropout_p < 0.f || dropout_p >= 1.f) return fail(PLAGNN_ERR_ARG, "spmm_sum", "dropout_p must be in [0,1)");
+    SpmmArgs a{indptr, indices, eids, w, plan, plan_counts, num_rows, x, ldx, feat, nullptr, nullptr, out, nullptr, ldo,
+               partial, partial_bytes, SpmmEpilogue{scale, bias, act, slope, dropout_p, (unsigned long long)dropout_seed}};
+    return spmm_dispatch<MODE_SUM>(a, "spmm_sum", (cudaStream_t)stream);
+}
+
+int plagnn_dropout_scale(float* grad, int64_t rows, int64_t feat, int64_t ld, float dropout_p, uint64_t dropout_seed,
+                         plagnn_stream_t stream) {
+    if (!grad || rows <= 0 || feat <= 0 || dropout_p < 0.f || dropout_p >= 1.f) return fail(PLAGNN_ERR_ARG, "dropout_scale", "bad arguments");
+    if (dropout_p == 0.f) return PLAGNN_OK;
+    const int64_t total = rows * feat;
+    const int grid = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 16 ? ceil_div(total, 256) : (int64_t)sm_count() * 16);
+    dropout_scale_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(grad, rows, (int)feat, ld, dropout_p,
+                                                                 (unsigned long long)dropout_seed);
+    return check_launch("dropout_scale");
+}
+
+}  // extern "C"

@@ -1,0 +1,336 @@
+"""Layers of the drop-in, each a ``torch.autograd.Function`` over the C-ABI kernels.
+
+Mirrors the reference's operator interface for the hot path:
+
+* ``SAGEConv``  — same constructor / forward signature as ``dgl.nn.pytorch.SAGEConv`` as used at
+  ``code/model.py:13-15,20,22,24`` (aggregator 'pool'; 'mean' / 'gcn' reach the sum kernels).
+* ``GNN32``     — same constructor / forward signature and attribute names as ``code/model.py:10-31``.
+  Its forward is ONE autograd Function spanning the whole network, so that every activation and
+  activation-gradient is fused into a GEMM epilogue and no intermediate leaves the kernels' layout.
+* ``GraphConvSum`` / ``GCN`` — the copy_u/u_mul_e + sum member of the same kernel family for the
+  synthetic throughput configs (BASELINE.json configs[3-4]).
+
+No function here falls back to PyTorch math: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID
+
+DETERMINISTIC_BACKWARD = False   # True: ordered gather instead of fp32 reductions for the max backward
+
+
+# ==================================================================================================
+# engine pieces (no autograd): forward / backward of one SAGEConv-pool layer and one Linear layer
+# ==================================================================================================
+def sage_pool_forward(g, x, w_pool, b_pool, w_self, w_neigh, bias, out_act):
+    """rst = act( x W_self^T + max_{u in in(v)} relu(x W_pool^T + b_pool)[u] W_neigh^T + bias )
+    (DGL 0.8 SAGEConv 'pool').  Returns (rst, saved)."""
+    csc = g.csc()
+    x = ops.aligned(x)
+    n, f = x.shape
+    o = w_self.shape[0]
+    wp, ws, wn = ops.aligned(w_pool), ops.aligned(w_self), ops.aligned(w_neigh)
+    m = ops.gemm(n, f, [(x, 0, wp, 0, f)], bias=b_pool, act=ACT_RELU)
+    neigh, arg = ops.spmm_max_fwd(csc, m)
+    del m   # relu'(m[arg]) == (neigh > 0): the pooled activations themselves are not needed again
+    rst = ops.gemm(n, o, [(x, 0, ws, 0, f), (neigh, 0, wn, 0, f)], bias=bias, act=out_act)
+    return rst, (x, neigh, arg)
+
+
+def sage_pool_backward(g, saved, w_pool, w_self, w_neigh, drst, has_bias, need_dx, gate=None, gate_act=ACT_NONE):
+    """drst = gradient w.r.t. the pre-activation output.  Returns (dx, dWp, dbp, dWs, dWn, db).
+    When `gate` is given, dx is already multiplied by act'(gate) (the previous layer's activation)."""
+    x, neigh, arg = saved
+    n, f = x.shape
+    o = w_self.shape[0]
+    drst = ops.aligned(drst)
+    db = ops.colsum(drst) if has_bias else None
+    d_ws = ops.gemm(o, f, [(drst, 1, x, 1, n)], out=torch.empty_like(w_self))
+    d_wn = ops.gemm(o, f, [(drst, 1, neigh, 1, n)], out=torch.empty_like(w_neigh))
+    wn_t = ops.transpose(w_neigh)                       # [f x o], K(=o)-contiguous operand
+    dneigh = ops.gemm(n, f, [(drst, 0, wn_t, 0, o)])
+    if DETERMINISTIC_BACKWARD:
+        dm = ops.spmm_max_bwd_gather(g.csr(), dneigh, arg, neigh)
+    else:
+        dm = ops.spmm_max_bwd(dneigh, arg, neigh, n)    # relu' folded in through neigh > 0
+    del dneigh
+    d_wp = ops.gemm(f, f, [(dm, 1, x, 1, n)], out=torch.empty_like(w_pool))
+    d_bp = ops.colsum(dm)
+    dx = None
+    if need_dx:
+        ws_t, wp_t = ops.transpose(w_self), ops.transpose(w_pool)
+        dx = ops.gemm(n, f, [(drst, 0, ws_t, 0, o), (dm, 0, wp_t, 0, f)], gate=gate, gate_act=gate_act)
+    return dx, d_wp, d_bp, d_ws, d_wn, db
+
+
+def linear_forward(x, w, b, act):
+    x = ops.aligned(x)
+    return ops.gemm(x.shape[0], w.shape[0], [(x, 0, ops.aligned(w), 0, x.shape[1])], bias=b, act=act), x
+
+
+def linear_backward(x, w, dz, has_bias, need_dx, gate=None, gate_act=ACT_NONE):
+    """dz = gradient w.r.t. the pre-activation output.  Returns (dx, dW, db)."""
+    n, k = x.shape
+    o = w.shape[0]
+    dz = ops.aligned(dz)
+    d_w = ops.gemm(o, k, [(dz, 1, x, 1, n)], out=torch.empty_like(w))
+    d_b = ops.colsum(dz) if has_bias else None
+    dx = None
+    if need_dx:
+        dx = ops.gemm(n, k, [(dz, 0, ops.transpose(w), 0, o)], gate=gate, gate_act=gate_act)
+    return dx, d_w, d_b
+
+
+# ==================================================================================================
+# autograd Functions
+# ==================================================================================================
+class SAGEPoolFunction(torch.autograd.Function):
+    """One SAGEConv('pool') layer (no output activation)."""
+
+    @staticmethod
+    def forward(ctx, g, x, w_pool, b_pool, w_self, w_neigh, bias):
+        rst, saved = sage_pool_forward(g, x.detach(), w_pool.detach(), b_pool.detach(), w_self.detach(),
+                                       w_neigh.detach(), None if bias is None else bias.detach(), ACT_NONE)
+        ctx.g, ctx.saved, ctx.has_bias = g, saved, bias is not None
+        ctx.save_for_backward(w_pool, w_self, w_neigh)
+        return rst
+
+    @staticmethod
+    def backward(ctx, drst):
+        w_pool, w_self, w_neigh = ctx.saved_tensors
+        dx, d_wp, d_bp, d_ws, d_wn, db = sage_pool_backward(ctx.g, ctx.saved, w_pool.detach(), w_self.detach(),
+                                                            w_neigh.detach(), drst, ctx.has_bias,
+                                                            ctx.needs_input_grad[1])
+        return None, dx, d_wp, d_bp, d_ws, d_wn, db
+
+
+class LinearActFunction(torch.autograd.Function):
+    """y = act(x W^T + b) with the activation fused into the GEMM epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        y, xa = linear_forward(x.detach(), w.detach(), None if b is None else b.detach(), act)
+        ctx.act, ctx.has_bias = act, b is not None
+        ctx.xa, ctx.y = xa, y
+        ctx.save_for_backward(w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (w,) = ctx.saved_tensors
+        dz = ops.act_backward(dy, ctx.y, ctx.act) if ctx.act != ACT_NONE else dy
+        dx, d_w, d_b = linear_backward(ctx.xa, w.detach(), dz, ctx.has_bias, ctx.needs_input_grad[0])
+        return dx, d_w, d_b, None
+
+
+class GNN32Function(torch.autograd.Function):
+    """Whole GNN32 forward/backward (code/model.py:19-31 and its autograd) as one Function.
+    Parameter order: conv{1,2,3}.(fc_pool.weight, fc_pool.bias, fc_self.weight, fc_neigh.weight, bias),
+    liner1.(weight, bias), liner2.(weight, bias)."""
+
+    @staticmethod
+    def forward(ctx, g, x, *params):
+        p = [t.detach() for t in params]
+        convs = [p[0:5], p[5:10], p[10:15]]
+        h = x.detach()
+        saved = []
+        for c in convs:
+            h, s = sage_pool_forward(g, h, c[0], c[1], c[2], c[3], c[4], ACT_LEAKY)
+            saved.append(s)
+        h4, h3 = linear_forward(h, p[15], p[16], ACT_LEAKY)
+        prob, h4 = linear_forward(h4, p[17], p[18], ACT_SIGMOID)
+        ctx.g, ctx.saved, ctx.h3, ctx.h4, ctx.prob = g, saved, h3, h4, prob
+        ctx.save_for_backward(*params)
+        return prob
+
+    @staticmethod
+    def backward(ctx, dprob):
+        p = [t.detach() for t in ctx.saved_tensors]
+        convs = [p[0:5], p[5:10], p[10:15]]
+        saved = ctx.saved
+        dz5 = ops.act_backward(dprob, ctx.prob, ACT_SIGMOID)
+        dz4, d_w2, d_b2 = linear_backward(ctx.h4, p[17], dz5, True, True, gate=ctx.h4, gate_act=ACT_LEAKY)
+        drst, d_w1, d_b1 = linear_backward(ctx.h3, p[15], dz4, True, True, gate=ctx.h3, gate_act=ACT_LEAKY)
+        grads = [None] * 15
+        for li in (2, 1, 0):
+            c = convs[li]
+            need_dx = li > 0 or ctx.needs_input_grad[1]
+            gate = saved[li][0] if li > 0 else None        # layer input == previous layer's activated output
+            dx, d_wp, d_bp, d_ws, d_wn, db = sage_pool_backward(ctx.g, saved[li], c[0], c[2], c[3], drst, True, need_dx,
+                                                                gate=gate, gate_act=ACT_LEAKY if li > 0 else ACT_NONE)
+            grads[5 * li:5 * li + 5] = [d_wp, d_bp, d_ws, d_wn, db]
+            drst = dx
+        return (None, drst if ctx.needs_input_grad[1] else None, *grads, d_w1, d_b1, d_w2, d_b2)
+
+
+class GraphConvSumFunction(torch.autograd.Function):
+    """out = act( scale_v * sum_{u->v} w_uv (x W^T)[u] + b ), backward through the transposed SpMM."""
+
+    @staticmethod
+    def forward(ctx, g, x, w, b, edge_weight, scale, act, dropout_p, seed):
+        xa = ops.aligned(x.detach())
+        wa = ops.aligned(w.detach())
+        t = ops.gemm(xa.shape[0], wa.shape[0], [(xa, 0, wa, 0, xa.shape[1])])
+        out = ops.spmm_sum(g.csc(), t, w=edge_weight, scale=scale, bias=None if b is None else b.detach(), act=act,
+                           dropout_p=dropout_p, dropout_seed=seed)
+        ctx.g, ctx.xa, ctx.out, ctx.ew, ctx.scale, ctx.act = g, xa, out, edge_weight, scale, act
+        ctx.dropout, ctx.has_bias = (dropout_p, seed), b is not None
+        ctx.save_for_backward(w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (w,) = ctx.saved_tensors
+        w = w.detach()
+        dz = ops.aligned(dout)
+        if ctx.dropout[0] > 0:
+            dz = ops.dropout_scale_(dz.clone() if dz is dout else dz, *ctx.dropout)
+        if ctx.act != ACT_NONE:
+            # with dropout the saved output is y*mask/(1-p); its sign still equals the sign of y where kept
+            dz = ops.act_backward(dz, ctx.out, ctx.act)
+        db = ops.colsum(dz) if ctx.has_bias else None
+        if ctx.scale is not None:
+            dz = ops.row_scale(dz, ctx.scale)
+        dt = ops.spmm_sum(ctx.g.csr(), dz, w=ctx.ew)
+        n, k = ctx.xa.shape
+        o = w.shape[0]
+        d_w = ops.gemm(o, k, [(dt, 1, ctx.xa, 1, n)], out=torch.empty_like(w))
+        dx = ops.gemm(n, k, [(dt, 0, ops.transpose(w), 0, o)]) if ctx.needs_input_grad[1] else None
+        return None, dx, d_w, db, None, None, None, None, None
+
+
+# ==================================================================================================
+# modules
+# ==================================================================================================
+class SAGEConv(nn.Module):
+    """Drop-in for ``dgl.nn.pytorch.SAGEConv`` (DGL 0.8.x parameter layout: fc_pool with bias, bias-free
+    fc_self / fc_neigh, separate ``bias``).  'pool' is the reference's aggregator (code/model.py:13-15);
+    'mean' and 'gcn' are served by the sum kernels."""
+
+    def __init__(self, in_feats, out_feats, aggregator_type, feat_drop=0.0, bias=True, norm=None, activation=None):
+        super().__init__()
+        if aggregator_type not in ("pool", "mean", "gcn"):
+            raise KeyError(f"Invalid aggregator_type {aggregator_type!r}: supported are 'pool', 'mean', 'gcn'")
+        self._in_src_feats = self._in_dst_feats = int(in_feats)
+        self._out_feats = int(out_feats)
+        self._aggre_type = aggregator_type
+        self.norm = norm
+        self.feat_drop = nn.Dropout(feat_drop)
+        self.activation = activation
+        if aggregator_type == "pool":
+            self.fc_pool = nn.Linear(in_feats, in_feats)
+        if aggregator_type != "gcn":
+            self.fc_self = nn.Linear(in_feats, out_feats, bias=False)
+        self.fc_neigh = nn.Linear(in_feats, out_feats, bias=False)
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_feats))
+        else:
+            self.register_buffer("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        gain = nn.init.calculate_gain("relu")
+        if self._aggre_type == "pool":
+            nn.init.xavier_uniform_(self.fc_pool.weight, gain=gain)
+        if self._aggre_type != "gcn":
+            nn.init.xavier_uniform_(self.fc_self.weight, gain=gain)
+        nn.init.xavier_uniform_(self.fc_neigh.weight, gain=gain)
+
+    def forward(self, graph, feat, edge_weight=None):
+        feat = self.feat_drop(feat)
+        if self._aggre_type == "pool":
+            if edge_weight is not None:
+                raise NotImplementedError("edge_weight with the 'pool' aggregator (the reference never passes one)")
+            rst = SAGEPoolFunction.apply(graph, feat, self.fc_pool.weight, self.fc_pool.bias, self.fc_self.weight,
+                                         self.fc_neigh.weight, self.bias)
+        else:
+            deg = graph.in_degrees().to(torch.float32)
+            if self._aggre_type == "mean":
+                scale = 1.0 / deg.clamp(min=1.0)
+                neigh = GraphConvSumFunction.apply(graph, feat, self.fc_neigh.weight, None, edge_weight, scale, ACT_NONE,
+                                                   0.0, 0)
+                rst = neigh + LinearActFunction.apply(feat, self.fc_self.weight, None, ACT_NONE)
+            else:   # 'gcn': (sum_neigh + self) / (deg + 1), projected by fc_neigh
+                scale = 1.0 / (deg + 1.0)
+                neigh = GraphConvSumFunction.apply(graph, feat, self.fc_neigh.weight, None, edge_weight, scale, ACT_NONE,
+                                                   0.0, 0)
+                rst = neigh + LinearActFunction.apply(feat, self.fc_neigh.weight, None, ACT_NONE) * scale.unsqueeze(1)
+            if self.bias is not None:
+                rst = rst + self.bias
+        if self.activation is not None:
+            rst = self.activation(rst)
+        if self.norm is not None:
+            rst = self.norm(rst)
+        return rst
+
+
+class GNN32(nn.Module):
+    """Drop-in for ``code/model.py:10-31``: same constructor, same ``forward(g, in_feat)``, same attribute
+    names (conv1..3, liner1..2).  ``dropout`` is accepted and unused, as in the reference."""
+
+    def __init__(self, in_feats, h1_feats, h2_feats, h3_feats, h4_feats, num_classes, dropout=0.5):
+        super().__init__()
+        self.conv1 = SAGEConv(in_feats, h1_feats, "pool")
+        self.conv2 = SAGEConv(h1_feats, h2_feats, "pool")
+        self.conv3 = SAGEConv(h2_feats, h3_feats, "pool")
+        self.liner1 = nn.Linear(h3_feats, h4_feats)
+        self.liner2 = nn.Linear(h4_feats, num_classes)
+
+    def hot_path_parameters(self):
+        out = []
+        for c in (self.conv1, self.conv2, self.conv3):
+            out += [c.fc_pool.weight, c.fc_pool.bias, c.fc_self.weight, c.fc_neigh.weight, c.bias]
+        return out + [self.liner1.weight, self.liner1.bias, self.liner2.weight, self.liner2.bias]
+
+    def forward(self, g, in_feat):
+        return GNN32Function.apply(g, in_feat, *self.hot_path_parameters())
+
+    def forward_layerwise(self, g, in_feat):
+        """Same arithmetic through the per-layer Functions (used by tests to cross-check the fused path)."""
+        h = in_feat
+        for c in (self.conv1, self.conv2, self.conv3):
+            h = torch.nn.functional.leaky_relu(c(g, h))
+        h = LinearActFunction.apply(h, self.liner1.weight, self.liner1.bias, ACT_LEAKY)
+        return LinearActFunction.apply(h, self.liner2.weight, self.liner2.bias, ACT_SIGMOID)
+
+
+class GraphConvSum(nn.Module):
+    """h' = act( scale_v * sum_{u->v} w_uv (h W^T)[u] + b ): edge-weighted copy_u+sum aggregation with
+    degree normalisation and fused bias / activation / dropout epilogue (north_star kernel (2))."""
+
+    def __init__(self, in_feats, out_feats, activation=ACT_NONE, dropout=0.0, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_feats, in_feats))
+        self.bias = nn.Parameter(torch.zeros(out_feats)) if bias else None
+        self.activation, self.dropout = activation, float(dropout)
+        self._calls = 0
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+
+    def forward(self, g, x, edge_weight=None, scale=None):
+        p = self.dropout if self.training else 0.0
+        self._calls += 1
+        return GraphConvSumFunction.apply(g, x, self.weight, self.bias, edge_weight, scale, self.activation, p,
+                                          self._calls * 7919 + 17)
+
+
+class GCN(nn.Module):
+    """L x GraphConvSum with leaky_relu between layers (synthetic throughput family; mirrors
+    oracle GCNSumRef when dropout == 0)."""
+
+    def __init__(self, dims, dropout=0.0):
+        super().__init__()
+        self.layers = nn.ModuleList([
+            GraphConvSum(dims[i], dims[i + 1], ACT_LEAKY if i + 2 < len(dims) else ACT_NONE,
+                         dropout if i + 2 < len(dims) else 0.0) for i in range(len(dims) - 1)])
+
+    def forward(self, g, x, edge_weight=None, scale=None):
+        h = x
+        for layer in self.layers:
+            h = layer(g, h, edge_weight, scale)
+        return h

@@ -1,0 +1,254 @@
+"""Thin torch-tensor wrappers over the C ABI (include/plagnn.h).
+
+PyTorch is used here for device memory and streams only; every computation below is a call into
+libplagnn.so on the current CUDA stream.  All functions raise on failure (no fallback path).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, REDUCE_MAX,
+                   REDUCE_SUM, GemmPair, check)
+
+LEAKY_SLOPE = 0.01          # F.leaky_relu default, code/model.py:21,23,25,27
+ROW_ALIGN = 32              # floats: rows of internal matrices start on 128-byte boundaries
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: torch.Tensor | None) -> ctypes.c_void_p | None:
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def pitch_of(cols: int) -> int:
+    return (cols + ROW_ALIGN - 1) // ROW_ALIGN * ROW_ALIGN
+
+
+def alloc(rows: int, cols: int, device, dtype=torch.float32, zero: bool = False) -> torch.Tensor:
+    """rows x cols matrix whose rows are 128-byte aligned (a [:, :cols] view of a padded buffer)."""
+    pitch = pitch_of(cols)
+    buf = (torch.zeros if zero else torch.empty)((rows, pitch), device=device, dtype=dtype)
+    return buf[:, :cols]
+
+
+def is_aligned(x: torch.Tensor) -> bool:
+    return (x.dim() == 2 and x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.stride(0) >= (x.shape[1] + 3) // 4 * 4
+            and x.data_ptr() % 16 == 0)
+
+
+def _require_cuda_f32(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.PlagnnError("plagnn kernels run on CUDA tensors only (no CPU fallback)")
+        if t.dtype != torch.float32:
+            raise _lib.PlagnnError(f"expected float32, got {t.dtype}")
+
+
+def aligned(x: torch.Tensor) -> torch.Tensor:
+    """Returns x if its rows are 16-byte aligned, else a padded copy made by plagnn_pad_copy."""
+    _require_cuda_f32(x)
+    if is_aligned(x):
+        return x
+    if x.dim() != 2 or x.stride(1) != 1:
+        x = x.contiguous()
+    out = alloc(x.shape[0], x.shape[1], x.device)
+    check(_lib.load().plagnn_pad_copy(_p(x), x.shape[0], x.shape[1], x.stride(0), _p(out), out.stride(0), _stream()),
+          "pad_copy")
+    return out
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    """x^T as a new row-aligned matrix (used for the K-contiguous weight operand of the input-gradient GEMMs)."""
+    _require_cuda_f32(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    out = alloc(x.shape[1], x.shape[0], x.device)
+    check(_lib.load().plagnn_transpose(_p(x), x.shape[0], x.shape[1], x.stride(0), _p(out), out.stride(0), _stream()),
+          "transpose")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# workspace cache (per device + stream; reuse is ordered by the stream)
+# ------------------------------------------------------------------------------------------------
+_WS: dict = {}
+
+
+def workspace(nbytes: int, device, tag: str = "ws") -> torch.Tensor | None:
+    if nbytes <= 0:
+        return None
+    key = (str(device), torch.cuda.current_stream().cuda_stream, tag)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 dense contraction
+# ------------------------------------------------------------------------------------------------
+def gemm(m: int, n: int, pairs, bias=None, act=ACT_NONE, gate=None, gate_act=ACT_NONE, out=None,
+         slope: float = LEAKY_SLOPE, backend: int = GEMM_AUTO) -> torch.Tensor:
+    """C[m x n] = epilogue(sum_p op(A_p) op(B_p)).  pairs: list of (a, a_trans, b, b_trans, k)."""
+    lib = _lib.load()
+    dev = pairs[0][0].device
+    arr = (GemmPair * len(pairs))()
+    ktot = 0
+    for i, (a, a_trans, b, b_trans, k) in enumerate(pairs):
+        _require_cuda_f32(a, b)
+        assert a.stride(1) == 1 and b.stride(1) == 1
+        arr[i] = GemmPair(a.data_ptr(), a.stride(0), int(a_trans), b.data_ptr(), b.stride(0), int(b_trans), int(k))
+        ktot += int(k)
+    if out is None:
+        out = alloc(m, n, dev)
+    _require_cuda_f32(out, bias, gate)
+    ws_bytes = lib.plagnn_gemm_workspace_bytes(m, n, ktot)
+    ws = workspace(ws_bytes, dev, "gemm")
+    check(lib.plagnn_gemm(m, n, len(pairs), arr, _p(bias), act, slope, _p(gate), gate.stride(0) if gate is not None else 0,
+                          gate_act, _p(out), out.stride(0), _p(ws), ws_bytes if ws is not None else 0, backend, _stream()),
+          "gemm")
+    return out
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _require_cuda_f32(x)
+    rows, cols = x.shape
+    out = torch.empty(cols, device=x.device, dtype=torch.float32)
+    nb = lib.plagnn_colsum_workspace_bytes(rows, cols)
+    ws = workspace(nb, x.device, "colsum")
+    check(lib.plagnn_colsum(_p(x), rows, cols, x.stride(0), _p(out), _p(ws), nb, _stream()), "colsum")
+    return out
+
+
+def act_backward(dy: torch.Tensor, y: torch.Tensor | None, act: int, slope: float = LEAKY_SLOPE,
+                 row_scale: torch.Tensor | None = None) -> torch.Tensor:
+    """dz = dy * act'(y) * row_scale[:, None]   (y / row_scale optional)."""
+    _require_cuda_f32(dy, y, row_scale)
+    if dy.stride(1) != 1:
+        dy = dy.contiguous()
+    out = alloc(dy.shape[0], dy.shape[1], dy.device)
+    check(_lib.load().plagnn_act_backward(_p(dy), dy.stride(0), _p(y), y.stride(0) if y is not None else 0, dy.shape[0],
+                                          dy.shape[1], act, slope, _p(row_scale), _p(out), out.stride(0), _stream()),
+          "act_backward")
+    return out
+
+
+def row_scale(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    return act_backward(x, None, ACT_NONE, row_scale=scale)
+
+
+# ------------------------------------------------------------------------------------------------
+# K2 aggregation
+# ------------------------------------------------------------------------------------------------
+def spmm_max_fwd(csc, x: torch.Tensor):
+    """csc: graph.Csr (in-edge structure + plan).  Returns (out, arg) with x's row pitch."""
+    lib = _lib.load()
+    x = aligned(x)
+    n, f = csc.num_rows, x.shape[1]
+    out = alloc(n, f, x.device)
+    arg = alloc(n, f, x.device, dtype=torch.int32)
+    nb = lib.plagnn_spmm_partial_bytes(csc.counts[2], f, REDUCE_MAX)
+    part = workspace(nb, x.device, "spmm_partial")
+    check(lib.plagnn_spmm_max_fwd(_p(csc.indptr), _p(csc.indices), _p(csc.plan), csc.counts_c, n, _p(x), x.stride(0), f,
+                                  _p(out), _p(arg), out.stride(0), _p(part), nb, _stream()), "spmm_max_fwd")
+    return out, arg
+
+
+def spmm_max_bwd(dz: torch.Tensor, arg: torch.Tensor, z: torch.Tensor | None, n_src: int) -> torch.Tensor:
+    """dx[arg[v,f], f] += dz[v,f] (* (z>0) when z is given).  dz/arg/z must share one row pitch."""
+    lib = _lib.load()
+    dz = aligned(dz)
+    if dz.stride(0) != arg.stride(0) or (z is not None and z.stride(0) != arg.stride(0)):
+        raise _lib.PlagnnError("spmm_max_bwd: dz, arg and z must have the same row pitch")
+    f = dz.shape[1]
+    dx = alloc(n_src, f, dz.device)
+    check(lib.plagnn_spmm_max_bwd(_p(dz), _p(arg), _p(z), dz.shape[0], f, dz.stride(0), _p(dx), n_src, dx.stride(0),
+                                  _stream()), "spmm_max_bwd")
+    return dx
+
+
+def spmm_max_bwd_gather(csr, dz: torch.Tensor, arg: torch.Tensor, z: torch.Tensor | None) -> torch.Tensor:
+    """Ordered twin of spmm_max_bwd over the out-edge structure `csr`."""
+    lib = _lib.load()
+    dz = aligned(dz)
+    if dz.stride(0) != arg.stride(0) or (z is not None and z.stride(0) != arg.stride(0)):
+        raise _lib.PlagnnError("spmm_max_bwd_gather: dz, arg and z must have the same row pitch")
+    n_src, f = csr.num_rows, dz.shape[1]
+    dx = alloc(n_src, f, dz.device)
+    nb = lib.plagnn_spmm_partial_bytes(csr.counts[2], f, REDUCE_SUM)
+    part = workspace(nb, dz.device, "spmm_partial")
+    check(lib.plagnn_spmm_max_bwd_gather(_p(csr.indptr), _p(csr.indices), _p(csr.plan), csr.counts_c, n_src, _p(dz),
+                                         _p(arg), _p(z), dz.stride(0), f, _p(dx), dx.stride(0), _p(part), nb, _stream()),
+          "spmm_max_bwd_gather")
+    return dx
+
+
+def spmm_sum(csx, x: torch.Tensor, w=None, scale=None, bias=None, act=ACT_NONE, dropout_p: float = 0.0,
+             dropout_seed: int = 0, slope: float = LEAKY_SLOPE) -> torch.Tensor:
+    lib = _lib.load()
+    x = aligned(x)
+    n, f = csx.num_rows, x.shape[1]
+    out = alloc(n, f, x.device)
+    nb = lib.plagnn_spmm_partial_bytes(csx.counts[2], f, REDUCE_SUM)
+    part = workspace(nb, x.device, "spmm_partial")
+    check(lib.plagnn_spmm_sum(_p(csx.indptr), _p(csx.indices), _p(csx.eids) if w is not None else None, _p(csx.plan),
+                              csx.counts_c, n, _p(w), _p(scale), _p(x), x.stride(0), f, _p(bias), act, slope,
+                              float(dropout_p), int(dropout_seed), _p(out), out.stride(0), _p(part), nb, _stream()),
+          "spmm_sum")
+    return out
+
+
+def dropout_scale_(grad: torch.Tensor, p: float, seed: int) -> torch.Tensor:
+    check(_lib.load().plagnn_dropout_scale(_p(grad), grad.shape[0], grad.shape[1], grad.stride(0), float(p), int(seed),
+                                           _stream()), "dropout_scale")
+    return grad
+
+
+# ------------------------------------------------------------------------------------------------
+# K4 loss / optimiser / label decision
+# ------------------------------------------------------------------------------------------------
+def bce_weighted(prob: torch.Tensor, target: torch.Tensor, index: torch.Tensor | None, cw: torch.Tensor,
+                 cwp1: torch.Tensor, want_grad: bool = True, grad_scale: float = 1.0):
+    """Returns (loss[1], dprob[N x C] or None).  index: int64 device tensor of selected rows or None."""
+    lib = _lib.load()
+    _require_cuda_f32(prob, target, cw, cwp1)
+    assert prob.stride(1) == 1 and target.stride(1) == 1
+    n, c = prob.shape
+    r = n if index is None else index.numel()
+    loss = torch.empty(1, device=prob.device, dtype=torch.float32)
+    dprob = alloc(n, c, prob.device) if want_grad else None
+    nb = lib.plagnn_bce_workspace_bytes(r, c)
+    ws = workspace(nb, prob.device, "bce")
+    check(lib.plagnn_bce_weighted(_p(prob), prob.stride(0), _p(target), target.stride(0), _p(index), r, n, c, _p(cw),
+                                  _p(cwp1), float(grad_scale), _p(loss), _p(dprob),
+                                  dprob.stride(0) if dprob is not None else 0, _p(ws), nb, _stream()), "bce_weighted")
+    return loss, dprob
+
+
+def loc_correction(prob: torch.Tensor, alpha: float) -> torch.Tensor:
+    lib = _lib.load()
+    _require_cuda_f32(prob)
+    n, c = prob.shape
+    pred = torch.empty((n, c), device=prob.device, dtype=torch.float32)
+    nb = lib.plagnn_loc_correction_workspace_bytes(c)
+    ws = workspace(nb, prob.device, "loc")
+    check(lib.plagnn_loc_correction(_p(prob), prob.stride(0), n, c, float(alpha), _p(pred), pred.stride(0), _p(ws), nb,
+                                    _stream()), "loc_correction")
+    return pred
+
+
+def adam_multi(table: torch.Tensor, count: int, max_numel: int, lr: float, beta1: float, beta2: float, eps: float,
+               step: int) -> None:
+    bc1 = 1.0 - beta1 ** step
+    bc2_sqrt = math.sqrt(1.0 - beta2 ** step)
+    check(_lib.load().plagnn_adam_multi(_p(table), count, max_numel, lr, beta1, beta2, eps, bc1, bc2_sqrt, _stream()),
+          "adam_multi")
