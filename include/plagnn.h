@@ -44,6 +44,8 @@ enum { PLAGNN_GEMM_AUTO = 0, PLAGNN_GEMM_SIMT = 1, PLAGNN_GEMM_TCGEN05 = 2 };
 enum { PLAGNN_REDUCE_SUM = 0, PLAGNN_REDUCE_MAX = 1 };
 
 int plagnn_version(void);
+/* number of kernels this library has launched so far in this process (host-side counter) */
+long long plagnn_launch_count(void);
 const char* plagnn_last_error(void);
 /* 1 if the current device is compute capability 10.x (the only target), else 0. */
 int plagnn_device_supported(void);

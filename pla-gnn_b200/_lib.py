@@ -36,6 +36,7 @@ class AdamTensor(Structure):
 # name -> (restype, argtypes); every symbol declared in include/plagnn.h appears here
 PROTOTYPES = {
     "plagnn_version": (c_int, []),
+    "plagnn_launch_count": (ctypes.c_longlong, []),
     "plagnn_last_error": (c_char_p, []),
     "plagnn_device_supported": (c_int, []),
     "plagnn_csr_build_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),

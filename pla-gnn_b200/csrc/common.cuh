@@ -15,8 +15,12 @@ inline int fail(int code, const char* what, const char* detail = "") {
     return code;
 }
 
+// Host-side count of kernels launched by this library (bench.py's "gpu_launches").
+void count_launches(int n);
+
 // Checks the launch (not the execution): entry points never synchronise the stream.
-inline int check_launch(const char* what) {
+inline int check_launch(const char* what, int launched = 1) {
+    count_launches(launched);
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) {
         cudaGetLastError();

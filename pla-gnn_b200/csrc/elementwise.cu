@@ -246,7 +246,7 @@ int plagnn_bce_weighted(const float* prob, int64_t ldp, const float* target, int
     bce_kernel<<<blocks, BCE_THREADS, 0, st>>>(prob, ldp, target, ldt, index, num_index, num_rows, (int)classes,
                                                 class_weight, class_weight_plus1, grad_scale, part, dprob, lddp, bad);
     bce_finalize_kernel<<<1, BCE_MAX_CLASSES, 0, st>>>(part, blocks, (int)classes, num_index, loss);
-    return check_launch("bce_weighted");
+    return check_launch("bce_weighted", 2);
 }
 
 int plagnn_adam_multi(const plagnn_adam_tensor* tensors, int32_t count, int64_t max_numel, float lr, float beta1,
@@ -277,7 +277,7 @@ int plagnn_colsum(const float* x, int64_t rows, int64_t cols, int64_t ldx, float
     dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)chunks);
     colsum_partial_kernel<<<grid, 256, 0, st>>>(x, rows, (int)cols, ldx, (float*)workspace);
     colsum_final_kernel<<<(unsigned)ceil_div(cols, 128), 128, 0, st>>>((const float*)workspace, chunks, (int)cols, out);
-    return check_launch("colsum");
+    return check_launch("colsum", 2);
 }
 
 size_t plagnn_loc_correction_workspace_bytes(int64_t classes) {
@@ -295,7 +295,7 @@ int plagnn_loc_correction(const float* prob, int64_t ldp, int64_t num_rows, int6
     colminmax_partial_kernel<<<nparts, 256, 0, st>>>(prob, ldp, num_rows, (int)classes, (float*)workspace);
     loc_decide_kernel<<<(unsigned)ceil_div(num_rows, 128), 128, 0, st>>>(prob, ldp, num_rows, (int)classes, alpha,
                                                                           (const float*)workspace, nparts, pred, ldpred);
-    return check_launch("loc_correction");
+    return check_launch("loc_correction", 2);
 }
 
 int plagnn_pad_copy(const float* src, int64_t rows, int64_t cols, int64_t lds, float* dst, int64_t ldd,

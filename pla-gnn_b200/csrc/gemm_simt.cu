@@ -261,7 +261,7 @@ int gemm_simt_launch(GemmParams& P, void* workspace, size_t workspace_bytes, cud
         const int g = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 8 ? ceil_div(total, 256) : (int64_t)sm_count() * 8);
         gemm_splitk_reduce_kernel<<<g, 256, 0, st>>>(P);
     }
-    return check_launch("gemm_simt");
+    return check_launch("gemm_simt", P.splits > 1 ? 2 : 1);
 }
 
 }  // namespace plagnn

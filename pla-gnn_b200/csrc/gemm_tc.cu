@@ -419,7 +419,7 @@ int gemm_tc_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair*
         const int g = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 8 ? ceil_div(total, 256) : (int64_t)sm_count() * 8);
         gemm_tc_reduce_kernel<<<g, 256, 0, st>>>(P);
     }
-    return check_launch("gemm_tc");
+    return check_launch("gemm_tc", P.splits > 1 ? 2 : 1);
 }
 
 }  // namespace plagnn

@@ -2,7 +2,7 @@
 //
 // Replaces the lazy COO->CSR/CSC conversion DGL performs for the graph the reference builds in
 // code/utils.py:44-45 (dgl.graph((start,end), num_nodes) ; dgl.add_self_loop(g)).  The result must be
-// bit-exact with a stable sort of edge ids by key (oracle/plagnn_oracle.py:coo_to_csc), so the sort
+// bit-exact with a stable sort of edge ids by key (the CPU oracle's coo_to_csc), so the sort
 // is a hand-written *stable* LSD radix sort (8-bit digits) rather than an atomic scatter.
 //
 // All of this is HBM-bound integer work: coalesced streaming reads, shared-memory digit counters,
@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include <cstdarg>
 #include <cstring>
+#include <atomic>
 
 namespace plagnn {
 
@@ -20,6 +21,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 148;
@@ -295,6 +299,7 @@ using namespace plagnn;
 extern "C" {
 
 int plagnn_version(void) { return 100; }
+long long plagnn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* plagnn_last_error(void) { return g_err; }
 
 int plagnn_device_supported(void) {
@@ -366,7 +371,7 @@ int plagnn_csr_build(const int32_t* key, const int32_t* other, int64_t num_edges
     }
     finalize_csr_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(keys[cur], vals[cur], other, num_edges, n,
                                                                    num_nodes, indptr, indices, eids);
-    int rc = check_launch("csr_build");
+    int rc = check_launch("csr_build", 2 + passes * 5);
     if (rc) return rc;
     int host_flag = 0;
     PLAGNN_CUDA_TRY(cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -396,7 +401,7 @@ int plagnn_spmm_plan_build(const int32_t* indptr, int64_t num_rows, int64_t num_
     exclusive_scan_i32(P + L.slot_ptr, num_rows + 1, P + L.scan, st);
     exclusive_scan_i32(P + L.hub_ptr, num_rows + 1, P + L.scan, st);
     plan_fill_kernel<<<g, 256, 0, st>>>(num_rows, P + L.item_ptr, P + L.hub_ptr, P + L.item_row, P + L.hub_rows);
-    int rc = check_launch("spmm_plan_build");
+    int rc = check_launch("spmm_plan_build", 5);
     if (rc) return rc;
     int32_t tot[3] = {0, 0, 0};
     PLAGNN_CUDA_TRY(cudaMemcpyAsync(&tot[0], P + L.item_ptr + num_rows, 4, cudaMemcpyDeviceToHost, st));

@@ -330,7 +330,7 @@ static int spmm_dispatch(const SpmmArgs& a, const char* name, cudaStream_t st) {
         spmm_combine_kernel<MODE><<<grid, SPMM_WARPS * 32, 0, st>>>(item_ptr, slot_ptr, hub_rows, (int)n_hubs, (int)a.feat,
                                                                      pv, pa, pld, a.out, a.arg_out, a.ldo, a.ep);
     }
-    return check_launch(name);
+    return check_launch(name, n_hubs > 0 ? 2 : 1);
 }
 
 }  // namespace plagnn

@@ -18,6 +18,44 @@ LEAKY_SLOPE = 0.01          # F.leaky_relu default, code/model.py:21,23,25,27
 ROW_ALIGN = 32              # floats: rows of internal matrices start on 128-byte boundaries
 
 
+class KernelTimer:
+    """Optional CUDA-event timing of individual kernel calls on the launching stream (bench.py roofline)."""
+
+    def __init__(self):
+        self.records = {}
+
+    def add(self, key, start, end):
+        self.records.setdefault(key, []).append((start, end))
+
+    def summary(self):
+        return {k: (len(v), sum(s.elapsed_time(e) for s, e in v) / len(v)) for k, v in self.records.items()}
+
+
+TIMER: KernelTimer | None = None
+
+
+class _timed:
+    def __init__(self, key):
+        self.key = key
+
+    def __enter__(self):
+        if TIMER is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *a):
+        if TIMER is not None:
+            self.e.record()
+            TIMER.add(self.key, self.s, self.e)
+        return False
+
+
+def launch_count() -> int:
+    return int(_lib.load().plagnn_launch_count())
+
+
 def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -112,9 +150,10 @@ def gemm(m: int, n: int, pairs, bias=None, act=ACT_NONE, gate=None, gate_act=ACT
     _require_cuda_f32(out, bias, gate)
     ws_bytes = lib.plagnn_gemm_workspace_bytes(m, n, ktot)
     ws = workspace(ws_bytes, dev, "gemm")
-    check(lib.plagnn_gemm(m, n, len(pairs), arr, _p(bias), act, slope, _p(gate), gate.stride(0) if gate is not None else 0,
-                          gate_act, _p(out), out.stride(0), _p(ws), ws_bytes if ws is not None else 0, backend, _stream()),
-          "gemm")
+    with _timed(("gemm", m, n, ktot)):
+        check(lib.plagnn_gemm(m, n, len(pairs), arr, _p(bias), act, slope, _p(gate),
+                              gate.stride(0) if gate is not None else 0, gate_act, _p(out), out.stride(0), _p(ws),
+                              ws_bytes if ws is not None else 0, backend, _stream()), "gemm")
     return out
 
 
@@ -158,8 +197,9 @@ def spmm_max_fwd(csc, x: torch.Tensor):
     arg = alloc(n, f, x.device, dtype=torch.int32)
     nb = lib.plagnn_spmm_partial_bytes(csc.counts[2], f, REDUCE_MAX)
     part = workspace(nb, x.device, "spmm_partial")
-    check(lib.plagnn_spmm_max_fwd(_p(csc.indptr), _p(csc.indices), _p(csc.plan), csc.counts_c, n, _p(x), x.stride(0), f,
-                                  _p(out), _p(arg), out.stride(0), _p(part), nb, _stream()), "spmm_max_fwd")
+    with _timed(("spmm_max_fwd", f)):
+        check(lib.plagnn_spmm_max_fwd(_p(csc.indptr), _p(csc.indices), _p(csc.plan), csc.counts_c, n, _p(x), x.stride(0),
+                                      f, _p(out), _p(arg), out.stride(0), _p(part), nb, _stream()), "spmm_max_fwd")
     return out, arg
 
 
@@ -171,8 +211,9 @@ def spmm_max_bwd(dz: torch.Tensor, arg: torch.Tensor, z: torch.Tensor | None, n_
         raise _lib.PlagnnError("spmm_max_bwd: dz, arg and z must have the same row pitch")
     f = dz.shape[1]
     dx = alloc(n_src, f, dz.device)
-    check(lib.plagnn_spmm_max_bwd(_p(dz), _p(arg), _p(z), dz.shape[0], f, dz.stride(0), _p(dx), n_src, dx.stride(0),
-                                  _stream()), "spmm_max_bwd")
+    with _timed(("spmm_max_bwd", f)):
+        check(lib.plagnn_spmm_max_bwd(_p(dz), _p(arg), _p(z), dz.shape[0], f, dz.stride(0), _p(dx), n_src, dx.stride(0),
+                                      _stream()), "spmm_max_bwd")
     return dx
 
 
@@ -200,10 +241,11 @@ def spmm_sum(csx, x: torch.Tensor, w=None, scale=None, bias=None, act=ACT_NONE, 
     out = alloc(n, f, x.device)
     nb = lib.plagnn_spmm_partial_bytes(csx.counts[2], f, REDUCE_SUM)
     part = workspace(nb, x.device, "spmm_partial")
-    check(lib.plagnn_spmm_sum(_p(csx.indptr), _p(csx.indices), _p(csx.eids) if w is not None else None, _p(csx.plan),
-                              csx.counts_c, n, _p(w), _p(scale), _p(x), x.stride(0), f, _p(bias), act, slope,
-                              float(dropout_p), int(dropout_seed), _p(out), out.stride(0), _p(part), nb, _stream()),
-          "spmm_sum")
+    with _timed(("spmm_sum", f)):
+        check(lib.plagnn_spmm_sum(_p(csx.indptr), _p(csx.indices), _p(csx.eids) if w is not None else None,
+                                  _p(csx.plan), csx.counts_c, n, _p(w), _p(scale), _p(x), x.stride(0), f, _p(bias), act,
+                                  slope, float(dropout_p), int(dropout_seed), _p(out), out.stride(0), _p(part), nb,
+                                  _stream()), "spmm_sum")
     return out
 
 

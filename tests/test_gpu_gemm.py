@@ -1,0 +1,123 @@
+"""K3 parity: both GEMM backends vs a float64 torch reference (the tolerance is the north_star's 1e-5
+relative, checked norm-wise; the FFMA backend is expected to be ~1e-6, the 3xTF32 tensor-core one too)."""
+import pytest
+import torch
+
+from plagnn_b200 import ops
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def ref_gemm(pairs, bias, act, gate, gate_act):
+    acc = 0
+    for a, at, b, bt, k in pairs:
+        A = a.double().cpu().t() if at else a.double().cpu()
+        B = b.double().cpu() if bt else b.double().cpu().t()
+        acc = acc + A @ B
+    if bias is not None:
+        acc = acc + bias.double().cpu()
+    if act == ops.ACT_RELU:
+        acc = torch.relu(acc)
+    elif act == ops.ACT_LEAKY:
+        acc = torch.nn.functional.leaky_relu(acc, 0.01)
+    elif act == ops.ACT_SIGMOID:
+        acc = torch.sigmoid(acc)
+    if gate is not None:
+        y = gate.double().cpu()
+        d = {ops.ACT_RELU: (y > 0).double(), ops.ACT_LEAKY: torch.where(y > 0, 1.0, 0.01),
+             ops.ACT_SIGMOID: y * (1 - y)}[gate_act]
+        acc = acc * d
+    return acc
+
+
+def rel(a, b):
+    return ((a.double().cpu() - b).abs().max() / b.abs().max()).item()
+
+
+def operand(rows, k, trans, dev, seed, pad):
+    g = torch.Generator().manual_seed(seed)
+    shape = (k, rows) if trans else (rows, k)
+    t = torch.randn(shape, generator=g)
+    if pad:
+        return ops.aligned(t.to(dev))
+    return t.to(dev)        # contiguous: pitch = cols (unaligned when cols % 4 != 0)
+
+
+BACKENDS = [ops.GEMM_SIMT, ops.GEMM_TCGEN05]
+
+
+@pytest.mark.parametrize("backend", BACKENDS, ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("m,n,k", [(128, 128, 32), (300, 200, 100), (1000, 503, 503), (257, 100, 200), (128, 16, 8),
+                                   (2500, 400, 12)])
+@pytest.mark.parametrize("at,bt", [(0, 0), (0, 1), (1, 1), (1, 0)])
+def test_gemm_layouts(cuda, backend, m, n, k, at, bt):
+    a = operand(m, k, at, cuda, 1, pad=True)
+    b = operand(n, k, bt, cuda, 2, pad=True)
+    pairs = [(a, at, b, bt, k)]
+    got = ops.gemm(m, n, pairs, backend=backend)
+    assert rel(got, ref_gemm(pairs, None, 0, None, 0)) < TOL
+
+
+@pytest.mark.parametrize("backend", BACKENDS, ids=["simt", "tcgen05"])
+def test_gemm_unaligned_operands_and_output(cuda, backend):
+    m, n, k = 333, 503, 503
+    a = operand(m, k, 0, cuda, 3, pad=False)           # pitch 503: scalar load path
+    b = operand(n, k, 0, cuda, 4, pad=False)
+    out = torch.empty(m, n, device=cuda)               # pitch 503: scalar store path
+    pairs = [(a, 0, b, 0, k)]
+    ops.gemm(m, n, pairs, out=out, backend=backend)
+    assert rel(out, ref_gemm(pairs, None, 0, None, 0)) < TOL
+
+
+@pytest.mark.parametrize("backend", BACKENDS, ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("act,gate_act", [(ops.ACT_RELU, 0), (ops.ACT_LEAKY, 0), (ops.ACT_SIGMOID, 0),
+                                          (0, ops.ACT_LEAKY), (0, ops.ACT_RELU), (0, ops.ACT_SIGMOID)])
+def test_gemm_two_pairs_and_epilogues(cuda, backend, act, gate_act):
+    m, n, k1, k2 = 700, 300, 400, 200
+    a1, b1 = operand(m, k1, 0, cuda, 5, True), operand(n, k1, 0, cuda, 6, True)
+    a2, b2 = operand(m, k2, 0, cuda, 7, True), operand(n, k2, 0, cuda, 8, True)
+    bias = torch.randn(n, device=cuda)
+    gate = None
+    if gate_act:
+        gate = ops.aligned(torch.randn(m, n, device=cuda))
+        if gate_act == ops.ACT_SIGMOID:
+            gate = ops.aligned(torch.sigmoid(gate))
+    pairs = [(a1, 0, b1, 0, k1), (a2, 0, b2, 0, k2)]
+    got = ops.gemm(m, n, pairs, bias=bias, act=act, gate=gate, gate_act=gate_act, backend=backend)
+    want = ref_gemm(pairs, bias, act, gate, gate_act)
+    assert rel(got, want) < TOL
+
+
+@pytest.mark.parametrize("backend", BACKENDS, ids=["simt", "tcgen05"])
+def test_gemm_weight_gradient_shape_split_k(cuda, backend):
+    # dW[400 x 503] = dZ^T[400 x 24041] X[24041 x 503]: few output tiles, long K -> split-K path
+    nodes, o, f = 24041, 400, 503
+    dz = ops.aligned(torch.randn(nodes, o, generator=torch.Generator().manual_seed(1)).to(cuda))
+    x = ops.aligned(torch.randn(nodes, f, generator=torch.Generator().manual_seed(2)).to(cuda))
+    out = torch.empty(o, f, device=cuda)
+    pairs = [(dz, 1, x, 1, nodes)]
+    ops.gemm(o, f, pairs, out=out, backend=backend)
+    want = ref_gemm(pairs, None, 0, None, 0)
+    assert rel(out, want) < TOL
+    out2 = torch.empty(o, f, device=cuda)
+    ops.gemm(o, f, pairs, out=out2, backend=backend)
+    assert torch.equal(out, out2)                      # ordered split-K reduction: bit-stable
+
+
+def test_gemm_tiny_n_falls_to_simt_in_auto(cuda):
+    a, b = operand(500, 100, 0, cuda, 1, True), operand(12, 100, 0, cuda, 2, True)
+    pairs = [(a, 0, b, 0, 100)]
+    got = ops.gemm(500, 12, pairs, act=ops.ACT_SIGMOID)
+    assert rel(got, ref_gemm(pairs, None, ops.ACT_SIGMOID, None, 0)) < TOL
+
+
+def test_tcgen05_and_simt_agree_on_ppi_layer_shape(cuda):
+    n, f = 24041, 503
+    x = ops.aligned(torch.randn(n, f, generator=torch.Generator().manual_seed(3)).to(cuda))
+    w = ops.aligned((torch.randn(f, f, generator=torch.Generator().manual_seed(4)) * 0.05).to(cuda))
+    bias = torch.randn(f, device=cuda) * 0.1
+    pairs = [(x, 0, w, 0, f)]
+    s = ops.gemm(n, f, pairs, bias=bias, act=ops.ACT_RELU, backend=ops.GEMM_SIMT)
+    t = ops.gemm(n, f, pairs, bias=bias, act=ops.ACT_RELU, backend=ops.GEMM_TCGEN05)
+    assert ((s - t).abs().max() / s.abs().max()).item() < TOL

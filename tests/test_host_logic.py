@@ -1,0 +1,72 @@
+"""Host-side logic that needs no GPU: graph object surface, synthetic generators, class weights."""
+import json
+import os
+
+import numpy as np
+import torch
+
+import plagnn_b200 as P
+from plagnn_b200 import synth
+from oracle import plagnn_oracle as orc
+
+
+def test_graph_surface_like_the_reference_uses_it():
+    g = P.graph(([0, 1, 2], [1, 2, 0]), num_nodes=4)
+    g = P.add_self_loop(g)
+    assert g.num_nodes() == 4 and g.num_edges() == 7
+    s, d = g.edges()
+    assert s.tolist() == [0, 1, 2, 0, 1, 2, 3] and d.tolist() == [1, 2, 0, 0, 1, 2, 3]
+    g.nodes[list(range(4))].data["feat"] = torch.arange(8.0).reshape(4, 2)
+    assert g.ndata["feat"].shape == (4, 2)
+    g.nodes[[1, 3]].data["x"] = torch.ones(2, 3)
+    assert g.ndata["x"].sum() == 6 and g.ndata["x"][0].sum() == 0
+
+
+def test_create_graph_matches_oracle_node_data():
+    prob = synth.ppi_problem(200, 1600, "normal", 3, feat_dims=(3, 10, 10))
+    ids = list(range(200))
+    g = P.create_graph(prob.scipy_ppi(), prob.ecc, prob.gcn, prob.scipy_loc(), prob.expr, ids)
+    go = orc.create_graph(prob.scipy_ppi(), prob.ecc, prob.gcn, prob.scipy_loc(), prob.expr, ids)
+    assert torch.equal(g.ndata["feat"], go.ndata["feat"]) and torch.equal(g.ndata["loc"], go.ndata["loc"])
+    s, d = g.edges()
+    assert np.array_equal(s.numpy(), go.src) and np.array_equal(d.numpy(), go.dst)
+    assert g.ndata["feat"].dtype == torch.float32 and g.ndata["feat"].shape[1] == 23
+
+
+def test_powerlaw_generator_properties():
+    n, e = 3000, 60000
+    src, dst = synth.powerlaw_edges(n, e, 2.2, 5)
+    assert src.numel() == e and (src != dst).all()
+    key = src * n + dst
+    assert torch.unique(key).numel() == e                     # simple graph
+    assert torch.equal(torch.sort(key).values, torch.sort(dst * n + src).values)   # symmetric
+    deg = torch.bincount(dst, minlength=n)
+    assert deg.min() >= 1 and deg.max() > 20 * deg.float().median()   # heavy tail, no isolated node
+    s2, d2 = synth.powerlaw_edges(n, e, 2.2, 5)
+    assert torch.equal(src, s2) and torch.equal(dst, d2)      # seeded
+
+
+def test_reference_tree_formats(tmp_path):
+    normal, inter = synth.write_reference_tree(str(tmp_path), "GSE74572", 120, 900, seed=1)
+    gm = tmp_path / "data" / "generate_materials"
+    from scipy.sparse import load_npz
+    ppi = load_npz(gm / "PPI_normal.npz")
+    assert ppi.format == "coo" and ppi.dtype == np.int64 and ppi.shape == (120, 120) and (ppi.data == 1).all()
+    assert np.load(gm / "ECC_normal_pca.npy").shape == (120, 250)
+    assert np.load(gm / "GSE74572_data" / "expr_inter.npy").shape == (120, 3)
+    lab = json.load(open(gm / "label_with_loc_list.json"))
+    loc = load_npz(gm / "loc_matrix.npz").toarray()
+    assert (loc[lab].sum(1) > 0).all() and (loc.sum(0) > 0).all()
+    assert len(json.load(open(gm / "label_list.json"))) == 120
+    inter_ppi = load_npz(gm / "GSE74572_data" / "PPI_inter.npz")
+    k = inter_ppi.row.astype(np.int64) * 120 + inter_ppi.col
+    assert (np.diff(k) > 0).all()                             # row-major COO order for the 'inter' form
+
+
+def test_weight_cal_matches_oracle():
+    loc, _ = synth.labels(500, 12, 0.4, 2)
+    assert np.array_equal(P.weight_cal(loc), orc.weight_cal(loc))
+
+
+def test_import_shim_and_package_dir():
+    assert os.path.basename(os.path.dirname(P.__file__)) == "pla-gnn_b200"
