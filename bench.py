@@ -144,12 +144,16 @@ def run_ours(args):
     ids = list(range(n))
 
     # ---- host (pinned) copies of what one epoch consumes: features, labels, training rows ----------
-    feat_h = torch.from_numpy(prob.features).pin_memory()
-    loc_h = torch.from_numpy(prob.loc.astype(np.float32)).pin_memory()
-    idx_h = torch.from_numpy(train_index).pin_memory()
     g = P.create_graph(prob.scipy_ppi(), prob.ecc, prob.gcn, prob.scipy_loc(), prob.expr, ids).to(dev)
     csc = g.csc()
     features, labels = g.ndata["feat"], g.ndata["loc"]
+    # pinned host images in the device layout (rows padded to 128 bytes) so each H2D is one contiguous copy
+    feat_dev, loc_dev = features._base, labels._base
+    feat_h = torch.zeros(feat_dev.shape, dtype=torch.float32).pin_memory()
+    feat_h[:, :features.shape[1]] = torch.from_numpy(prob.features)
+    loc_h = torch.zeros(loc_dev.shape, dtype=torch.float32).pin_memory()
+    loc_h[:, :labels.shape[1]] = torch.from_numpy(prob.loc.astype(np.float32))
+    idx_h = torch.from_numpy(train_index).pin_memory()
     idx_d = idx_h.to(dev)
     i_weight = P.weight_cal(prob.loc)
     torch.manual_seed(70)
@@ -167,12 +171,12 @@ def run_ours(args):
         return logits, loss
 
     def epoch_e2e():
-        features.copy_(feat_h, non_blocking=True)            # H2D: this step's inputs
-        labels.copy_(loc_h, non_blocking=True)
+        feat_dev.copy_(feat_h, non_blocking=True)            # H2D: this step's inputs
+        loc_dev.copy_(loc_h, non_blocking=True)
         idx_d.copy_(idx_h, non_blocking=True)
         logits, loss = epoch()
         loss_h.copy_(loss.detach().reshape(1), non_blocking=True)   # D2H: loss and the N x 12 output the loop reads
-        logits_h.copy_(logits.detach(), non_blocking=True)
+        logits_h.copy_(logits.detach().contiguous(), non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -258,6 +262,9 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(prob, train_index, args.cpu_seconds)
     print(json.dumps(out))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"bench_kernels_n{world}.json"), "w") as fh:
+        json.dump(kernels, fh, indent=1)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -98,15 +98,18 @@ int plagnn_spmm_max_fwd(const int32_t* indptr, const int32_t* indices, const voi
  * SAGEConv-pool into the scatter (x[arg] == z, so relu'(x[arg]) == (z > 0)).
  * dx (n_src x feat, pitch lddx) is zeroed by the call.  Accumulation uses fp32 red.global.add,
  * like DGL's own backward (order not fixed; see plagnn_spmm_max_bwd_gather for the ordered twin). */
-int plagnn_spmm_max_bwd(const float* dz, const int32_t* arg, const float* z, int64_t num_rows,
-                        int64_t feat, int64_t ldz, float* dx, int64_t n_src, int64_t lddx,
-                        plagnn_stream_t stream);
+int plagnn_spmm_max_bwd(const float* dz, int64_t lddz, const int32_t* arg, int64_t ldarg,
+                        const float* z, int64_t ldz, int64_t num_rows, int64_t feat,
+                        float* dx, int64_t n_src, int64_t lddx, plagnn_stream_t stream);
 
 /* Ordered (run-to-run bit-stable) twin of the above: per SOURCE row u, walk the out-edge CSR and
- * add dz[v,f] for the edges whose arg[v,f] == u, in out-edge order.  Costs a full pass over E'. */
+ * add dz[v,f] for the edges whose arg[v,f] == u, in out-edge order.  Costs a full pass over E'.
+ * Needs a graph without duplicate (u,v) edges (a duplicate would be counted once per copy); the PPI
+ * adjacency is simple (built from a set of pairs, code/data_preprocess.py:83-108). */
 int plagnn_spmm_max_bwd_gather(const int32_t* out_indptr, const int32_t* out_indices, const void* out_plan,
-                               const int64_t* out_plan_counts /* host[3] */, int64_t n_src, const float* dz, const int32_t* arg, const float* z,
-                               int64_t ldz, int64_t feat, float* dx, int64_t lddx,
+                               const int64_t* out_plan_counts /* host[3] */, int64_t n_src,
+                               const float* dz, int64_t lddz, const int32_t* arg, int64_t ldarg,
+                               const float* z, int64_t ldz, int64_t feat, float* dx, int64_t lddx,
                                void* partial, size_t partial_bytes, plagnn_stream_t stream);
 
 /* sum family (copy_u / u_mul_e + sum, optional per-destination scale = mean / right norm):
@@ -191,7 +194,7 @@ typedef struct {
     float* param; const float* grad; float* exp_avg; float* exp_avg_sq; int64_t numel;
 } plagnn_adam_tensor;
 int plagnn_adam_multi(const plagnn_adam_tensor* tensors /* device */, int32_t count, int64_t max_numel,
-                      float lr, float beta1, float beta2, float eps,
+                      double lr, double beta1, double beta2, double eps,
                       double bias_correction1, double bias_correction2_sqrt, plagnn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

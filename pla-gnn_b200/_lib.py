@@ -47,10 +47,11 @@ PROTOTYPES = {
     "plagnn_spmm_partial_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "plagnn_spmm_max_fwd": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64, c_void_p, c_int64, c_int64,
                                     c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
-    "plagnn_spmm_max_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64,
-                                    c_void_p]),
-    "plagnn_spmm_max_bwd_gather": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64, c_void_p, c_void_p,
-                                           c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "plagnn_spmm_max_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
+                                    c_void_p, c_int64, c_int64, c_void_p]),
+    "plagnn_spmm_max_bwd_gather": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64, c_void_p, c_int64,
+                                           c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64,
+                                           c_void_p, c_size_t, c_void_p]),
     "plagnn_spmm_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64, c_void_p, c_void_p,
                                 c_void_p, c_int64, c_int64, c_void_p, c_int, c_float, c_float, c_uint64,
                                 c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
@@ -65,7 +66,7 @@ PROTOTYPES = {
     "plagnn_bce_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "plagnn_bce_weighted": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
                                     c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
-    "plagnn_adam_multi": (c_int, [c_void_p, c_int32, c_int64, c_float, c_float, c_float, c_float, c_double, c_double,
+    "plagnn_adam_multi": (c_int, [c_void_p, c_int32, c_int64, c_double, c_double, c_double, c_double, c_double, c_double,
                                   c_void_p]),
     "plagnn_loc_correction_workspace_bytes": (c_size_t, [c_int64]),
     "plagnn_loc_correction": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_int64, c_void_p, c_size_t,

@@ -101,30 +101,30 @@ adam_kernel(const plagnn_adam_tensor* __restrict__ tensors, float lerp_w, float 
 // ---------------------------------------------------------------------------------------------
 constexpr int CS_ROWS_PER_CHUNK = 512;
 __global__ void __launch_bounds__(256)
-colsum_partial_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ldx, float* __restrict__ part) {
-    __shared__ float red[8][33];
+colsum_partial_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ldx, double* __restrict__ part) {
+    __shared__ double red[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
     const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS_PER_CHUNK;
     const int64_t r1 = r0 + CS_ROWS_PER_CHUNK < rows ? r0 + CS_ROWS_PER_CHUNK : rows;
-    float s = 0.f;
+    double s = 0.0;   // double accumulation: column sums of gradients cancel heavily
     if (c < cols)
-        for (int64_t r = r0 + ty; r < r1; r += 8) s += __ldg(x + r * ldx + c);
+        for (int64_t r = r0 + ty; r < r1; r += 8) s += (double)__ldg(x + r * ldx + c);
     red[ty][tx] = s;
     __syncthreads();
     if (ty == 0 && c < cols) {
-        float t = 0.f;
+        double t = 0.0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += red[i][tx];
         part[(int64_t)blockIdx.y * cols + c] = t;
     }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ part, int chunks, int cols, float* __restrict__ out) {
+__global__ void colsum_final_kernel(const double* __restrict__ part, int chunks, int cols, float* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
-    float s = 0.f;
+    double s = 0.0;
     for (int k = 0; k < chunks; ++k) s += part[(int64_t)k * cols + c];
-    out[c] = s;
+    out[c] = (float)s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -249,22 +249,23 @@ int plagnn_bce_weighted(const float* prob, int64_t ldp, const float* target, int
     return check_launch("bce_weighted", 2);
 }
 
-int plagnn_adam_multi(const plagnn_adam_tensor* tensors, int32_t count, int64_t max_numel, float lr, float beta1,
-                      float beta2, float eps, double bias_correction1, double bias_correction2_sqrt,
+int plagnn_adam_multi(const plagnn_adam_tensor* tensors, int32_t count, int64_t max_numel, double lr, double beta1,
+                      double beta2, double eps, double bias_correction1, double bias_correction2_sqrt,
                       plagnn_stream_t stream) {
     if (!tensors || count <= 0 || max_numel <= 0 || bias_correction1 <= 0.0 || bias_correction2_sqrt <= 0.0)
         return fail(PLAGNN_ERR_ARG, "adam_multi", "bad arguments");
-    const float step_size = (float)((double)lr / bias_correction1);
-    const float lerp_w = (float)(1.0 - (double)beta1);
-    const float omb2 = (float)(1.0 - (double)beta2);
+    // scalars are formed in double on the host and rounded once to fp32, as torch does with Python floats
+    const float step_size = (float)(lr / bias_correction1);
+    const float lerp_w = (float)(1.0 - beta1);
+    const float omb2 = (float)(1.0 - beta2);
     dim3 grid((unsigned)capped_grid(max_numel, 256, 4), (unsigned)count);
-    adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tensors, lerp_w, beta2, omb2, eps, step_size,
+    adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tensors, lerp_w, (float)beta2, omb2, (float)eps, step_size,
                                                         (float)bias_correction2_sqrt);
     return check_launch("adam_multi");
 }
 
 size_t plagnn_colsum_workspace_bytes(int64_t rows, int64_t cols) {
-    return align_up((size_t)ceil_div(rows > 0 ? rows : 1, CS_ROWS_PER_CHUNK) * (size_t)cols * sizeof(float), 256);
+    return align_up((size_t)ceil_div(rows > 0 ? rows : 1, CS_ROWS_PER_CHUNK) * (size_t)cols * sizeof(double), 256);
 }
 
 int plagnn_colsum(const float* x, int64_t rows, int64_t cols, int64_t ldx, float* out, void* workspace,
@@ -275,8 +276,8 @@ int plagnn_colsum(const float* x, int64_t rows, int64_t cols, int64_t ldx, float
         return fail(PLAGNN_ERR_WORKSPACE, "colsum", "workspace too small");
     const int chunks = (int)ceil_div(rows, CS_ROWS_PER_CHUNK);
     dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)chunks);
-    colsum_partial_kernel<<<grid, 256, 0, st>>>(x, rows, (int)cols, ldx, (float*)workspace);
-    colsum_final_kernel<<<(unsigned)ceil_div(cols, 128), 128, 0, st>>>((const float*)workspace, chunks, (int)cols, out);
+    colsum_partial_kernel<<<grid, 256, 0, st>>>(x, rows, (int)cols, ldx, (double*)workspace);
+    colsum_final_kernel<<<(unsigned)ceil_div(cols, 128), 128, 0, st>>>((const double*)workspace, chunks, (int)cols, out);
     return check_launch("colsum", 2);
 }
 

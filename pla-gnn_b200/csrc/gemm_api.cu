@@ -10,6 +10,7 @@ int gemm_simt_entry(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
                     float slope, const float* gate, int64_t ldg, int gate_act, float* c, int64_t ldc, void* workspace,
                     size_t workspace_bytes, cudaStream_t st);
 // gemm_tc.cu
+size_t gemm_tc_workspace_bytes(int64_t m, int64_t n, int64_t k_total);
 bool gemm_tc_eligible(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs);
 int gemm_tc_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs, const float* bias, int act,
                    float slope, const float* gate, int64_t ldg, int gate_act, float* c, int64_t ldc, void* workspace,
@@ -23,10 +24,14 @@ extern "C" {
 size_t plagnn_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k_total) {
     // split-K partials: at most 64 splits, only used when the output has fewer tiles than SMs
     const int64_t tiles = ceil_div(m, 128) * ceil_div(n, 128);
-    if (tiles >= 148 * 2 || k_total < 128) return 0;
-    int64_t s = ceil_div((int64_t)2 * 148, tiles);
-    if (s > 64) s = 64;
-    return align_up((size_t)s * (size_t)m * (size_t)n * sizeof(float), 256);
+    size_t simt = 0;
+    if (tiles < 148 * 2 && k_total >= 128) {
+        int64_t s = ceil_div((int64_t)2 * 148, tiles);
+        if (s > 64) s = 64;
+        simt = (size_t)s * (size_t)m * (size_t)n * sizeof(float);
+    }
+    const size_t tc = gemm_tc_workspace_bytes(m, n, k_total);
+    return align_up(simt > tc ? simt : tc, 256);
 }
 
 int plagnn_gemm(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs, const float* bias, int act,

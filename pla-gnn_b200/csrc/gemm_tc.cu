@@ -360,14 +360,30 @@ __global__ void __launch_bounds__(256) gemm_tc_reduce_kernel(const TcParams P) {
     }
 }
 
+// The tensor core accumulates in fp32 with truncation, so the error of one TMEM accumulation chain grows
+// (with a bias) with its length: measured 1.8e-5 relative at K = 24 041 in one chain vs ~1e-6 at K <= 1 000.
+// Chains are therefore capped at TC_MAX_CHAIN k-blocks (K = 1 280); longer contractions are split and the
+// partials are summed in fp32 with round-to-nearest by the ordered reduction kernel.
+constexpr int TC_MAX_CHAIN = 40;
+
 static int tc_choose_splits(int64_t m, int64_t n, int total_kblocks) {
     const int64_t tiles = ceil_div(m, TC_BM) * ceil_div(n, TC_BN);
     const int sms = sm_count();
-    if (tiles >= sms || total_kblocks < 8) return 1;
-    int64_t s = sms / tiles;   // one wave: tiles * splits <= SM count (1 CTA per SM)
-    if (s > total_kblocks / 4) s = total_kblocks / 4;
-    if (s > 64) s = 64;
-    return s < 1 ? 1 : (int)s;
+    int64_t s = 1;
+    if (tiles < sms && total_kblocks >= 8) {
+        s = sms / tiles;   // one wave: tiles * splits <= SM count (1 CTA per SM)
+        if (s > total_kblocks / 4) s = total_kblocks / 4;
+        if (s > 64) s = 64;
+        if (s < 1) s = 1;
+    }
+    const int64_t for_accuracy = ceil_div(total_kblocks, TC_MAX_CHAIN);
+    return (int)(s > for_accuracy ? s : for_accuracy);
+}
+
+size_t gemm_tc_workspace_bytes(int64_t m, int64_t n, int64_t k_total) {
+    const int kb = (int)ceil_div(k_total, TC_BK) + PLAGNN_GEMM_MAX_PAIRS;
+    const int s = tc_choose_splits(m, n, kb);
+    return s > 1 ? (size_t)s * (size_t)m * (size_t)n * sizeof(float) : 0;
 }
 
 bool gemm_tc_eligible(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs) {
@@ -396,7 +412,8 @@ int gemm_tc_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair*
     P.bias = bias; P.act = act; P.slope = slope; P.gate = gate; P.ldg = ldg; P.gate_act = gate_act;
     P.c = c; P.ldc = ldc;
     int splits = tc_choose_splits(m, n, P.total_kblocks);
-    if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * m * n * sizeof(float))) splits = 1;
+    if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * m * n * sizeof(float)))
+        return fail(PLAGNN_ERR_WORKSPACE, "gemm_tc", "split-K workspace too small (see plagnn_gemm_workspace_bytes)");
     P.kblocks_per_split = (int)ceil_div(P.total_kblocks, splits);
     P.splits = (int)ceil_div(P.total_kblocks, P.kblocks_per_split);
     P.partial = P.splits > 1 ? (float*)workspace : nullptr;

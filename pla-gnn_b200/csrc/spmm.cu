@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32)
 spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int32_t* __restrict__ eids,
             const float* __restrict__ ew, const int32_t* __restrict__ plan_hdr, const int32_t* __restrict__ item_ptr,
             const int32_t* __restrict__ slot_ptr, const int32_t* __restrict__ item_row, int n_items,
-            const float* __restrict__ x, int64_t ldx, int feat, const int32_t* __restrict__ argm,
-            const float* __restrict__ zfwd, float* __restrict__ out, int32_t* __restrict__ arg_out, int64_t ldo,
+            const float* __restrict__ x, int64_t ldx, int feat, const int32_t* __restrict__ argm, int64_t ldarg,
+            const float* __restrict__ zfwd, int64_t ldzf, float* __restrict__ out, int32_t* __restrict__ arg_out, int64_t ldo,
             float* __restrict__ part_val, int32_t* __restrict__ part_arg, int part_ld, SpmmEpilogue ep) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
@@ -138,8 +138,8 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
                     if (live && cok[q]) {
                         v[t][q] = ldg_f4(xr + col[q]);
                         if (MODE == MODE_MATCH) {
-                            am[t][q] = __ldg(reinterpret_cast<const int4*>(argm + (int64_t)u[t] * ldx + col[q]));
-                            if (zfwd) zz[t][q] = ldg_f4(zfwd + (int64_t)u[t] * ldx + col[q]);
+                            am[t][q] = __ldg(reinterpret_cast<const int4*>(argm + (int64_t)u[t] * ldarg + col[q]));
+                            if (zfwd) zz[t][q] = ldg_f4(zfwd + (int64_t)u[t] * ldzf + col[q]);
                         }
                     } else {
                         v[t][q] = make_float4(init, init, init, init);
@@ -241,15 +241,16 @@ spmm_combine_kernel(const int32_t* __restrict__ item_ptr, const int32_t* __restr
 
 // reverse of the max reducer with fp32 reductions to global memory (RED.E.ADD.F32)
 __global__ void __launch_bounds__(256)
-spmm_max_scatter_kernel(const float* __restrict__ dz, const int32_t* __restrict__ arg, const float* __restrict__ z,
-                        int64_t n_rows, int feat, int64_t ldz, float* __restrict__ dx, int64_t lddx) {
+spmm_max_scatter_kernel(const float* __restrict__ dz, int64_t lddz, const int32_t* __restrict__ arg, int64_t ldarg,
+                        const float* __restrict__ z, int64_t ldz, int64_t n_rows, int feat, float* __restrict__ dx,
+                        int64_t lddx) {
     const int f4 = (feat + 3) >> 2;
     const int64_t total = n_rows * f4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t v = i / f4;
         const int c = (int)(i - v * f4) * 4;
-        const float4 g = ldg_f4(dz + v * ldz + c);
-        const int4 a = __ldg(reinterpret_cast<const int4*>(arg + v * ldz + c));
+        const float4 g = ldg_f4(dz + v * lddz + c);
+        const int4 a = __ldg(reinterpret_cast<const int4*>(arg + v * ldarg + c));
         float4 zz = make_float4(1.f, 1.f, 1.f, 1.f);
         if (z) zz = ldg_f4(z + v * ldz + c);
         if (a.x >= 0 && g.x != 0.f && zz.x > 0.f && c + 0 < feat) atomicAdd(dx + (int64_t)a.x * lddx + c + 0, g.x);
@@ -279,7 +280,9 @@ struct SpmmArgs {
     int64_t ldx;
     int64_t feat;
     const int32_t* argm;
+    int64_t ldarg;
     const float* zfwd;
+    int64_t ldzf;
     float* out;
     int32_t* arg_out;
     int64_t ldo;
@@ -297,7 +300,7 @@ static void launch_main(const SpmmArgs& a, const int32_t* item_ptr, const int32_
     dim3 grid((unsigned)ceil_div(n_items, SPMM_WARPS), (unsigned)ceil_div((a.feat + 3) / 4, 32 * VEC));
     spmm_kernel<MODE, VEC, NB><<<grid, SPMM_WARPS * 32, 0, st>>>(
         a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, n_items, a.x, a.ldx,
-        (int)a.feat, a.argm, a.zfwd, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep);
+        (int)a.feat, a.argm, a.ldarg, a.zfwd, a.ldzf, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep);
 }
 
 template <int MODE>
@@ -308,7 +311,9 @@ static int spmm_dispatch(const SpmmArgs& a, const char* name, cudaStream_t st) {
     if (a.ldx < f4 || a.ldo < f4 || (a.ldx & 3) || (a.ldo & 3) || !aligned16(a.x) || !aligned16(a.out) ||
         (a.arg_out && !aligned16(a.arg_out)))
         return fail(PLAGNN_ERR_ALIGN, name, "feature matrices need 16-byte aligned rows (pitch % 4 == 0, pitch >= roundup4(feat))");
-    if (MODE == MODE_MATCH && (!a.argm || !aligned16(a.argm))) return fail(PLAGNN_ERR_ARG, name, "arg matrix missing/unaligned");
+    if (MODE == MODE_MATCH && (!a.argm || !aligned16(a.argm) || a.ldarg < f4 || (a.ldarg & 3) ||
+                               (a.zfwd && (!aligned16(a.zfwd) || a.ldzf < f4 || (a.ldzf & 3)))))
+        return fail(PLAGNN_ERR_ALIGN, name, "arg / z matrices need 16-byte aligned rows");
     const int64_t n_items = a.counts[0], n_hubs = a.counts[1], n_slots = a.counts[2];
     if (n_items <= 0 || n_items >= ((int64_t)1 << 31)) return fail(PLAGNN_ERR_ARG, name, "bad plan counts");
     const int pld = part_ld_of(a.feat);
@@ -349,32 +354,32 @@ int plagnn_spmm_max_fwd(const int32_t* indptr, const int32_t* indices, const voi
                         int64_t num_rows, const float* x, int64_t ldx, int64_t feat, float* out, int32_t* arg,
                         int64_t ldo, void* partial, size_t partial_bytes, plagnn_stream_t stream) {
     if (!arg) return fail(PLAGNN_ERR_ARG, "spmm_max_fwd", "arg output is required");
-    SpmmArgs a{indptr, indices, nullptr, nullptr, plan, plan_counts, num_rows, x, ldx, feat, nullptr, nullptr,
+    SpmmArgs a{indptr, indices, nullptr, nullptr, plan, plan_counts, num_rows, x, ldx, feat, nullptr, 0, nullptr, 0,
                out, arg, ldo, partial, partial_bytes, SpmmEpilogue{nullptr, nullptr, 0, 0.f, 0.f, 0ull}};
     return spmm_dispatch<MODE_MAX>(a, "spmm_max_fwd", (cudaStream_t)stream);
 }
 
-int plagnn_spmm_max_bwd(const float* dz, const int32_t* arg, const float* z, int64_t num_rows, int64_t feat,
-                        int64_t ldz, float* dx, int64_t n_src, int64_t lddx, plagnn_stream_t stream) {
+int plagnn_spmm_max_bwd(const float* dz, int64_t lddz, const int32_t* arg, int64_t ldarg, const float* z, int64_t ldz,
+                        int64_t num_rows, int64_t feat, float* dx, int64_t n_src, int64_t lddx, plagnn_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!dz || !arg || !dx || num_rows <= 0 || feat <= 0 || n_src <= 0) return fail(PLAGNN_ERR_ARG, "spmm_max_bwd", "bad arguments");
     const int64_t f4 = (feat + 3) / 4 * 4;
-    if (ldz < f4 || (ldz & 3) || lddx < feat || !aligned16(dz) || !aligned16(arg) || (z && !aligned16(z)))
+    if (lddz < f4 || (lddz & 3) || ldarg < f4 || (ldarg & 3) || lddx < feat || !aligned16(dz) || !aligned16(arg) ||
+        (z && (!aligned16(z) || ldz < f4 || (ldz & 3))))
         return fail(PLAGNN_ERR_ALIGN, "spmm_max_bwd", "dz/arg/z need 16-byte aligned rows");
     PLAGNN_CUDA_TRY(cudaMemset2DAsync(dx, lddx * sizeof(float), 0, (size_t)(lddx < f4 ? feat : f4) * sizeof(float), n_src, st));
     const int64_t total = num_rows * (f4 / 4);
     const int grid = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 16 ? ceil_div(total, 256) : (int64_t)sm_count() * 16);
-    spmm_max_scatter_kernel<<<grid, 256, 0, st>>>(dz, arg, z, num_rows, (int)feat, ldz, dx, lddx);
+    spmm_max_scatter_kernel<<<grid, 256, 0, st>>>(dz, lddz, arg, ldarg, z, ldz, num_rows, (int)feat, dx, lddx);
     return check_launch("spmm_max_bwd");
 }
 
 int plagnn_spmm_max_bwd_gather(const int32_t* out_indptr, const int32_t* out_indices, const void* out_plan,
-                               const int64_t* out_plan_counts, int64_t n_src, const float* dz, const int32_t* arg,
-                               const float* z, int64_t ldz, int64_t feat, float* dx, int64_t lddx, void* partial,
-                               size_t partial_bytes, plagnn_stream_t stream) {
-    if (z && !aligned16(z)) return fail(PLAGNN_ERR_ALIGN, "spmm_max_bwd_gather", "z unaligned");
-    SpmmArgs a{out_indptr, out_indices, nullptr, nullptr, out_plan, out_plan_counts, n_src, dz, ldz, feat, arg, z,
-               dx, nullptr, lddx, partial, partial_bytes, SpmmEpilogue{nullptr, nullptr, 0, 0.f, 0.f, 0ull}};
+                               const int64_t* out_plan_counts, int64_t n_src, const float* dz, int64_t lddz,
+                               const int32_t* arg, int64_t ldarg, const float* z, int64_t ldz, int64_t feat, float* dx,
+                               int64_t lddx, void* partial, size_t partial_bytes, plagnn_stream_t stream) {
+    SpmmArgs a{out_indptr, out_indices, nullptr, nullptr, out_plan, out_plan_counts, n_src, dz, lddz, feat, arg, ldarg,
+               z, ldz, dx, nullptr, lddx, partial, partial_bytes, SpmmEpilogue{nullptr, nullptr, 0, 0.f, 0.f, 0ull}};
     return spmm_dispatch<MODE_MATCH>(a, "spmm_max_bwd_gather", (cudaStream_t)stream);
 }
 
@@ -385,7 +390,7 @@ int plagnn_spmm_sum(const int32_t* indptr, const int32_t* indices, const int32_t
                     plagnn_stream_t stream) {
     if (act < PLAGNN_ACT_NONE || act > PLAGNN_ACT_SIGMOID) return fail(PLAGNN_ERR_ARG, "spmm_sum", "unknown activation");
     if (dropout_p < 0.f || dropout_p >= 1.f) return fail(PLAGNN_ERR_ARG, "spmm_sum", "dropout_p must be in [0,1)");
-    SpmmArgs a{indptr, indices, eids, w, plan, plan_counts, num_rows, x, ldx, feat, nullptr, nullptr, out, nullptr, ldo,
+    SpmmArgs a{indptr, indices, eids, w, plan, plan_counts, num_rows, x, ldx, feat, nullptr, 0, nullptr, 0, out, nullptr, ldo,
                partial, partial_bytes, SpmmEpilogue{scale, bias, act, slope, dropout_p, (unsigned long long)dropout_seed}};
     return spmm_dispatch<MODE_SUM>(a, "spmm_sum", (cudaStream_t)stream);
 }

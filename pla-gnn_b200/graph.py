@@ -195,6 +195,16 @@ class Graph:
     def in_degrees(self) -> torch.Tensor:
         return self.csc().degrees
 
+    def has_duplicate_edges(self) -> bool:
+        """True if some (src, dst) pair occurs more than once (bookkeeping, cached; torch ops on the COO arrays)."""
+        if getattr(self, "_dup", None) is None:
+            key = self._src.long() * self._n + self._dst.long()
+            dup = torch.unique(key).numel() != key.numel()
+            if self._loops and not dup:
+                dup = bool((self._src == self._dst).any())
+            self._dup = bool(dup)
+        return self._dup
+
 
 def _to_device_aligned(v: torch.Tensor, device) -> torch.Tensor:
     """2-D float32 node data lands in a row-padded buffer so that kernels can use it in place."""

@@ -56,6 +56,8 @@ def sage_pool_backward(g, saved, w_pool, w_self, w_neigh, drst, has_bias, need_d
     wn_t = ops.transpose(w_neigh)                       # [f x o], K(=o)-contiguous operand
     dneigh = ops.gemm(n, f, [(drst, 0, wn_t, 0, o)])
     if DETERMINISTIC_BACKWARD:
+        if g.has_duplicate_edges():
+            raise ops._lib.PlagnnError("the ordered max-backward needs a graph without duplicate edges")
         dm = ops.spmm_max_bwd_gather(g.csr(), dneigh, arg, neigh)
     else:
         dm = ops.spmm_max_bwd(dneigh, arg, neigh, n)    # relu' folded in through neigh > 0

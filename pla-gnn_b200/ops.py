@@ -204,32 +204,31 @@ def spmm_max_fwd(csc, x: torch.Tensor):
 
 
 def spmm_max_bwd(dz: torch.Tensor, arg: torch.Tensor, z: torch.Tensor | None, n_src: int) -> torch.Tensor:
-    """dx[arg[v,f], f] += dz[v,f] (* (z>0) when z is given).  dz/arg/z must share one row pitch."""
+    """dx[arg[v,f], f] += dz[v,f] (* (z>0) when z is given)."""
     lib = _lib.load()
     dz = aligned(dz)
-    if dz.stride(0) != arg.stride(0) or (z is not None and z.stride(0) != arg.stride(0)):
-        raise _lib.PlagnnError("spmm_max_bwd: dz, arg and z must have the same row pitch")
     f = dz.shape[1]
     dx = alloc(n_src, f, dz.device)
     with _timed(("spmm_max_bwd", f)):
-        check(lib.plagnn_spmm_max_bwd(_p(dz), _p(arg), _p(z), dz.shape[0], f, dz.stride(0), _p(dx), n_src, dx.stride(0),
+        check(lib.plagnn_spmm_max_bwd(_p(dz), dz.stride(0), _p(arg), arg.stride(0), _p(z),
+                                      z.stride(0) if z is not None else 0, dz.shape[0], f, _p(dx), n_src, dx.stride(0),
                                       _stream()), "spmm_max_bwd")
     return dx
 
 
 def spmm_max_bwd_gather(csr, dz: torch.Tensor, arg: torch.Tensor, z: torch.Tensor | None) -> torch.Tensor:
-    """Ordered twin of spmm_max_bwd over the out-edge structure `csr`."""
+    """Ordered twin of spmm_max_bwd over the out-edge structure `csr` (graph must have no duplicate edges)."""
     lib = _lib.load()
     dz = aligned(dz)
-    if dz.stride(0) != arg.stride(0) or (z is not None and z.stride(0) != arg.stride(0)):
-        raise _lib.PlagnnError("spmm_max_bwd_gather: dz, arg and z must have the same row pitch")
     n_src, f = csr.num_rows, dz.shape[1]
     dx = alloc(n_src, f, dz.device)
     nb = lib.plagnn_spmm_partial_bytes(csr.counts[2], f, REDUCE_SUM)
     part = workspace(nb, dz.device, "spmm_partial")
-    check(lib.plagnn_spmm_max_bwd_gather(_p(csr.indptr), _p(csr.indices), _p(csr.plan), csr.counts_c, n_src, _p(dz),
-                                         _p(arg), _p(z), dz.stride(0), f, _p(dx), dx.stride(0), _p(part), nb, _stream()),
-          "spmm_max_bwd_gather")
+    with _timed(("spmm_max_bwd_gather", f)):
+        check(lib.plagnn_spmm_max_bwd_gather(_p(csr.indptr), _p(csr.indices), _p(csr.plan), csr.counts_c, n_src, _p(dz),
+                                             dz.stride(0), _p(arg), arg.stride(0), _p(z),
+                                             z.stride(0) if z is not None else 0, f, _p(dx), dx.stride(0), _p(part), nb,
+                                             _stream()), "spmm_max_bwd_gather")
     return dx
 
 

@@ -47,14 +47,25 @@ def test_spmm_max_chunk_sizes_agree(cuda):
         assert torch.equal(out.cpu(), ref[0]) and torch.equal(arg.cpu(), ref[1])
 
 
+def make_simple(cuda, n, e, seed):
+    """Simple graph (no duplicate pairs) with a few hubs, + self-loops."""
+    from plagnn_b200 import synth
+    src, dst = synth.powerlaw_edges(n, e, 2.0, seed)
+    src, dst = src.numpy().astype(np.int32), dst.numpy().astype(np.int32)
+    g = P.graph((src, dst), num_nodes=n).add_self_loop().to(cuda)
+    so, do = orc.add_self_loop(src.astype(np.int64), dst.astype(np.int64), n)
+    return g, orc.OracleGraph(so, do, n)
+
+
 @pytest.mark.parametrize("f", [12, 300, 503])
 def test_spmm_max_backward_both_variants(cuda, f):
-    g, go = make(cuda, 700, 15000, 21, hubs=2, hub_deg=900)
+    g, go = make_simple(cuda, 700, 16000, 21)
+    assert not g.has_duplicate_edges() and g.csr().counts[1] > 0      # some rows are split over chunks
     x = torch.relu(torch.randn(700, f))
     out, arg = ops.spmm_max_fwd(g.csc(), x.to(cuda))
     dz = torch.randn(700, f)
     ref = orc.spmm_max_bwd_c(arg.cpu().contiguous(), dz, 700)
-    dzc = ops.aligned(dz.to(cuda))
+    dzc = dz.to(cuda)                                 # contiguous: a different pitch than arg's
     got = ops.spmm_max_bwd(dzc, arg, None, 700)
     assert rel_err(got, ref) < REL_TOL
     got2 = ops.spmm_max_bwd_gather(g.csr(), dzc, arg, None)
@@ -116,3 +127,14 @@ def test_full_size_ppi_aggregation(cuda):
     indptr, indices, _ = orc.coo_to_csc(s, d, prob.num_nodes)
     ro, ra = orc.spmm_max_c(indptr, indices, x)
     assert torch.equal(out.cpu(), ro) and torch.equal(arg.cpu(), ra)
+
+
+def test_spmm_max_backward_scatter_on_multigraph(cuda):
+    """Duplicate edges: the scatter form follows DGL (gradient goes once to the winning source node)."""
+    g, go = make(cuda, 500, 12000, 3, hubs=2, hub_deg=600)
+    assert g.has_duplicate_edges()
+    x = torch.relu(torch.randn(500, 77))
+    out, arg = ops.spmm_max_fwd(g.csc(), x.to(cuda))
+    dz = torch.randn(500, 77)
+    ref = orc.spmm_max_bwd_c(arg.cpu().contiguous(), dz, 500)
+    assert rel_err(ops.spmm_max_bwd(dz.to(cuda), arg, None, 500), ref) < REL_TOL
