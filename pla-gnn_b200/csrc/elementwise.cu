@@ -99,7 +99,7 @@ adam_kernel(const plagnn_adam_tensor* __restrict__ tensors, float lerp_w, float 
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int CS_ROWS_PER_CHUNK = 512;
+constexpr int CS_ROWS_PER_CHUNK = 128;
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ldx, double* __restrict__ part) {
     __shared__ double red[8][33];
@@ -108,8 +108,16 @@ colsum_partial_kernel(const float* __restrict__ x, int64_t rows, int cols, int64
     const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS_PER_CHUNK;
     const int64_t r1 = r0 + CS_ROWS_PER_CHUNK < rows ? r0 + CS_ROWS_PER_CHUNK : rows;
     double s = 0.0;   // double accumulation: column sums of gradients cancel heavily
-    if (c < cols)
-        for (int64_t r = r0 + ty; r < r1; r += 8) s += (double)__ldg(x + r * ldx + c);
+    if (c < cols) {
+        float v[CS_ROWS_PER_CHUNK / 8];
+#pragma unroll
+        for (int i = 0; i < CS_ROWS_PER_CHUNK / 8; ++i) {      // all loads first (16 in flight per thread)
+            const int64_t r = r0 + ty + 8 * i;
+            v[i] = r < r1 ? __ldg(x + r * ldx + c) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < CS_ROWS_PER_CHUNK / 8; ++i) s += (double)v[i];
+    }
     red[ty][tx] = s;
     __syncthreads();
     if (ty == 0 && c < cols) {

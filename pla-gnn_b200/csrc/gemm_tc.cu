@@ -25,7 +25,7 @@ constexpr int TC_THREADS = (TC_LOAD_WARPS + 1) * 32;
 constexpr int TC_PART_BYTES = TC_BM * TC_BK * 4;          // 16 KB: one tf32 tile (128 rows x 128 bytes)
 constexpr int TC_STAGE_BYTES = 4 * TC_PART_BYTES;         // A_hi, A_lo, B_hi, B_lo
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int TC_TMEM_COLS = 128;
+constexpr int TC_TMEM_COLS = 256;   // two fp32 accumulators: [0,128) hi*hi, [128,256) lo*hi + hi*lo
 
 struct TcParams {
     int64_t m, n;
@@ -174,6 +174,31 @@ __device__ __forceinline__ void tile_load(const float* __restrict__ p, int64_t l
     }
 }
 
+// Fast path: per-thread row pointers are set up once per operand pair (rows clamped into range: a clamped
+// row only feeds output rows / columns that are never stored), so an interior k-block is 4 unpredicated
+// 16-byte loads per operand.  Valid when the operand is 16-byte aligned (vec) and the k-block lies inside K.
+__device__ __forceinline__ void tile_ptrs(const float* __restrict__ p, int64_t ld, int trans, int64_t rows, int64_t r0,
+                                          const float* (&ptr)[4]) {
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (!trans) {
+            int64_t r = r0 + (t >> 3) + 32 * i;
+            r = r < rows ? r : rows - 1;
+            ptr[i] = p + r * ld + (t & 7) * 4;
+        } else {
+            int64_t r = r0 + 4 * (16 * (w >> 2) + 4 * i + (lane >> 3));
+            const int64_t last = ((rows - 1) >> 2) << 2;
+            r = r < last ? r : last;
+            ptr[i] = p + (int64_t)(8 * (w & 3) + (lane & 7)) * ld + r;
+        }
+    }
+}
+__device__ __forceinline__ void tile_load_fast(const float* const (&ptr)[4], int64_t koff, float4 (&v)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = ldg_f4(ptr[i] + koff);
+}
+
 // ---- registers -> split -> swizzled K-major shared tiles -----------------------------------------
 // byte offset of (row, 16-byte chunk c) inside a tile: row*128 + ((c ^ (row & 7)) << 4)
 __device__ __forceinline__ void tile_store(uint32_t s_hi, uint32_t s_lo, int trans, const float4 (&v)[4]) {
@@ -249,31 +274,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams P
 
     if (warp < TC_LOAD_WARPS) {
         // ================= loaders =================
-        float4 ca[4], cb[4], na[4], nb[4];
+        // register ring of depth 3: the loads of k-block it+2 are issued before k-block it is split and stored,
+        // so two k-blocks (64 KB per CTA) are in flight while the tensor core works on earlier stages
+        float4 ra[3][4], rb[3][4];
+        const float* pa[4];
+        const float* pb[4];
+        int ptr_pair = -1;
         auto issue = [&](int kb, float4 (&va)[4], float4 (&vb)[4]) {
             int p = 0, local = kb;
             if (P.npairs > 1 && local >= P.kblocks[0]) { local -= P.kblocks[0]; p = 1; }
             const int64_t k0 = (int64_t)local * TC_BK;
-            tile_load(P.a[p], P.lda[p], P.a_trans[p], P.a_vec[p], P.m, P.k[p], m0, k0, va);
-            tile_load(P.b[p], P.ldb[p], P.b_trans[p], P.b_vec[p], P.n, P.k[p], n0, k0, vb);
-            return p;
+            const bool interior = k0 + TC_BK <= P.k[p];
+            if (interior && P.a_vec[p] && P.b_vec[p]) {
+                if (ptr_pair != p) {
+                    tile_ptrs(P.a[p], P.lda[p], P.a_trans[p], P.m, m0, pa);
+                    tile_ptrs(P.b[p], P.ldb[p], P.b_trans[p], P.n, n0, pb);
+                    ptr_pair = p;
+                }
+                tile_load_fast(pa, P.a_trans[p] ? k0 * P.lda[p] : k0, va);
+                tile_load_fast(pb, P.b_trans[p] ? k0 * P.ldb[p] : k0, vb);
+            } else {
+                tile_load(P.a[p], P.lda[p], P.a_trans[p], P.a_vec[p], P.m, P.k[p], m0, k0, va);
+                tile_load(P.b[p], P.ldb[p], P.b_trans[p], P.b_vec[p], P.n, P.k[p], n0, k0, vb);
+            }
         };
-        int pcur = 0;
-        if (nkb > 0) pcur = issue(kb_beg, ca, cb);
-        for (int it = 0; it < nkb; ++it) {
+        auto pair_of = [&](int kb) { return (P.npairs > 1 && kb >= P.kblocks[0]) ? 1 : 0; };
+        auto commit = [&](int it, const float4 (&va)[4], const float4 (&vb)[4]) {
             const int s = it % TC_STAGES;
             const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
-            int pnext = 0;
-            if (it + 1 < nkb) pnext = issue(kb_beg + it + 1, na, nb);
+            const int p = pair_of(kb_beg + it);
             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
             const uint32_t st = tiles + s * TC_STAGE_BYTES;
-            tile_store(st, st + TC_PART_BYTES, P.a_trans[pcur], ca);
-            tile_store(st + 2 * TC_PART_BYTES, st + 3 * TC_PART_BYTES, P.b_trans[pcur], cb);
+            tile_store(st, st + TC_PART_BYTES, P.a_trans[p], va);
+            tile_store(st + 2 * TC_PART_BYTES, st + 3 * TC_PART_BYTES, P.b_trans[p], vb);
             fence_proxy_async_smem();
             mbar_arrive(bar_full + 8 * s);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
-            pcur = pnext;
+        };
+        if (nkb > 0) issue(kb_beg, ra[0], rb[0]);
+        if (nkb > 1) issue(kb_beg + 1, ra[1], rb[1]);
+        for (int it = 0; it < nkb; it += 3) {
+            if (it + 2 < nkb) issue(kb_beg + it + 2, ra[2], rb[2]);
+            commit(it, ra[0], rb[0]);
+            if (it + 1 < nkb) {
+                if (it + 3 < nkb) issue(kb_beg + it + 3, ra[0], rb[0]);
+                commit(it + 1, ra[1], rb[1]);
+            }
+            if (it + 2 < nkb) {
+                if (it + 4 < nkb) issue(kb_beg + it + 4, ra[1], rb[1]);
+                commit(it + 2, ra[2], rb[2]);
+            }
         }
 
         // ================= epilogue =================
@@ -289,8 +338,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams P
         for (int j = 0; j < 4; ++j) {
             const int cbase = 64 * ch + 16 * j;
             if (n0 + cbase >= P.n) break;   // warp-uniform
-            uint32_t acc[16];
+            uint32_t acc[16], acc_small[16];
             tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)cbase, acc);
+            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(TC_BN + cbase), acc_small);
             tmem_ld_wait();
             if (r < P.m) {
 #pragma unroll
@@ -300,7 +350,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams P
                     float v[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        v[e] = __uint_as_float(acc[4 * q + e]);
+                        v[e] = __uint_as_float(acc[4 * q + e]) + __uint_as_float(acc_small[4 * q + e]);
                         if (direct && c + e < P.n) v[e] = tc_epilogue_one(P, v[e], r, c + e);
                     }
                     if (vec_out && c + 3 < P.n) {
@@ -331,10 +381,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams P
 #pragma unroll
                 for (int kk = 0; kk < TC_BK / 8; ++kk) {
                     const uint64_t adv = (uint64_t)(kk * 2);   // 8 tf32 = 32 bytes = 2 x 16-byte units
-                    // small terms first, the hi*hi term last
-                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (it | kk) ? 1u : 0u);
-                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+                    // The tensor core adds into the fp32 accumulator with truncation, so the error of a chain grows
+                    // with the number of accumulations.  The two correction products go to their own accumulator
+                    // (2^-11 of the magnitude: its truncation is invisible) and the main one sees a third of the adds.
+                    const uint32_t acc_on = (it | kk) ? 1u : 0u;
+                    umma_tf32(tmem_base + TC_BN, a_lo + adv, b_hi + adv, idesc, acc_on);
+                    umma_tf32(tmem_base + TC_BN, a_hi + adv, b_lo + adv, idesc, 1u);
+                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, acc_on);
                 }
                 umma_commit(bar_empty + 8 * s);     // frees the stage when these MMAs have read it
             }

@@ -217,16 +217,30 @@ spmm_combine_kernel(const int32_t* __restrict__ item_ptr, const int32_t* __restr
     const float init = MODE == MODE_MAX ? -INFINITY : 0.f;
     float4 acc = make_float4(init, init, init, init);
     int4 arg = make_int4(-1, -1, -1, -1);
-    for (int k = 0; k < nch; ++k) {
-        const float4 v = *reinterpret_cast<const float4*>(part_val + (slot0 + k) * part_ld + col);
-        if (MODE == MODE_MAX) {
-            const int4 a = *reinterpret_cast<const int4*>(part_arg + (slot0 + k) * part_ld + col);
-            if (v.x > acc.x) { acc.x = v.x; arg.x = a.x; }
-            if (v.y > acc.y) { acc.y = v.y; arg.y = a.y; }
-            if (v.z > acc.z) { acc.z = v.z; arg.z = a.z; }
-            if (v.w > acc.w) { acc.w = v.w; arg.w = a.w; }
-        } else {
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    constexpr int CU = 8;   // partials in flight per lane (a hub of 16k edges has > 100 partials)
+    for (int k0 = 0; k0 < nch; k0 += CU) {
+        float4 v[CU];
+        int4 a[CU];
+#pragma unroll
+        for (int j = 0; j < CU; ++j) {
+            if (k0 + j < nch) {
+                v[j] = __ldg(reinterpret_cast<const float4*>(part_val + (slot0 + k0 + j) * part_ld + col));
+                if (MODE == MODE_MAX) a[j] = __ldg(reinterpret_cast<const int4*>(part_arg + (slot0 + k0 + j) * part_ld + col));
+            } else {
+                v[j] = make_float4(init, init, init, init);
+                a[j] = make_int4(-1, -1, -1, -1);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CU; ++j) {
+            if (MODE == MODE_MAX) {
+                if (v[j].x > acc.x) { acc.x = v[j].x; arg.x = a[j].x; }
+                if (v[j].y > acc.y) { acc.y = v[j].y; arg.y = a[j].y; }
+                if (v[j].z > acc.z) { acc.z = v[j].z; arg.z = a[j].z; }
+                if (v[j].w > acc.w) { acc.w = v[j].w; arg.w = a[j].w; }
+            } else {
+                acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w;
+            }
         }
     }
     if (MODE == MODE_MAX) {

@@ -119,7 +119,9 @@ class LinearActFunction(torch.autograd.Function):
     def forward(ctx, x, w, b, act):
         y, xa = linear_forward(x.detach(), w.detach(), None if b is None else b.detach(), act)
         ctx.act, ctx.has_bias = act, b is not None
-        ctx.xa, ctx.y = xa, y
+        # NB: the output object itself must not be stored on ctx (output.grad_fn is ctx -> reference cycle that
+        # only the cyclic GC frees, i.e. hundreds of MB of activations linger); keep a grad-less alias instead
+        ctx.xa, ctx.y = xa, y.detach()
         ctx.save_for_backward(w)
         return y
 
@@ -147,7 +149,7 @@ class GNN32Function(torch.autograd.Function):
             saved.append(s)
         h4, h3 = linear_forward(h, p[15], p[16], ACT_LEAKY)
         prob, h4 = linear_forward(h4, p[17], p[18], ACT_SIGMOID)
-        ctx.g, ctx.saved, ctx.h3, ctx.h4, ctx.prob = g, saved, h3, h4, prob
+        ctx.g, ctx.saved, ctx.h3, ctx.h4, ctx.prob = g, saved, h3, h4, prob.detach()   # alias, no cycle
         ctx.save_for_backward(*params)
         return prob
 
@@ -181,7 +183,7 @@ class GraphConvSumFunction(torch.autograd.Function):
         t = ops.gemm(xa.shape[0], wa.shape[0], [(xa, 0, wa, 0, xa.shape[1])])
         out = ops.spmm_sum(g.csc(), t, w=edge_weight, scale=scale, bias=None if b is None else b.detach(), act=act,
                            dropout_p=dropout_p, dropout_seed=seed)
-        ctx.g, ctx.xa, ctx.out, ctx.ew, ctx.scale, ctx.act = g, xa, out, edge_weight, scale, act
+        ctx.g, ctx.xa, ctx.out, ctx.ew, ctx.scale, ctx.act = g, xa, out.detach(), edge_weight, scale, act
         ctx.dropout, ctx.has_bias = (dropout_p, seed), b is not None
         ctx.save_for_backward(w)
         return out

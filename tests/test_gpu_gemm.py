@@ -75,8 +75,9 @@ def test_gemm_unaligned_operands_and_output(cuda, backend):
                                           (0, ops.ACT_LEAKY), (0, ops.ACT_RELU), (0, ops.ACT_SIGMOID)])
 def test_gemm_two_pairs_and_epilogues(cuda, backend, act, gate_act):
     m, n, k1, k2 = 700, 300, 400, 200
-    a1, b1 = operand(m, k1, 0, cuda, 5, True), operand(n, k1, 0, cuda, 6, True)
-    a2, b2 = operand(m, k2, 0, cuda, 7, True), operand(n, k2, 0, cuda, 8, True)
+    # weights scaled like a layer's (~1/sqrt(k)) so that pre-activations are O(1), as in the network
+    a1, b1 = operand(m, k1, 0, cuda, 5, True), operand(n, k1, 0, cuda, 6, True).mul_(k1 ** -0.5)
+    a2, b2 = operand(m, k2, 0, cuda, 7, True), operand(n, k2, 0, cuda, 8, True).mul_(k2 ** -0.5)
     bias = torch.randn(n, device=cuda)
     gate = None
     if gate_act:
