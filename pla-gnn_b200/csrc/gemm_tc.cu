@@ -116,9 +116,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     return ((uint64_t)hi << 32) | lo;
 }
-// kind::tf32, D = f32, A/B K-major, M = 128, N = n
-__device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+// MN-major operands (stored mn-contiguous, e.g. both operands of a weight-gradient GEMM).  For 32-bit elements the
+// only MN-major layout the tensor core reads is "128-byte swizzle with 32-byte atomicity" (layout type 1): swizzle
+// atom = 4 k-rows x 128 bytes (32 mn elements), the 32-byte chunk index of a row XORed with the row index
+// (address bits [5,7) ^= bits [7,9)).  Atoms of one k-group (4 k) sit 512 bytes apart along mn (LBO), k-groups
+// 2048 bytes apart (SBO); one tf32 MMA (K = 8) consumes two k-groups.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((512u >> 4) << 16);
+    const uint32_t hi = (2048u >> 4) | (1u << 14) | (1u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// kind::tf32, D = f32, M = 128, N = n; bit 15 / 16 = A / B stored MN-major
+__device__ __forceinline__ uint32_t make_idesc(uint32_t n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
+           ((n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -133,56 +144,20 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 
 // ---- operand tile: global fp32 -> registers ------------------------------------------------------
 // Tile = 128 (mn) x 32 (k).  Each of the 256 loader threads owns 4 float4.
-//   trans == 0 (k contiguous):  i-th float4 = row (t>>3)+32i, k-chunk c = t&7         (elements k = 4c..4c+3)
-//   trans == 1 (mn contiguous): i-th float4 = k-row 8*(w&3)+(lane&7), mn-quad 16*(w>>2)+4i+(lane>>3)
-__device__ __forceinline__ void tile_load(const float* __restrict__ p, int64_t ld, int trans, int vec, int64_t rows,
-                                          int64_t kdim, int64_t r0, int64_t k0, float4 (&v)[4]) {
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!trans) {
-            const int64_t r = r0 + (t >> 3) + 32 * i;
-            const int64_t kk = k0 + (t & 7) * 4;
-            if (r < rows && kk < kdim) {
-                const float* q = p + r * ld + kk;
-                if (vec && kk + 3 < kdim) {
-                    x = ldg_f4(q);
-                } else {
-                    x.x = __ldg(q);
-                    if (kk + 1 < kdim) x.y = __ldg(q + 1);
-                    if (kk + 2 < kdim) x.z = __ldg(q + 2);
-                    if (kk + 3 < kdim) x.w = __ldg(q + 3);
-                }
-            }
-        } else {
-            const int64_t kk = k0 + 8 * (w & 3) + (lane & 7);
-            const int64_t r = r0 + 4 * (16 * (w >> 2) + 4 * i + (lane >> 3));
-            if (kk < kdim && r < rows) {
-                const float* q = p + kk * ld + r;
-                if (vec && r + 3 < rows) {
-                    x = ldg_f4(q);
-                } else {
-                    x.x = __ldg(q);
-                    if (r + 1 < rows) x.y = __ldg(q + 1);
-                    if (r + 2 < rows) x.z = __ldg(q + 2);
-                    if (r + 3 < rows) x.w = __ldg(q + 3);
-                }
-            }
-        }
-        v[i] = x;
-    }
-}
-
-// Fast path: per-thread row pointers are set up once per operand pair (rows clamped into range: a clamped
-// row only feeds output rows / columns that are never stored), so an interior k-block is 4 unpredicated
-// 16-byte loads per operand.  Valid when the operand is 16-byte aligned (vec) and the k-block lies inside K.
-__device__ __forceinline__ void tile_ptrs(const float* __restrict__ p, int64_t ld, int trans, int64_t rows, int64_t r0,
+//   T == false (k contiguous):  i-th float4 = row (t>>3)+32i, k-chunk c = t&7         (elements k = 4c..4c+3)
+//   T == true (mn contiguous):  i-th float4 = k-row 8*(w&3)+(lane&7), mn-quad 16*(w>>2)+4i+(lane>>3)
+// Per-thread row pointers are set up once per operand pair with the row index clamped into range: a clamped
+// row only feeds output rows / columns that are never stored, so no row predicate is needed afterwards.
+// Only the K direction must contribute exact zeros beyond k = K (last k-block of a pair).
+// The kernel is instantiated per (AT, BT) and the code is kept small on purpose: the first version spent a
+// fifth of its issue slots in instruction-cache misses (ncu: stall_no_inst).
+template <bool T>
+__device__ __forceinline__ void tile_ptrs(const float* __restrict__ p, int64_t ld, int64_t rows, int64_t r0,
                                           const float* (&ptr)[4]) {
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        if (!trans) {
+        if (!T) {
             int64_t r = r0 + (t >> 3) + 32 * i;
             r = r < rows ? r : rows - 1;
             ptr[i] = p + r * ld + (t & 7) * 4;
@@ -194,14 +169,45 @@ __device__ __forceinline__ void tile_ptrs(const float* __restrict__ p, int64_t l
         }
     }
 }
-__device__ __forceinline__ void tile_load_fast(const float* const (&ptr)[4], int64_t koff, float4 (&v)[4]) {
+
+template <bool T>
+__device__ __forceinline__ void tile_load(const float* const (&ptr)[4], int64_t ld, int64_t k0, int64_t kdim,
+                                          float4 (&v)[4]) {
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (!T) {
+        const int64_t kk = k0 + (t & 7) * 4;
+        if (kk + 3 < kdim) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = ldg_f4(ptr[i] + koff);
+            for (int i = 0; i < 4; ++i) v[i] = ldg_f4(ptr[i] + k0);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kk < kdim) {
+                    const float* q = ptr[i] + k0;
+                    x.x = __ldg(q);
+                    if (kk + 1 < kdim) x.y = __ldg(q + 1);
+                    if (kk + 2 < kdim) x.z = __ldg(q + 2);
+                }
+                v[i] = x;
+            }
+        }
+    } else {
+        const int64_t kk = k0 + 8 * (w & 3) + (lane & 7);
+        if (kk < kdim) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = ldg_f4(ptr[i] + k0 * ld);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
 }
 
 // ---- registers -> split -> swizzled K-major shared tiles -----------------------------------------
 // byte offset of (row, 16-byte chunk c) inside a tile: row*128 + ((c ^ (row & 7)) << 4)
-__device__ __forceinline__ void tile_store(uint32_t s_hi, uint32_t s_lo, int trans, const float4 (&v)[4]) {
+template <bool T>
+__device__ __forceinline__ void tile_store(uint32_t s_hi, uint32_t s_lo, const float4 (&v)[4]) {
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -209,28 +215,22 @@ __device__ __forceinline__ void tile_store(uint32_t s_hi, uint32_t s_lo, int tra
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) split_tf32(x[e], hi[e], lo[e]);
-        if (!trans) {
+        if (!T) {
             const int row = (t >> 3) + 32 * i;
             const int c = t & 7;
             const uint32_t off = (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4));
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
         } else {
-            const int kk = 8 * (w & 3) + (lane & 7);
-            const int jq = lane >> 3;
-            const int rbase = 4 * (16 * (w >> 2) + 4 * i + jq);
-            const int chunk = kk >> 2, el = kk & 3;
-            // rotate the element order per lane group so the 32 lanes of one store hit 32 different banks
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const int e = (s + jq) & 3;
-                const uint32_t h = e == 0 ? hi[0] : e == 1 ? hi[1] : e == 2 ? hi[2] : hi[3];
-                const uint32_t l = e == 0 ? lo[0] : e == 1 ? lo[1] : e == 2 ? lo[2] : lo[3];
-                const int row = rbase + e;
-                const uint32_t off = (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4) + el * 4);
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(s_hi + off), "r"(h) : "memory");
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(s_lo + off), "r"(l) : "memory");
-            }
+            // MN-major tile: atom (k-group kg4 of 4 rows, mn-group mg of 32 floats) at (kg4*4 + mg)*512;
+            // inside an atom: k-row r at r*128, 32-byte chunk c32 of the row stored at chunk (c32 ^ r)
+            const int k = 8 * (w & 3) + (lane & 7);
+            const int kg4 = k >> 2, r = k & 3;
+            const int mq = 16 * (w >> 2) + 4 * i + (lane >> 3);          // mn-quad 0..31 (4 floats = 16 bytes)
+            const int c16 = mq & 7;
+            const uint32_t off = (uint32_t)((kg4 * 4 + (mq >> 3)) * 512 + r * 128 + ((((c16 >> 1) ^ r) << 5) | ((c16 & 1) << 4)));
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
         }
     }
 }
@@ -242,6 +242,7 @@ __device__ __forceinline__ float tc_epilogue_one(const TcParams& P, float v, int
     return v;
 }
 
+template <bool AT, bool BT>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -274,55 +275,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams P
 
     if (warp < TC_LOAD_WARPS) {
         // ================= loaders =================
-        // register ring of depth 3: the loads of k-block it+2 are issued before k-block it is split and stored,
-        // so two k-blocks (64 KB per CTA) are in flight while the tensor core works on earlier stages
-        float4 ra[3][4], rb[3][4];
+        float4 ca[4], cb[4], na[4], nb[4];
         const float* pa[4];
         const float* pb[4];
         int ptr_pair = -1;
         auto issue = [&](int kb, float4 (&va)[4], float4 (&vb)[4]) {
             int p = 0, local = kb;
             if (P.npairs > 1 && local >= P.kblocks[0]) { local -= P.kblocks[0]; p = 1; }
-            const int64_t k0 = (int64_t)local * TC_BK;
-            const bool interior = k0 + TC_BK <= P.k[p];
-            if (interior && P.a_vec[p] && P.b_vec[p]) {
-                if (ptr_pair != p) {
-                    tile_ptrs(P.a[p], P.lda[p], P.a_trans[p], P.m, m0, pa);
-                    tile_ptrs(P.b[p], P.ldb[p], P.b_trans[p], P.n, n0, pb);
-                    ptr_pair = p;
-                }
-                tile_load_fast(pa, P.a_trans[p] ? k0 * P.lda[p] : k0, va);
-                tile_load_fast(pb, P.b_trans[p] ? k0 * P.ldb[p] : k0, vb);
-            } else {
-                tile_load(P.a[p], P.lda[p], P.a_trans[p], P.a_vec[p], P.m, P.k[p], m0, k0, va);
-                tile_load(P.b[p], P.ldb[p], P.b_trans[p], P.b_vec[p], P.n, P.k[p], n0, k0, vb);
+            if (ptr_pair != p) {
+                tile_ptrs<AT>(P.a[p], P.lda[p], P.m, m0, pa);
+                tile_ptrs<BT>(P.b[p], P.ldb[p], P.n, n0, pb);
+                ptr_pair = p;
             }
+            const int64_t k0 = (int64_t)local * TC_BK;
+            tile_load<AT>(pa, P.lda[p], k0, P.k[p], va);
+            tile_load<BT>(pb, P.ldb[p], k0, P.k[p], vb);
         };
-        auto pair_of = [&](int kb) { return (P.npairs > 1 && kb >= P.kblocks[0]) ? 1 : 0; };
-        auto commit = [&](int it, const float4 (&va)[4], const float4 (&vb)[4]) {
+        if (nkb > 0) issue(kb_beg, ca, cb);
+#pragma unroll 1
+        for (int it = 0; it < nkb; ++it) {
             const int s = it % TC_STAGES;
             const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
-            const int p = pair_of(kb_beg + it);
+            if (it + 1 < nkb) issue(kb_beg + it + 1, na, nb);      // next k-block's loads fly during the split
             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
             const uint32_t st = tiles + s * TC_STAGE_BYTES;
-            tile_store(st, st + TC_PART_BYTES, P.a_trans[p], va);
-            tile_store(st + 2 * TC_PART_BYTES, st + 3 * TC_PART_BYTES, P.b_trans[p], vb);
+            tile_store<AT>(st, st + TC_PART_BYTES, ca);
+            tile_store<BT>(st + 2 * TC_PART_BYTES, st + 3 * TC_PART_BYTES, cb);
             fence_proxy_async_smem();
             mbar_arrive(bar_full + 8 * s);
-        };
-        if (nkb > 0) issue(kb_beg, ra[0], rb[0]);
-        if (nkb > 1) issue(kb_beg + 1, ra[1], rb[1]);
-        for (int it = 0; it < nkb; it += 3) {
-            if (it + 2 < nkb) issue(kb_beg + it + 2, ra[2], rb[2]);
-            commit(it, ra[0], rb[0]);
-            if (it + 1 < nkb) {
-                if (it + 3 < nkb) issue(kb_beg + it + 3, ra[0], rb[0]);
-                commit(it + 1, ra[1], rb[1]);
-            }
-            if (it + 2 < nkb) {
-                if (it + 4 < nkb) issue(kb_beg + it + 4, ra[1], rb[1]);
-                commit(it + 2, ra[2], rb[2]);
-            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
         }
 
         // ================= epilogue =================
@@ -369,25 +351,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams P
         if (lane == 0) {
             const int64_t nrem = P.n - n0;
             const uint32_t n_eff = nrem >= TC_BN ? TC_BN : (uint32_t)((nrem + 15) / 16 * 16);
-            const uint32_t idesc = make_idesc(n_eff);
+            const uint32_t idesc = make_idesc(n_eff, AT, BT);
+            // descriptor start-address step per K = 8: 32 bytes inside a K-major row, one 4096-byte k-group if MN-major
+            constexpr uint64_t a_step = AT ? (4096u >> 4) : 2u, b_step = BT ? (4096u >> 4) : 2u;
             for (int it = 0; it < nkb; ++it) {
                 const int s = it % TC_STAGES;
                 const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
                 mbar_wait(bar_full + 8 * s, ph);
                 tc_fence_after();
                 const uint32_t st = tiles + s * TC_STAGE_BYTES;
-                const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + TC_PART_BYTES);
-                const uint64_t b_hi = make_smem_desc(st + 2 * TC_PART_BYTES), b_lo = make_smem_desc(st + 3 * TC_PART_BYTES);
+                const uint64_t a_hi = AT ? make_smem_desc_mn(st) : make_smem_desc(st);
+                const uint64_t a_lo = AT ? make_smem_desc_mn(st + TC_PART_BYTES) : make_smem_desc(st + TC_PART_BYTES);
+                const uint64_t b_hi = BT ? make_smem_desc_mn(st + 2 * TC_PART_BYTES) : make_smem_desc(st + 2 * TC_PART_BYTES);
+                const uint64_t b_lo = BT ? make_smem_desc_mn(st + 3 * TC_PART_BYTES) : make_smem_desc(st + 3 * TC_PART_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < TC_BK / 8; ++kk) {
-                    const uint64_t adv = (uint64_t)(kk * 2);   // 8 tf32 = 32 bytes = 2 x 16-byte units
+                    const uint64_t adv_a = (uint64_t)kk * a_step, adv_b = (uint64_t)kk * b_step;
                     // The tensor core adds into the fp32 accumulator with truncation, so the error of a chain grows
                     // with the number of accumulations.  The two correction products go to their own accumulator
                     // (2^-11 of the magnitude: its truncation is invisible) and the main one sees a third of the adds.
                     const uint32_t acc_on = (it | kk) ? 1u : 0u;
-                    umma_tf32(tmem_base + TC_BN, a_lo + adv, b_hi + adv, idesc, acc_on);
-                    umma_tf32(tmem_base + TC_BN, a_hi + adv, b_lo + adv, idesc, 1u);
-                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, acc_on);
+                    umma_tf32(tmem_base + TC_BN, a_lo + adv_a, b_hi + adv_b, idesc, acc_on);
+                    umma_tf32(tmem_base + TC_BN, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
+                    umma_tf32(tmem_base, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
                 }
                 umma_commit(bar_empty + 8 * s);     // frees the stage when these MMAs have read it
             }
@@ -439,10 +425,16 @@ size_t gemm_tc_workspace_bytes(int64_t m, int64_t n, int64_t k_total) {
     return s > 1 ? (size_t)s * (size_t)m * (size_t)n * sizeof(float) : 0;
 }
 
+// The tensor-core path takes 16-byte aligned operands (row pitch % 4 == 0) whose pairs share one storage
+// order; anything else goes to the FFMA backend.
 bool gemm_tc_eligible(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs) {
     if (n < 16 || m < 1) return false;
-    for (int p = 0; p < npairs; ++p)
-        if (pairs[p].k < 8) return false;
+    for (int p = 0; p < npairs; ++p) {
+        const plagnn_gemm_pair& q = pairs[p];
+        if (q.k < 8) return false;
+        if ((q.lda & 3) || (q.ldb & 3) || !aligned16(q.a) || !aligned16(q.b)) return false;
+        if ((q.a_trans != 0) != (pairs[0].a_trans != 0) || (q.b_trans != 0) != (pairs[0].b_trans != 0)) return false;
+    }
     return true;
 }
 
@@ -471,19 +463,24 @@ int gemm_tc_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair*
     P.splits = (int)ceil_div(P.total_kblocks, P.kblocks_per_split);
     P.partial = P.splits > 1 ? (float*)workspace : nullptr;
 
+    using KernelFn = void (*)(const TcParams);
+    static const KernelFn kernels[4] = {gemm_tc_kernel<false, false>, gemm_tc_kernel<false, true>,
+                                        gemm_tc_kernel<true, false>, gemm_tc_kernel<true, true>};
     static thread_local int attr_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (attr_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-        if (e != cudaSuccess) {
-            set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return PLAGNN_ERR_CUDA;
+        for (int i = 0; i < 4; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+            if (e != cudaSuccess) {
+                set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+                return PLAGNN_ERR_CUDA;
+            }
         }
         attr_dev = dev;
     }
     dim3 grid((unsigned)ceil_div(n, TC_BN), (unsigned)ceil_div(m, TC_BM), (unsigned)P.splits);
-    gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(P);
+    kernels[(P.a_trans[0] ? 2 : 0) + (P.b_trans[0] ? 1 : 0)]<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(P);
     if (P.splits > 1) {
         const int64_t total = m * n;
         const int g = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 8 ? ceil_div(total, 256) : (int64_t)sm_count() * 8);

@@ -66,8 +66,19 @@ def test_gemm_unaligned_operands_and_output(cuda, backend):
     b = operand(n, k, 0, cuda, 4, pad=False)
     out = torch.empty(m, n, device=cuda)               # pitch 503: scalar store path
     pairs = [(a, 0, b, 0, k)]
+    if backend == ops.GEMM_TCGEN05:
+        # the tensor-core path takes 16-byte aligned operands only: explicit request fails loudly, AUTO uses FFMA
+        import plagnn_b200 as P
+        with pytest.raises(P.PlagnnError):
+            ops.gemm(m, n, pairs, out=out, backend=backend)
+        backend = ops.GEMM_AUTO
     ops.gemm(m, n, pairs, out=out, backend=backend)
     assert rel(out, ref_gemm(pairs, None, 0, None, 0)) < TOL
+    # aligned operands, unaligned output pitch: tensor-core kernel with the scalar store epilogue
+    out2 = torch.empty(m, n, device=cuda)
+    pairs2 = [(ops.aligned(a), 0, ops.aligned(b), 0, k)]
+    ops.gemm(m, n, pairs2, out=out2, backend=ops.GEMM_TCGEN05 if backend != ops.GEMM_SIMT else backend)
+    assert rel(out2, ref_gemm(pairs, None, 0, None, 0)) < TOL
 
 
 @pytest.mark.parametrize("backend", BACKENDS, ids=["simt", "tcgen05"])

@@ -49,5 +49,8 @@ if __name__ == "__main__":
     errs.append(run(128, 128, 64, at=1, bt=1, pattern="index"))
     errs.append(run(300, 200, 1000, at=1, bt=1))
     errs.append(run(300, 200, 100, at=0, bt=1))
+    errs.append(run(128, 128, 32, at=0, bt=1, pattern="index"))
+    errs.append(run(128, 128, 32, at=1, bt=0, pattern="index"))
+    errs.append(run(260, 136, 70, at=1, bt=0))
     errs.append(run(400, 503, 24041, at=1, bt=1))
     print("max err", max(errs))

@@ -1,0 +1,35 @@
+"""Runs each hot kernel a few times on the PPI-shaped sizes (for ncu --set full captures)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import plagnn_b200 as P
+from plagnn_b200 import ops, synth
+
+dev = torch.device("cuda:0")
+N = 24041
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+torch.manual_seed(0)
+if which in ("all", "gemm"):
+    x = ops.aligned(torch.randn(N, 503, device=dev))
+    w = ops.aligned(torch.randn(503, 503, device=dev) * 0.05)
+    b = torch.randn(503, device=dev)
+    for _ in range(3):
+        ops.gemm(N, 503, [(x, 0, w, 0, 503)], bias=b, act=ops.ACT_RELU, backend=ops.GEMM_TCGEN05)
+    dz = ops.aligned(torch.randn(N, 400, device=dev))
+    out = torch.empty(400, 503, device=dev)
+    for _ in range(3):
+        ops.gemm(400, 503, [(dz, 1, x, 1, N)], out=out, backend=ops.GEMM_TCGEN05)
+if which in ("all", "spmm"):
+    prob = synth.ppi_problem(state="inter")
+    g = P.graph((prob.ppi_row, prob.ppi_col), num_nodes=N).add_self_loop().to(dev)
+    m = ops.aligned(torch.relu(torch.randn(N, 503, device=dev)))
+    for _ in range(3):
+        o, a = ops.spmm_max_fwd(g.csc(), m)
+    dzz = ops.aligned(torch.randn(N, 503, device=dev))
+    for _ in range(3):
+        ops.spmm_max_bwd(dzz, a, o, N)
+torch.cuda.synchronize()
+print("ok")
