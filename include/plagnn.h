@@ -46,6 +46,12 @@ enum { PLAGNN_REDUCE_SUM = 0, PLAGNN_REDUCE_MAX = 1 };
 int plagnn_version(void);
 /* number of kernels this library has launched so far in this process (host-side counter) */
 long long plagnn_launch_count(void);
+/* Optional per-call timing with CUDA events on the launching stream (used by bench.py for the roofline):
+ * enable(1) clears and starts recording, enable(0) stops; report() synchronises the recorded events and
+ * writes lines "name tag0 tag1 tag2 calls total_ms" (gemm: m n k; spmm_*: feat rows flag).  Returns the
+ * number of bytes needed. */
+int plagnn_profile_enable(int on);
+size_t plagnn_profile_report(char* buf, size_t cap);
 const char* plagnn_last_error(void);
 /* 1 if the current device is compute capability 10.x (the only target), else 0. */
 int plagnn_device_supported(void);
@@ -205,6 +211,37 @@ size_t plagnn_loc_correction_workspace_bytes(int64_t classes);
 int plagnn_loc_correction(const float* prob, int64_t ldp, int64_t num_rows, int64_t classes, float alpha,
                           float* pred, int64_t ldpred, void* workspace, size_t workspace_bytes,
                           plagnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-network calls — replace, as a unit,  code/model.py:19-31  GNN32.forward(g, in_feat)
+ * (3x SAGEConv('pool') + leaky_relu, liner1 + leaky_relu, liner2 + sigmoid) and the autograd
+ * backward that  code/train.py:204  runs through it.  One C call per direction; every
+ * intermediate lives in a caller-owned arena (plagnn_gnn32_arena_bytes), so an epoch allocates
+ * nothing.  The arena must be zero-filled once after allocation and must not be touched between
+ * a forward and its backward.
+ *   params / grads: HOST arrays of 19 DEVICE pointers to contiguous tensors, in the order
+ *     conv{1,2,3}: fc_pool.weight [F x F], fc_pool.bias [F], fc_self.weight [O x F],
+ *                  fc_neigh.weight [O x F], bias [O];   liner1.weight, liner1.bias, liner2.weight, liner2.bias
+ *   x: N x in_feats, 16-byte aligned rows.  prob: N x classes probabilities (saved by the caller for backward).
+ *   dx may be NULL (the reference's features do not require a gradient).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t num_nodes;
+    int32_t in_feats, h1, h2, h3, h4, classes;
+    const int32_t* indptr;    /* in-edge CSR of the graph (plagnn_csr_build, key = destination) */
+    const int32_t* indices;
+    const void* plan;         /* plagnn_spmm_plan_build */
+    int64_t plan_counts[3];
+} plagnn_gnn32_shape;
+
+size_t plagnn_gnn32_arena_bytes(const plagnn_gnn32_shape* shape);
+int plagnn_gnn32_forward(const plagnn_gnn32_shape* shape, const float* x, int64_t ldx,
+                         const float* const* params /* host[19] */, void* arena, size_t arena_bytes,
+                         float* prob, int64_t ldprob, plagnn_stream_t stream);
+int plagnn_gnn32_backward(const plagnn_gnn32_shape* shape, const float* x, int64_t ldx,
+                          const float* const* params /* host[19] */, void* arena, size_t arena_bytes,
+                          const float* prob, int64_t ldprob, const float* dprob, int64_t lddprob,
+                          float* const* grads /* host[19] */, float* dx, int64_t lddx, plagnn_stream_t stream);
 
 /* small utilities used by the host layer */
 int plagnn_pad_copy(const float* src, int64_t rows, int64_t cols, int64_t lds, float* dst, int64_t ldd,

@@ -28,6 +28,12 @@ class GemmPair(Structure):
                 ("k", c_int64)]
 
 
+class Gnn32Shape(Structure):
+    _fields_ = [("num_nodes", c_int64), ("in_feats", c_int32), ("h1", c_int32), ("h2", c_int32), ("h3", c_int32),
+                ("h4", c_int32), ("classes", c_int32), ("indptr", c_void_p), ("indices", c_void_p), ("plan", c_void_p),
+                ("plan_counts", c_int64 * 3)]
+
+
 class AdamTensor(Structure):
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
                 ("numel", c_int64)]
@@ -37,6 +43,8 @@ class AdamTensor(Structure):
 PROTOTYPES = {
     "plagnn_version": (c_int, []),
     "plagnn_launch_count": (ctypes.c_longlong, []),
+    "plagnn_profile_enable": (c_int, [c_int]),
+    "plagnn_profile_report": (c_size_t, [c_char_p, c_size_t]),
     "plagnn_last_error": (c_char_p, []),
     "plagnn_device_supported": (c_int, []),
     "plagnn_csr_build_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
@@ -70,6 +78,12 @@ PROTOTYPES = {
                                   c_void_p]),
     "plagnn_loc_correction_workspace_bytes": (c_size_t, [c_int64]),
     "plagnn_loc_correction": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_int64, c_void_p, c_size_t,
+                                      c_void_p]),
+    "plagnn_gnn32_arena_bytes": (c_size_t, [POINTER(Gnn32Shape)]),
+    "plagnn_gnn32_forward": (c_int, [POINTER(Gnn32Shape), c_void_p, c_int64, POINTER(c_void_p), c_void_p, c_size_t,
+                                     c_void_p, c_int64, c_void_p]),
+    "plagnn_gnn32_backward": (c_int, [POINTER(Gnn32Shape), c_void_p, c_int64, POINTER(c_void_p), c_void_p, c_size_t,
+                                      c_void_p, c_int64, c_void_p, c_int64, POINTER(c_void_p), c_void_p, c_int64,
                                       c_void_p]),
     "plagnn_pad_copy": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "plagnn_transpose": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),

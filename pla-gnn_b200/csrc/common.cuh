@@ -39,6 +39,15 @@ inline int check_launch(const char* what, int launched = 1) {
         }                                                                          \
     } while (0)
 
+// Optional per-call CUDA-event timing on the launching stream (plagnn_profile_enable / _report): lets bench.py
+// measure each kernel's duration inside its own timed region without a profiler attached.
+struct ProfileScope {
+    int slot;
+    cudaStream_t st;
+    ProfileScope(const char* name, long long t0, long long t1, long long t2, plagnn_stream_t stream);
+    ~ProfileScope();
+};
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -246,6 +246,7 @@ int plagnn_bce_weighted(const float* prob, int64_t ldp, const float* target, int
         return fail(PLAGNN_ERR_ARG, "bce_weighted", "bad arguments");
     const size_t need = plagnn_bce_workspace_bytes(num_index, classes);
     if (!workspace || workspace_bytes < need) return fail(PLAGNN_ERR_WORKSPACE, "bce_weighted", "workspace too small");
+    ProfileScope prof("bce_weighted", num_index, classes, 0, stream);
     const int blocks = (int)ceil_div(num_index, BCE_THREADS);
     double* part = (double*)workspace;
     int* bad = (int*)((char*)workspace + need - 256);
@@ -262,6 +263,7 @@ int plagnn_adam_multi(const plagnn_adam_tensor* tensors, int32_t count, int64_t 
                       plagnn_stream_t stream) {
     if (!tensors || count <= 0 || max_numel <= 0 || bias_correction1 <= 0.0 || bias_correction2_sqrt <= 0.0)
         return fail(PLAGNN_ERR_ARG, "adam_multi", "bad arguments");
+    ProfileScope prof("adam_multi", count, max_numel, 0, stream);
     // scalars are formed in double on the host and rounded once to fp32, as torch does with Python floats
     const float step_size = (float)(lr / bias_correction1);
     const float lerp_w = (float)(1.0 - beta1);
@@ -280,6 +282,7 @@ int plagnn_colsum(const float* x, int64_t rows, int64_t cols, int64_t ldx, float
                   size_t workspace_bytes, plagnn_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!x || !out || rows <= 0 || cols <= 0 || ldx < cols) return fail(PLAGNN_ERR_ARG, "colsum", "bad arguments");
+    ProfileScope prof("colsum", rows, cols, 0, stream);
     if (!workspace || workspace_bytes < plagnn_colsum_workspace_bytes(rows, cols))
         return fail(PLAGNN_ERR_WORKSPACE, "colsum", "workspace too small");
     const int chunks = (int)ceil_div(rows, CS_ROWS_PER_CHUNK);
@@ -310,6 +313,7 @@ int plagnn_loc_correction(const float* prob, int64_t ldp, int64_t num_rows, int6
 int plagnn_pad_copy(const float* src, int64_t rows, int64_t cols, int64_t lds, float* dst, int64_t ldd,
                     plagnn_stream_t stream) {
     if (!src || !dst || rows <= 0 || cols <= 0 || lds < cols || ldd < cols) return fail(PLAGNN_ERR_ARG, "pad_copy", "bad arguments");
+    ProfileScope prof("pad_copy", rows, cols, 0, stream);
     pad_copy_kernel<<<capped_grid(rows * ldd, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, rows, (int)cols, lds, dst, ldd);
     return check_launch("pad_copy");
 }
@@ -317,6 +321,7 @@ int plagnn_pad_copy(const float* src, int64_t rows, int64_t cols, int64_t lds, f
 int plagnn_transpose(const float* src, int64_t rows, int64_t cols, int64_t lds, float* dst, int64_t ldd,
                      plagnn_stream_t stream) {
     if (!src || !dst || rows <= 0 || cols <= 0 || lds < cols || ldd < rows) return fail(PLAGNN_ERR_ARG, "transpose", "bad arguments");
+    ProfileScope prof("transpose", rows, cols, 0, stream);
     dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
     transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, rows, cols, lds, dst, ldd);
     return check_launch("transpose");
@@ -349,6 +354,7 @@ extern "C" int plagnn_act_backward(const float* dy, int64_t lddy, const float* y
     using namespace plagnn;
     if (!dy || !dz || rows <= 0 || cols <= 0 || lddy < cols || (y && ldy < cols) || lddz < cols)
         return fail(PLAGNN_ERR_ARG, "act_backward", "bad arguments");
+    ProfileScope prof("act_backward", rows, cols, 0, stream);
     act_backward_kernel<<<capped_grid(rows * cols, 256, 8), 256, 0, (cudaStream_t)stream>>>(dy, lddy, y, ldy, rows,
                                                                                           (int)cols, act, slope, row_scale, dz, lddz);
     return check_launch("act_backward");

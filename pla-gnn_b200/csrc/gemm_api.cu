@@ -38,6 +38,9 @@ int plagnn_gemm(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pa
                 float slope, const float* gate, int64_t ldg, int gate_act, float* c, int64_t ldc, void* workspace,
                 size_t workspace_bytes, int backend, plagnn_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    long long ktot = 0;
+    for (int p = 0; pairs && p < npairs && p < PLAGNN_GEMM_MAX_PAIRS; ++p) ktot += pairs[p].k;
+    ProfileScope prof("gemm", m, n, ktot, stream);
     if (m <= 0 || n <= 0 || npairs < 1 || npairs > PLAGNN_GEMM_MAX_PAIRS || !pairs || !c)
         return fail(PLAGNN_ERR_ARG, "gemm", "bad sizes or null pointers");
     if (act < PLAGNN_ACT_NONE || act > PLAGNN_ACT_SIGMOID || gate_act < PLAGNN_ACT_NONE || gate_act > PLAGNN_ACT_SIGMOID)

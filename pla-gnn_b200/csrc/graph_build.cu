@@ -11,6 +11,10 @@
 #include <cstdarg>
 #include <cstring>
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 namespace plagnn {
 
@@ -24,6 +28,34 @@ void set_error(const char* fmt, ...) {
 
 static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- optional event profile ---------------------------------------------------------------------
+struct ProfRec {
+    char name[24];
+    long long tag[3];
+    cudaEvent_t beg, end;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static std::atomic<int> g_prof_on{0};
+
+ProfileScope::ProfileScope(const char* name, long long t0, long long t1, long long t2, plagnn_stream_t stream)
+    : slot(-1), st((cudaStream_t)stream) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRec r{};
+    snprintf(r.name, sizeof(r.name), "%s", name);
+    r.tag[0] = t0; r.tag[1] = t1; r.tag[2] = t2;
+    if (cudaEventCreate(&r.beg) != cudaSuccess || cudaEventCreate(&r.end) != cudaSuccess) return;
+    cudaEventRecord(r.beg, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+ProfileScope::~ProfileScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].end, st);
+}
 
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 148;
@@ -300,6 +332,43 @@ extern "C" {
 
 int plagnn_version(void) { return 100; }
 long long plagnn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int plagnn_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (on) {
+        for (auto& r : g_prof) { cudaEventDestroy(r.beg); cudaEventDestroy(r.end); }
+        g_prof.clear();
+    }
+    g_prof_on.store(on ? 1 : 0);
+    return PLAGNN_OK;
+}
+
+// Synchronises the recorded events and writes one line per (name, tags): "name t0 t1 t2 calls total_ms\n".
+size_t plagnn_profile_report(char* buf, size_t cap) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<long long, double>> agg;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.end) != cudaSuccess || cudaEventElapsedTime(&ms, r.beg, r.end) != cudaSuccess) continue;
+        char key[96];
+        snprintf(key, sizeof(key), "%s %lld %lld %lld", r.name, r.tag[0], r.tag[1], r.tag[2]);
+        auto& a = agg[key];
+        a.first += 1;
+        a.second += ms;
+    }
+    std::string out;
+    for (auto& kv : agg) {
+        char line[160];
+        snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (buf && cap) {
+        const size_t nb = out.size() < cap - 1 ? out.size() : cap - 1;
+        memcpy(buf, out.data(), nb);
+        buf[nb] = 0;
+    }
+    return out.size() + 1;
+}
 const char* plagnn_last_error(void) { return g_err; }
 
 int plagnn_device_supported(void) {

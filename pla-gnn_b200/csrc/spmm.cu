@@ -368,6 +368,7 @@ int plagnn_spmm_max_fwd(const int32_t* indptr, const int32_t* indices, const voi
                         int64_t num_rows, const float* x, int64_t ldx, int64_t feat, float* out, int32_t* arg,
                         int64_t ldo, void* partial, size_t partial_bytes, plagnn_stream_t stream) {
     if (!arg) return fail(PLAGNN_ERR_ARG, "spmm_max_fwd", "arg output is required");
+    ProfileScope prof("spmm_max_fwd", feat, num_rows, 0, stream);
     SpmmArgs a{indptr, indices, nullptr, nullptr, plan, plan_counts, num_rows, x, ldx, feat, nullptr, 0, nullptr, 0,
                out, arg, ldo, partial, partial_bytes, SpmmEpilogue{nullptr, nullptr, 0, 0.f, 0.f, 0ull}};
     return spmm_dispatch<MODE_MAX>(a, "spmm_max_fwd", (cudaStream_t)stream);
@@ -376,6 +377,7 @@ int plagnn_spmm_max_fwd(const int32_t* indptr, const int32_t* indices, const voi
 int plagnn_spmm_max_bwd(const float* dz, int64_t lddz, const int32_t* arg, int64_t ldarg, const float* z, int64_t ldz,
                         int64_t num_rows, int64_t feat, float* dx, int64_t n_src, int64_t lddx, plagnn_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    ProfileScope prof("spmm_max_bwd", feat, num_rows, 0, stream);
     if (!dz || !arg || !dx || num_rows <= 0 || feat <= 0 || n_src <= 0) return fail(PLAGNN_ERR_ARG, "spmm_max_bwd", "bad arguments");
     const int64_t f4 = (feat + 3) / 4 * 4;
     if (lddz < f4 || (lddz & 3) || ldarg < f4 || (ldarg & 3) || lddx < feat || !aligned16(dz) || !aligned16(arg) ||
@@ -392,6 +394,7 @@ int plagnn_spmm_max_bwd_gather(const int32_t* out_indptr, const int32_t* out_ind
                                const int64_t* out_plan_counts, int64_t n_src, const float* dz, int64_t lddz,
                                const int32_t* arg, int64_t ldarg, const float* z, int64_t ldz, int64_t feat, float* dx,
                                int64_t lddx, void* partial, size_t partial_bytes, plagnn_stream_t stream) {
+    ProfileScope prof("spmm_max_bwd_gather", feat, n_src, 0, stream);
     SpmmArgs a{out_indptr, out_indices, nullptr, nullptr, out_plan, out_plan_counts, n_src, dz, lddz, feat, arg, ldarg,
                z, ldz, dx, nullptr, lddx, partial, partial_bytes, SpmmEpilogue{nullptr, nullptr, 0, 0.f, 0.f, 0ull}};
     return spmm_dispatch<MODE_MATCH>(a, "spmm_max_bwd_gather", (cudaStream_t)stream);
@@ -402,6 +405,7 @@ int plagnn_spmm_sum(const int32_t* indptr, const int32_t* indices, const int32_t
                     int64_t ldx, int64_t feat, const float* bias, int act, float slope, float dropout_p,
                     uint64_t dropout_seed, float* out, int64_t ldo, void* partial, size_t partial_bytes,
                     plagnn_stream_t stream) {
+    ProfileScope prof("spmm_sum", feat, num_rows, w ? 1 : 0, stream);
     if (act < PLAGNN_ACT_NONE || act > PLAGNN_ACT_SIGMOID) return fail(PLAGNN_ERR_ARG, "spmm_sum", "unknown activation");
     if (dropout_p < 0.f || dropout_p >= 1.f) return fail(PLAGNN_ERR_ARG, "spmm_sum", "dropout_p must be in [0,1)");
     SpmmArgs a{indptr, indices, eids, w, plan, plan_counts, num_rows, x, ldx, feat, nullptr, 0, nullptr, 0, out, nullptr, ldo,

@@ -173,6 +173,78 @@ class GNN32Function(torch.autograd.Function):
         return (None, drst if ctx.needs_input_grad[1] else None, *grads, d_w1, d_b1, d_w2, d_b2)
 
 
+class _EngineState:
+    """Arena pool + shape descriptor of the C++ whole-network engine for one (dims, graph) pair."""
+
+    def __init__(self, g, dims):
+        import ctypes
+        from ._lib import Gnn32Shape
+        csc = g.csc()
+        self.csc = csc                                     # keeps the device arrays alive
+        self.shape = Gnn32Shape(csc.num_rows, *dims, csc.indptr.data_ptr(), csc.indices.data_ptr(), csc.plan.data_ptr(),
+                                (ctypes.c_int64 * 3)(*csc.counts))
+        self.shape_ref = ctypes.byref(self.shape)
+        self.arena_bytes = ops._lib.load().plagnn_gnn32_arena_bytes(self.shape_ref)
+        if self.arena_bytes == 0:
+            raise ops._lib.PlagnnError("gnn32 engine: bad shape")
+        self.device = csc.indptr.device
+        self.free = []
+
+    def acquire(self):
+        if self.free:
+            return self.free.pop()
+        return torch.zeros(self.arena_bytes, dtype=torch.uint8, device=self.device)   # zero-filled once
+
+    def release(self, arena):
+        if len(self.free) < 2:
+            self.free.append(arena)
+
+
+def _ptr_array(tensors):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+class GNN32EngineFunction(torch.autograd.Function):
+    """GNN32 forward / backward through the two whole-network C calls (plagnn_gnn32_forward / _backward)."""
+
+    @staticmethod
+    def forward(ctx, state, x, *params):
+        lib = ops._lib.load()
+        xa = ops.aligned(x.detach())
+        p = [t.detach() if t.is_contiguous() else t.detach().contiguous() for t in params]
+        ops._require_cuda_f32(xa, *p)
+        n, c = state.shape.num_nodes, state.shape.classes
+        prob = ops.alloc(n, c, xa.device)
+        arena = state.acquire()
+        with ops._timed(("gnn32_forward",)):
+            ops.check(lib.plagnn_gnn32_forward(state.shape_ref, ops._p(xa), xa.stride(0), _ptr_array(p), ops._p(arena),
+                                               arena.numel(), ops._p(prob), prob.stride(0), ops._stream()), "gnn32_forward")
+        if any(ctx.needs_input_grad):
+            ctx.state, ctx.arena, ctx.xa, ctx.prob = state, arena, xa, prob.detach()
+            ctx.save_for_backward(*params)
+        else:
+            state.release(arena)
+        return prob
+
+    @staticmethod
+    def backward(ctx, dprob):
+        lib = ops._lib.load()
+        params = ctx.saved_tensors
+        p = [t.detach() if t.is_contiguous() else t.detach().contiguous() for t in params]
+        dp = dprob if dprob.stride(1) == 1 else dprob.contiguous()
+        grads = [torch.empty_like(t, memory_format=torch.contiguous_format) for t in p]
+        dx = ops.alloc(ctx.xa.shape[0], ctx.xa.shape[1], ctx.xa.device) if ctx.needs_input_grad[1] else None
+        with ops._timed(("gnn32_backward",)):
+            ops.check(lib.plagnn_gnn32_backward(ctx.state.shape_ref, ops._p(ctx.xa), ctx.xa.stride(0), _ptr_array(p),
+                                                ops._p(ctx.arena), ctx.arena.numel(), ops._p(ctx.prob), ctx.prob.stride(0),
+                                                ops._p(dp), dp.stride(0), _ptr_array(grads), ops._p(dx),
+                                                dx.stride(0) if dx is not None else 0, ops._stream()), "gnn32_backward")
+        ctx.state.release(ctx.arena)
+        ctx.arena = None
+        return (None, dx, *grads)
+
+
 class GraphConvSumFunction(torch.autograd.Function):
     """out = act( scale_v * sum_{u->v} w_uv (x W^T)[u] + b ), backward through the transposed SpMM."""
 
@@ -292,7 +364,22 @@ class GNN32(nn.Module):
             out += [c.fc_pool.weight, c.fc_pool.bias, c.fc_self.weight, c.fc_neigh.weight, c.bias]
         return out + [self.liner1.weight, self.liner1.bias, self.liner2.weight, self.liner2.bias]
 
+    engine = "c"      # "c": two whole-network C calls per epoch; "python": same kernels, orchestrated from nn.py
+
+    def _engine_state(self, g):
+        dims = (self.conv1._in_src_feats, self.conv1._out_feats, self.conv2._out_feats, self.conv3._out_feats,
+                self.liner1.out_features, self.liner2.out_features)
+        cache = self.__dict__.setdefault("_engine_states", {})
+        key = (id(g), dims)
+        st = cache.get(key)
+        if st is None or st.csc is not g.csc():
+            cache.clear()                                  # one graph at a time (the reference trains on one)
+            st = cache[key] = _EngineState(g, dims)
+        return st
+
     def forward(self, g, in_feat):
+        if self.engine == "c" and not DETERMINISTIC_BACKWARD:
+            return GNN32EngineFunction.apply(self._engine_state(g), in_feat, *self.hot_path_parameters())
         return GNN32Function.apply(g, in_feat, *self.hot_path_parameters())
 
     def forward_layerwise(self, g, in_feat):

@@ -52,6 +52,25 @@ class _timed:
         return False
 
 
+def profile_start() -> None:
+    """Start per-call CUDA-event timing inside the library (all entry points, C- or Python-orchestrated)."""
+    _lib.load().plagnn_profile_enable(1)
+
+
+def profile_stop() -> dict:
+    """Stop and return {(name, t0, t1, t2): (calls, total_ms)}."""
+    lib = _lib.load()
+    lib.plagnn_profile_enable(0)
+    need = lib.plagnn_profile_report(None, 0)
+    buf = ctypes.create_string_buffer(need + 16)
+    lib.plagnn_profile_report(buf, need + 16)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, t0, t1, t2, calls, ms = line.split()
+        out[(name, int(t0), int(t1), int(t2))] = (int(calls), float(ms))
+    return out
+
+
 def launch_count() -> int:
     return int(_lib.load().plagnn_launch_count())
 

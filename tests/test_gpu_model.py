@@ -56,6 +56,7 @@ def test_forward_backward_parity(cuda, backend, monkeypatch):
     orig = ops.gemm
     monkeypatch.setattr(ops, "gemm", lambda *a, **k: orig(*a, **{**k, "backend": forced}))
     prob, g, go, m, mo = build_pair(cuda)
+    m.engine = "python" if backend == "simt" else "c"       # python-orchestrated FFMA path vs the C engine (tcgen05)
     w = orc.weight_cal(prob.loc)
     idx = [int(i) for i in prob.labelled[: len(prob.labelled) * 9 // 10]]
     lo = mo(go, go.ndata["feat"])
@@ -93,16 +94,32 @@ def test_forward_backward_parity(cuda, backend, monkeypatch):
     assert torch.equal(pred_same_input, pred_o)                     # same probabilities -> identical labels
 
 
-def test_fused_function_equals_layerwise_path(cuda):
+def test_engine_paths_agree(cuda):
+    """C engine (two whole-network calls), python-orchestrated fused Function and per-layer Functions."""
     prob, g, go, m, mo = build_pair(cuda, n=800, e=16000, dims=(3, 20, 20))
     x = g.ndata["feat"]
+    m.engine = "c"
     a = m(g, x)
+    m.engine = "python"
+    a2 = m(g, x)
     b = m.forward_layerwise(g, x)
+    assert torch.equal(a, a2)                           # same kernels, same order -> bit-identical
     assert rel_err(a, b) < 1e-6
     ga = torch.autograd.grad(a.sum(), list(m.parameters()))
+    ga2 = torch.autograd.grad(a2.sum(), list(m.parameters()))
     gb = torch.autograd.grad(b.sum(), list(m.parameters()))
-    for u, v in zip(ga, gb):
+    for u, u2, v in zip(ga, ga2, gb):
+        assert rel_err(u, u2) < 1e-5                    # fp32 reductions of the scatter are unordered
         assert rel_err(u, v) < 1e-5
+    # a second forward before the first backward must not clobber the first one's saved state
+    m.engine = "c"
+    y1 = m(g, x)
+    y2 = m(g, x * 0.5)
+    g1 = torch.autograd.grad(y1.sum(), list(m.parameters()))
+    for u, v in zip(ga, g1):
+        assert rel_err(u, v) < 1e-5
+    with torch.no_grad():
+        assert torch.equal(m(g, x), y1)
 
 
 def test_deterministic_backward_option(cuda):
