@@ -228,6 +228,10 @@ def scaled_graph(num_nodes: int = 1_000_000, num_directed: int = 100_000_000, se
     src, dst = powerlaw_edges(num_nodes, num_directed, 2.2, seed, max_degree=max_degree, device=device)
     gen = torch.Generator(device=device)
     gen.manual_seed(seed + 2)
+    # the generator numbers nodes by decreasing expected degree; relabel at random so that contiguous row blocks
+    # (the 1-D partition) hold comparable numbers of rows AND in-edges
+    relabel = torch.randperm(num_nodes, generator=gen, device=device)
+    src, dst = relabel[src], relabel[dst]
     # symmetric weights: w(u,v) == w(v,u) (first half and second half of the arrays mirror each other)
     half = src.numel() // 2
     wh = 1.0 - torch.rand(half, generator=gen, device=device, dtype=torch.float32)

@@ -1,0 +1,142 @@
+"""N > 1 host logic on CPU: world_size-2 gloo run of the row-partitioned GCN choreography with a CPU compute backend
+(oracle kernels), compared with the single-process oracle model.  No CUDA involved."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import plagnn_oracle as orc
+from plagnn_b200 import synth
+from plagnn_b200.dist import DistGCN, RowPartitionPlan, block_bounds, dist_gcn_forward_backward
+
+
+class _Csx:
+    def __init__(self, key, other, n_rows):
+        self.indptr, self.indices, self.eids = orc.coo_to_csc(other.numpy(), key.numpy(), n_rows)
+        self.num_rows = n_rows
+
+
+class CpuBackend:
+    """Same method names as plagnn_b200.dist.CudaBackend, computed with torch-CPU + the oracle's C SpMM."""
+
+    def gemm_nt(self, a, w): return a @ w.t()
+    def gemm_nn(self, a, w): return a @ w
+    def gemm_tn(self, a, b): return a.t() @ b
+    def colsum(self, x): return x.sum(0)
+
+    def spmm(self, csx, x, w, scale, bias, act):
+        out = orc.spmm_sum_c(csx.indptr, csx.indices, x.contiguous(), eids=csx.eids if w is not None else None, w=w,
+                             scale=scale)
+        if bias is not None:
+            out = out + bias
+        return torch.nn.functional.leaky_relu(out) if act else out
+
+    def act_backward(self, dy, y, scale):
+        if y is not None:
+            dy = dy * torch.where(y > 0, 1.0, 0.01)
+        if scale is not None:
+            dy = dy * scale.unsqueeze(1)
+        return dy
+
+    def all_gather_rows(self, t, world, group):
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t.contiguous(), group=group)
+        return torch.cat(parts)
+
+    def reduce_scatter_rows(self, partial, world, group):
+        full = partial.clone()
+        dist.all_reduce(full, group=group)
+        per = full.shape[0] // world
+        r = dist.get_rank(group)
+        return full[r * per:(r + 1) * per].contiguous()
+
+    def all_reduce_grads(self, grads, world, group):
+        out = []
+        for g in grads:
+            g = g.clone()
+            dist.all_reduce(g, group=group)
+            out.append(g)
+        return out
+
+
+class _PG:
+    def __init__(self, plan, weight):
+        self.csc = _Csx(plan.dst_local, plan.src_global, plan.per)
+        self.csr_t = _Csx(plan.src_global, plan.dst_local, plan.n_padded)
+        self.edge_weight = weight[plan.edge_ids]
+        self.scale = plan.scale_local
+
+
+def _problem(n=403, e=6000, f=24):
+    sg = synth.scaled_graph(n, e, seed=5, max_degree=200)
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(1))
+    return sg, x
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sg, x = _problem()
+    n, f = sg.num_nodes, x.shape[1]
+    plan = RowPartitionPlan(sg.src, sg.dst, n, rank, world)
+    pg = _PG(plan, sg.weight)
+    model = DistGCN([f, 16, 8], seed=3)
+    h0 = torch.zeros(plan.per, f)
+    h0[:plan.n_local] = x[plan.r0:plan.r1]
+    mask = (torch.arange(plan.per) < plan.n_local).float().unsqueeze(1)
+    out, grads = dist_gcn_forward_backward(model, pg, h0, CpuBackend(), None, lambda o: o * mask / n)
+    torch.save({"out": out[:plan.n_local], "grads": grads, "r0": plan.r0, "r1": plan.r1},
+               os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def _reference():
+    sg, x = _problem()
+    n, f = sg.num_nodes, x.shape[1]
+    g = orc.OracleGraph(sg.src.numpy(), sg.dst.numpy(), n)
+    model = DistGCN([f, 16, 8], seed=3)
+    ref = orc.GCNSumRef([f, 16, 8])
+    with torch.no_grad():
+        for lin, w, b in zip(ref.lins, model.weights, model.biases):
+            lin.weight.copy_(w); lin.bias.copy_(b)
+    scale = 1.0 / torch.bincount(sg.dst, minlength=n).clamp(min=1).float()
+    out = ref(g, x, sg.weight, scale)
+    (0.5 * (out ** 2).sum() / n).backward()
+    grads = [t.grad for lin in ref.lins for t in (lin.weight, lin.bias)]
+    return out.detach(), grads
+
+
+def test_block_bounds_and_plan_cover_every_edge_once():
+    sg, _ = _problem()
+    n = sg.num_nodes
+    for world in (1, 2, 3, 8):
+        per, b = block_bounds(n, world)
+        assert b[0] == 0 and b[-1] == n and all(b[i + 1] - b[i] <= per for i in range(world))
+        seen = torch.zeros(sg.src.numel(), dtype=torch.int32)
+        for r in range(world):
+            plan = RowPartitionPlan(sg.src, sg.dst, n, r, world)
+            seen[plan.edge_ids] += 1
+            assert (plan.dst_local >= 0).all() and (plan.dst_local < plan.n_local).all()
+            assert torch.equal(sg.dst[plan.edge_ids] - plan.r0, plan.dst_local)
+        assert (seen == 1).all()
+    # shuffled ids: rows and in-edges balance together
+    plans = [RowPartitionPlan(sg.src, sg.dst, n, r, 2) for r in range(2)]
+    assert abs(plans[0].num_local_edges - plans[1].num_local_edges) < 0.25 * sg.src.numel()
+
+
+def test_two_rank_gloo_matches_single_process_oracle(tmp_path):
+    world, port = 2, 29500 + os.getpid() % 2000
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")
+    # spawn, not fork: the parent already runs OpenMP / MKL threads
+    mp.start_processes(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    out_ref, grads_ref = _reference()
+    parts = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
+    out = torch.cat([p["out"] for p in parts])
+    assert torch.allclose(out, out_ref, rtol=1e-5, atol=1e-6)
+    for r in range(world):                                   # replicated, all-reduced gradients agree on every rank
+        for g, gr in zip(parts[r]["grads"], grads_ref):
+            assert torch.allclose(g, gr, rtol=1e-4, atol=1e-7)
