@@ -16,11 +16,17 @@
 // over with mbarriers: loaders -> full[s] -> MMA -> tcgen05.commit -> empty[s]; accumulator hand-off
 // to the epilogue through a third mbarrier.  One 128 x 128 output tile per CTA, optional split-K.
 #include "common.cuh"
+#include <cstdlib>
+#include <cstdint>
+#include <climits>
+#ifndef PLAGNN_TC_DEBUG
+#define PLAGNN_TC_DEBUG 0
+#endif
 
 namespace plagnn {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
-constexpr int TC_LOAD_WARPS = 8;
+constexpr int TC_LOAD_WARPS = 16;  // warps 0-7 stage the A tile, warps 8-15 the B tile (4 float4 per thread and k-block)
 constexpr int TC_THREADS = (TC_LOAD_WARPS + 1) * 32;
 constexpr int TC_PART_BYTES = TC_BM * TC_BK * 4;          // 16 KB: one tf32 tile (128 rows x 128 bytes)
 constexpr int TC_STAGE_BYTES = 4 * TC_PART_BYTES;         // A_hi, A_lo, B_hi, B_lo
@@ -47,6 +53,8 @@ struct TcParams {
     float* c;
     int64_t ldc;
     float* partial;
+    int debug;   // PLAGNN_TC_DEBUG: 1 = loaders skip global loads / smem stores after the first k-block (MMA-bound
+                 // timing), 2 = the issuer skips the MMAs (loader-bound timing).  Results are garbage; timing only.
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -108,6 +116,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), descriptor version 1
@@ -132,14 +150,15 @@ __device__ __forceinline__ uint32_t make_idesc(uint32_t n, bool a_mn, bool b_mn)
            ((n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// fp32 -> (hi, lo) with hi, lo on the tf32 grid (10 explicit mantissa bits) and hi + lo = x up to 2^-22 |x|.
+// Rounding is done with integer arithmetic on the bit pattern (add half an ulp of tf32 to the magnitude, clear the
+// low 13 bits): 2 instructions instead of the ~7-instruction sequence ptxas emits for cvt.rna.tf32.f32 on sm_100a
+// (ncu: that sequence was 60 % of all issued instructions of the first versions).  Finite inputs only, which is what
+// the layers produce; x - hi is exact in fp32.
+__device__ __forceinline__ uint32_t round_tf32_bits(uint32_t b) { return (b + 0x1000u) & 0xFFFFE000u; }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = to_tf32(x);
-    lo = to_tf32(x - __uint_as_float(hi));
+    hi = round_tf32_bits(__float_as_uint(x));
+    lo = round_tf32_bits(__float_as_uint(x - __uint_as_float(hi)));
 }
 
 // ---- operand tile: global fp32 -> registers ------------------------------------------------------
@@ -154,7 +173,7 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 template <bool T>
 __device__ __forceinline__ void tile_ptrs(const float* __restrict__ p, int64_t ld, int64_t rows, int64_t r0,
                                           const float* (&ptr)[4]) {
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int t = threadIdx.x & 255, lane = t & 31, w = t >> 5;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         if (!T) {
@@ -173,7 +192,7 @@ __device__ __forceinline__ void tile_ptrs(const float* __restrict__ p, int64_t l
 template <bool T>
 __device__ __forceinline__ void tile_load(const float* const (&ptr)[4], int64_t ld, int64_t k0, int64_t kdim,
                                           float4 (&v)[4]) {
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int t = threadIdx.x & 255, lane = t & 31, w = t >> 5;
     if (!T) {
         const int64_t kk = k0 + (t & 7) * 4;
         if (kk + 3 < kdim) {
@@ -208,7 +227,7 @@ __device__ __forceinline__ void tile_load(const float* const (&ptr)[4], int64_t 
 // byte offset of (row, 16-byte chunk c) inside a tile: row*128 + ((c ^ (row & 7)) << 4)
 template <bool T>
 __device__ __forceinline__ void tile_store(uint32_t s_hi, uint32_t s_lo, const float4 (&v)[4]) {
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int t = threadIdx.x & 255, lane = t & 31, w = t >> 5;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
@@ -259,6 +278,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams P
     const int kb_end = min(P.total_kblocks, kb_beg + P.kblocks_per_split);
     const int nkb = kb_end - kb_beg;
 
+    const bool is_b = warp >= 8;
+    float4 ring[3][4];
+    const float* ptr[4];
+    int ptr_pair = -1;
+    auto issue = [&](int kb, float4 (&v)[4]) {
+        int p = 0, local = kb;
+        if (P.npairs > 1 && local >= P.kblocks[0]) { local -= P.kblocks[0]; p = 1; }
+        if (ptr_pair != p) {
+            if (!is_b) tile_ptrs<AT>(P.a[p], P.lda[p], P.m, m0, ptr);
+            else tile_ptrs<BT>(P.b[p], P.ldb[p], P.n, n0, ptr);
+            ptr_pair = p;
+        }
+        const int64_t k0 = (int64_t)local * TC_BK;
+#if PLAGNN_TC_DEBUG
+        if (P.debug == 1 && kb > kb_beg) return;
+#endif
+        if (!is_b) tile_load<AT>(ptr, P.lda[p], k0, P.k[p], v);
+        else tile_load<BT>(ptr, P.ldb[p], k0, P.k[p], v);
+    };
+    // the first two k-blocks are requested before the barrier / TMEM set-up below, hiding ~1 us of load latency
+    if (warp < TC_LOAD_WARPS) {
+        if (nkb > 0) issue(kb_beg, ring[0]);
+        if (nkb > 1) issue(kb_beg + 1, ring[1]);
+    }
+
     if (t == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(bar_full + 8 * s, TC_LOAD_WARPS * 32);
@@ -275,72 +319,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams P
 
     if (warp < TC_LOAD_WARPS) {
         // ================= loaders =================
-        float4 ca[4], cb[4], na[4], nb[4];
-        const float* pa[4];
-        const float* pb[4];
-        int ptr_pair = -1;
-        auto issue = [&](int kb, float4 (&va)[4], float4 (&vb)[4]) {
-            int p = 0, local = kb;
-            if (P.npairs > 1 && local >= P.kblocks[0]) { local -= P.kblocks[0]; p = 1; }
-            if (ptr_pair != p) {
-                tile_ptrs<AT>(P.a[p], P.lda[p], P.m, m0, pa);
-                tile_ptrs<BT>(P.b[p], P.ldb[p], P.n, n0, pb);
-                ptr_pair = p;
-            }
-            const int64_t k0 = (int64_t)local * TC_BK;
-            tile_load<AT>(pa, P.lda[p], k0, P.k[p], va);
-            tile_load<BT>(pb, P.ldb[p], k0, P.k[p], vb);
-        };
-        if (nkb > 0) issue(kb_beg, ca, cb);
-#pragma unroll 1
-        for (int it = 0; it < nkb; ++it) {
+        // Register ring of depth 3: while k-block `it` is split and stored, the loads of `it+1` and `it+2` are in
+        // flight (64 KB per SM), which is what the ~1.2 us loaded L2 latency needs to keep the tensor core fed.
+        // 16 loader warps (4 per scheduler) so that the fixed-latency ALU chains of the split interleave.
+        auto commit = [&](int it, const float4 (&v)[4]) {
             const int s = it % TC_STAGES;
             const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
-            if (it + 1 < nkb) issue(kb_beg + it + 1, na, nb);      // next k-block's loads fly during the split
             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
             const uint32_t st = tiles + s * TC_STAGE_BYTES;
-            tile_store<AT>(st, st + TC_PART_BYTES, ca);
-            tile_store<BT>(st + 2 * TC_PART_BYTES, st + 3 * TC_PART_BYTES, cb);
+#if PLAGNN_TC_DEBUG
+            if (!(P.debug == 1 && it > 0))
+#endif
+            {
+                if (!is_b) tile_store<AT>(st, st + TC_PART_BYTES, v);
+                else tile_store<BT>(st + 2 * TC_PART_BYTES, st + 3 * TC_PART_BYTES, v);
+            }
             fence_proxy_async_smem();
             mbar_arrive(bar_full + 8 * s);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
+        };
+#pragma unroll 1
+        for (int it = 0; it < nkb; it += 3) {
+            if (it + 2 < nkb) issue(kb_beg + it + 2, ring[2]);
+            commit(it, ring[0]);
+            if (it + 1 < nkb) {
+                if (it + 3 < nkb) issue(kb_beg + it + 3, ring[0]);
+                commit(it + 1, ring[1]);
+            }
+            if (it + 2 < nkb) {
+                if (it + 4 < nkb) issue(kb_beg + it + 4, ring[1]);
+                commit(it + 2, ring[2]);
+            }
         }
 
         // ================= epilogue =================
         mbar_wait(bar_acc, 0);
         tc_fence_after();
-        const int lg = warp & 3, ch = warp >> 2;
+        const int lg = warp & 3, cq = warp >> 2;      // TMEM lane group (warp % 4) and 32-column quarter
         const int64_t r = m0 + lg * 32 + lane;
         const bool direct = P.splits == 1;
         float* dst = direct ? P.c : P.partial + (int64_t)split * P.m * P.n;
         const int64_t ldd = direct ? P.ldc : P.n;
         const bool vec_out = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-            const int cbase = 64 * ch + 16 * j;
-            if (n0 + cbase >= P.n) break;   // warp-uniform
-            uint32_t acc[16], acc_small[16];
-            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)cbase, acc);
-            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(TC_BN + cbase), acc_small);
-            tmem_ld_wait();
-            if (r < P.m) {
+        {
+            // both accumulators of this warp's 32 rows x 32 columns in one round trip to tensor memory
+            const int cbase = 32 * cq;
+            if (n0 + cbase < P.n) {   // warp-uniform
+                uint32_t acc[32], acc_small[32];
+                tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)cbase, acc);
+                tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(TC_BN + cbase), acc_small);
+                tmem_ld_wait();
+                if (r < P.m) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int64_t c = n0 + cbase + 4 * q;
-                    if (c >= P.n) break;
-                    float v[4];
+                    for (int q = 0; q < 8; ++q) {
+                        const int64_t c = n0 + cbase + 4 * q;
+                        if (c >= P.n) break;
+                        float v[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        v[e] = __uint_as_float(acc[4 * q + e]) + __uint_as_float(acc_small[4 * q + e]);
-                        if (direct && c + e < P.n) v[e] = tc_epilogue_one(P, v[e], r, c + e);
-                    }
-                    if (vec_out && c + 3 < P.n) {
-                        *reinterpret_cast<float4*>(dst + r * ldd + c) = make_float4(v[0], v[1], v[2], v[3]);
-                    } else {
+                        for (int e = 0; e < 4; ++e) {
+                            v[e] = __uint_as_float(acc[4 * q + e]) + __uint_as_float(acc_small[4 * q + e]);
+                            if (direct && c + e < P.n) v[e] = tc_epilogue_one(P, v[e], r, c + e);
+                        }
+                        if (vec_out && c + 3 < P.n) {
+                            *reinterpret_cast<float4*>(dst + r * ldd + c) = make_float4(v[0], v[1], v[2], v[3]);
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (c + e < P.n) dst[r * ldd + c + e] = v[e];
+                            for (int e = 0; e < 4; ++e)
+                                if (c + e < P.n) dst[r * ldd + c + e] = v[e];
+                        }
                     }
                 }
             }
@@ -366,6 +411,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams P
                 const uint64_t b_lo = BT ? make_smem_desc_mn(st + 3 * TC_PART_BYTES) : make_smem_desc(st + 3 * TC_PART_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < TC_BK / 8; ++kk) {
+#if PLAGNN_TC_DEBUG
+                    if (P.debug == 2) break;
+#endif
                     const uint64_t adv_a = (uint64_t)kk * a_step, adv_b = (uint64_t)kk * b_step;
                     // The tensor core adds into the fp32 accumulator with truncation, so the error of a chain grows
                     // with the number of accumulations.  The two correction products go to their own accumulator
@@ -416,12 +464,29 @@ static int tc_choose_splits(int64_t m, int64_t n, int total_kblocks) {
         if (s < 1) s = 1;
     }
     const int64_t for_accuracy = ceil_div(total_kblocks, TC_MAX_CHAIN);
-    return (int)(s > for_accuracy ? s : for_accuracy);
+    int64_t s0 = s > for_accuracy ? s : for_accuracy;
+    if (s0 > 1) {
+        // wave quantisation: 1 CTA per SM, so time ~ ceil(tiles*s/SMs) * ceil(kblocks/s); look a little around s0
+        // (one step below is allowed: chains of up to 48 k-blocks keep the measured error below 4e-6)
+        int64_t best = s0, best_cost = INT64_MAX;
+        const int64_t lo = (s0 > 1 && ceil_div(total_kblocks, s0 - 1) <= 48) ? s0 - 1 : s0;
+        for (int64_t c = lo; c <= s0 + 8 && c <= total_kblocks; ++c) {
+            const int64_t cost = ceil_div(tiles * c, (int64_t)sms) * (ceil_div(total_kblocks, c) + 6);   // +6: prologue/epilogue
+            if (cost < best_cost) { best_cost = cost; best = c; }
+        }
+        s0 = best;
+    }
+    return (int)s0;
 }
 
 size_t gemm_tc_workspace_bytes(int64_t m, int64_t n, int64_t k_total) {
-    const int kb = (int)ceil_div(k_total, TC_BK) + PLAGNN_GEMM_MAX_PAIRS;
-    const int s = tc_choose_splits(m, n, kb);
+    // k_total may be split over up to PLAGNN_GEMM_MAX_PAIRS pairs, each rounded up to whole k-blocks
+    const int kb = (int)ceil_div(k_total, TC_BK);
+    int s = 1;
+    for (int extra = 0; extra <= PLAGNN_GEMM_MAX_PAIRS; ++extra) {
+        const int c = tc_choose_splits(m, n, kb + extra);
+        s = c > s ? c : s;
+    }
     return s > 1 ? (size_t)s * (size_t)m * (size_t)n * sizeof(float) : 0;
 }
 
@@ -456,6 +521,8 @@ int gemm_tc_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair*
     }
     P.bias = bias; P.act = act; P.slope = slope; P.gate = gate; P.ldg = ldg; P.gate_act = gate_act;
     P.c = c; P.ldc = ldc;
+    static const int dbg = [] { const char* e = getenv("PLAGNN_TC_DEBUG"); return e ? atoi(e) : 0; }();
+    P.debug = dbg;
     int splits = tc_choose_splits(m, n, P.total_kblocks);
     if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * m * n * sizeof(float)))
         return fail(PLAGNN_ERR_WORKSPACE, "gemm_tc", "split-K workspace too small (see plagnn_gemm_workspace_bytes)");
