@@ -129,6 +129,16 @@ int plagnn_spmm_sum(const int32_t* indptr, const int32_t* indices, const int32_t
                     const float* x, int64_t ldx, int64_t feat,
                     const float* bias, int act, float slope, float dropout_p, uint64_t dropout_seed,
                     float* out, int64_t ldo, void* partial, size_t partial_bytes, plagnn_stream_t stream);
+/* Row-range variant (multi-GPU pipelining: rows [row_begin,row_end) of the plan are aggregated while the exchange of
+ * the previous chunk is in flight).  plagnn_spmm_plan_range (set-up call, synchronises) turns a row range into the
+ * host[4] = {item_begin, item_end, hub_begin, hub_end} handle that plagnn_spmm_sum_rows takes. */
+int plagnn_spmm_plan_range(const void* plan, int64_t num_rows, int64_t row_begin, int64_t row_end,
+                           int64_t* host_range /* [4] */, plagnn_stream_t stream);
+int plagnn_spmm_sum_rows(const int32_t* indptr, const int32_t* indices, const int32_t* eids, const void* plan,
+                         const int64_t* plan_counts /* host[3] */, const int64_t* row_range /* host[4] */,
+                         int64_t num_rows, const float* w, const float* scale,
+                         const float* x, int64_t ldx, int64_t feat, const float* bias, int act, float slope,
+                         float* out, int64_t ldo, void* partial, size_t partial_bytes, plagnn_stream_t stream);
 /* backward companion of the dropout epilogue: grad[r,c] *= keep(r,c)/(1-p) with the same counter-based mask */
 int plagnn_dropout_scale(float* grad, int64_t rows, int64_t feat, int64_t ld, float dropout_p,
                          uint64_t dropout_seed, plagnn_stream_t stream);

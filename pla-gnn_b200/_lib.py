@@ -63,6 +63,10 @@ PROTOTYPES = {
     "plagnn_spmm_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64, c_void_p, c_void_p,
                                 c_void_p, c_int64, c_int64, c_void_p, c_int, c_float, c_float, c_uint64,
                                 c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "plagnn_spmm_plan_range": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(c_int64), c_void_p]),
+    "plagnn_spmm_sum_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_int64,
+                                     c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_float,
+                                     c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "plagnn_dropout_scale": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_uint64, c_void_p]),
     "plagnn_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "plagnn_gemm": (c_int, [c_int64, c_int64, c_int32, POINTER(GemmPair), c_void_p, c_int, c_float,

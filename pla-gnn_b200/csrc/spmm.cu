@@ -78,12 +78,12 @@ template <int MODE, int VEC, int NB>
 __global__ void __launch_bounds__(SPMM_WARPS * 32)
 spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int32_t* __restrict__ eids,
             const float* __restrict__ ew, const int32_t* __restrict__ plan_hdr, const int32_t* __restrict__ item_ptr,
-            const int32_t* __restrict__ slot_ptr, const int32_t* __restrict__ item_row, int n_items,
+            const int32_t* __restrict__ slot_ptr, const int32_t* __restrict__ item_row, int item_begin, int n_items,
             const float* __restrict__ x, int64_t ldx, int feat, const int32_t* __restrict__ argm, int64_t ldarg,
             const float* __restrict__ zfwd, int64_t ldzf, float* __restrict__ out, int32_t* __restrict__ arg_out, int64_t ldo,
             float* __restrict__ part_val, int32_t* __restrict__ part_arg, int part_ld, SpmmEpilogue ep) {
     const int lane = threadIdx.x & 31;
-    const int item = blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+    const int item = item_begin + blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
     const int chunk = __ldg(plan_hdr);
     const int row = __ldg(item_row + item);
@@ -203,11 +203,12 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
 template <int MODE>
 __global__ void __launch_bounds__(SPMM_WARPS * 32)
 spmm_combine_kernel(const int32_t* __restrict__ item_ptr, const int32_t* __restrict__ slot_ptr,
-                    const int32_t* __restrict__ hub_rows, int n_hubs, int feat, const float* __restrict__ part_val,
+                    const int32_t* __restrict__ hub_rows, int hub_begin, int n_hubs, int feat,
+                    const float* __restrict__ part_val,
                     const int32_t* __restrict__ part_arg, int part_ld, float* __restrict__ out,
                     int32_t* __restrict__ arg_out, int64_t ldo, SpmmEpilogue ep) {
     const int lane = threadIdx.x & 31;
-    const int h = blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+    const int h = hub_begin + blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
     if (h >= n_hubs) return;
     const int col = blockIdx.y * 128 + lane * 4;
     if (col >= feat) return;
@@ -303,6 +304,7 @@ struct SpmmArgs {
     void* partial;
     size_t partial_bytes;
     SpmmEpilogue ep;
+    const int64_t* range = nullptr;   // optional host[4]: item_begin, item_end, hub_begin, hub_end (row-range launch)
 };
 
 static inline int part_ld_of(int64_t feat) { return (int)((feat + 3) / 4 * 4); }
@@ -310,10 +312,12 @@ static inline int part_ld_of(int64_t feat) { return (int)((feat + 3) / 4 * 4); }
 template <int MODE, int VEC, int NB>
 static void launch_main(const SpmmArgs& a, const int32_t* item_ptr, const int32_t* slot_ptr, const int32_t* item_row,
                         float* pv, int32_t* pa, cudaStream_t st) {
-    const int n_items = (int)a.counts[0];
-    dim3 grid((unsigned)ceil_div(n_items, SPMM_WARPS), (unsigned)ceil_div((a.feat + 3) / 4, 32 * VEC));
+    const int item_begin = a.range ? (int)a.range[0] : 0;
+    const int n_items = a.range ? (int)a.range[1] : (int)a.counts[0];
+    if (n_items <= item_begin) return;
+    dim3 grid((unsigned)ceil_div(n_items - item_begin, SPMM_WARPS), (unsigned)ceil_div((a.feat + 3) / 4, 32 * VEC));
     spmm_kernel<MODE, VEC, NB><<<grid, SPMM_WARPS * 32, 0, st>>>(
-        a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, n_items, a.x, a.ldx,
+        a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, item_begin, n_items, a.x, a.ldx,
         (int)a.feat, a.argm, a.ldarg, a.zfwd, a.ldzf, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep);
 }
 
@@ -344,12 +348,15 @@ static int spmm_dispatch(const SpmmArgs& a, const char* name, cudaStream_t st) {
     else if (groups <= 64) launch_main<MODE, 2, 4>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
     else if (groups <= 96) launch_main<MODE, 3, 2>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
     else launch_main<MODE, 4, 2>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
-    if (n_hubs > 0) {
-        dim3 grid((unsigned)ceil_div(n_hubs, SPMM_WARPS), (unsigned)ceil_div(a.feat, 128));
-        spmm_combine_kernel<MODE><<<grid, SPMM_WARPS * 32, 0, st>>>(item_ptr, slot_ptr, hub_rows, (int)n_hubs, (int)a.feat,
+    const int64_t hub_begin = a.range ? a.range[2] : 0, hub_end = a.range ? a.range[3] : n_hubs;
+    if (a.range && (a.range[0] < 0 || a.range[1] > n_items || a.range[2] < 0 || a.range[3] > n_hubs))
+        return fail(PLAGNN_ERR_ARG, name, "row range outside the plan");
+    if (hub_end > hub_begin) {
+        dim3 grid((unsigned)ceil_div(hub_end - hub_begin, SPMM_WARPS), (unsigned)ceil_div(a.feat, 128));
+        spmm_combine_kernel<MODE><<<grid, SPMM_WARPS * 32, 0, st>>>(item_ptr, slot_ptr, hub_rows, (int)hub_begin, (int)hub_end, (int)a.feat,
                                                                      pv, pa, pld, a.out, a.arg_out, a.ldo, a.ep);
     }
-    return check_launch(name, n_hubs > 0 ? 2 : 1);
+    return check_launch(name, hub_end > hub_begin ? 2 : 1);
 }
 
 }  // namespace plagnn
@@ -411,6 +418,38 @@ int plagnn_spmm_sum(const int32_t* indptr, const int32_t* indices, const int32_t
     SpmmArgs a{indptr, indices, eids, w, plan, plan_counts, num_rows, x, ldx, feat, nullptr, 0, nullptr, 0, out, nullptr, ldo,
                partial, partial_bytes, SpmmEpilogue{scale, bias, act, slope, dropout_p, (unsigned long long)dropout_seed}};
     return spmm_dispatch<MODE_SUM>(a, "spmm_sum", (cudaStream_t)stream);
+}
+
+int plagnn_spmm_plan_range(const void* plan, int64_t num_rows, int64_t row_begin, int64_t row_end, int64_t* host_range,
+                           plagnn_stream_t stream) {
+    if (!plan || !host_range || row_begin < 0 || row_end < row_begin || row_end > num_rows)
+        return fail(PLAGNN_ERR_ARG, "spmm_plan_range", "bad arguments");
+    const int32_t *item_ptr, *slot_ptr, *item_row, *hub_rows;
+    plan_pointers(plan, num_rows, &item_ptr, &slot_ptr, &item_row, &hub_rows);
+    const int32_t* hub_ptr = slot_ptr + (slot_ptr - item_ptr);     // item_ptr | slot_ptr | hub_ptr are equally spaced
+    int32_t v[4];
+    cudaStream_t st = (cudaStream_t)stream;
+    PLAGNN_CUDA_TRY(cudaMemcpyAsync(&v[0], item_ptr + row_begin, 4, cudaMemcpyDeviceToHost, st));
+    PLAGNN_CUDA_TRY(cudaMemcpyAsync(&v[1], item_ptr + row_end, 4, cudaMemcpyDeviceToHost, st));
+    PLAGNN_CUDA_TRY(cudaMemcpyAsync(&v[2], hub_ptr + row_begin, 4, cudaMemcpyDeviceToHost, st));
+    PLAGNN_CUDA_TRY(cudaMemcpyAsync(&v[3], hub_ptr + row_end, 4, cudaMemcpyDeviceToHost, st));
+    PLAGNN_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < 4; ++i) host_range[i] = v[i];
+    return PLAGNN_OK;
+}
+
+int plagnn_spmm_sum_rows(const int32_t* indptr, const int32_t* indices, const int32_t* eids, const void* plan,
+                         const int64_t* plan_counts, const int64_t* row_range, int64_t num_rows, const float* w,
+                         const float* scale, const float* x, int64_t ldx, int64_t feat, const float* bias, int act,
+                         float slope, float* out, int64_t ldo, void* partial, size_t partial_bytes,
+                         plagnn_stream_t stream) {
+    if (!row_range) return fail(PLAGNN_ERR_ARG, "spmm_sum_rows", "row_range is required");
+    if (act < PLAGNN_ACT_NONE || act > PLAGNN_ACT_SIGMOID) return fail(PLAGNN_ERR_ARG, "spmm_sum_rows", "unknown activation");
+    ProfileScope prof("spmm_sum", feat, row_range[1] - row_range[0], w ? 1 : 0, stream);
+    SpmmArgs a{indptr, indices, eids, w, plan, plan_counts, num_rows, x, ldx, feat, nullptr, 0, nullptr, 0, out, nullptr, ldo,
+               partial, partial_bytes, SpmmEpilogue{scale, bias, act, slope, 0.f, 0ull}};
+    a.range = row_range;
+    return spmm_dispatch<MODE_SUM>(a, "spmm_sum_rows", (cudaStream_t)stream);
 }
 
 int plagnn_dropout_scale(float* grad, int64_t rows, int64_t feat, int64_t ld, float dropout_p, uint64_t dropout_seed,

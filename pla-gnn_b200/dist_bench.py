@@ -27,7 +27,8 @@ def run(args):
     f = args.feat
     t0 = time.perf_counter()
     sg = synth.scaled_graph(n, e, seed=1234, device=dev)                  # identical on every rank (seeded)
-    plan = RowPartitionPlan(sg.src, sg.dst, n, rank, world)
+    chunks = int(os.environ.get("PLAGNN_DIST_CHUNKS", "4" if world > 1 else "1"))
+    plan = RowPartitionPlan(sg.src, sg.dst, n, rank, world, chunks)
     pg = PartitionedGraph(plan, sg.weight, P.build_csr, dev)
     del sg
     torch.cuda.empty_cache()
@@ -38,7 +39,7 @@ def run(args):
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
     h0 = ops.alloc(plan.per, f, dev, zero=True)
     h0[:plan.n_local].copy_(torch.randn(plan.n_local, f, generator=gen, device=dev))
-    backend = CudaBackend()
+    backend = CudaBackend(pg)
     row_mask = (torch.arange(plan.per, device=dev) < plan.n_local).float().unsqueeze(1)
     inv = 1.0 / (n * f)
 
@@ -88,7 +89,7 @@ def run(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"row-partitioned weighted-sum GCN [{f},{f},{f}] on power-law graph N={n}, E={e} "
-                                   f"(BASELINE configs[3]), right-normalised, Adam", "parallelism": f"1-D row partition x{world}, "
+                                   f"(BASELINE configs[3]), right-normalised, Adam", "parallelism": f"1-D row partition x{world}, {chunks} row chunks per rank pipelined: "
                        "all-gather(fwd) / reduce-scatter(bwd) / all-reduce(weight grads) over NCCL",
                        "l2": "inputs (>= 1 GB gathered features) larger than L2", "build_seconds": round(t_build, 2),
                        "local_edges_rank0": el},

@@ -267,6 +267,26 @@ def spmm_sum(csx, x: torch.Tensor, w=None, scale=None, bias=None, act=ACT_NONE, 
     return out
 
 
+def plan_range(csx, row_begin: int, row_end: int):
+    """Host handle (ctypes int64[4]) for aggregating only rows [row_begin, row_end) of `csx` (set-up call)."""
+    rng = (ctypes.c_int64 * 4)()
+    check(_lib.load().plagnn_spmm_plan_range(_p(csx.plan), csx.num_rows, row_begin, row_end, rng, _stream()), "spmm_plan_range")
+    return rng
+
+
+def spmm_sum_rows(csx, rng, x: torch.Tensor, out: torch.Tensor, w=None, scale=None, bias=None, act=ACT_NONE,
+                  slope: float = LEAKY_SLOPE) -> torch.Tensor:
+    """Row-range aggregation into the rows of a preallocated `out` (other rows untouched)."""
+    lib = _lib.load()
+    f = x.shape[1]
+    nb = lib.plagnn_spmm_partial_bytes(csx.counts[2], f, REDUCE_SUM)
+    part = workspace(nb, x.device, "spmm_partial")
+    check(lib.plagnn_spmm_sum_rows(_p(csx.indptr), _p(csx.indices), _p(csx.eids) if w is not None else None, _p(csx.plan),
+                                   csx.counts_c, rng, csx.num_rows, _p(w), _p(scale), _p(x), x.stride(0), f, _p(bias), act,
+                                   slope, _p(out), out.stride(0), _p(part), nb, _stream()), "spmm_sum_rows")
+    return out
+
+
 def dropout_scale_(grad: torch.Tensor, p: float, seed: int) -> torch.Tensor:
     check(_lib.load().plagnn_dropout_scale(_p(grad), grad.shape[0], grad.shape[1], grad.stride(0), float(p), int(seed),
                                            _stream()), "dropout_scale")

@@ -19,19 +19,22 @@ class _Csx:
 
 
 class CpuBackend:
-    """Same method names as plagnn_b200.dist.CudaBackend, computed with torch-CPU + the oracle's C SpMM."""
+    """Same method names as plagnn_b200.dist.CudaBackend, computed with torch-CPU + the oracle's C SpMM (synchronous)."""
 
-    def gemm_nt(self, a, w): return a @ w.t()
+    def alloc(self, rows, cols): return torch.zeros(rows, cols)
+    @staticmethod
+    def rows(t, a, b): return t[a:b]
+    def gemm_nt_into(self, a, w, out): out.copy_(a @ w.t())
     def gemm_nn(self, a, w): return a @ w
     def gemm_tn(self, a, b): return a.t() @ b
     def colsum(self, x): return x.sum(0)
 
-    def spmm(self, csx, x, w, scale, bias, act):
-        out = orc.spmm_sum_c(csx.indptr, csx.indices, x.contiguous(), eids=csx.eids if w is not None else None, w=w,
-                             scale=scale)
+    def spmm_rows(self, csx, key, a, b, x, out, w, scale, bias, act):
+        r = orc.spmm_sum_c(csx.indptr[a:b + 1], csx.indices, x.contiguous(), eids=csx.eids if w is not None else None, w=w,
+                           scale=None if scale is None else scale[a:b].contiguous())
         if bias is not None:
-            out = out + bias
-        return torch.nn.functional.leaky_relu(out) if act else out
+            r = r + bias
+        out[a:b] = torch.nn.functional.leaky_relu(r) if act else r
 
     def act_backward(self, dy, y, scale):
         if y is not None:
@@ -40,17 +43,22 @@ class CpuBackend:
             dy = dy * scale.unsqueeze(1)
         return dy
 
-    def all_gather_rows(self, t, world, group):
-        parts = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(parts, t.contiguous(), group=group)
-        return torch.cat(parts)
+    def all_gather_chunk(self, slab, local_chunk, world, group):
+        parts = [torch.empty_like(local_chunk) for _ in range(world)]
+        dist.all_gather(parts, local_chunk.contiguous(), group=group)
+        slab.copy_(torch.cat(parts))
+        return None
 
-    def reduce_scatter_rows(self, partial, world, group):
-        full = partial.clone()
+    def reduce_scatter_chunk(self, out_chunk, slab, world, group):
+        full = slab.clone()
         dist.all_reduce(full, group=group)
-        per = full.shape[0] // world
+        n = out_chunk.shape[0]
         r = dist.get_rank(group)
-        return full[r * per:(r + 1) * per].contiguous()
+        out_chunk.copy_(full[r * n:(r + 1) * n])
+        return None
+
+    @staticmethod
+    def wait(pending): pass
 
     def all_reduce_grads(self, grads, world, group):
         out = []
@@ -63,8 +71,9 @@ class CpuBackend:
 
 class _PG:
     def __init__(self, plan, weight):
-        self.csc = _Csx(plan.dst_local, plan.src_global, plan.per)
-        self.csr_t = _Csx(plan.src_global, plan.dst_local, plan.n_padded)
+        self.plan = plan
+        self.csc = _Csx(plan.dst_local, plan.src_gathered, plan.per)
+        self.csr_t = _Csx(plan.src_gathered, plan.dst_local, plan.n_padded)
         self.edge_weight = weight[plan.edge_ids]
         self.scale = plan.scale_local
 
@@ -81,7 +90,7 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sg, x = _problem()
     n, f = sg.num_nodes, x.shape[1]
-    plan = RowPartitionPlan(sg.src, sg.dst, n, rank, world)
+    plan = RowPartitionPlan(sg.src, sg.dst, n, rank, world, chunks=3)
     pg = _PG(plan, sg.weight)
     model = DistGCN([f, 16, 8], seed=3)
     h0 = torch.zeros(plan.per, f)
@@ -116,11 +125,24 @@ def test_block_bounds_and_plan_cover_every_edge_once():
         per, b = block_bounds(n, world)
         assert b[0] == 0 and b[-1] == n and all(b[i + 1] - b[i] <= per for i in range(world))
         seen = torch.zeros(sg.src.numel(), dtype=torch.int32)
+        gathered = []
         for r in range(world):
-            plan = RowPartitionPlan(sg.src, sg.dst, n, r, world)
+            plan = RowPartitionPlan(sg.src, sg.dst, n, r, world, chunks=3)
             seen[plan.edge_ids] += 1
+            # chunk-major gathered numbering: the all-gather of local chunk c fills slab c
+            own = torch.arange(plan.r0, plan.r1)
+            gid = plan.gathered_id(own)
+            for c in range(plan.chunks):
+                a, e_ = plan.local_rows(c)
+                sa, sb = plan.slab_rows(c)
+                g_c = gid[a:min(e_, plan.n_local)]
+                assert ((g_c >= sa) & (g_c < sb)).all()
+                assert torch.equal(g_c - sa, r * plan.cr + torch.arange(g_c.numel()))
+            gathered.append(gid)
             assert (plan.dst_local >= 0).all() and (plan.dst_local < plan.n_local).all()
             assert torch.equal(sg.dst[plan.edge_ids] - plan.r0, plan.dst_local)
+        gathered = torch.cat(gathered)
+        assert torch.unique(gathered).numel() == n and gathered.max() < plan.n_padded
         assert (seen == 1).all()
     # shuffled ids: rows and in-edges balance together
     plans = [RowPartitionPlan(sg.src, sg.dst, n, r, 2) for r in range(2)]
