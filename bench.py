@@ -170,13 +170,50 @@ def run_ours(args):
         opt.step()
         return logits, loss
 
+    # End-to-end step: the inputs of EVERY step come from pinned host memory and the loss + N x 12 output go back to
+    # the host.  The copies run on a second stream into double-buffered device tensors, so the upload of step i+1
+    # overlaps the compute of step i (a prefetching input pipeline); all of it is inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    feat_bufs = [feat_dev, torch.zeros_like(feat_dev)]
+    loc_bufs = [loc_dev, torch.zeros_like(loc_dev)]
+    idx_bufs = [idx_d, torch.zeros_like(idx_d)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]         # upload of buffer b finished
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]      # compute that read buffer b finished
+    state = {"step": 0, "primed": False}
+
+    def upload(b):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])              # do not overwrite inputs still being read
+            feat_bufs[b].copy_(feat_h, non_blocking=True)
+            loc_bufs[b].copy_(loc_h, non_blocking=True)
+            idx_bufs[b].copy_(idx_h, non_blocking=True)
+            ready[b].record(copy_stream)
+
     def epoch_e2e():
-        feat_dev.copy_(feat_h, non_blocking=True)            # H2D: this step's inputs
-        loc_dev.copy_(loc_h, non_blocking=True)
-        idx_d.copy_(idx_h, non_blocking=True)
-        logits, loss = epoch()
-        loss_h.copy_(loss.detach().reshape(1), non_blocking=True)   # D2H: loss and the N x 12 output the loop reads
-        logits_h.copy_(logits.detach().contiguous(), non_blocking=True)
+        b = state["step"] & 1
+        if not state["primed"]:
+            consumed[0].record(); consumed[1].record()
+            upload(b)
+            state["primed"] = True
+        upload(b ^ 1)                                        # prefetch the next step's inputs
+        torch.cuda.current_stream().wait_event(ready[b])
+        f_view = feat_bufs[b][:, :features.shape[1]]
+        l_view = loc_bufs[b][:, :labels.shape[1]]
+        opt.zero_grad()
+        logits = model(g, f_view)
+        loss = P.multi_loss_indexed(logits, l_view, idx_bufs[b], i_weight)
+        loss.backward()
+        opt.step()
+        consumed[b].record()
+        out_dev = logits.detach().contiguous()
+        done = torch.cuda.Event()
+        done.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            loss_h.copy_(loss.detach().reshape(1), non_blocking=True)   # D2H: loss and the N x 12 output the loop reads
+            logits_h.copy_(out_dev, non_blocking=True)
+            out_dev.record_stream(copy_stream)
+        state["step"] += 1
 
     def barrier():
         if world > 1:
@@ -215,7 +252,25 @@ def run_ours(args):
     # ---- end-to-end timed region (host buffers in, loss + logits out) ------------------------------
     for _ in range(3):
         epoch_e2e()
-    ms_e2e = timed(epoch_e2e, args.steps)
+
+    def timed_e2e(steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            epoch_e2e()
+        torch.cuda.current_stream().wait_stream(copy_stream)   # the last step's results must have reached the host
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            import torch.distributed as dist
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = tt.item()
+        return ms
+
+    ms_e2e = timed_e2e(args.steps)
 
     if rank != 0:
         return

@@ -53,6 +53,7 @@ struct TcParams {
     float* c;
     int64_t ldc;
     float* partial;
+    int tiles_m, tiles_n, total_tiles;   // persistent kernel: tile = split * tiles_m * tiles_n + mt * tiles_n + nt
     int debug;   // PLAGNN_TC_DEBUG: 1 = loaders skip global loads / smem stores after the first k-block (MMA-bound
                  // timing), 2 = the issuer skips the MMAs (loader-bound timing).  Results are garbage; timing only.
 };
@@ -436,6 +437,209 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams P
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks tiles (tile = blockIdx.x + i * gridDim.x); four extra epilogue warps
+// drain accumulator stage a while the loaders / issuer already work on the next tile in stage a^1 (TMEM holds two
+// accumulator stages of 2 x 128 columns).  The register ring of the loaders simply runs on across tile boundaries,
+// so there is no pipeline drain between tiles and the barrier / TMEM set-up is paid once per SM instead of per tile.
+// ------------------------------------------------------------------------------------------------------
+constexpr int TCP_EPI_WARPS = 4;
+constexpr int TCP_THREADS = (TC_LOAD_WARPS + 1 + TCP_EPI_WARPS) * 32;
+constexpr int TCP_TMEM_COLS = 512;
+
+struct TileCoord {
+    int64_t m0, n0;
+    int split, kb_beg, nkb;
+};
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& P, int tile) {
+    TileCoord c;
+    const int per_split = P.tiles_m * P.tiles_n;
+    c.split = tile / per_split;
+    const int rem = tile - c.split * per_split;
+    const int mt = rem / P.tiles_n;
+    c.m0 = (int64_t)mt * TC_BM;
+    c.n0 = (int64_t)(rem - mt * P.tiles_n) * TC_BN;
+    c.kb_beg = c.split * P.kblocks_per_split;
+    c.nkb = min(P.total_kblocks, c.kb_beg + P.kblocks_per_split) - c.kb_beg;
+    return c;
+}
+
+template <bool AT, bool BT>
+__global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persistent_kernel(const TcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles = (raw + 1023u) & ~1023u;
+    const uint32_t bars = tiles + TC_STAGES * TC_STAGE_BYTES;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * TC_STAGES;
+    const uint32_t bar_tfull = bars + 16 * TC_STAGES, bar_tempty = bar_tfull + 16;   // 2 accumulator stages each
+    const uint32_t tmem_slot = bar_tempty + 16;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int first_tile = blockIdx.x, tile_step = gridDim.x;
+
+    // ---- loader state: the issue cursor runs two k-blocks ahead of the commit cursor, across tile boundaries
+    const bool is_b = warp >= 8;
+    float4 ring[2][4];   // depth 2 here: 21 warps leave 80 registers per thread
+    const float* ptr[4];
+    int ptr_pair = -1;
+    int is_tile = first_tile, is_kb = 0;
+    TileCoord ic = tile_coord(P, first_tile < P.total_tiles ? first_tile : 0);
+    auto issue = [&](float4 (&v)[4]) {
+        if (is_tile >= P.total_tiles) return;
+        const int kb = ic.kb_beg + is_kb;
+        int p = 0, local = kb;
+        if (P.npairs > 1 && local >= P.kblocks[0]) { local -= P.kblocks[0]; p = 1; }
+        if (ptr_pair != p) {
+            if (!is_b) tile_ptrs<AT>(P.a[p], P.lda[p], P.m, ic.m0, ptr);
+            else tile_ptrs<BT>(P.b[p], P.ldb[p], P.n, ic.n0, ptr);
+            ptr_pair = p;
+        }
+        const int64_t k0 = (int64_t)local * TC_BK;
+        if (!is_b) tile_load<AT>(ptr, P.lda[p], k0, P.k[p], v);
+        else tile_load<BT>(ptr, P.ldb[p], k0, P.k[p], v);
+        if (++is_kb == ic.nkb) {
+            is_tile += tile_step;
+            is_kb = 0;
+            ptr_pair = -1;
+            if (is_tile < P.total_tiles) ic = tile_coord(P, is_tile);
+        }
+    };
+    if (warp < TC_LOAD_WARPS) issue(ring[0]);          // first request before the barrier / TMEM set-up
+
+    if (t == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, TC_LOAD_WARPS * 32);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, TCP_EPI_WARPS * 32);
+        }
+        fence_mbar_init();
+    }
+    if (warp == TC_LOAD_WARPS) tmem_alloc(tmem_slot, TCP_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp < TC_LOAD_WARPS) {
+        // ================= loaders =================
+        int total_it = 0;
+        for (int tl = first_tile; tl < P.total_tiles; tl += tile_step) total_it += tile_coord(P, tl).nkb;
+        auto commit = [&](int it, const float4 (&v)[4]) {
+            const int s = it % TC_STAGES;
+            const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            const uint32_t st = tiles + s * TC_STAGE_BYTES;
+            if (!is_b) tile_store<AT>(st, st + TC_PART_BYTES, v);
+            else tile_store<BT>(st + 2 * TC_PART_BYTES, st + 3 * TC_PART_BYTES, v);
+            fence_proxy_async_smem();
+            mbar_arrive(bar_full + 8 * s);
+        };
+#pragma unroll 1
+        for (int it = 0; it < total_it; it += 2) {
+            issue(ring[1]);
+            commit(it, ring[0]);
+            if (it + 1 < total_it) {
+                issue(ring[0]);
+                commit(it + 1, ring[1]);
+            }
+        }
+    } else if (warp == TC_LOAD_WARPS) {
+        // ================= MMA issuer (one elected lane) =================
+        if (lane == 0) {
+            constexpr uint64_t a_step = AT ? (4096u >> 4) : 2u, b_step = BT ? (4096u >> 4) : 2u;
+            int it = 0, tl_idx = 0;
+            for (int tl = first_tile; tl < P.total_tiles; tl += tile_step, ++tl_idx) {
+                const TileCoord tc = tile_coord(P, tl);
+                const int a = tl_idx & 1;
+                mbar_wait(bar_tempty + 8 * a, (uint32_t)(((tl_idx >> 1) & 1) ^ 1));   // epilogue has drained this stage
+                tc_fence_after();
+                const int64_t nrem = P.n - tc.n0;
+                const uint32_t n_eff = nrem >= TC_BN ? TC_BN : (uint32_t)((nrem + 15) / 16 * 16);
+                const uint32_t idesc = make_idesc(n_eff, AT, BT);
+                const uint32_t acc_big = tmem_base + (uint32_t)(a * 2 * TC_BN), acc_small = acc_big + TC_BN;
+                for (int kb = 0; kb < tc.nkb; ++kb, ++it) {
+                    const int s = it % TC_STAGES;
+                    const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
+                    mbar_wait(bar_full + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t st = tiles + s * TC_STAGE_BYTES;
+                    const uint64_t a_hi = AT ? make_smem_desc_mn(st) : make_smem_desc(st);
+                    const uint64_t a_lo = AT ? make_smem_desc_mn(st + TC_PART_BYTES) : make_smem_desc(st + TC_PART_BYTES);
+                    const uint64_t b_hi = BT ? make_smem_desc_mn(st + 2 * TC_PART_BYTES) : make_smem_desc(st + 2 * TC_PART_BYTES);
+                    const uint64_t b_lo = BT ? make_smem_desc_mn(st + 3 * TC_PART_BYTES) : make_smem_desc(st + 3 * TC_PART_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                        const uint64_t adv_a = (uint64_t)kk * a_step, adv_b = (uint64_t)kk * b_step;
+                        const uint32_t acc_on = (kb | kk) ? 1u : 0u;
+                        umma_tf32(acc_small, a_lo + adv_a, b_hi + adv_b, idesc, acc_on);
+                        umma_tf32(acc_small, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
+                        umma_tf32(acc_big, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
+                    }
+                    umma_commit(bar_empty + 8 * s);
+                }
+                umma_commit(bar_tfull + 8 * a);      // this tile's accumulators are complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue warps =================
+        const int lg = warp & 3;                       // TMEM lane group this warp may touch (warp % 4)
+        int tl_idx = 0;
+        for (int tl = first_tile; tl < P.total_tiles; tl += tile_step, ++tl_idx) {
+            const TileCoord tc = tile_coord(P, tl);
+            const int a = tl_idx & 1;
+            mbar_wait(bar_tfull + 8 * a, (uint32_t)((tl_idx >> 1) & 1));
+            tc_fence_after();
+            const int64_t r = tc.m0 + lg * 32 + lane;
+            const bool direct = P.splits == 1;
+            float* dst = direct ? P.c : P.partial + (int64_t)tc.split * P.m * P.n;
+            const int64_t ldd = direct ? P.ldc : P.n;
+            const bool vec_out = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+            const uint32_t acc_big = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * 2 * TC_BN);
+#pragma unroll 1
+            for (int cq = 0; cq < 8; ++cq) {           // 16 columns at a time: 21 warps leave 80 registers per thread
+                const int cbase = 16 * cq;
+                if (tc.n0 + cbase >= P.n) break;       // warp-uniform
+                uint32_t acc[16], acc_small[16];
+                tmem_ld16(acc_big + (uint32_t)cbase, acc);
+                tmem_ld16(acc_big + (uint32_t)(TC_BN + cbase), acc_small);
+                tmem_ld_wait();
+                if (r < P.m) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int64_t c = tc.n0 + cbase + 4 * q;
+                        if (c >= P.n) break;
+                        float v[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            v[e] = __uint_as_float(acc[4 * q + e]) + __uint_as_float(acc_small[4 * q + e]);
+                            if (direct && c + e < P.n) v[e] = tc_epilogue_one(P, v[e], r, c + e);
+                        }
+                        if (vec_out && c + 3 < P.n) {
+                            *reinterpret_cast<float4*>(dst + r * ldd + c) = make_float4(v[0], v[1], v[2], v[3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (c + e < P.n) dst[r * ldd + c + e] = v[e];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * a);           // all TMEM reads of this stage are done
+        }
+    }
+    __syncthreads();
+    if (warp == TC_LOAD_WARPS) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TCP_TMEM_COLS);
+    }
+}
+
 // ordered reduction of split-K partials + epilogue
 __global__ void __launch_bounds__(256) gemm_tc_reduce_kernel(const TcParams P) {
     const int64_t total = P.m * P.n;
@@ -531,13 +735,23 @@ int gemm_tc_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair*
     P.partial = P.splits > 1 ? (float*)workspace : nullptr;
 
     using KernelFn = void (*)(const TcParams);
-    static const KernelFn kernels[4] = {gemm_tc_kernel<false, false>, gemm_tc_kernel<false, true>,
-                                        gemm_tc_kernel<true, false>, gemm_tc_kernel<true, true>};
+    static const KernelFn kernels[8] = {gemm_tc_kernel<false, false>, gemm_tc_kernel<false, true>,
+                                        gemm_tc_kernel<true, false>, gemm_tc_kernel<true, true>,
+                                        gemm_tc_persistent_kernel<false, false>, gemm_tc_persistent_kernel<false, true>,
+                                        gemm_tc_persistent_kernel<true, false>, gemm_tc_persistent_kernel<true, true>};
+    // The persistent variant (overlapped epilogue) measured FASTER only for long contractions (8192^3: 142 vs 140 TF,
+    // weight gradients 54 vs 52 TF) and SLOWER on the K ~ 500 layer shapes (76 vs 94 TF): with 21 warps only 80
+    // registers per thread are available (2-deep instead of 3-deep load ring) and its 4 epilogue warps need longer
+    // than a 16-k-block main loop.  It is therefore opt-in (PLAGNN_TC_PERSISTENT=1).
+    static const int persistent = [] { const char* e = getenv("PLAGNN_TC_PERSISTENT"); return e ? atoi(e) : 0; }();
+    P.tiles_m = (int)ceil_div(m, TC_BM);
+    P.tiles_n = (int)ceil_div(n, TC_BN);
+    P.total_tiles = P.tiles_m * P.tiles_n * P.splits;
     static thread_local int attr_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (attr_dev != dev) {
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 8; ++i) {
             cudaError_t e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
             if (e != cudaSuccess) {
                 set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -546,8 +760,14 @@ int gemm_tc_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair*
         }
         attr_dev = dev;
     }
-    dim3 grid((unsigned)ceil_div(n, TC_BN), (unsigned)ceil_div(m, TC_BM), (unsigned)P.splits);
-    kernels[(P.a_trans[0] ? 2 : 0) + (P.b_trans[0] ? 1 : 0)]<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(P);
+    const int kidx = (P.a_trans[0] ? 2 : 0) + (P.b_trans[0] ? 1 : 0);
+    if (persistent) {
+        const int ctas = P.total_tiles < sm_count() ? P.total_tiles : sm_count();
+        kernels[4 + kidx]<<<ctas, TCP_THREADS, TC_SMEM_BYTES, st>>>(P);
+    } else {
+        dim3 grid((unsigned)ceil_div(n, TC_BN), (unsigned)ceil_div(m, TC_BM), (unsigned)P.splits);
+        kernels[kidx]<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(P);
+    }
     if (P.splits > 1) {
         const int64_t total = m * n;
         const int g = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 8 ? ceil_div(total, 256) : (int64_t)sm_count() * 8);
