@@ -112,9 +112,10 @@ static int gemm1(int64_t m, int64_t n, const float* a, int64_t lda, int at, cons
                        PLAGNN_GEMM_AUTO, st);
 }
 static int gemm2(int64_t m, int64_t n, const float* a0, int64_t lda0, const float* b0, int64_t ldb0, int64_t k0,
-                 const float* a1, int64_t lda1, const float* b1, int64_t ldb1, int64_t k1, const float* bias, int act,
-                 const float* gate, int64_t ldg, int gate_act, float* c, int64_t ldc, const Layout& L, plagnn_stream_t st) {
-    plagnn_gemm_pair p[2] = {{a0, lda0, 0, b0, ldb0, 0, k0}, {a1, lda1, 0, b1, ldb1, 0, k1}};
+                 const float* a1, int64_t lda1, const float* b1, int64_t ldb1, int64_t k1, int b_trans, const float* bias,
+                 int act, const float* gate, int64_t ldg, int gate_act, float* c, int64_t ldc, const Layout& L,
+                 plagnn_stream_t st) {
+    plagnn_gemm_pair p[2] = {{a0, lda0, 0, b0, ldb0, b_trans, k0}, {a1, lda1, 0, b1, ldb1, b_trans, k1}};
     return plagnn_gemm(m, n, 2, p, bias, act, 0.01f, gate, ldg, gate_act, c, ldc, L.gemm_ws, L.gemm_ws_bytes,
                        PLAGNN_GEMM_AUTO, st);
 }
@@ -147,6 +148,8 @@ int plagnn_gnn32_forward(const plagnn_gnn32_shape* shape, const float* x, int64_
     for (int l = 0; l < 3; ++l) {
         const int64_t f = L.d[l], o = L.d[l + 1], pf = pitch32(f), po = pitch32(o);
         const float* const* P = params + 5 * l;
+        // row-padded copies of the weights (pitch % 32 == 0: aligned rows for the tensor-core loaders, also in
+        // backward where they are read MN-major)
         TRY(plagnn_pad_copy(P[0], f, f, f, L.wp[l], pf, stream));
         TRY(plagnn_pad_copy(P[2], o, f, f, L.ws[l], pf, stream));
         TRY(plagnn_pad_copy(P[3], o, f, f, L.wn[l], pf, stream));
@@ -154,7 +157,7 @@ int plagnn_gnn32_forward(const plagnn_gnn32_shape* shape, const float* x, int64_
         TRY(gemm1(n, f, h, ldh, 0, L.wp[l], pf, 0, f, P[1], PLAGNN_ACT_RELU, nullptr, 0, 0, L.m, pf, L, stream));
         TRY(plagnn_spmm_max_fwd(shape->indptr, shape->indices, shape->plan, shape->plan_counts, n, L.m, pf, f,
                                 L.neigh[l], L.arg[l], pf, L.spmm_ws, L.spmm_ws_bytes, stream));
-        TRY(gemm2(n, o, h, ldh, L.ws[l], pf, f, L.neigh[l], pf, L.wn[l], pf, f, P[4], PLAGNN_ACT_LEAKY, nullptr, 0, 0,
+        TRY(gemm2(n, o, h, ldh, L.ws[l], pf, f, L.neigh[l], pf, L.wn[l], pf, f, 0, P[4], PLAGNN_ACT_LEAKY, nullptr, 0, 0,
                   L.h[l], po, L, stream));
         h = L.h[l];
         ldh = po;
@@ -183,14 +186,13 @@ int plagnn_gnn32_backward(const plagnn_gnn32_shape* shape, const float* x, int64
     TRY(plagnn_act_backward(dprob, lddprob, prob, ldprob, n, c, PLAGNN_ACT_SIGMOID, 0.01f, nullptr, L.dz5, pc, stream));
     TRY(gemm1(c, d4, L.dz5, pc, 1, L.h4, p4, 1, n, nullptr, 0, nullptr, 0, 0, grads[17], d4, L, stream));
     TRY(plagnn_colsum(L.dz5, n, c, pc, grads[18], L.colsum_ws, L.colsum_ws_bytes, stream));
-    TRY(plagnn_transpose(L.w2, c, d4, p4, L.wt[0], pitch32(c), stream));
-    TRY(gemm1(n, d4, L.dz5, pc, 0, L.wt[0], pitch32(c), 0, c, nullptr, 0, L.h4, p4, PLAGNN_ACT_LEAKY, L.dz4, p4, L, stream));
+    // input gradients read the weights [out x in] as an MN-major B operand (b_trans = 1): no transposed copies
+    TRY(gemm1(n, d4, L.dz5, pc, 0, L.w2, p4, 1, c, nullptr, 0, L.h4, p4, PLAGNN_ACT_LEAKY, L.dz4, p4, L, stream));
     const float* h3 = L.h[2];
     TRY(gemm1(d4, d3, L.dz4, p4, 1, h3, p3, 1, n, nullptr, 0, nullptr, 0, 0, grads[15], d3, L, stream));
     TRY(plagnn_colsum(L.dz4, n, d4, p4, grads[16], L.colsum_ws, L.colsum_ws_bytes, stream));
-    TRY(plagnn_transpose(L.w1, d4, d3, p3, L.wt[0], pitch32(d4), stream));
     float* drst = L.drst[0];
-    TRY(gemm1(n, d3, L.dz4, p4, 0, L.wt[0], pitch32(d4), 0, d4, nullptr, 0, h3, p3, PLAGNN_ACT_LEAKY, drst, p3, L, stream));
+    TRY(gemm1(n, d3, L.dz4, p4, 0, L.w1, p3, 1, d4, nullptr, 0, h3, p3, PLAGNN_ACT_LEAKY, drst, p3, L, stream));
     int cur = 0;
     for (int l = 2; l >= 0; --l) {
         const int64_t f = L.d[l], o = L.d[l + 1], pf = pitch32(f), po = pitch32(o);
@@ -200,18 +202,15 @@ int plagnn_gnn32_backward(const plagnn_gnn32_shape* shape, const float* x, int64
         TRY(plagnn_colsum(drst, n, o, po, G[4], L.colsum_ws, L.colsum_ws_bytes, stream));
         TRY(gemm1(o, f, drst, po, 1, hin, ldin, 1, n, nullptr, 0, nullptr, 0, 0, G[2], f, L, stream));
         TRY(gemm1(o, f, drst, po, 1, L.neigh[l], pf, 1, n, nullptr, 0, nullptr, 0, 0, G[3], f, L, stream));
-        TRY(plagnn_transpose(L.wn[l], o, f, pf, L.wt[0], po, stream));
-        TRY(gemm1(n, f, drst, po, 0, L.wt[0], po, 0, o, nullptr, 0, nullptr, 0, 0, L.dneigh, pf, L, stream));
+        TRY(gemm1(n, f, drst, po, 0, L.wn[l], pf, 1, o, nullptr, 0, nullptr, 0, 0, L.dneigh, pf, L, stream));
         TRY(plagnn_spmm_max_bwd(L.dneigh, pf, L.arg[l], pf, L.neigh[l], pf, n, f, L.dm, n, pf, stream));
         TRY(gemm1(f, f, L.dm, pf, 1, hin, ldin, 1, n, nullptr, 0, nullptr, 0, 0, G[0], f, L, stream));
         TRY(plagnn_colsum(L.dm, n, f, pf, G[1], L.colsum_ws, L.colsum_ws_bytes, stream));
         if (l > 0 || dx) {
-            TRY(plagnn_transpose(L.ws[l], o, f, pf, L.wt[0], po, stream));
-            TRY(plagnn_transpose(L.wp[l], f, f, pf, L.wt[1], pf, stream));
             float* out = l > 0 ? L.drst[cur ^ 1] : dx;
             const int64_t ldo = l > 0 ? pf : lddx;
             // d(input) = drst Ws + dm Wp, times leaky'(input) when the input is the previous layer's activation
-            TRY(gemm2(n, f, drst, po, L.wt[0], po, o, L.dm, pf, L.wt[1], pf, f, nullptr, 0, l > 0 ? hin : nullptr, ldin,
+            TRY(gemm2(n, f, drst, po, L.ws[l], pf, o, L.dm, pf, L.wp[l], pf, f, 1, nullptr, 0, l > 0 ? hin : nullptr, ldin,
                       l > 0 ? PLAGNN_ACT_LEAKY : PLAGNN_ACT_NONE, out, ldo, L, stream));
             drst = out;
             cur ^= 1;

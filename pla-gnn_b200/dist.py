@@ -201,7 +201,7 @@ class CudaBackend:
     def gemm_nn(self, a, w):
         ops = self.ops
         a = ops.aligned(a)
-        return ops.gemm(a.shape[0], w.shape[1], [(a, 0, ops.transpose(w), 0, a.shape[1])])
+        return ops.gemm(a.shape[0], w.shape[1], [(a, 0, ops.aligned(w), 1, a.shape[1])])
 
     def gemm_tn(self, a, b):
         ops = self.ops

@@ -53,8 +53,8 @@ def sage_pool_backward(g, saved, w_pool, w_self, w_neigh, drst, has_bias, need_d
     db = ops.colsum(drst) if has_bias else None
     d_ws = ops.gemm(o, f, [(drst, 1, x, 1, n)], out=torch.empty_like(w_self))
     d_wn = ops.gemm(o, f, [(drst, 1, neigh, 1, n)], out=torch.empty_like(w_neigh))
-    wn_t = ops.transpose(w_neigh)                       # [f x o], K(=o)-contiguous operand
-    dneigh = ops.gemm(n, f, [(drst, 0, wn_t, 0, o)])
+    # input gradients read the weight [o x f] as an MN-major B operand (b_trans = 1): no transposed copy needed
+    dneigh = ops.gemm(n, f, [(drst, 0, ops.aligned(w_neigh), 1, o)])
     if DETERMINISTIC_BACKWARD:
         if g.has_duplicate_edges():
             raise ops._lib.PlagnnError("the ordered max-backward needs a graph without duplicate edges")
@@ -66,8 +66,8 @@ def sage_pool_backward(g, saved, w_pool, w_self, w_neigh, drst, has_bias, need_d
     d_bp = ops.colsum(dm)
     dx = None
     if need_dx:
-        ws_t, wp_t = ops.transpose(w_self), ops.transpose(w_pool)
-        dx = ops.gemm(n, f, [(drst, 0, ws_t, 0, o), (dm, 0, wp_t, 0, f)], gate=gate, gate_act=gate_act)
+        dx = ops.gemm(n, f, [(drst, 0, ops.aligned(w_self), 1, o), (dm, 0, ops.aligned(w_pool), 1, f)], gate=gate,
+                      gate_act=gate_act)
     return dx, d_wp, d_bp, d_ws, d_wn, db
 
 
@@ -85,7 +85,7 @@ def linear_backward(x, w, dz, has_bias, need_dx, gate=None, gate_act=ACT_NONE):
     d_b = ops.colsum(dz) if has_bias else None
     dx = None
     if need_dx:
-        dx = ops.gemm(n, k, [(dz, 0, ops.transpose(w), 0, o)], gate=gate, gate_act=gate_act)
+        dx = ops.gemm(n, k, [(dz, 0, ops.aligned(w), 1, o)], gate=gate, gate_act=gate_act)
     return dx, d_w, d_b
 
 
@@ -277,7 +277,7 @@ class GraphConvSumFunction(torch.autograd.Function):
         n, k = ctx.xa.shape
         o = w.shape[0]
         d_w = ops.gemm(o, k, [(dt, 1, ctx.xa, 1, n)], out=torch.empty_like(w))
-        dx = ops.gemm(n, k, [(dt, 0, ops.transpose(w), 0, o)]) if ctx.needs_input_grad[1] else None
+        dx = ops.gemm(n, k, [(dt, 0, ops.aligned(w), 1, o)]) if ctx.needs_input_grad[1] else None
         return None, dx, d_w, db, None, None, None, None, None
 
 
