@@ -14,6 +14,7 @@
 //     in chunk order, which keeps "first maximum wins" and makes sums order-stable.
 #include "common.cuh"
 #include <math.h>
+#include <cstdlib>
 
 namespace plagnn {
 
@@ -344,10 +345,21 @@ static int spmm_dispatch(const SpmmArgs& a, const char* name, cudaStream_t st) {
     plan_pointers(a.plan, a.n_rows, &item_ptr, &slot_ptr, &item_row, &hub_rows);
 
     const int64_t groups = (a.feat + 3) / 4;   // float4 column groups
-    if (groups <= 32) launch_main<MODE, 1, 8>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
-    else if (groups <= 64) launch_main<MODE, 2, 4>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
-    else if (groups <= 96) launch_main<MODE, 3, 2>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
-    else launch_main<MODE, 4, 2>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
+    // NB neighbour rows in flight per lane.  Measured on the PPI-shaped graph (F = 503, chunk 512): NB = 2 -> 0.2115 ms,
+    // NB = 4 -> 0.2174 ms (128 registers, lower occupancy); the deeper variant only wins for chunks >= 1024 and stays
+    // opt-in (PLAGNN_SPMM_DEEP=1).
+    static const int deep = [] { const char* e = getenv("PLAGNN_SPMM_DEEP"); return e ? atoi(e) : 0; }();
+    if (MODE == MODE_MATCH || !deep) {
+        if (groups <= 32) launch_main<MODE, 1, 8>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
+        else if (groups <= 64) launch_main<MODE, 2, 4>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
+        else if (groups <= 96) launch_main<MODE, 3, 2>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
+        else launch_main<MODE, 4, 2>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
+    } else {
+        if (groups <= 32) launch_main<MODE, 1, 16>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
+        else if (groups <= 64) launch_main<MODE, 2, 8>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
+        else if (groups <= 96) launch_main<MODE, 3, 4>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
+        else launch_main<MODE, 4, 4>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
+    }
     const int64_t hub_begin = a.range ? a.range[2] : 0, hub_end = a.range ? a.range[3] : n_hubs;
     if (a.range && (a.range[0] < 0 || a.range[1] > n_items || a.range[2] < 0 || a.range[3] > n_hubs))
         return fail(PLAGNN_ERR_ARG, name, "row range outside the plan");

@@ -16,7 +16,9 @@ pytestmark = pytest.mark.gpu
 def test_spmm_row_ranges_tile_the_full_result(cuda):
     n, e, f = 3000, 90000, 96
     sg = synth.scaled_graph(n, e, seed=3, max_degree=4000)
-    g = P.graph((sg.src.numpy(), sg.dst.numpy()), num_nodes=n).to(cuda)
+    g = P.graph((sg.src.numpy(), sg.dst.numpy()), num_nodes=n)
+    g.chunk = 64
+    g = g.to(cuda)
     csc = g.csc()
     assert csc.counts[1] > 0                               # some rows are split over chunks
     x = ops.aligned(torch.randn(n, f, device=cuda))

@@ -52,7 +52,9 @@ def make_simple(cuda, n, e, seed):
     from plagnn_b200 import synth
     src, dst = synth.powerlaw_edges(n, e, 2.0, seed)
     src, dst = src.numpy().astype(np.int32), dst.numpy().astype(np.int32)
-    g = P.graph((src, dst), num_nodes=n).add_self_loop().to(cuda)
+    g = P.graph((src, dst), num_nodes=n)
+    g.chunk = 64                                      # small chunks so that some rows are split even on small graphs
+    g = g.add_self_loop().to(cuda)
     so, do = orc.add_self_loop(src.astype(np.int64), dst.astype(np.int64), n)
     return g, orc.OracleGraph(so, do, n)
 
