@@ -40,7 +40,7 @@ enum {
 };
 
 enum { PLAGNN_ACT_NONE = 0, PLAGNN_ACT_RELU = 1, PLAGNN_ACT_LEAKY = 2, PLAGNN_ACT_SIGMOID = 3 };
-enum { PLAGNN_GEMM_AUTO = 0, PLAGNN_GEMM_SIMT = 1, PLAGNN_GEMM_TCGEN05 = 2 };
+enum { PLAGNN_GEMM_AUTO = 0, PLAGNN_GEMM_SIMT = 1, PLAGNN_GEMM_TCGEN05 = 2, PLAGNN_GEMM_TMA = 3 };
 enum { PLAGNN_REDUCE_SUM = 0, PLAGNN_REDUCE_MAX = 1 };
 
 int plagnn_version(void);
@@ -170,6 +170,28 @@ int plagnn_gemm(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pa
                 const float* gate, int64_t ldg, int gate_act,
                 float* c, int64_t ldc, void* workspace, size_t workspace_bytes,
                 int backend, plagnn_stream_t stream);
+
+/* The same contraction with TMA-fed operands (backend PLAGNN_GEMM_TMA, what AUTO picks when shapes allow).
+ * The tensor core reads an fp32 word as tf32 by dropping its low 13 bits, so the fp32 matrix itself is the "hi" part
+ * of the 3xTF32 split and the only derived data is the COMPANION matrix
+ *     lo = rn_tf32(x - trunc_tf32(x))          (plagnn_tf32_lo, or written by the producer's epilogue: c_lo below)
+ * stored like x (same shape and storage order, own pitch).  plagnn_gemm() derives the companions itself into its
+ * workspace on every call; plagnn_gemm_ex() takes them from the caller, which is how the whole-network engine
+ * (plagnn_gnn32_*) avoids that pass.  c_lo (optional, pitch ldc) receives the companion of the output.
+ * Same reference call sites as plagnn_gemm. */
+typedef struct {
+    const float* a; const float* a_lo; int64_t lda; int64_t lda_lo; int32_t a_trans;
+    const float* b; const float* b_lo; int64_t ldb; int64_t ldb_lo; int32_t b_trans;
+    int64_t k;
+} plagnn_gemm_pair_ex;
+size_t plagnn_gemm_ex_workspace_bytes(int64_t m, int64_t n, int64_t k_total);
+int plagnn_gemm_ex(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair_ex* pairs /* host */,
+                   const float* bias, int act, float slope,
+                   const float* gate, int64_t ldg, int gate_act,
+                   float* c, float* c_lo, int64_t ldc, void* workspace, size_t workspace_bytes,
+                   plagnn_stream_t stream);
+int plagnn_tf32_lo(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* lo, int64_t ldlo,
+                   plagnn_stream_t stream);
 
 /* column sums: out[j] = sum_i x[i,j]   (bias gradients). workspace >= plagnn_colsum_workspace_bytes. */
 size_t plagnn_colsum_workspace_bytes(int64_t rows, int64_t cols);

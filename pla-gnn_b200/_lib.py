@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG, "libplagnn.so")
 
 OK = 0
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
-GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_TMA = 0, 1, 2, 3
 REDUCE_SUM, REDUCE_MAX = 0, 1
 GEMM_MAX_PAIRS = 2
 
@@ -25,6 +25,12 @@ class PlagnnError(RuntimeError):
 class GemmPair(Structure):
     _fields_ = [("a", c_void_p), ("lda", c_int64), ("a_trans", c_int32),
                 ("b", c_void_p), ("ldb", c_int64), ("b_trans", c_int32),
+                ("k", c_int64)]
+
+
+class GemmPairEx(Structure):
+    _fields_ = [("a", c_void_p), ("a_lo", c_void_p), ("lda", c_int64), ("lda_lo", c_int64), ("a_trans", c_int32),
+                ("b", c_void_p), ("b_lo", c_void_p), ("ldb", c_int64), ("ldb_lo", c_int64), ("b_trans", c_int32),
                 ("k", c_int64)]
 
 
@@ -71,6 +77,10 @@ PROTOTYPES = {
     "plagnn_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "plagnn_gemm": (c_int, [c_int64, c_int64, c_int32, POINTER(GemmPair), c_void_p, c_int, c_float,
                             c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_size_t, c_int, c_void_p]),
+    "plagnn_gemm_ex_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "plagnn_gemm_ex": (c_int, [c_int64, c_int64, c_int32, POINTER(GemmPairEx), c_void_p, c_int, c_float,
+                               c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "plagnn_tf32_lo": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "plagnn_colsum_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "plagnn_colsum": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "plagnn_act_backward": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_float,

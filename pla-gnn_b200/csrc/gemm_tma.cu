@@ -1,0 +1,620 @@
+// K3 (second generation) — dense feature x weight contraction: TMA-fed tcgen05 with CTA pairs, sm_100a.
+//
+// Replaces the cuBLAS SGEMMs behind nn.Linear in code/model.py:16-17,20-28 (fc_pool / fc_self / fc_neigh inside
+// SAGEConv, liner1, liner2) and their autograd backward, like gemm_tc.cu, but without any SIMT work in the main loop.
+//
+// fp32-level accuracy on TF32 tensor cores (3xTF32):  x = hi + lo,  x*y ~ hi*hi + lo*hi + hi*lo.
+// Measured on B200 (tools/mma_probe.cu): the tensor core TRUNCATES an fp32 word to tf32 (drops the low 13 bits).
+// So the raw fp32 matrix IS the "hi" operand, and the only derived data is the companion matrix
+//     lo = rn_tf32(x - trunc_tf32(x))
+// which the producer of x writes next to it (GEMM epilogue, plagnn_tf32_lo).  All four operand tiles
+// (A, A_lo, B, B_lo) are brought in by TMA straight into the swizzled layouts the UMMA descriptors read:
+//     k-contiguous operand  : box {32 k, 128 rows}, SWIZZLE_128B                  (K-major descriptor)
+//     mn-contiguous operand : 4 boxes {32 mn, 32 k}, SWIZZLE_128B_ATOM_32B         (MN-major descriptor)
+// Out-of-bounds parts of a box read as zero, which handles every K / M / N tail.
+//
+// CTA pair (cta_group::2, cluster 2x1x1): one 256 x 256 output tile per pair.  Each CTA stages its own 128 rows of A
+// and its own half (128 rows) of B; the leader CTA issues 256x256x8 MMAs that read both CTAs' shared memory; the
+// accumulators (hi*hi in TMEM columns [0,256), lo*hi + hi*lo in [256,512)) live in each CTA's tensor memory for its
+// 128 rows.  Per CTA and k-block of 32: 64 KB by TMA for 12 MMAs of 128 cycles each: 43 B/clk from L2 and
+// 64 B/clk of operand reads from shared memory, where a 128 x 128 single-CTA tile needs 85 and 128.
+// CG = 1 (128 x 128 tile, one CTA) is kept for bring-up and as a cross-check.
+//
+// Warps: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue (TMEM -> registers -> global).
+#include "common.cuh"
+#include <cuda.h>
+#include <cstdlib>
+#include <cstring>
+#include <climits>
+#include <unordered_map>
+#include <string>
+
+namespace plagnn {
+
+constexpr int TM_BK = 32, TM_STAGES = 3;
+constexpr int TM_PART_BYTES = 128 * TM_BK * 4;           // 16 KB: 128 rows x 32 fp32
+constexpr int TM_STAGE_BYTES = 4 * TM_PART_BYTES;        // A, A_lo, B, B_lo
+constexpr int TM_SMEM_BYTES = TM_STAGES * TM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TM_EPI_WARPS = 8;
+constexpr int TM_THREADS = (2 + TM_EPI_WARPS) * 32;
+constexpr int TM_MAX_CHAIN = 40;    // k-blocks per TMEM accumulation chain (see gemm_tc.cu: truncating accumulate)
+
+struct alignas(64) TmParams {
+    CUtensorMap map[PLAGNN_GEMM_MAX_PAIRS][4];    // [pair][A, A_lo, B, B_lo]
+    int64_t m, n;
+    int npairs;
+    int kblocks[PLAGNN_GEMM_MAX_PAIRS];
+    int total_kblocks, kblocks_per_split, splits;
+    const float* bias;
+    int act;
+    float slope;
+    const float* gate;
+    int64_t ldg;
+    int gate_act;
+    float* c;
+    float* c_lo;
+    int64_t ldc;
+    float* partial;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+namespace tm {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void prefetch_map(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+    if (CG == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// arrive on `bar` (same shared offset in every CTA of the pair) when all MMAs issued so far have completed
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    if (CG == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    if (CG == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+// 2-D tiled TMA load into this CTA's shared memory; completion bytes go to `bar` (a shared::cluster address, which for
+// CG = 2 is the LEADER CTA's barrier)
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    if (CG == 1)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// MN-major operand as four TMA boxes {32 mn, 32 k} with SWIZZLE_128B_ATOM_32B: swizzle atom = 4 k-rows x 128 bytes;
+// the atoms of one box (k-groups of 4) are 512 bytes apart (SBO), boxes (32 mn each) 4096 bytes apart (LBO).
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((4096u >> 4) << 16);
+    const uint32_t hi = (512u >> 4) | (1u << 14) | (1u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// kind::tf32, D = f32; bit 15 / 16 = A / B stored MN-major
+__device__ __forceinline__ uint32_t make_idesc(uint32_t m, uint32_t n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) | ((n >> 3) << 17) |
+           ((m >> 4) << 24);
+}
+}  // namespace tm
+
+// lo = rn_tf32(x - trunc_tf32(x)) : what the tensor core does not see of x, on the tf32 grid (finite inputs)
+__device__ __forceinline__ float tf32_lo(float x) {
+    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    return __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
+}
+
+__device__ __forceinline__ float tm_epilogue_one(const TmParams& P, float v, int64_t r, int64_t c) {
+    if (P.bias) v += __ldg(P.bias + c);
+    v = apply_act(v, P.act, P.slope);
+    if (P.gate) v *= act_grad_from_output(__ldg(P.gate + r * P.ldg + c), P.gate_act, P.slope);
+    return v;
+}
+
+template <int CG, bool AT, bool BT>
+__global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_constant__ TmParams P) {
+    using namespace tm;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles = (raw + 1023u) & ~1023u;                  // 1024-byte aligned (swizzle atoms)
+    const uint32_t bars = tiles + TM_STAGES * TM_STAGE_BYTES;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * TM_STAGES, bar_acc = bars + 16 * TM_STAGES;
+    const uint32_t tmem_slot = bar_acc + 8;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    constexpr int TILE_M = 128 * CG, TILE_N = 128 * CG;
+    constexpr uint32_t TMEM_COLS = 2 * TILE_N;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int64_t m0 = (int64_t)(blockIdx.x / CG) * TILE_M, n0 = (int64_t)blockIdx.y * TILE_N;
+    const int split = blockIdx.z;
+    const int kb_beg = split * P.kblocks_per_split;
+    const int kb_end = min(P.total_kblocks, kb_beg + P.kblocks_per_split);
+    const int nkb = kb_end - kb_beg;
+    // columns of this tile that exist, rounded to what one MMA can produce (CG = 2: both halves multiples of 32)
+    const int64_t nrem = P.n - n0;
+    const uint32_t n_eff = nrem >= TILE_N ? (uint32_t)TILE_N : (uint32_t)((nrem + 32 * CG - 1) / (32 * CG) * (32 * CG));
+    const uint32_t n_half = n_eff / CG;       // rows of B this CTA stages
+
+    if (t == 0) {
+        for (int s = 0; s < TM_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        fence_mbar_init();
+#pragma unroll
+        for (int p = 0; p < PLAGNN_GEMM_MAX_PAIRS; ++p)
+            if (p < P.npairs)
+                for (int q = 0; q < 4; ++q) prefetch_map(&P.map[p][q]);
+    }
+    if (warp == 1) tmem_alloc<CG>(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer (one elected lane) =================
+        if (lane == 0) {
+            const uint32_t full0 = CG == 2 ? mapa(bar_full, 0) : bar_full;    // the leader's barriers collect both CTAs' bytes
+            const int a_row = (int)(m0 + rank * 128), b_row = (int)(n0 + rank * n_half);
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % TM_STAGES;
+                const uint32_t ph = (uint32_t)((it / TM_STAGES) & 1);
+                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                int p = 0, local = kb_beg + it;
+                if (P.npairs > 1 && local >= P.kblocks[0]) { local -= P.kblocks[0]; p = 1; }
+                const int k0 = local * TM_BK;
+                const uint32_t st = tiles + s * TM_STAGE_BYTES;
+                const uint32_t fb = full0 + 8 * s;
+                if (rank == 0) mbar_expect_tx(bar_full + 8 * s, CG * TM_STAGE_BYTES);
+                if (!AT) {
+                    tma_load_2d<CG>(st, &P.map[p][0], k0, a_row, fb);
+                    tma_load_2d<CG>(st + TM_PART_BYTES, &P.map[p][1], k0, a_row, fb);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        tma_load_2d<CG>(st + j * 4096, &P.map[p][0], a_row + 32 * j, k0, fb);
+                        tma_load_2d<CG>(st + TM_PART_BYTES + j * 4096, &P.map[p][1], a_row + 32 * j, k0, fb);
+                    }
+                }
+                if (!BT) {
+                    tma_load_2d<CG>(st + 2 * TM_PART_BYTES, &P.map[p][2], k0, b_row, fb);
+                    tma_load_2d<CG>(st + 3 * TM_PART_BYTES, &P.map[p][3], k0, b_row, fb);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        tma_load_2d<CG>(st + 2 * TM_PART_BYTES + j * 4096, &P.map[p][2], b_row + 32 * j, k0, fb);
+                        tma_load_2d<CG>(st + 3 * TM_PART_BYTES + j * 4096, &P.map[p][3], b_row + 32 * j, k0, fb);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer (one elected lane of the leader CTA) =================
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = make_idesc(TILE_M, n_eff, AT, BT);
+            // descriptor start-address step per K = 8: 32 bytes inside a K-major row; two k-groups of 512 bytes if MN-major
+            constexpr uint64_t a_step = AT ? (1024u >> 4) : 2u, b_step = BT ? (1024u >> 4) : 2u;
+            const uint32_t acc_main = tmem_base, acc_corr = tmem_base + TILE_N;
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % TM_STAGES;
+                const uint32_t ph = (uint32_t)((it / TM_STAGES) & 1);
+                mbar_wait(bar_full + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t st = tiles + s * TM_STAGE_BYTES;
+                const uint64_t a_hi = AT ? desc_mnmajor(st) : desc_kmajor(st);
+                const uint64_t a_lo = AT ? desc_mnmajor(st + TM_PART_BYTES) : desc_kmajor(st + TM_PART_BYTES);
+                const uint64_t b_hi = BT ? desc_mnmajor(st + 2 * TM_PART_BYTES) : desc_kmajor(st + 2 * TM_PART_BYTES);
+                const uint64_t b_lo = BT ? desc_mnmajor(st + 3 * TM_PART_BYTES) : desc_kmajor(st + 3 * TM_PART_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < TM_BK / 8; ++kk) {
+                    const uint64_t adv_a = (uint64_t)kk * a_step, adv_b = (uint64_t)kk * b_step;
+                    // corrections go to their own accumulator: the tensor core adds into TMEM with truncation, and the
+                    // main accumulator then sees a third of the additions (gemm_tc.cu has the measurements)
+                    const uint32_t acc_on = (it | kk) ? 1u : 0u;
+                    umma_tf32<CG>(acc_corr, a_lo + adv_a, b_hi + adv_b, idesc, acc_on);
+                    umma_tf32<CG>(acc_corr, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
+                    umma_tf32<CG>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
+                }
+                umma_commit<CG>(bar_empty + 8 * s);     // frees the stage in both CTAs when these MMAs have read it
+            }
+            umma_commit<CG>(bar_acc);                   // accumulators complete (both CTAs)
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue: TMEM -> registers -> global =================
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        const int lg = warp & 3;                        // TMEM lane group this warp may read (warp % 4)
+        const int chalf = (warp - 2) >> 2;              // column half of the tile
+        const int64_t r = m0 + rank * 128 + lg * 32 + lane;
+        const bool direct = P.splits == 1;
+        float* dst = direct ? P.c : P.partial + (int64_t)split * P.m * P.n;
+        const int64_t ldd = direct ? P.ldc : P.n;
+        const bool vec_out = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+        float* dlo = direct ? P.c_lo : nullptr;
+        constexpr int CHUNKS = TILE_N / 32 / 2;
+#pragma unroll 1
+        for (int ch = 0; ch < CHUNKS; ++ch) {
+            const int cbase = (chalf * CHUNKS + ch) * 32;
+            if (cbase >= (int)n_eff || n0 + cbase >= P.n) break;     // warp-uniform
+            uint32_t acc[32], acc_small[32];
+            const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)cbase;
+            tmem_ld32(ta, acc);
+            tmem_ld32(ta + TILE_N, acc_small);
+            tmem_ld_wait();
+            if (r < P.m) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int64_t c = n0 + cbase + 4 * q;
+                    if (c >= P.n) break;
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        v[e] = __uint_as_float(acc[4 * q + e]) + __uint_as_float(acc_small[4 * q + e]);
+                        if (direct && c + e < P.n) v[e] = tm_epilogue_one(P, v[e], r, c + e);
+                    }
+                    if (vec_out && c + 3 < P.n) {
+                        *reinterpret_cast<float4*>(dst + r * ldd + c) = make_float4(v[0], v[1], v[2], v[3]);
+                        if (dlo)
+                            *reinterpret_cast<float4*>(dlo + r * ldd + c) =
+                                make_float4(tf32_lo(v[0]), tf32_lo(v[1]), tf32_lo(v[2]), tf32_lo(v[3]));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (c + e < P.n) {
+                                dst[r * ldd + c + e] = v[e];
+                                if (dlo) dlo[r * ldd + c + e] = tf32_lo(v[e]);
+                            }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+    }
+}
+
+// ordered reduction of split-K partials + epilogue (+ companion)
+__global__ void __launch_bounds__(256) gemm_tma_reduce_kernel(const __grid_constant__ TmParams P) {
+    const int64_t total = P.m * P.n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int z = 0; z < P.splits; ++z) s += P.partial[(int64_t)z * total + i];
+        const int64_t r = i / P.n, c = i - r * P.n;
+        const float v = tm_epilogue_one(P, s, r, c);
+        P.c[r * P.ldc + c] = v;
+        if (P.c_lo) P.c_lo[r * P.ldc + c] = tf32_lo(v);
+    }
+}
+
+// companion matrix of an fp32 matrix (same pitch conventions as the source; columns [cols, ldlo) are not touched)
+__global__ void __launch_bounds__(256) tf32_lo_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int64_t cols,
+                                                      float* __restrict__ lo, int64_t ldlo, int vec) {
+    if (vec) {
+        const int64_t c4 = cols >> 2, total = rows * c4;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = i / c4, q = i - r * c4;
+            const float4 v = ldg_f4(x + r * ldx + 4 * q);
+            *reinterpret_cast<float4*>(lo + r * ldlo + 4 * q) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+        }
+    } else {
+        const int64_t total = rows * cols;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = i / cols, c = i - r * cols;
+            lo[r * ldlo + c] = tf32_lo(__ldg(x + r * ldx + c));
+        }
+    }
+}
+
+int tf32_lo_launch(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* lo, int64_t ldlo, cudaStream_t st) {
+    // whole padded rows when both pitches allow it: the pad columns of x are finite (zero) by the library's convention
+    int64_t c = cols;
+    const bool al = aligned16(x) && aligned16(lo) && (ldx & 3) == 0 && (ldlo & 3) == 0;
+    const int64_t c_up = (cols + 3) / 4 * 4;
+    const int vec = al && c_up <= ldx && c_up <= ldlo;
+    if (vec) c = c_up;
+    const int64_t work = vec ? rows * (c >> 2) : rows * c;
+    int64_t g = ceil_div(work, 256);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    tf32_lo_kernel<<<(unsigned)g, 256, 0, st>>>(x, ldx, rows, c, lo, ldlo, vec);
+    return check_launch("tf32_lo");
+}
+
+// ---- host side: tensor maps ---------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+struct MapKey {
+    const void* base;
+    int64_t inner, outer, pitch;
+    int mn_major;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && inner == o.inner && outer == o.outer && pitch == o.pitch && mn_major == o.mn_major;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.base);
+        h = h * 1315423911u ^ (size_t)k.inner;
+        h = h * 1315423911u ^ (size_t)k.outer;
+        h = h * 1315423911u ^ (size_t)k.pitch;
+        return h * 2 + (size_t)k.mn_major;
+    }
+};
+
+// operand stored [outer][inner] fp32 with row pitch `pitch` elements.  k-contiguous operands: inner = k, box {32, 128}.
+// mn-contiguous operands: inner = mn, box {32, 32}.  Encodings are cached per thread (the arena pointers of the
+// whole-network engine repeat every epoch).
+static int get_map(CUtensorMap* out, const float* base, int64_t inner, int64_t outer, int64_t pitch, int mn_major) {
+    static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{base, inner, outer, pitch, mn_major};
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return PLAGNN_OK;
+    }
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(PLAGNN_ERR_CUDA, "gemm_tma", "cuTensorMapEncodeTiled not available");
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+    cuuint32_t box[2] = {32u, mn_major ? 32u : 128u};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("gemm_tma: cuTensorMapEncodeTiled failed (%d) base=%p inner=%lld outer=%lld pitch=%lld", (int)r, (const void*)base,
+                  (long long)inner, (long long)outer, (long long)pitch);
+        return PLAGNN_ERR_CUDA;
+    }
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, m);
+    *out = m;
+    return PLAGNN_OK;
+}
+
+// PLAGNN_TMA_CG=1 selects the single-CTA 128 x 128 tile (bring-up / cross-check); read per call so tests can flip it
+static int tm_cg() {
+    const char* e = getenv("PLAGNN_TMA_CG");
+    return (e && e[0] == '1') ? 1 : 2;
+}
+
+static int tm_choose_splits(int64_t m, int64_t n, int total_kblocks, int cg) {
+    const int64_t tile = 128 * cg;
+    const int64_t tiles = ceil_div(m, tile) * ceil_div(n, tile);
+    const int64_t units = sm_count() / cg;          // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
+    int64_t s = 1;
+    if (tiles < units && total_kblocks >= 8) {
+        s = units / tiles;
+        if (s > total_kblocks / 4) s = total_kblocks / 4;
+        if (s > 64) s = 64;
+        if (s < 1) s = 1;
+    }
+    const int64_t for_accuracy = ceil_div(total_kblocks, TM_MAX_CHAIN);
+    int64_t s0 = s > for_accuracy ? s : for_accuracy;
+    if (s0 > 1) {
+        int64_t best = s0, best_cost = INT64_MAX;
+        const int64_t lo = (s0 > 1 && ceil_div(total_kblocks, s0 - 1) <= 48) ? s0 - 1 : s0;
+        for (int64_t c = lo; c <= s0 + 8 && c <= total_kblocks; ++c) {
+            const int64_t cost = ceil_div(tiles * c, units) * (ceil_div(total_kblocks, c) + 4);   // +4: prologue/epilogue
+            if (cost < best_cost) { best_cost = cost; best = c; }
+        }
+        s0 = best;
+    }
+    return (int)s0;
+}
+
+size_t gemm_tma_partial_bytes(int64_t m, int64_t n, int64_t k_total) {
+    const int kb = (int)ceil_div(k_total, TM_BK);
+    int s = 1;
+    for (int cg = 1; cg <= 2; ++cg)
+        for (int extra = 0; extra <= PLAGNN_GEMM_MAX_PAIRS; ++extra) {
+            const int c = tm_choose_splits(m, n, kb + extra, cg);
+            s = c > s ? c : s;
+        }
+    return s > 1 ? align_up((size_t)s * (size_t)m * (size_t)n * sizeof(float), 256) : 0;
+}
+
+bool gemm_tma_eligible(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair_ex* pairs) {
+    if (n < 16 || m < 1) return false;
+    for (int p = 0; p < npairs; ++p) {
+        const plagnn_gemm_pair_ex& q = pairs[p];
+        if (q.k < 8) return false;
+        if ((q.lda & 3) || (q.ldb & 3) || !aligned16(q.a) || !aligned16(q.b)) return false;
+        if ((q.lda_lo & 3) || (q.ldb_lo & 3) || !aligned16(q.a_lo) || !aligned16(q.b_lo)) return false;
+        if ((q.a_trans != 0) != (pairs[0].a_trans != 0) || (q.b_trans != 0) != (pairs[0].b_trans != 0)) return false;
+        if (q.k > INT_MAX - 64 || m > INT_MAX - 512 || n > INT_MAX - 512) return false;
+    }
+    return true;
+}
+
+// Every pair must carry its companions (a_lo / b_lo with their own pitches).
+int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair_ex* pairs, const float* bias, int act,
+                    float slope, const float* gate, int64_t ldg, int gate_act, float* c, float* c_lo, int64_t ldc,
+                    void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    TmParams P;
+    memset(&P, 0, sizeof(P));
+    P.m = m; P.n = n; P.npairs = npairs;
+    P.total_kblocks = 0;
+    for (int p = 0; p < npairs; ++p) {
+        const plagnn_gemm_pair_ex& q = pairs[p];
+        if (!q.a_lo || !q.b_lo) return fail(PLAGNN_ERR_ARG, "gemm_tma", "missing tf32 companion operand");
+        P.kblocks[p] = (int)ceil_div(q.k, TM_BK);
+        P.total_kblocks += P.kblocks[p];
+        int rc;
+        if (!q.a_trans) {
+            if ((rc = get_map(&P.map[p][0], q.a, q.k, m, q.lda, 0))) return rc;
+            if ((rc = get_map(&P.map[p][1], q.a_lo, q.k, m, q.lda_lo, 0))) return rc;
+        } else {
+            if ((rc = get_map(&P.map[p][0], q.a, m, q.k, q.lda, 1))) return rc;
+            if ((rc = get_map(&P.map[p][1], q.a_lo, m, q.k, q.lda_lo, 1))) return rc;
+        }
+        if (!q.b_trans) {
+            if ((rc = get_map(&P.map[p][2], q.b, q.k, n, q.ldb, 0))) return rc;
+            if ((rc = get_map(&P.map[p][3], q.b_lo, q.k, n, q.ldb_lo, 0))) return rc;
+        } else {
+            if ((rc = get_map(&P.map[p][2], q.b, n, q.k, q.ldb, 1))) return rc;
+            if ((rc = get_map(&P.map[p][3], q.b_lo, n, q.k, q.ldb_lo, 1))) return rc;
+        }
+    }
+    P.bias = bias; P.act = act; P.slope = slope; P.gate = gate; P.ldg = ldg; P.gate_act = gate_act;
+    P.c = c; P.c_lo = c_lo; P.ldc = ldc;
+    const int cg = tm_cg();
+    const int splits = tm_choose_splits(m, n, P.total_kblocks, cg);
+    if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * m * n * sizeof(float)))
+        return fail(PLAGNN_ERR_WORKSPACE, "gemm_tma", "split-K workspace too small (see plagnn_gemm_workspace_bytes)");
+    P.kblocks_per_split = (int)ceil_div(P.total_kblocks, splits);
+    P.splits = (int)ceil_div(P.total_kblocks, P.kblocks_per_split);
+    P.partial = P.splits > 1 ? (float*)workspace : nullptr;
+
+    using KernelFn = void (*)(const TmParams);
+    static const KernelFn kernels[8] = {
+        gemm_tma_kernel<1, false, false>, gemm_tma_kernel<1, false, true>, gemm_tma_kernel<1, true, false>, gemm_tma_kernel<1, true, true>,
+        gemm_tma_kernel<2, false, false>, gemm_tma_kernel<2, false, true>, gemm_tma_kernel<2, true, false>, gemm_tma_kernel<2, true, true>};
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
+        for (int i = 0; i < 8; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BYTES);
+            if (e != cudaSuccess) {
+                set_error("gemm_tma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+                return PLAGNN_ERR_CUDA;
+            }
+        }
+        attr_dev = dev;
+    }
+    const int kidx = (cg == 2 ? 4 : 0) + (pairs[0].a_trans ? 2 : 0) + (pairs[0].b_trans ? 1 : 0);
+    const int64_t tile = 128 * cg;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ceil_div(m, tile) * cg), (unsigned)ceil_div(n, tile), (unsigned)P.splits);
+    cfg.blockDim = dim3(TM_THREADS);
+    cfg.dynamicSmemBytes = TM_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernels[kidx], P);
+    if (e != cudaSuccess) {
+        set_error("gemm_tma: launch: %s", cudaGetErrorString(e));
+        return PLAGNN_ERR_CUDA;
+    }
+    if (P.splits > 1) {
+        const int64_t total = m * n;
+        const int g = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 8 ? ceil_div(total, 256) : (int64_t)sm_count() * 8);
+        gemm_tma_reduce_kernel<<<g, 256, 0, st>>>(P);
+    }
+    return check_launch("gemm_tma", P.splits > 1 ? 2 : 1);
+}
+
+}  // namespace plagnn

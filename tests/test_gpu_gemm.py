@@ -44,10 +44,11 @@ def operand(rows, k, trans, dev, seed, pad):
     return t.to(dev)        # contiguous: pitch = cols (unaligned when cols % 4 != 0)
 
 
-BACKENDS = [ops.GEMM_SIMT, ops.GEMM_TCGEN05]
+BACKENDS = [ops.GEMM_SIMT, ops.GEMM_TCGEN05, ops.GEMM_TMA]
+IDS = ["simt", "tcgen05", "tma"]
 
 
-@pytest.mark.parametrize("backend", BACKENDS, ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("backend", BACKENDS, ids=IDS)
 @pytest.mark.parametrize("m,n,k", [(128, 128, 32), (300, 200, 100), (1000, 503, 503), (257, 100, 200), (128, 16, 8),
                                    (2500, 400, 12)])
 @pytest.mark.parametrize("at,bt", [(0, 0), (0, 1), (1, 1), (1, 0)])
@@ -59,14 +60,15 @@ def test_gemm_layouts(cuda, backend, m, n, k, at, bt):
     assert rel(got, ref_gemm(pairs, None, 0, None, 0)) < TOL
 
 
-@pytest.mark.parametrize("backend", BACKENDS, ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("backend", BACKENDS, ids=IDS)
 def test_gemm_unaligned_operands_and_output(cuda, backend):
     m, n, k = 333, 503, 503
     a = operand(m, k, 0, cuda, 3, pad=False)           # pitch 503: scalar load path
     b = operand(n, k, 0, cuda, 4, pad=False)
     out = torch.empty(m, n, device=cuda)               # pitch 503: scalar store path
     pairs = [(a, 0, b, 0, k)]
-    if backend == ops.GEMM_TCGEN05:
+    backend0 = backend
+    if backend in (ops.GEMM_TCGEN05, ops.GEMM_TMA):
         # the tensor-core path takes 16-byte aligned operands only: explicit request fails loudly, AUTO uses FFMA
         import plagnn_b200 as P
         with pytest.raises(P.PlagnnError):
@@ -77,11 +79,11 @@ def test_gemm_unaligned_operands_and_output(cuda, backend):
     # aligned operands, unaligned output pitch: tensor-core kernel with the scalar store epilogue
     out2 = torch.empty(m, n, device=cuda)
     pairs2 = [(ops.aligned(a), 0, ops.aligned(b), 0, k)]
-    ops.gemm(m, n, pairs2, out=out2, backend=ops.GEMM_TCGEN05 if backend != ops.GEMM_SIMT else backend)
+    ops.gemm(m, n, pairs2, out=out2, backend=backend0)
     assert rel(out2, ref_gemm(pairs, None, 0, None, 0)) < TOL
 
 
-@pytest.mark.parametrize("backend", BACKENDS, ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("backend", BACKENDS, ids=IDS)
 @pytest.mark.parametrize("act,gate_act", [(ops.ACT_RELU, 0), (ops.ACT_LEAKY, 0), (ops.ACT_SIGMOID, 0),
                                           (0, ops.ACT_LEAKY), (0, ops.ACT_RELU), (0, ops.ACT_SIGMOID)])
 def test_gemm_two_pairs_and_epilogues(cuda, backend, act, gate_act):
@@ -101,7 +103,7 @@ def test_gemm_two_pairs_and_epilogues(cuda, backend, act, gate_act):
     assert rel(got, want) < TOL
 
 
-@pytest.mark.parametrize("backend", BACKENDS, ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("backend", BACKENDS, ids=IDS)
 def test_gemm_weight_gradient_shape_split_k(cuda, backend):
     # dW[400 x 503] = dZ^T[400 x 24041] X[24041 x 503]: few output tiles, long K -> split-K path
     nodes, o, f = 24041, 400, 503
@@ -133,3 +135,62 @@ def test_tcgen05_and_simt_agree_on_ppi_layer_shape(cuda):
     s = ops.gemm(n, f, pairs, bias=bias, act=ops.ACT_RELU, backend=ops.GEMM_SIMT)
     t = ops.gemm(n, f, pairs, bias=bias, act=ops.ACT_RELU, backend=ops.GEMM_TCGEN05)
     assert ((s - t).abs().max() / s.abs().max()).item() < TOL
+
+
+# ---- TMA-fed kernel: both tile configurations, caller-provided companions, companion of the output ----
+@pytest.fixture(params=["1", "2"], ids=["cg1", "cg2"])
+def cta_group(request, monkeypatch):
+    monkeypatch.setenv("PLAGNN_TMA_CG", request.param)
+    return request.param
+
+
+def tf32_lo_ref(x):
+    b = x.cpu().contiguous().view(torch.int32)
+    hi = (b & -8192).view(torch.float32)
+    d = (x.cpu() - hi).contiguous().view(torch.int32)
+    return ((d + 0x1000) & -8192).view(torch.float32)
+
+
+def test_tf32_lo_bit_exact(cuda):
+    x = ops.aligned(torch.randn(333, 503, generator=torch.Generator().manual_seed(11)).to(cuda) * 37.0)
+    lo = ops.tf32_lo(x)
+    assert torch.equal(lo.cpu()[:, :503], tf32_lo_ref(x)[:, :503])
+    # hi + lo reproduces x to 2^-21 |x| and lo is on the tf32 grid
+    hi = (x.cpu().contiguous().view(torch.int32) & -8192).view(torch.float32)
+    assert ((hi + lo.cpu() - x.cpu()).abs() <= x.cpu().abs() * 2.0 ** -21).all()
+    assert ((lo.cpu().contiguous().view(torch.int32) & 8191) == 0).all()
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 32), (256, 256, 64), (300, 200, 100), (1000, 503, 503), (257, 100, 200),
+                                   (128, 16, 8), (2500, 400, 12), (513, 300, 1000)])
+@pytest.mark.parametrize("at,bt", [(0, 0), (0, 1), (1, 1), (1, 0)])
+def test_gemm_tma_layouts_both_tile_configs(cuda, cta_group, m, n, k, at, bt):
+    a = operand(m, k, at, cuda, 1, pad=True)
+    b = operand(n, k, bt, cuda, 2, pad=True)
+    pairs = [(a, at, b, bt, k)]
+    got = ops.gemm(m, n, pairs, backend=ops.GEMM_TMA)
+    assert rel(got, ref_gemm(pairs, None, 0, None, 0)) < TOL
+
+
+def test_gemm_ex_companions_two_pairs_and_output_companion(cuda, cta_group):
+    m, n, k1, k2 = 700, 300, 400, 200
+    a1, b1 = operand(m, k1, 0, cuda, 5, True), operand(n, k1, 0, cuda, 6, True).mul_(k1 ** -0.5)
+    a2, b2 = operand(m, k2, 0, cuda, 7, True), operand(n, k2, 0, cuda, 8, True).mul_(k2 ** -0.5)
+    bias = torch.randn(n, device=cuda)
+    out = ops.alloc(m, n, cuda)
+    out_lo = ops.alloc(m, n, cuda)
+    ex = [(a1, ops.tf32_lo(a1), 0, b1, ops.tf32_lo(b1), 0, k1), (a2, ops.tf32_lo(a2), 0, b2, ops.tf32_lo(b2), 0, k2)]
+    ops.gemm_ex(m, n, ex, bias=bias, act=ops.ACT_LEAKY, out=out, out_lo=out_lo)
+    want = ref_gemm([(a1, 0, b1, 0, k1), (a2, 0, b2, 0, k2)], bias, ops.ACT_LEAKY, None, 0)
+    assert rel(out, want) < TOL
+    assert torch.equal(out_lo.cpu(), tf32_lo_ref(out))
+
+
+def test_gemm_tma_weight_gradient_split_k_both_tile_configs(cuda, cta_group):
+    nodes, o, f = 24041, 400, 503
+    dz = ops.aligned(torch.randn(nodes, o, generator=torch.Generator().manual_seed(1)).to(cuda))
+    x = ops.aligned(torch.randn(nodes, f, generator=torch.Generator().manual_seed(2)).to(cuda))
+    out = torch.empty(o, f, device=cuda)
+    pairs = [(dz, 1, x, 1, nodes)]
+    ops.gemm(o, f, pairs, out=out, backend=ops.GEMM_TMA)
+    assert rel(out, ref_gemm(pairs, None, 0, None, 0)) < TOL

@@ -1,9 +1,57 @@
-import os, sys
+"""GEMM backends on the PPI layer shapes: old in-kernel-split tcgen05 kernel vs the TMA-fed kernel (with the companion
+pre-pass of plagnn_gemm, and through plagnn_gemm_ex with companions resident).  CUDA events, warm.
+    python tools/gemm_bench.py [cg]  > gpurun_out/gemm_bench.log"""
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+
 from plagnn_b200 import ops
-from tools.microbench import gemm_case
+
+dev = torch.device("cuda:0")
+if len(sys.argv) > 1:
+    os.environ["PLAGNN_TMA_CG"] = sys.argv[1]
+
+
+def timeit(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / reps
+
+
 N = 24041
-for (m, n, k, at, bt, pr) in [(N, 503, 503, 0, 0, 1), (N, 400, 503, 0, 0, 2), (400, 503, N, 1, 1, 1), (8192, 8192, 8192, 0, 0, 1)]:
-    ms, tf = gemm_case(m, n, k, at, bt, ops.GEMM_TCGEN05, pr)
-    print(f"dbg={os.environ.get('PLAGNN_TC_DEBUG','0')} m={m} n={n} k={k} at={at} pairs={pr}: {ms:.4f} ms {tf:.1f} TF", flush=True)
+shapes = [(N, 503, 503, 0, 0, 1), (N, 400, 503, 0, 0, 2), (N, 400, 400, 0, 0, 1), (N, 300, 400, 0, 0, 2),
+          (N, 503, 400, 0, 1, 1), (N, 400, 350, 0, 1, 2), (400, 503, N, 1, 1, 1), (503, 503, N, 1, 1, 1),
+          (300, 400, N, 1, 1, 1), (200, 300, N, 1, 1, 1), (N, 100, 200, 0, 0, 1), (8192, 8192, 8192, 0, 0, 1)]
+print(f"PLAGNN_TMA_CG={os.environ.get('PLAGNN_TMA_CG', '2')}")
+for (m, n, k, at, bt, pr) in shapes:
+    a = ops.aligned(torch.randn((k, m) if at else (m, k), device=dev))
+    b = ops.aligned(torch.randn((k, n) if bt else (n, k), device=dev))
+    out = ops.alloc(m, n, dev)
+    out_lo = ops.alloc(m, n, dev)
+    fl = 2.0 * m * n * k * pr
+    row = f"m={m:6d} n={n:5d} k={k:6d} at={at} bt={bt} pairs={pr}: "
+    pairs = [(a, at, b, bt, k)] * pr
+    ref = None
+    for name, be in (("tcgen05", ops.GEMM_TCGEN05), ("tma+prepass", ops.GEMM_TMA)):
+        ms = timeit(lambda: ops.gemm(m, n, pairs, out=out, backend=be))
+        row += f"{name} {ms:.4f} ms {fl / ms / 1e9:.1f} TF | "
+        if ref is None:
+            ref = out.clone()
+        else:
+            row += f"(diff {((out - ref).abs().max() / ref.abs().max()).item():.1e}) "
+    al, bl = ops.tf32_lo(a), ops.tf32_lo(b)
+    ex = [(a, al, at, b, bl, bt, k)] * pr
+    ms = timeit(lambda: ops.gemm_ex(m, n, ex, out=out, out_lo=out_lo))
+    row += f"tma ex+c_lo {ms:.4f} ms {fl / ms / 1e9:.1f} TF (diff {((out - ref).abs().max() / ref.abs().max()).item():.1e})"
+    ms = timeit(lambda: ops.tf32_lo(a, out=al))
+    row += f" | lo(A) {ms:.4f} ms"
+    print(row, flush=True)
