@@ -41,6 +41,9 @@ constexpr int TM_MAX_CHAIN = 40;    // k-blocks per TMEM accumulation chain (see
 
 struct alignas(64) TmParams {
     CUtensorMap map[PLAGNN_GEMM_MAX_PAIRS][4];    // [pair][A, A_lo, B, B_lo]
+    CUtensorMap map_out[2];                       // C (or the split-K partials) and C_lo as {n, m, splits}, box {32, 32, 1}
+    int tma_store;                                // 1: epilogue leaves through shared memory + TMA stores (aligned output)
+    int64_t ldp;                                  // row pitch of the split-K partials
     int64_t m, n;
     int npairs;
     int kblocks[PLAGNN_GEMM_MAX_PAIRS];
@@ -55,6 +58,8 @@ struct alignas(64) TmParams {
     float* c_lo;
     int64_t ldc;
     float* partial;
+    int debug;   // PLAGNN_TMA_DEBUG (timing experiments, results are garbage): 1 = TMA loads only for the first ring pass,
+                 // 2 = no MMAs, 3 = no stores in the epilogue, 4 = shared-memory images written but not stored
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -150,6 +155,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+// bulk tensor store of one {32 cols, 32 rows, 1} box from shared memory; out-of-bounds elements are not written
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -210,7 +228,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     constexpr uint32_t TMEM_COLS = 2 * TILE_N;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
-    const int64_t m0 = (int64_t)(blockIdx.x / CG) * TILE_M, n0 = (int64_t)blockIdx.y * TILE_N;
+    // N tiles fastest in launch order: the column tiles of one row block run together, so A streams from HBM once
+    const int64_t m0 = (int64_t)blockIdx.y * TILE_M, n0 = (int64_t)(blockIdx.x / CG) * TILE_N;
     const int split = blockIdx.z;
     const int kb_beg = split * P.kblocks_per_split;
     const int kb_end = min(P.total_kblocks, kb_beg + P.kblocks_per_split);
@@ -231,6 +250,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
         for (int p = 0; p < PLAGNN_GEMM_MAX_PAIRS; ++p)
             if (p < P.npairs)
                 for (int q = 0; q < 4; ++q) prefetch_map(&P.map[p][q]);
+        if (P.tma_store) { prefetch_map(&P.map_out[0]); prefetch_map(&P.map_out[1]); }
     }
     if (warp == 1) tmem_alloc<CG>(tmem_slot, TMEM_COLS);
     tc_fence_before();
@@ -253,6 +273,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 const int k0 = local * TM_BK;
                 const uint32_t st = tiles + s * TM_STAGE_BYTES;
                 const uint32_t fb = full0 + 8 * s;
+                if (P.debug == 1 && it >= TM_STAGES) {
+                    if (rank == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8 * s) : "memory");
+                    continue;
+                }
                 if (rank == 0) mbar_expect_tx(bar_full + 8 * s, CG * TM_STAGE_BYTES);
                 if (!AT) {
                     tma_load_2d<CG>(st, &P.map[p][0], k0, a_row, fb);
@@ -296,6 +320,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 const uint64_t b_lo = BT ? desc_mnmajor(st + 3 * TM_PART_BYTES) : desc_kmajor(st + 3 * TM_PART_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < TM_BK / 8; ++kk) {
+                    if (P.debug == 2) break;
                     const uint64_t adv_a = (uint64_t)kk * a_step, adv_b = (uint64_t)kk * b_step;
                     // corrections go to their own accumulator: the tensor core adds into TMEM with truncation, and the
                     // main accumulator then sees a third of the additions (gemm_tc.cu has the measurements)
@@ -317,11 +342,61 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
         const int chalf = (warp - 2) >> 2;              // column half of the tile
         const int64_t r = m0 + rank * 128 + lg * 32 + lane;
         const bool direct = P.splits == 1;
-        float* dst = direct ? P.c : P.partial + (int64_t)split * P.m * P.n;
-        const int64_t ldd = direct ? P.ldc : P.n;
+        constexpr int CHUNKS = TILE_N / 32 / 2;
+        if (P.tma_store) {
+            // Each warp turns its 32 rows x 32 columns into a 4 KB SWIZZLE_128B image in shared memory (the pipeline
+            // stages are free: every MMA has completed) and one lane stores it with a bulk tensor copy: whole 128-byte
+            // lines leave the SM, rows >= m / columns >= n are clipped by the tensor map.  Two images in flight per warp.
+            const bool want_lo = direct && P.c_lo != nullptr;
+            const uint32_t stg = tiles + (uint32_t)(warp - 2) * 16384u;      // [buffer 0/1][C 4 KB | C_lo 4 KB]
+            const uint32_t row_off = (uint32_t)lane * 128u;
+            const int row0 = (int)(m0 + rank * 128 + lg * 32);
+            int buf = 0;
+#pragma unroll 1
+            for (int ch = 0; ch < CHUNKS; ++ch) {
+                const int cbase = (chalf * CHUNKS + ch) * 32;
+                if (cbase >= (int)n_eff || n0 + cbase >= P.n) break;     // warp-uniform
+                uint32_t acc[32], acc_small[32];
+                const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)cbase;
+                tmem_ld32(ta, acc);
+                tmem_ld32(ta + TILE_N, acc_small);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = __uint_as_float(acc[j]) + __uint_as_float(acc_small[j]);
+                    const int64_t c = n0 + cbase + j;
+                    if (direct && r < P.m && c < P.n) v[j] = tm_epilogue_one(P, v[j], r, c);
+                }
+                if (lane == 0) bulk_wait_read<1>();      // the image written two chunks ago has been read
+                __syncwarp();
+                const uint32_t img = stg + (uint32_t)buf * 8192u;
+                if (P.debug != 3) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t off = row_off + (uint32_t)((q ^ (lane & 7)) << 4);
+                        sts_v4(img + off, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        if (want_lo)
+                            sts_v4(img + 4096u + off, tf32_lo(v[4 * q]), tf32_lo(v[4 * q + 1]), tf32_lo(v[4 * q + 2]),
+                                   tf32_lo(v[4 * q + 3]));
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && P.debug != 4) {
+                        tma_store_3d(&P.map_out[0], img, (int)(n0 + cbase), row0, direct ? 0 : split);
+                        if (want_lo) tma_store_3d(&P.map_out[1], img + 4096u, (int)(n0 + cbase), row0, 0);
+                        bulk_commit();
+                    }
+                }
+                buf ^= 1;
+            }
+            if (lane == 0) bulk_wait_all();
+            __syncwarp();
+        } else {
+        float* dst = direct ? P.c : P.partial + (int64_t)split * P.m * P.ldp;
+        const int64_t ldd = direct ? P.ldc : P.ldp;
         const bool vec_out = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
         float* dlo = direct ? P.c_lo : nullptr;
-        constexpr int CHUNKS = TILE_N / 32 / 2;
 #pragma unroll 1
         for (int ch = 0; ch < CHUNKS; ++ch) {
             const int cbase = (chalf * CHUNKS + ch) * 32;
@@ -331,7 +406,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             tmem_ld32(ta, acc);
             tmem_ld32(ta + TILE_N, acc_small);
             tmem_ld_wait();
-            if (r < P.m) {
+            if (r < P.m && P.debug != 3) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const int64_t c = n0 + cbase + 4 * q;
@@ -358,6 +433,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 }
             }
         }
+        }
         tc_fence_before();
     }
     __syncthreads();
@@ -373,8 +449,9 @@ __global__ void __launch_bounds__(256) gemm_tma_reduce_kernel(const __grid_const
     const int64_t total = P.m * P.n;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         float s = 0.f;
-        for (int z = 0; z < P.splits; ++z) s += P.partial[(int64_t)z * total + i];
         const int64_t r = i / P.n, c = i - r * P.n;
+        const float* q = P.partial + r * P.ldp + c;
+        for (int z = 0; z < P.splits; ++z) s += q[(int64_t)z * P.m * P.ldp];
         const float v = tm_epilogue_one(P, s, r, c);
         P.c[r * P.ldc + c] = v;
         if (P.c_lo) P.c_lo[r * P.ldc + c] = tf32_lo(v);
@@ -482,6 +559,36 @@ static int get_map(CUtensorMap* out, const float* base, int64_t inner, int64_t o
     return PLAGNN_OK;
 }
 
+// output (or split-K partials) as a 3-D tensor {n, m, depth} with row pitch `pitch` and slice pitch m * pitch; box {32, 32, 1}
+static int get_out_map(CUtensorMap* out, const float* base, int64_t n, int64_t m, int64_t depth, int64_t pitch) {
+    static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{base, n, m, pitch, (int)depth};
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return PLAGNN_OK;
+    }
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(PLAGNN_ERR_CUDA, "gemm_tma", "cuTensorMapEncodeTiled not available");
+    cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)m, (cuuint64_t)depth};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)m * (cuuint64_t)pitch * 4};
+    cuuint32_t box[3] = {32u, 32u, 1u};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMap t;
+    const CUresult r = enc(&t, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("gemm_tma: cuTensorMapEncodeTiled (output) failed (%d) base=%p n=%lld m=%lld depth=%lld pitch=%lld", (int)r,
+                  (const void*)base, (long long)n, (long long)m, (long long)depth, (long long)pitch);
+        return PLAGNN_ERR_CUDA;
+    }
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, t);
+    *out = t;
+    return PLAGNN_OK;
+}
+
 // PLAGNN_TMA_CG=1 selects the single-CTA 128 x 128 tile (bring-up / cross-check); read per call so tests can flip it
 static int tm_cg() {
     const char* e = getenv("PLAGNN_TMA_CG");
@@ -521,7 +628,7 @@ size_t gemm_tma_partial_bytes(int64_t m, int64_t n, int64_t k_total) {
             const int c = tm_choose_splits(m, n, kb + extra, cg);
             s = c > s ? c : s;
         }
-    return s > 1 ? align_up((size_t)s * (size_t)m * (size_t)n * sizeof(float), 256) : 0;
+    return s > 1 ? align_up((size_t)s * (size_t)m * (size_t)((n + 3) / 4 * 4) * sizeof(float), 256) : 0;
 }
 
 bool gemm_tma_eligible(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair_ex* pairs) {
@@ -568,13 +675,34 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
     }
     P.bias = bias; P.act = act; P.slope = slope; P.gate = gate; P.ldg = ldg; P.gate_act = gate_act;
     P.c = c; P.c_lo = c_lo; P.ldc = ldc;
+    { const char* e = getenv("PLAGNN_TMA_DEBUG"); P.debug = e ? atoi(e) : 0; }
     const int cg = tm_cg();
     const int splits = tm_choose_splits(m, n, P.total_kblocks, cg);
-    if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * m * n * sizeof(float)))
+    P.ldp = (n + 3) / 4 * 4;
+    if (splits > 1 && (!workspace || !aligned16(workspace) || workspace_bytes < (size_t)splits * m * P.ldp * sizeof(float)))
         return fail(PLAGNN_ERR_WORKSPACE, "gemm_tma", "split-K workspace too small (see plagnn_gemm_workspace_bytes)");
     P.kblocks_per_split = (int)ceil_div(P.total_kblocks, splits);
     P.splits = (int)ceil_div(P.total_kblocks, P.kblocks_per_split);
     P.partial = P.splits > 1 ? (float*)workspace : nullptr;
+    // the epilogue leaves through TMA stores when the destination rows are 16-byte aligned (always true for the partials)
+    {
+        static const bool no_store = getenv("PLAGNN_TMA_NO_STORE") != nullptr;
+        int rc;
+        if (no_store) {
+            P.tma_store = 0;
+        } else if (P.splits > 1) {
+            P.tma_store = 1;
+            if ((rc = get_out_map(&P.map_out[0], P.partial, n, m, P.splits, P.ldp))) return rc;
+            P.map_out[1] = P.map_out[0];
+        } else if ((ldc & 3) == 0 && aligned16(c) && (!c_lo || aligned16(c_lo))) {
+            P.tma_store = 1;
+            if ((rc = get_out_map(&P.map_out[0], c, n, m, 1, ldc))) return rc;
+            if (c_lo) { if ((rc = get_out_map(&P.map_out[1], c_lo, n, m, 1, ldc))) return rc; }
+            else P.map_out[1] = P.map_out[0];
+        } else {
+            P.tma_store = 0;
+        }
+    }
 
     using KernelFn = void (*)(const TmParams);
     static const KernelFn kernels[8] = {
@@ -596,7 +724,7 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
     const int kidx = (cg == 2 ? 4 : 0) + (pairs[0].a_trans ? 2 : 0) + (pairs[0].b_trans ? 1 : 0);
     const int64_t tile = 128 * cg;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(ceil_div(m, tile) * cg), (unsigned)ceil_div(n, tile), (unsigned)P.splits);
+    cfg.gridDim = dim3((unsigned)(ceil_div(n, tile) * cg), (unsigned)ceil_div(m, tile), (unsigned)P.splits);
     cfg.blockDim = dim3(TM_THREADS);
     cfg.dynamicSmemBytes = TM_SMEM_BYTES;
     cfg.stream = st;

@@ -348,6 +348,110 @@ static void run_tma() {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// 4. shared-memory contention: MMA issue rate (cta_group::2, 256x256x8, SS) while HW other warps stream LDS.128 + STS.128
+//    through a separate 64 KB region (what an in-SM hi/lo split of TMA-loaded tiles would do)
+// ---------------------------------------------------------------------------------------------------
+template <int HW>
+__global__ void __launch_bounds__(64 + 32 * (HW > 0 ? HW : 1), 1) contend_kernel(int iters, long long* cycles, long long* moved) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int CG = 2, N = 256;
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles = (raw + 1023u) & ~1023u;
+    constexpr int A_BYTES = 128 * 128, B_BYTES = 128 * 128, STAGE = 2 * A_BYTES + 2 * B_BYTES, STAGES = 2;
+    __shared__ uint64_t bar_store;
+    __shared__ uint32_t tmem_slot;
+    __shared__ volatile int done;
+    const uint32_t bar = smem_u32(&bar_store);
+    const int t = threadIdx.x, warp = t >> 5;
+    const uint32_t rank = cluster_ctarank();
+    float* f = reinterpret_cast<float*>(smem_raw + (tiles - raw));
+    for (int i = t; i < (STAGES * STAGE + 65536) / 4; i += blockDim.x) f[i] = 1.0f + 1e-3f * (float)(i & 255);
+    if (t == 0) { mbar_init(bar, 1); fence_mbar_init(); done = 0; }
+    if (warp == 0) tmem_alloc<CG>(smem_u32(&tmem_slot), 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (t == 32 && rank == 0) {
+        const uint32_t idesc = make_idesc(256, N);
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            const uint32_t st = tiles + (it % STAGES) * STAGE;
+            const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + A_BYTES);
+            const uint64_t b_hi = make_smem_desc(st + 2 * A_BYTES), b_lo = make_smem_desc(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t on = (it | kk) ? 1u : 0u;
+                umma_ss<CG>(tmem_base + N, a_lo + 2 * kk, b_hi + 2 * kk, idesc, on);
+                umma_ss<CG>(tmem_base + N, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1u);
+                umma_ss<CG>(tmem_base, a_hi + 2 * kk, b_hi + 2 * kk, idesc, on);
+            }
+        }
+        umma_commit<CG>(bar);
+        mbar_wait(bar, 0);
+        cycles[blockIdx.x] = clock64() - t0;
+        done = 1;
+    } else if (t == 32) {
+        mbar_wait(bar, 0);
+        done = 1;
+    } else if (warp >= 2 && HW > 0) {
+        // hammer: each warp streams 16-byte vectors through the 64 KB region behind the stages
+        const uint32_t region = tiles + STAGES * STAGE;
+        const int hw = warp - 2, lane = t & 31;
+        long long n = 0;
+        uint32_t off = (uint32_t)((hw * 32 + lane) * 16);
+        while (!done) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                float4 v;
+                const uint32_t a = region + ((off + u * HW * 512) & 32767u);
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+                v.x += 1.f;
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a + 32768u), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            }
+            n += 8;
+            off += 4096;
+        }
+        if (lane == 0) atomicAdd((unsigned long long*)&moved[blockIdx.x], (unsigned long long)(n * 1024));   // LDS + STS bytes per warp
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc<CG>(tmem_base, 512); }
+}
+
+template <int HW>
+static void run_contend() {
+    const int smem = 2 * 65536 + 65536 + 1024;
+    auto k = contend_kernel<HW>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = 148;
+    long long *d, *mv;
+    CK(cudaMalloc(&d, grid * sizeof(long long))); CK(cudaMalloc(&mv, grid * sizeof(long long)));
+    CK(cudaMemset(d, 0, grid * sizeof(long long))); CK(cudaMemset(mv, 0, grid * sizeof(long long)));
+    const int iters = 400;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * (HW > 0 ? HW : 1)); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, k, iters, d, mv));
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> h(grid), m(grid);
+    CK(cudaMemcpy(h.data(), d, grid * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(m.data(), mv, grid * 8, cudaMemcpyDeviceToHost));
+    long long mx = 0; double bytes = 0; int nb = 0;
+    for (int i = 0; i < grid; i += 2) { mx = h[i] > mx ? h[i] : mx; }
+    for (int i = 0; i < grid; ++i) { bytes += (double)m[i]; ++nb; }
+    printf("contend: %d hammer warps/CTA: cycles/MMA %.1f, hammer LDS+STS %.1f B/clk per SM (%.1f KB per 1536 cycles)\n", HW,
+           (double)mx / (iters * 12.0), bytes / nb / (double)mx, bytes / nb / (double)mx * 1536 / 1024);
+    CK(cudaFree(d)); CK(cudaFree(mv));
+}
+
 int main(int argc, char** argv) {
     const char* which = argc > 1 ? argv[1] : "all";
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
@@ -361,6 +465,9 @@ int main(int argc, char** argv) {
         run_rate<1, 256, true>("TS cta_group::1 128x256x8");
         run_rate<2, 128, false>("SS cta_group::2 256x128x8");
         run_rate<2, 256, false>("SS cta_group::2 256x256x8");
+    }
+    if (!strcmp(which, "all") || !strcmp(which, "contend")) {
+        run_contend<0>(); run_contend<1>(); run_contend<2>(); run_contend<4>(); run_contend<8>(); run_contend<16>();
     }
     return 0;
 }
