@@ -122,7 +122,17 @@ int plagnn_gemm(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pa
     plagnn_gemm_pair_ex ex[PLAGNN_GEMM_MAX_PAIRS];
     bool tma_ok = tc_ok;
     const size_t part_bytes = gemm_tma_partial_bytes(m, n, ktot);
-    if (tma_ok) {
+    // default: lo tiles derived inside the kernel; PLAGNN_TMA_COMPANION=1 derives companion matrices first (comparison)
+    static const bool companion_mode = getenv("PLAGNN_TMA_COMPANION") != nullptr;
+    if (tma_ok && !companion_mode) {
+        for (int p = 0; p < npairs; ++p) {
+            const plagnn_gemm_pair& q = pairs[p];
+            ex[p].a = q.a; ex[p].lda = q.lda; ex[p].a_trans = q.a_trans; ex[p].a_lo = nullptr; ex[p].lda_lo = 0;
+            ex[p].b = q.b; ex[p].ldb = q.ldb; ex[p].b_trans = q.b_trans; ex[p].b_lo = nullptr; ex[p].ldb_lo = 0;
+            ex[p].k = q.k;
+        }
+        tma_ok = (part_bytes == 0 || (workspace && part_bytes <= workspace_bytes)) && gemm_tma_eligible(m, n, npairs, ex);
+    } else if (tma_ok) {
         size_t off = part_bytes;
         for (int p = 0; p < npairs; ++p) {
             const plagnn_gemm_pair& q = pairs[p];
@@ -148,7 +158,7 @@ int plagnn_gemm(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pa
         return fail(PLAGNN_ERR_UNSUPPORTED, "gemm", "tcgen05 backend needs n >= 16 and k >= 8");
     if (backend == PLAGNN_GEMM_AUTO) backend = tma_ok ? PLAGNN_GEMM_TMA : tc_ok ? PLAGNN_GEMM_TCGEN05 : PLAGNN_GEMM_SIMT;
     if (backend == PLAGNN_GEMM_TMA) {
-        for (int p = 0; p < npairs; ++p) {
+        for (int p = 0; companion_mode && p < npairs; ++p) {
             const plagnn_gemm_pair_ex& q = ex[p];
             int rc = tf32_lo_launch(q.a, q.lda, q.a_trans ? q.k : m, q.a_trans ? m : q.k, const_cast<float*>(q.a_lo), q.lda_lo, st);
             if (rc) return rc;

@@ -42,6 +42,7 @@ constexpr int TM_MAX_CHAIN = 40;    // k-blocks per TMEM accumulation chain (see
 struct alignas(64) TmParams {
     CUtensorMap map[PLAGNN_GEMM_MAX_PAIRS][4];    // [pair][A, A_lo, B, B_lo]
     CUtensorMap map_out[2];                       // C (or the split-K partials) and C_lo as {n, m, splits}, box {32, 32, 1}
+    int inline_lo;                                // 1: no companions; the lo tiles are derived in shared memory by warps 2..9
     int tma_store;                                // 1: epilogue leaves through shared memory + TMA stores (aligned output)
     int64_t ldp;                                  // row pitch of the split-K partials
     int64_t m, n;
@@ -58,6 +59,7 @@ struct alignas(64) TmParams {
     float* c_lo;
     int64_t ldc;
     float* partial;
+    long long* trace;   // PLAGNN_TMA_TRACE: per-CTA clock64 stamps (16 per CTA, first 64 CTAs), else null
     int debug;   // PLAGNN_TMA_DEBUG (timing experiments, results are garbage): 1 = TMA loads only for the first ring pass,
                  // 2 = no MMAs, 3 = no stores in the epilogue, 4 = shared-memory images written but not stored
 };
@@ -87,6 +89,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+// arrive (release at cluster scope) on a barrier given by its shared::cluster address (own or peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
@@ -221,13 +245,17 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     const uint32_t tiles = (raw + 1023u) & ~1023u;                  // 1024-byte aligned (swizzle atoms)
     const uint32_t bars = tiles + TM_STAGES * TM_STAGE_BYTES;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * TM_STAGES, bar_acc = bars + 16 * TM_STAGES;
-    const uint32_t tmem_slot = bar_acc + 8;
+    const uint32_t bar_raw = bar_acc + 8;                             // [TM_STAGES]: raw tiles landed (inline_lo mode)
+    const uint32_t tmem_slot = bar_raw + 8 * TM_STAGES;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
     constexpr int TILE_M = 128 * CG, TILE_N = 128 * CG;
     constexpr uint32_t TMEM_COLS = 2 * TILE_N;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int lin_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    long long* tr = (P.trace && lin_cta < 64) ? P.trace + 16 * lin_cta : nullptr;
+    if (tr && t == 0) tr[0] = clock64();
     // N tiles fastest in launch order: the column tiles of one row block run together, so A streams from HBM once
     const int64_t m0 = (int64_t)blockIdx.y * TILE_M, n0 = (int64_t)(blockIdx.x / CG) * TILE_N;
     const int split = blockIdx.z;
@@ -241,15 +269,17 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
 
     if (t == 0) {
         for (int s = 0; s < TM_STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_full + 8 * s, P.inline_lo ? (uint32_t)(CG * TM_EPI_WARPS) : 1u);
             mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_raw + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
         fence_mbar_init();
 #pragma unroll
         for (int p = 0; p < PLAGNN_GEMM_MAX_PAIRS; ++p)
             if (p < P.npairs)
-                for (int q = 0; q < 4; ++q) prefetch_map(&P.map[p][q]);
+                for (int q = 0; q < 4; ++q)
+                    if (!P.inline_lo || !(q & 1)) prefetch_map(&P.map[p][q]);
         if (P.tma_store) { prefetch_map(&P.map_out[0]); prefetch_map(&P.map_out[1]); }
     }
     if (warp == 1) tmem_alloc<CG>(tmem_slot, TMEM_COLS);
@@ -258,6 +288,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     if (CG == 2) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    if (tr && t == 0) tr[1] = clock64();
 
     if (warp == 0) {
         // ================= TMA producer (one elected lane) =================
@@ -267,7 +298,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             for (int it = 0; it < nkb; ++it) {
                 const int s = it % TM_STAGES;
                 const uint32_t ph = (uint32_t)((it / TM_STAGES) & 1);
+                const long long w0 = tr ? clock64() : 0;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                if (tr) tr[8] += clock64() - w0;
                 int p = 0, local = kb_beg + it;
                 if (P.npairs > 1 && local >= P.kblocks[0]) { local -= P.kblocks[0]; p = 1; }
                 const int k0 = local * TM_BK;
@@ -275,6 +308,25 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 const uint32_t fb = full0 + 8 * s;
                 if (P.debug == 1 && it >= TM_STAGES) {
                     if (rank == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8 * s) : "memory");
+                    continue;
+                }
+                if (P.inline_lo) {
+                    // raw tiles only, completion on this CTA's own barrier; warps 2..9 derive the lo tiles
+                    const uint32_t rb = bar_raw + 8 * s;
+                    mbar_expect_tx(rb, 2 * TM_PART_BYTES);
+                    if (!AT) {
+                        tma_load_2d<1>(st, &P.map[p][0], k0, a_row, rb);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) tma_load_2d<1>(st + j * 4096, &P.map[p][0], a_row + 32 * j, k0, rb);
+                    }
+                    if (!BT) {
+                        tma_load_2d<1>(st + 2 * TM_PART_BYTES, &P.map[p][2], k0, b_row, rb);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            tma_load_2d<1>(st + 2 * TM_PART_BYTES + j * 4096, &P.map[p][2], b_row + 32 * j, k0, rb);
+                    }
                     continue;
                 }
                 if (rank == 0) mbar_expect_tx(bar_full + 8 * s, CG * TM_STAGE_BYTES);
@@ -311,8 +363,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             for (int it = 0; it < nkb; ++it) {
                 const int s = it % TM_STAGES;
                 const uint32_t ph = (uint32_t)((it / TM_STAGES) & 1);
-                mbar_wait(bar_full + 8 * s, ph);
+                const long long w0 = tr ? clock64() : 0;
+                if (CG == 2) mbar_wait_cluster(bar_full + 8 * s, ph);
+                else mbar_wait(bar_full + 8 * s, ph);
                 tc_fence_after();
+                if (tr) { const long long w1 = clock64(); tr[9] += w1 - w0; if (it == 0) tr[2] = w1; }
                 const uint32_t st = tiles + s * TM_STAGE_BYTES;
                 const uint64_t a_hi = AT ? desc_mnmajor(st) : desc_kmajor(st);
                 const uint64_t a_lo = AT ? desc_mnmajor(st + TM_PART_BYTES) : desc_kmajor(st + TM_PART_BYTES);
@@ -332,108 +387,164 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 umma_commit<CG>(bar_empty + 8 * s);     // frees the stage in both CTAs when these MMAs have read it
             }
             umma_commit<CG>(bar_acc);                   // accumulators complete (both CTAs)
+            if (tr) tr[3] = clock64();
         }
         __syncwarp();
     } else {
+        if (P.inline_lo) {
+            // ================= hi/lo split in shared memory =================
+            // The tensor core reads the raw fp32 tile as the hi operand (it drops the low 13 bits itself); the lo tile
+            // has the same swizzled layout 16 KB further on, so the pass is purely elementwise.  Tensor-core operand
+            // reads do not compete with LDS/STS for bandwidth (tools/mma_probe.cu, "contend").
+            const int ct = t - 64;                                  // 0..255
+            const uint32_t full0 = CG == 2 ? mapa(bar_full, 0) : bar_full;
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % TM_STAGES;
+                const uint32_t ph = (uint32_t)((it / TM_STAGES) & 1);
+                const long long w0 = (tr && t == 64) ? clock64() : 0;
+                mbar_wait(bar_raw + 8 * s, ph);
+                if (tr && t == 64) tr[10] += clock64() - w0;
+                const uint32_t st = tiles + s * TM_STAGE_BYTES;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t src = st + (uint32_t)half * 2u * TM_PART_BYTES + (uint32_t)ct * 16u;
+                    float4 v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(src + (uint32_t)i * 4096u));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        sts_v4(src + TM_PART_BYTES + (uint32_t)i * 4096u, tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z),
+                               tf32_lo(v[i].w));
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_cluster(full0 + 8 * s);
+                    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8 * s) : "memory");
+                }
+            }
+        }
         // ================= epilogue: TMEM -> registers -> global =================
         mbar_wait(bar_acc, 0);
         tc_fence_after();
+        if (tr && t == 64) tr[4] = clock64();
         const int lg = warp & 3;                        // TMEM lane group this warp may read (warp % 4)
         const int chalf = (warp - 2) >> 2;              // column half of the tile
         const int64_t r = m0 + rank * 128 + lg * 32 + lane;
         const bool direct = P.splits == 1;
         constexpr int CHUNKS = TILE_N / 32 / 2;
-        if (P.tma_store) {
-            // Each warp turns its 32 rows x 32 columns into a 4 KB SWIZZLE_128B image in shared memory (the pipeline
-            // stages are free: every MMA has completed) and one lane stores it with a bulk tensor copy: whole 128-byte
-            // lines leave the SM, rows >= m / columns >= n are clipped by the tensor map.  Two images in flight per warp.
-            const bool want_lo = direct && P.c_lo != nullptr;
-            const uint32_t stg = tiles + (uint32_t)(warp - 2) * 16384u;      // [buffer 0/1][C 4 KB | C_lo 4 KB]
-            const uint32_t row_off = (uint32_t)lane * 128u;
-            const int row0 = (int)(m0 + rank * 128 + lg * 32);
-            int buf = 0;
-#pragma unroll 1
-            for (int ch = 0; ch < CHUNKS; ++ch) {
-                const int cbase = (chalf * CHUNKS + ch) * 32;
-                if (cbase >= (int)n_eff || n0 + cbase >= P.n) break;     // warp-uniform
-                uint32_t acc[32], acc_small[32];
-                const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)cbase;
-                tmem_ld32(ta, acc);
-                tmem_ld32(ta + TILE_N, acc_small);
-                tmem_ld_wait();
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    v[j] = __uint_as_float(acc[j]) + __uint_as_float(acc_small[j]);
-                    const int64_t c = n0 + cbase + j;
-                    if (direct && r < P.m && c < P.n) v[j] = tm_epilogue_one(P, v[j], r, c);
-                }
-                if (lane == 0) bulk_wait_read<1>();      // the image written two chunks ago has been read
-                __syncwarp();
-                const uint32_t img = stg + (uint32_t)buf * 8192u;
-                if (P.debug != 3) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t off = row_off + (uint32_t)((q ^ (lane & 7)) << 4);
-                        sts_v4(img + off, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        if (want_lo)
-                            sts_v4(img + 4096u + off, tf32_lo(v[4 * q]), tf32_lo(v[4 * q + 1]), tf32_lo(v[4 * q + 2]),
-                                   tf32_lo(v[4 * q + 3]));
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0 && P.debug != 4) {
-                        tma_store_3d(&P.map_out[0], img, (int)(n0 + cbase), row0, direct ? 0 : split);
-                        if (want_lo) tma_store_3d(&P.map_out[1], img + 4096u, (int)(n0 + cbase), row0, 0);
-                        bulk_commit();
-                    }
-                }
-                buf ^= 1;
-            }
-            if (lane == 0) bulk_wait_all();
-            __syncwarp();
-        } else {
+        // Shared-memory path: each warp turns its 32 rows x 32 columns into a 4 KB SWIZZLE_128B image (the pipeline
+        // stages are free: every MMA has completed) and one lane stores it with a bulk tensor copy: whole 128-byte lines
+        // leave the SM, rows >= m / columns >= n are clipped by the tensor map.  Two images in flight per warp.
+        // The activation / gate switches sit OUTSIDE the element loops: the first version branched per element and
+        // spent 25 000 of its 28 000 epilogue cycles per tile fetching instructions (PLAGNN_TMA_TRACE).
+        const bool want_lo = direct && P.c_lo != nullptr;
+        const uint32_t stg = tiles + (uint32_t)(warp - 2) * 16384u;      // [buffer 0/1][C 4 KB | C_lo 4 KB]
+        const uint32_t row_off = (uint32_t)lane * 128u;
+        const int row0 = (int)(m0 + rank * 128 + lg * 32);
+        const int64_t r_ld = r < P.m ? r : P.m - 1;                      // clamped row for gate loads (clipped rows are never stored)
         float* dst = direct ? P.c : P.partial + (int64_t)split * P.m * P.ldp;
         const int64_t ldd = direct ? P.ldc : P.ldp;
-        const bool vec_out = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
-        float* dlo = direct ? P.c_lo : nullptr;
+        int buf = 0;
 #pragma unroll 1
         for (int ch = 0; ch < CHUNKS; ++ch) {
             const int cbase = (chalf * CHUNKS + ch) * 32;
             if (cbase >= (int)n_eff || n0 + cbase >= P.n) break;     // warp-uniform
-            uint32_t acc[32], acc_small[32];
-            const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)cbase;
-            tmem_ld32(ta, acc);
-            tmem_ld32(ta + TILE_N, acc_small);
-            tmem_ld_wait();
-            if (r < P.m && P.debug != 3) {
+            const int64_t c0 = n0 + cbase;
+            const int ncol = (int)((P.n - c0) < 32 ? (P.n - c0) : 32);   // valid columns of this chunk
+            float v[32];
+            {
+                uint32_t acc[32], acc_small[32];
+                const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)cbase;
+                const long long e0 = (tr && t == 64) ? clock64() : 0;
+                tmem_ld32(ta, acc);
+                tmem_ld32(ta + TILE_N, acc_small);
+                tmem_ld_wait();
+                if (tr && t == 64) tr[13] += clock64() - e0;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int64_t c = n0 + cbase + 4 * q;
-                    if (c >= P.n) break;
-                    float v[4];
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + __uint_as_float(acc_small[j]);
+            }
+            if (direct) {
+                if (P.bias) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        v[e] = __uint_as_float(acc[4 * q + e]) + __uint_as_float(acc_small[4 * q + e]);
-                        if (direct && c + e < P.n) v[e] = tm_epilogue_one(P, v[e], r, c + e);
-                    }
-                    if (vec_out && c + 3 < P.n) {
-                        *reinterpret_cast<float4*>(dst + r * ldd + c) = make_float4(v[0], v[1], v[2], v[3]);
-                        if (dlo)
-                            *reinterpret_cast<float4*>(dlo + r * ldd + c) =
-                                make_float4(tf32_lo(v[0]), tf32_lo(v[1]), tf32_lo(v[2]), tf32_lo(v[3]));
-                    } else {
+                    for (int j = 0; j < 32; ++j) v[j] += __ldg(P.bias + c0 + (j < ncol ? j : 0));
+                }
+                if (P.act == PLAGNN_ACT_RELU) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (c + e < P.n) {
-                                dst[r * ldd + c + e] = v[e];
-                                if (dlo) dlo[r * ldd + c + e] = tf32_lo(v[e]);
-                            }
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
+                } else if (P.act == PLAGNN_ACT_LEAKY) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * P.slope;
+                } else if (P.act == PLAGNN_ACT_SIGMOID) {
+#pragma unroll 4
+                    for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+                }
+                if (P.gate) {
+                    const float* g = P.gate + r_ld * P.ldg + c0;
+                    if (P.gate_act == PLAGNN_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __ldg(g + (j < ncol ? j : 0)) > 0.f ? v[j] : 0.f;
+                    } else if (P.gate_act == PLAGNN_ACT_LEAKY) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __ldg(g + (j < ncol ? j : 0)) > 0.f ? v[j] : v[j] * P.slope;
+                    } else if (P.gate_act == PLAGNN_ACT_SIGMOID) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float y = __ldg(g + (j < ncol ? j : 0));
+                            v[j] *= y * (1.f - y);
+                        }
                     }
                 }
             }
+            if (P.debug == 3) continue;
+            if (P.tma_store) {
+                const long long e1 = (tr && t == 64) ? clock64() : 0;
+                if (lane == 0) bulk_wait_read<1>();      // the image written two chunks ago has been read
+                __syncwarp();
+                if (tr && t == 64) tr[14] += clock64() - e1;
+                const uint32_t img = stg + (uint32_t)buf * 8192u;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t off = row_off + (uint32_t)((q ^ (lane & 7)) << 4);
+                    sts_v4(img + off, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+                if (want_lo) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t off = row_off + (uint32_t)((q ^ (lane & 7)) << 4);
+                        sts_v4(img + 4096u + off, tf32_lo(v[4 * q]), tf32_lo(v[4 * q + 1]), tf32_lo(v[4 * q + 2]),
+                               tf32_lo(v[4 * q + 3]));
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && P.debug != 4) {
+                    tma_store_3d(&P.map_out[0], img, (int)c0, row0, direct ? 0 : split);
+                    if (want_lo) tma_store_3d(&P.map_out[1], img + 4096u, (int)c0, row0, 0);
+                    bulk_commit();
+                }
+                if (tr && t == 64) tr[15] += clock64() - e1;
+                buf ^= 1;
+            } else if (r < P.m) {
+                // unaligned destination (row pitch % 4 != 0): plain scalar stores
+                float* drow = dst + r * ldd + c0;
+                float* lrow = want_lo ? P.c_lo + r * ldd + c0 : nullptr;
+#pragma unroll 4
+                for (int j = 0; j < 32; ++j)
+                    if (j < ncol) {
+                        drow[j] = v[j];
+                        if (lrow) lrow[j] = tf32_lo(v[j]);
+                    }
+            }
         }
+        if (tr && t == 64) tr[5] = clock64();
+        if (P.tma_store) {
+            if (lane == 0) bulk_wait_all();
+            __syncwarp();
         }
+        if (tr && t == 64) tr[6] = clock64();
         tc_fence_before();
     }
     __syncthreads();
@@ -442,6 +553,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
         tc_fence_after();
         tmem_dealloc<CG>(tmem_base, TMEM_COLS);
     }
+    if (tr && t == 0) { tr[7] = clock64(); tr[11] = nkb; tr[12] = rank; }
 }
 
 // ordered reduction of split-K partials + epilogue (+ companion)
@@ -589,6 +701,21 @@ static int get_out_map(CUtensorMap* out, const float* base, int64_t n, int64_t m
     return PLAGNN_OK;
 }
 
+// PLAGNN_TMA_TRACE=1: clock64 stamps of the first 64 CTAs of the LAST launch (plagnn_tma_trace reads them back)
+static long long* g_trace = nullptr;
+static long long* trace_buffer(cudaStream_t st) {
+    static const bool on = getenv("PLAGNN_TMA_TRACE") != nullptr;
+    if (!on) return nullptr;
+    if (!g_trace && cudaMalloc(&g_trace, 64 * 16 * sizeof(long long)) != cudaSuccess) return nullptr;
+    cudaMemsetAsync(g_trace, 0, 64 * 16 * sizeof(long long), st);
+    return g_trace;
+}
+extern "C" int plagnn_tma_trace(long long* host_out /* 64 x 16 */) {
+    if (!g_trace) return -1;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(host_out, g_trace, 64 * 16 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+
 // PLAGNN_TMA_CG=1 selects the single-CTA 128 x 128 tile (bring-up / cross-check); read per call so tests can flip it
 static int tm_cg() {
     const char* e = getenv("PLAGNN_TMA_CG");
@@ -637,14 +764,14 @@ bool gemm_tma_eligible(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_p
         const plagnn_gemm_pair_ex& q = pairs[p];
         if (q.k < 8) return false;
         if ((q.lda & 3) || (q.ldb & 3) || !aligned16(q.a) || !aligned16(q.b)) return false;
-        if ((q.lda_lo & 3) || (q.ldb_lo & 3) || !aligned16(q.a_lo) || !aligned16(q.b_lo)) return false;
+        if ((q.a_lo || q.b_lo) && ((q.lda_lo & 3) || (q.ldb_lo & 3) || !aligned16(q.a_lo) || !aligned16(q.b_lo))) return false;
         if ((q.a_trans != 0) != (pairs[0].a_trans != 0) || (q.b_trans != 0) != (pairs[0].b_trans != 0)) return false;
         if (q.k > INT_MAX - 64 || m > INT_MAX - 512 || n > INT_MAX - 512) return false;
     }
     return true;
 }
 
-// Every pair must carry its companions (a_lo / b_lo with their own pitches).
+// Either every pair carries its companions (a_lo / b_lo with their own pitches) or none does (lo tiles derived in-SM).
 int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair_ex* pairs, const float* bias, int act,
                     float slope, const float* gate, int64_t ldg, int gate_act, float* c, float* c_lo, int64_t ldc,
                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -652,30 +779,37 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
     memset(&P, 0, sizeof(P));
     P.m = m; P.n = n; P.npairs = npairs;
     P.total_kblocks = 0;
+    bool any_lo = false, all_lo = true;
+    for (int p = 0; p < npairs; ++p) {
+        any_lo = any_lo || pairs[p].a_lo || pairs[p].b_lo;
+        all_lo = all_lo && pairs[p].a_lo && pairs[p].b_lo;
+    }
+    if (any_lo && !all_lo) return fail(PLAGNN_ERR_ARG, "gemm_tma", "companions must be given for every operand or for none");
+    P.inline_lo = any_lo ? 0 : 1;
     for (int p = 0; p < npairs; ++p) {
         const plagnn_gemm_pair_ex& q = pairs[p];
-        if (!q.a_lo || !q.b_lo) return fail(PLAGNN_ERR_ARG, "gemm_tma", "missing tf32 companion operand");
         P.kblocks[p] = (int)ceil_div(q.k, TM_BK);
         P.total_kblocks += P.kblocks[p];
         int rc;
         if (!q.a_trans) {
             if ((rc = get_map(&P.map[p][0], q.a, q.k, m, q.lda, 0))) return rc;
-            if ((rc = get_map(&P.map[p][1], q.a_lo, q.k, m, q.lda_lo, 0))) return rc;
+            if (any_lo && (rc = get_map(&P.map[p][1], q.a_lo, q.k, m, q.lda_lo, 0))) return rc;
         } else {
             if ((rc = get_map(&P.map[p][0], q.a, m, q.k, q.lda, 1))) return rc;
-            if ((rc = get_map(&P.map[p][1], q.a_lo, m, q.k, q.lda_lo, 1))) return rc;
+            if (any_lo && (rc = get_map(&P.map[p][1], q.a_lo, m, q.k, q.lda_lo, 1))) return rc;
         }
         if (!q.b_trans) {
             if ((rc = get_map(&P.map[p][2], q.b, q.k, n, q.ldb, 0))) return rc;
-            if ((rc = get_map(&P.map[p][3], q.b_lo, q.k, n, q.ldb_lo, 0))) return rc;
+            if (any_lo && (rc = get_map(&P.map[p][3], q.b_lo, q.k, n, q.ldb_lo, 0))) return rc;
         } else {
             if ((rc = get_map(&P.map[p][2], q.b, n, q.k, q.ldb, 1))) return rc;
-            if ((rc = get_map(&P.map[p][3], q.b_lo, n, q.k, q.ldb_lo, 1))) return rc;
+            if (any_lo && (rc = get_map(&P.map[p][3], q.b_lo, n, q.k, q.ldb_lo, 1))) return rc;
         }
     }
     P.bias = bias; P.act = act; P.slope = slope; P.gate = gate; P.ldg = ldg; P.gate_act = gate_act;
     P.c = c; P.c_lo = c_lo; P.ldc = ldc;
     { const char* e = getenv("PLAGNN_TMA_DEBUG"); P.debug = e ? atoi(e) : 0; }
+    P.trace = trace_buffer(st);
     const int cg = tm_cg();
     const int splits = tm_choose_splits(m, n, P.total_kblocks, cg);
     P.ldp = (n + 3) / 4 * 4;

@@ -41,7 +41,7 @@ for (m, n, k, at, bt, pr) in shapes:
     row = f"m={m:6d} n={n:5d} k={k:6d} at={at} bt={bt} pairs={pr}: "
     pairs = [(a, at, b, bt, k)] * pr
     ref = None
-    for name, be in (("tcgen05", ops.GEMM_TCGEN05), ("tma+prepass", ops.GEMM_TMA)):
+    for name, be in (("tcgen05", ops.GEMM_TCGEN05), ("tma inline-lo", ops.GEMM_TMA)):
         ms = timeit(lambda: ops.gemm(m, n, pairs, out=out, backend=be))
         row += f"{name} {ms:.4f} ms {fl / ms / 1e9:.1f} TF | "
         if ref is None:
@@ -51,7 +51,7 @@ for (m, n, k, at, bt, pr) in shapes:
     al, bl = ops.tf32_lo(a), ops.tf32_lo(b)
     ex = [(a, al, at, b, bl, bt, k)] * pr
     ms = timeit(lambda: ops.gemm_ex(m, n, ex, out=out, out_lo=out_lo))
-    row += f"tma ex+c_lo {ms:.4f} ms {fl / ms / 1e9:.1f} TF (diff {((out - ref).abs().max() / ref.abs().max()).item():.1e})"
+    row += f"tma companions+c_lo {ms:.4f} ms {fl / ms / 1e9:.1f} TF (diff {((out - ref).abs().max() / ref.abs().max()).item():.1e})"
     ms = timeit(lambda: ops.tf32_lo(a, out=al))
     row += f" | lo(A) {ms:.4f} ms"
     print(row, flush=True)

@@ -452,6 +452,97 @@ static void run_contend() {
     CK(cudaFree(d)); CK(cudaFree(mv));
 }
 
+// ---------------------------------------------------------------------------------------------------
+// 5. ring probe: cta_group::2 256x256x8 MMAs issued like the GEMM main loop does: 12 MMAs per k-block, one commit per
+//    k-block onto a ring of RING barriers, the issuer waits for the commit of k-block (it - RING + 1) before issuing
+//    k-block it + 1 (i.e. at most RING k-blocks of MMAs queued).  RING = 0: a single commit at the end.
+// ---------------------------------------------------------------------------------------------------
+template <int RING>
+__global__ void __launch_bounds__(128, 1) ring_kernel(int iters, long long* cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int CG = 2, N = 256;
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles = (raw + 1023u) & ~1023u;
+    constexpr int A_BYTES = 128 * 128, B_BYTES = 128 * 128, STAGE = 2 * A_BYTES + 2 * B_BYTES, STAGES = 3;
+    __shared__ uint64_t bar_store[8];
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    const uint32_t rank = cluster_ctarank();
+    float* f = reinterpret_cast<float*>(smem_raw + (tiles - raw));
+    for (int i = t; i < STAGES * STAGE / 4; i += blockDim.x) f[i] = 1.0f + 1e-3f * (float)((i * 2654435761u) >> 20);
+    if (t == 0) { for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bar_store[i]), 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc<CG>(smem_u32(&tmem_slot), 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (t == 32 && rank == 0) {
+        const uint32_t idesc = make_idesc(256, N);
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            if (RING > 0 && it >= RING) {
+                const int w = it - RING;
+                mbar_wait(smem_u32(&bar_store[w % RING]), (uint32_t)((w / RING) & 1));
+                tc_fence_after();
+            }
+            const uint32_t st = tiles + (it % STAGES) * STAGE;
+            const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + A_BYTES);
+            const uint64_t b_hi = make_smem_desc(st + 2 * A_BYTES), b_lo = make_smem_desc(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t on = (it | kk) ? 1u : 0u;
+                umma_ss<CG>(tmem_base + N, a_lo + 2 * kk, b_hi + 2 * kk, idesc, on);
+                umma_ss<CG>(tmem_base + N, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1u);
+                umma_ss<CG>(tmem_base, a_hi + 2 * kk, b_hi + 2 * kk, idesc, on);
+            }
+            if (RING > 0) umma_commit<CG>(smem_u32(&bar_store[it % RING]));
+        }
+        umma_commit<CG>(smem_u32(&bar_store[7]));
+        mbar_wait(smem_u32(&bar_store[7]), 0);
+        cycles[blockIdx.x] = clock64() - t0;
+    } else if (t == 32) {
+        mbar_wait(smem_u32(&bar_store[7]), 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc<CG>(tmem_base, 512); }
+}
+
+template <int RING>
+static void run_ring(int iters) {
+    const int smem = 3 * 65536 + 1024;
+    auto k = ring_kernel<RING>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = 148;
+    long long* d;
+    CK(cudaMalloc(&d, grid * sizeof(long long)));
+    CK(cudaMemset(d, 0, grid * sizeof(long long)));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaLaunchKernelEx(&cfg, k, 10, d));
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    CK(cudaLaunchKernelEx(&cfg, k, iters, d));
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    std::vector<long long> h(grid);
+    CK(cudaMemcpy(h.data(), d, grid * 8, cudaMemcpyDeviceToHost));
+    long long mx = 0; for (int i = 0; i < grid; i += 2) mx = h[i] > mx ? h[i] : mx;
+    printf("ring %d, %d k-blocks: cycles/MMA %.1f, %.3f ms -> SM clock ~%.0f MHz, %.0f TFLOP/s tf32\n", RING, iters,
+           (double)mx / (iters * 12.0), ms, (double)mx / ms / 1e3, 2.0 * 256 * 256 * 8 * 12.0 * iters * 74 / (ms * 1e-3) / 1e12);
+    CK(cudaFree(d));
+}
+
 int main(int argc, char** argv) {
     const char* which = argc > 1 ? argv[1] : "all";
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
@@ -465,6 +556,9 @@ int main(int argc, char** argv) {
         run_rate<1, 256, true>("TS cta_group::1 128x256x8");
         run_rate<2, 128, false>("SS cta_group::2 256x128x8");
         run_rate<2, 256, false>("SS cta_group::2 256x256x8");
+    }
+    if (!strcmp(which, "all") || !strcmp(which, "ring")) {
+        run_ring<0>(400); run_ring<1>(400); run_ring<2>(400); run_ring<3>(400); run_ring<0>(20000); run_ring<3>(20000); run_ring<3>(200000);
     }
     if (!strcmp(which, "all") || !strcmp(which, "contend")) {
         run_contend<0>(); run_contend<1>(); run_contend<2>(); run_contend<4>(); run_contend<8>(); run_contend<16>();
