@@ -244,11 +244,18 @@ def run_ours(args):
     if sampler:
         sampler.start()
     launches0 = ops.launch_count()
-    ops.profile_start()                      # per-call CUDA events on the launching stream, inside the library
+    # CUDA events on the launching stream, recorded inside the library around the aggregation entry points only (12 event
+    # records per epoch); the roofline figure comes from these, i.e. from inside the timed region
+    ops.profile_start(aggregation_only=True)
     ms_total = timed(epoch, args.steps)
-    prof = ops.profile_stop()
+    prof_agg = ops.profile_stop()
     launches = ops.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
+    # second pass of the same K steps with events around EVERY entry point (~150 event records per epoch, which costs
+    # host time): per-kernel breakdown only, not part of `value`
+    ops.profile_start()
+    ms_profiled = timed(epoch, args.steps)
+    prof = ops.profile_stop()
     # ---- end-to-end timed region (host buffers in, loss + logits out) ------------------------------
     for _ in range(3):
         epoch_e2e()
@@ -280,13 +287,13 @@ def run_ours(args):
     kernels = []
     for key, (cnt, tot) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
         kernels.append({"kernel": "/".join(str(k) for k in key), "calls_per_step": cnt / args.steps,
-                        "avg_ms": round(tot / cnt, 5), "share_of_step": round(tot / ms_total, 4)})
-    cnt, tot = prof[("spmm_max_fwd", f_in, n, 0)]
+                        "avg_ms": round(tot / cnt, 5), "share_of_step": round(tot / ms_profiled, 4)})
+    cnt, tot = prof_agg[("spmm_max_fwd", f_in, n, 0)]
     spmm_ms = tot / cnt
     alg = algorithmic_spmm_bytes(n, e_prime, f_in)
     achieved = alg / (spmm_ms * 1e-3) / 1e9
     gemm_ms = sum(t for k, (c, t) in prof.items() if k[0] == "gemm") / args.steps
-    spmm_all_ms = sum(t for k, (c, t) in prof.items() if k[0].startswith("spmm")) / args.steps
+    spmm_all_ms = sum(t for k, (c, t) in prof_agg.items() if k[0].startswith("spmm")) / args.steps
     flops_epoch = dense_flops(n, f_in)
     out = {
         "metric": METRIC, "value": world * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -309,7 +316,9 @@ def run_ours(args):
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes": alg, "avg_ms": spmm_ms,
                      "edges_per_s": e_prime / (spmm_ms * 1e-3)},
         "gemm": {"ms_per_step": gemm_ms, "tflops_fp32_equiv": flops_epoch / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
-                 "flops_per_step": flops_epoch, "backend": os.environ.get("PLAGNN_GEMM", "auto(tcgen05 3xTF32)")},
+                 "flops_per_step": flops_epoch, "backend": os.environ.get("PLAGNN_GEMM", "auto (TMA-fed tcgen05, CTA pairs, 3xTF32)"),
+                 "measured_in": "second pass with per-call events (ms_per_step_profiled)"},
+        "ms_per_step_profiled": ms_profiled / args.steps,
         "spmm": {"ms_per_step": spmm_all_ms},
         "kernels": kernels[:10],
     }

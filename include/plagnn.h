@@ -47,7 +47,8 @@ int plagnn_version(void);
 /* number of kernels this library has launched so far in this process (host-side counter) */
 long long plagnn_launch_count(void);
 /* Optional per-call timing with CUDA events on the launching stream (used by bench.py for the roofline):
- * enable(1) clears and starts recording, enable(0) stops; report() synchronises the recorded events and
+ * enable(1) clears and starts recording every entry point, enable(2) only the aggregation (spmm_*) entry points
+ * (a handful of events per epoch: cheap enough to stay on inside a timed region), enable(0) stops; report() synchronises the recorded events and
  * writes lines "name tag0 tag1 tag2 calls total_ms" (gemm: m n k; spmm_*: feat rows flag).  Returns the
  * number of bytes needed. */
 int plagnn_profile_enable(int on);
@@ -155,7 +156,8 @@ int plagnn_dropout_scale(float* grad, int64_t rows, int64_t feat, int64_t ld, fl
  *   epilogue: v = acc (+ bias[n]);  v = act(v);  if gate: v *= act'(gate[m,n]) with the derivative
  *   written in terms of the saved forward OUTPUT (relu/leaky: sign test, sigmoid: y(1-y)).
  *   Up to PLAGNN_GEMM_MAX_PAIRS pairs accumulate into one tile (fc_self + fc_neigh in one pass).
- *   backend: AUTO picks tcgen05 (3xTF32 split, fp32-level accuracy) when shapes allow.
+ *   backend: AUTO picks PLAGNN_GEMM_TMA (TMA-fed tcgen05 on CTA pairs, 3xTF32 split, fp32-level accuracy) when the
+ *   operands have 16-byte aligned rows, else TCGEN05 (first-generation kernel) / SIMT (exact fp32 FFMA).
  * ---------------------------------------------------------------------------------------- */
 #define PLAGNN_GEMM_MAX_PAIRS 2
 typedef struct {
@@ -170,28 +172,6 @@ int plagnn_gemm(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pa
                 const float* gate, int64_t ldg, int gate_act,
                 float* c, int64_t ldc, void* workspace, size_t workspace_bytes,
                 int backend, plagnn_stream_t stream);
-
-/* The same contraction with TMA-fed operands (backend PLAGNN_GEMM_TMA, what AUTO picks when shapes allow).
- * The tensor core reads an fp32 word as tf32 by dropping its low 13 bits, so the fp32 matrix itself is the "hi" part
- * of the 3xTF32 split and the only derived data is the COMPANION matrix
- *     lo = rn_tf32(x - trunc_tf32(x))          (plagnn_tf32_lo, or written by the producer's epilogue: c_lo below)
- * stored like x (same shape and storage order, own pitch).  plagnn_gemm() derives the companions itself into its
- * workspace on every call; plagnn_gemm_ex() takes them from the caller, which is how the whole-network engine
- * (plagnn_gnn32_*) avoids that pass.  c_lo (optional, pitch ldc) receives the companion of the output.
- * Same reference call sites as plagnn_gemm. */
-typedef struct {
-    const float* a; const float* a_lo; int64_t lda; int64_t lda_lo; int32_t a_trans;
-    const float* b; const float* b_lo; int64_t ldb; int64_t ldb_lo; int32_t b_trans;
-    int64_t k;
-} plagnn_gemm_pair_ex;
-size_t plagnn_gemm_ex_workspace_bytes(int64_t m, int64_t n, int64_t k_total);
-int plagnn_gemm_ex(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair_ex* pairs /* host */,
-                   const float* bias, int act, float slope,
-                   const float* gate, int64_t ldg, int gate_act,
-                   float* c, float* c_lo, int64_t ldc, void* workspace, size_t workspace_bytes,
-                   plagnn_stream_t stream);
-int plagnn_tf32_lo(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* lo, int64_t ldlo,
-                   plagnn_stream_t stream);
 
 /* column sums: out[j] = sum_i x[i,j]   (bias gradients). workspace >= plagnn_colsum_workspace_bytes. */
 size_t plagnn_colsum_workspace_bytes(int64_t rows, int64_t cols);

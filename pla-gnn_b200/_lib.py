@@ -28,12 +28,6 @@ class GemmPair(Structure):
                 ("k", c_int64)]
 
 
-class GemmPairEx(Structure):
-    _fields_ = [("a", c_void_p), ("a_lo", c_void_p), ("lda", c_int64), ("lda_lo", c_int64), ("a_trans", c_int32),
-                ("b", c_void_p), ("b_lo", c_void_p), ("ldb", c_int64), ("ldb_lo", c_int64), ("b_trans", c_int32),
-                ("k", c_int64)]
-
-
 class Gnn32Shape(Structure):
     _fields_ = [("num_nodes", c_int64), ("in_feats", c_int32), ("h1", c_int32), ("h2", c_int32), ("h3", c_int32),
                 ("h4", c_int32), ("classes", c_int32), ("indptr", c_void_p), ("indices", c_void_p), ("plan", c_void_p),
@@ -77,10 +71,6 @@ PROTOTYPES = {
     "plagnn_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "plagnn_gemm": (c_int, [c_int64, c_int64, c_int32, POINTER(GemmPair), c_void_p, c_int, c_float,
                             c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_size_t, c_int, c_void_p]),
-    "plagnn_gemm_ex_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
-    "plagnn_gemm_ex": (c_int, [c_int64, c_int64, c_int32, POINTER(GemmPairEx), c_void_p, c_int, c_float,
-                               c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
-    "plagnn_tf32_lo": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "plagnn_colsum_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "plagnn_colsum": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "plagnn_act_backward": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_float,

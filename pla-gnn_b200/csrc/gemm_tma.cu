@@ -1,26 +1,28 @@
 // K3 (second generation) — dense feature x weight contraction: TMA-fed tcgen05 with CTA pairs, sm_100a.
 //
 // Replaces the cuBLAS SGEMMs behind nn.Linear in code/model.py:16-17,20-28 (fc_pool / fc_self / fc_neigh inside
-// SAGEConv, liner1, liner2) and their autograd backward, like gemm_tc.cu, but without any SIMT work in the main loop.
+// SAGEConv, liner1, liner2) and their autograd backward.  gemm_tc.cu (first generation, operands split by SIMT loader
+// warps) stays as backend PLAGNN_GEMM_TCGEN05 for cross-checks.
 //
 // fp32-level accuracy on TF32 tensor cores (3xTF32):  x = hi + lo,  x*y ~ hi*hi + lo*hi + hi*lo.
-// Measured on B200 (tools/mma_probe.cu): the tensor core TRUNCATES an fp32 word to tf32 (drops the low 13 bits).
-// So the raw fp32 matrix IS the "hi" operand, and the only derived data is the companion matrix
-//     lo = rn_tf32(x - trunc_tf32(x))
-// which the producer of x writes next to it (GEMM epilogue, plagnn_tf32_lo).  All four operand tiles
-// (A, A_lo, B, B_lo) are brought in by TMA straight into the swizzled layouts the UMMA descriptors read:
+// Measured on B200 (tools/mma_probe.cu): the tensor core TRUNCATES an fp32 word to tf32 (drops the low 13 bits), so the
+// raw fp32 tile IS the hi operand and the only derived data is  lo = rn_tf32(x - trunc_tf32(x)).
+// Raw tiles are brought in by TMA straight into the swizzled layouts the UMMA descriptors read:
 //     k-contiguous operand  : box {32 k, 128 rows}, SWIZZLE_128B                  (K-major descriptor)
 //     mn-contiguous operand : 4 boxes {32 mn, 32 k}, SWIZZLE_128B_ATOM_32B         (MN-major descriptor)
-// Out-of-bounds parts of a box read as zero, which handles every K / M / N tail.
+// (out-of-bounds parts of a box read as zero, which handles every K / M / N tail) and eight warps derive the lo tiles
+// in shared memory, elementwise, into a second ring.  Measured: tensor-core operand reads do not compete with LDS/STS
+// for shared-memory bandwidth (the MMA rate is unchanged with 117 B/clk of LDS+STS traffic next to it).
+// A variant that read precomputed lo matrices from global memory doubled L2 and HBM traffic and was dropped.
 //
 // CTA pair (cta_group::2, cluster 2x1x1): one 256 x 256 output tile per pair.  Each CTA stages its own 128 rows of A
-// and its own half (128 rows) of B; the leader CTA issues 256x256x8 MMAs that read both CTAs' shared memory; the
-// accumulators (hi*hi in TMEM columns [0,256), lo*hi + hi*lo in [256,512)) live in each CTA's tensor memory for its
-// 128 rows.  Per CTA and k-block of 32: 64 KB by TMA for 12 MMAs of 128 cycles each: 43 B/clk from L2 and
-// 64 B/clk of operand reads from shared memory, where a 128 x 128 single-CTA tile needs 85 and 128.
-// CG = 1 (128 x 128 tile, one CTA) is kept for bring-up and as a cross-check.
+// and its own half (128 rows) of B; the leader CTA issues 256x256x8 MMAs (128 cycles each, the full tf32 rate) that
+// read both CTAs' shared memory; the accumulators (hi*hi in TMEM columns [0,256), lo*hi + hi*lo in [256,512)) live in
+// each CTA's tensor memory for its 128 rows.  Per CTA and k-block of 32: 32 KB by TMA for 12 MMAs = 1536 cycles,
+// i.e. 21 B/clk from L2 (a 128 x 128 single-CTA tile needs 43).  CG = 1 (128 x 128, one CTA) is kept as a cross-check.
 //
-// Warps: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue (TMEM -> registers -> global).
+// Warps: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = hi/lo split, then epilogue
+// (TMEM -> registers -> swizzled shared-memory image -> TMA store: whole 128-byte lines, tails clipped by the map).
 #include "common.cuh"
 #include <cuda.h>
 #include <cstdlib>
@@ -31,18 +33,18 @@
 
 namespace plagnn {
 
-constexpr int TM_BK = 32, TM_STAGES = 3;
+constexpr int TM_BK = 32;
 constexpr int TM_PART_BYTES = 128 * TM_BK * 4;           // 16 KB: 128 rows x 32 fp32
-constexpr int TM_STAGE_BYTES = 4 * TM_PART_BYTES;        // A, A_lo, B, B_lo
-constexpr int TM_SMEM_BYTES = TM_STAGES * TM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TM_RAW_BYTES = 2 * TM_PART_BYTES;          // one ring stage: the A tile and the B tile of one k-block
+constexpr int TM_RAW_STAGES = 4, TM_LO_STAGES = 3;       // raw fp32 tiles (TMA) / derived lo tiles
+constexpr int TM_SMEM_BYTES = (TM_RAW_STAGES + TM_LO_STAGES) * TM_RAW_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TM_EPI_WARPS = 8;
 constexpr int TM_THREADS = (2 + TM_EPI_WARPS) * 32;
 constexpr int TM_MAX_CHAIN = 40;    // k-blocks per TMEM accumulation chain (see gemm_tc.cu: truncating accumulate)
 
 struct alignas(64) TmParams {
-    CUtensorMap map[PLAGNN_GEMM_MAX_PAIRS][4];    // [pair][A, A_lo, B, B_lo]
-    CUtensorMap map_out[2];                       // C (or the split-K partials) and C_lo as {n, m, splits}, box {32, 32, 1}
-    int inline_lo;                                // 1: no companions; the lo tiles are derived in shared memory by warps 2..9
+    CUtensorMap map[PLAGNN_GEMM_MAX_PAIRS][2];    // [pair][A, B]
+    CUtensorMap map_out;                          // C (or the split-K partials) as {n, m, splits}, box {32, 32, 1}
     int tma_store;                                // 1: epilogue leaves through shared memory + TMA stores (aligned output)
     int64_t ldp;                                  // row pitch of the split-K partials
     int64_t m, n;
@@ -56,10 +58,9 @@ struct alignas(64) TmParams {
     int64_t ldg;
     int gate_act;
     float* c;
-    float* c_lo;
     int64_t ldc;
     float* partial;
-    long long* trace;   // PLAGNN_TMA_TRACE: per-CTA clock64 stamps (16 per CTA, first 64 CTAs), else null
+    long long* trace;   // PLAGNN_TMA_TRACE: per-CTA clock64 stamps (32 per CTA, first 64 CTAs), else null
     int debug;   // PLAGNN_TMA_DEBUG (timing experiments, results are garbage): 1 = TMA loads only for the first ring pass,
                  // 2 = no MMAs, 3 = no stores in the epilogue, 4 = shared-memory images written but not stored
 };
@@ -168,16 +169,10 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
-// 2-D tiled TMA load into this CTA's shared memory; completion bytes go to `bar` (a shared::cluster address, which for
-// CG = 2 is the LEADER CTA's barrier)
-template <int CG>
+// 2-D tiled TMA load into this CTA's shared memory, completion bytes on this CTA's barrier
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    if (CG == 1)
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                     ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-    else
-        asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                     ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 // bulk tensor store of one {32 cols, 32 rows, 1} box from shared memory; out-of-bounds elements are not written
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
@@ -243,10 +238,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;                  // 1024-byte aligned (swizzle atoms)
-    const uint32_t bars = tiles + TM_STAGES * TM_STAGE_BYTES;
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * TM_STAGES, bar_acc = bars + 16 * TM_STAGES;
-    const uint32_t bar_raw = bar_acc + 8;                             // [TM_STAGES]: raw tiles landed (inline_lo mode)
-    const uint32_t tmem_slot = bar_raw + 8 * TM_STAGES;
+    const uint32_t lo_ring = tiles + TM_RAW_STAGES * TM_RAW_BYTES;
+    const uint32_t bars = lo_ring + TM_LO_STAGES * TM_RAW_BYTES;
+    const uint32_t bar_raw_full = bars, bar_raw_empty = bars + 8 * TM_RAW_STAGES;
+    const uint32_t bar_lo_full = bars + 16 * TM_RAW_STAGES, bar_lo_empty = bar_lo_full + 8 * TM_LO_STAGES;
+    const uint32_t bar_acc = bar_lo_empty + 8 * TM_LO_STAGES;
+    const uint32_t tmem_slot = bar_acc + 8;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
     constexpr int TILE_M = 128 * CG, TILE_N = 128 * CG;
@@ -254,7 +251,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
     const int lin_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    long long* tr = (P.trace && lin_cta < 64) ? P.trace + 16 * lin_cta : nullptr;
+    long long* tr = (P.trace && lin_cta < 64) ? P.trace + 32 * lin_cta : nullptr;
     if (tr && t == 0) tr[0] = clock64();
     // N tiles fastest in launch order: the column tiles of one row block run together, so A streams from HBM once
     const int64_t m0 = (int64_t)blockIdx.y * TILE_M, n0 = (int64_t)(blockIdx.x / CG) * TILE_N;
@@ -268,19 +265,20 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     const uint32_t n_half = n_eff / CG;       // rows of B this CTA stages
 
     if (t == 0) {
-        for (int s = 0; s < TM_STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, P.inline_lo ? (uint32_t)(CG * TM_EPI_WARPS) : 1u);
-            mbar_init(bar_empty + 8 * s, 1);
-            mbar_init(bar_raw + 8 * s, 1);
+        for (int s = 0; s < TM_RAW_STAGES; ++s) {
+            mbar_init(bar_raw_full + 8 * s, 1);
+            mbar_init(bar_raw_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < TM_LO_STAGES; ++s) {
+            mbar_init(bar_lo_full + 8 * s, (uint32_t)(CG * TM_EPI_WARPS));   // one arrival per splitting warp of the pair
+            mbar_init(bar_lo_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
         fence_mbar_init();
 #pragma unroll
         for (int p = 0; p < PLAGNN_GEMM_MAX_PAIRS; ++p)
-            if (p < P.npairs)
-                for (int q = 0; q < 4; ++q)
-                    if (!P.inline_lo || !(q & 1)) prefetch_map(&P.map[p][q]);
-        if (P.tma_store) { prefetch_map(&P.map_out[0]); prefetch_map(&P.map_out[1]); }
+            if (p < P.npairs) { prefetch_map(&P.map[p][0]); prefetch_map(&P.map[p][1]); }
+        if (P.tma_store) prefetch_map(&P.map_out);
     }
     if (warp == 1) tmem_alloc<CG>(tmem_slot, TMEM_COLS);
     tc_fence_before();
@@ -291,64 +289,33 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     if (tr && t == 0) tr[1] = clock64();
 
     if (warp == 0) {
-        // ================= TMA producer (one elected lane) =================
+        // ================= TMA producer (one elected lane): raw fp32 tiles of A and B =================
         if (lane == 0) {
-            const uint32_t full0 = CG == 2 ? mapa(bar_full, 0) : bar_full;    // the leader's barriers collect both CTAs' bytes
             const int a_row = (int)(m0 + rank * 128), b_row = (int)(n0 + rank * n_half);
             for (int it = 0; it < nkb; ++it) {
-                const int s = it % TM_STAGES;
-                const uint32_t ph = (uint32_t)((it / TM_STAGES) & 1);
+                const int s = it % TM_RAW_STAGES;
+                const uint32_t ph = (uint32_t)((it / TM_RAW_STAGES) & 1);
                 const long long w0 = tr ? clock64() : 0;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                mbar_wait(bar_raw_empty + 8 * s, ph ^ 1u);
                 if (tr) tr[8] += clock64() - w0;
                 int p = 0, local = kb_beg + it;
                 if (P.npairs > 1 && local >= P.kblocks[0]) { local -= P.kblocks[0]; p = 1; }
                 const int k0 = local * TM_BK;
-                const uint32_t st = tiles + s * TM_STAGE_BYTES;
-                const uint32_t fb = full0 + 8 * s;
-                if (P.debug == 1 && it >= TM_STAGES) {
-                    if (rank == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8 * s) : "memory");
-                    continue;
-                }
-                if (P.inline_lo) {
-                    // raw tiles only, completion on this CTA's own barrier; warps 2..9 derive the lo tiles
-                    const uint32_t rb = bar_raw + 8 * s;
-                    mbar_expect_tx(rb, 2 * TM_PART_BYTES);
-                    if (!AT) {
-                        tma_load_2d<1>(st, &P.map[p][0], k0, a_row, rb);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) tma_load_2d<1>(st + j * 4096, &P.map[p][0], a_row + 32 * j, k0, rb);
-                    }
-                    if (!BT) {
-                        tma_load_2d<1>(st + 2 * TM_PART_BYTES, &P.map[p][2], k0, b_row, rb);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            tma_load_2d<1>(st + 2 * TM_PART_BYTES + j * 4096, &P.map[p][2], b_row + 32 * j, k0, rb);
-                    }
-                    continue;
-                }
-                if (rank == 0) mbar_expect_tx(bar_full + 8 * s, CG * TM_STAGE_BYTES);
+                const uint32_t st = tiles + s * TM_RAW_BYTES;
+                const uint32_t rb = bar_raw_full + 8 * s;
+                mbar_expect_tx(rb, TM_RAW_BYTES);
+                if (tr && (it == 0 || it == 8)) tr[it ? 20 : 16] = clock64();
                 if (!AT) {
-                    tma_load_2d<CG>(st, &P.map[p][0], k0, a_row, fb);
-                    tma_load_2d<CG>(st + TM_PART_BYTES, &P.map[p][1], k0, a_row, fb);
+                    tma_load_2d(st, &P.map[p][0], k0, a_row, rb);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        tma_load_2d<CG>(st + j * 4096, &P.map[p][0], a_row + 32 * j, k0, fb);
-                        tma_load_2d<CG>(st + TM_PART_BYTES + j * 4096, &P.map[p][1], a_row + 32 * j, k0, fb);
-                    }
+                    for (int j = 0; j < 4; ++j) tma_load_2d(st + j * 4096, &P.map[p][0], a_row + 32 * j, k0, rb);
                 }
                 if (!BT) {
-                    tma_load_2d<CG>(st + 2 * TM_PART_BYTES, &P.map[p][2], k0, b_row, fb);
-                    tma_load_2d<CG>(st + 3 * TM_PART_BYTES, &P.map[p][3], k0, b_row, fb);
+                    tma_load_2d(st + TM_PART_BYTES, &P.map[p][1], k0, b_row, rb);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        tma_load_2d<CG>(st + 2 * TM_PART_BYTES + j * 4096, &P.map[p][2], b_row + 32 * j, k0, fb);
-                        tma_load_2d<CG>(st + 3 * TM_PART_BYTES + j * 4096, &P.map[p][3], b_row + 32 * j, k0, fb);
-                    }
+                    for (int j = 0; j < 4; ++j) tma_load_2d(st + TM_PART_BYTES + j * 4096, &P.map[p][1], b_row + 32 * j, k0, rb);
                 }
             }
         }
@@ -361,18 +328,19 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             constexpr uint64_t a_step = AT ? (1024u >> 4) : 2u, b_step = BT ? (1024u >> 4) : 2u;
             const uint32_t acc_main = tmem_base, acc_corr = tmem_base + TILE_N;
             for (int it = 0; it < nkb; ++it) {
-                const int s = it % TM_STAGES;
-                const uint32_t ph = (uint32_t)((it / TM_STAGES) & 1);
+                const int s = it % TM_RAW_STAGES, l = it % TM_LO_STAGES;
+                const uint32_t phl = (uint32_t)((it / TM_LO_STAGES) & 1);
                 const long long w0 = tr ? clock64() : 0;
-                if (CG == 2) mbar_wait_cluster(bar_full + 8 * s, ph);
-                else mbar_wait(bar_full + 8 * s, ph);
+                // the lo tiles of both CTAs are written (which also means the raw tiles have landed in both)
+                if (CG == 2) mbar_wait_cluster(bar_lo_full + 8 * l, phl);
+                else mbar_wait(bar_lo_full + 8 * l, phl);
                 tc_fence_after();
-                if (tr) { const long long w1 = clock64(); tr[9] += w1 - w0; if (it == 0) tr[2] = w1; }
-                const uint32_t st = tiles + s * TM_STAGE_BYTES;
+                if (tr) { const long long w1 = clock64(); tr[9] += w1 - w0; if (it == 0) tr[2] = w1; if (it == 0 || it == 8) tr[it ? 23 : 19] = w1; }
+                const uint32_t st = tiles + s * TM_RAW_BYTES, sl = lo_ring + l * TM_RAW_BYTES;
                 const uint64_t a_hi = AT ? desc_mnmajor(st) : desc_kmajor(st);
-                const uint64_t a_lo = AT ? desc_mnmajor(st + TM_PART_BYTES) : desc_kmajor(st + TM_PART_BYTES);
-                const uint64_t b_hi = BT ? desc_mnmajor(st + 2 * TM_PART_BYTES) : desc_kmajor(st + 2 * TM_PART_BYTES);
-                const uint64_t b_lo = BT ? desc_mnmajor(st + 3 * TM_PART_BYTES) : desc_kmajor(st + 3 * TM_PART_BYTES);
+                const uint64_t a_lo = AT ? desc_mnmajor(sl) : desc_kmajor(sl);
+                const uint64_t b_hi = BT ? desc_mnmajor(st + TM_PART_BYTES) : desc_kmajor(st + TM_PART_BYTES);
+                const uint64_t b_lo = BT ? desc_mnmajor(sl + TM_PART_BYTES) : desc_kmajor(sl + TM_PART_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < TM_BK / 8; ++kk) {
                     if (P.debug == 2) break;
@@ -384,45 +352,48 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     umma_tf32<CG>(acc_corr, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
                     umma_tf32<CG>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
                 }
-                umma_commit<CG>(bar_empty + 8 * s);     // frees the stage in both CTAs when these MMAs have read it
+                // both rings are released (in both CTAs) when the MMAs issued so far have read them
+                umma_commit<CG>(bar_lo_empty + 8 * l);
+                umma_commit<CG>(bar_raw_empty + 8 * s);
             }
             umma_commit<CG>(bar_acc);                   // accumulators complete (both CTAs)
             if (tr) tr[3] = clock64();
         }
         __syncwarp();
     } else {
-        if (P.inline_lo) {
-            // ================= hi/lo split in shared memory =================
-            // The tensor core reads the raw fp32 tile as the hi operand (it drops the low 13 bits itself); the lo tile
-            // has the same swizzled layout 16 KB further on, so the pass is purely elementwise.  Tensor-core operand
-            // reads do not compete with LDS/STS for bandwidth (tools/mma_probe.cu, "contend").
+        {
+            // ================= hi/lo split in shared memory (warps 2..9) =================
+            // The tensor core reads the raw fp32 tile as the hi operand (it drops the low 13 bits itself); the lo tile has
+            // the same swizzled layout, so the pass is purely elementwise: lo[i] = rn_tf32(x[i] - trunc_tf32(x[i])).
+            // Tensor-core operand reads do not compete with LDS/STS for bandwidth (tools/mma_probe.cu, "contend").
+            // The raw ring is 4 deep (TMA latency ~2.5 us), the lo ring 3 deep: the chain "MMAs done -> commit -> split warps -> STS ->
+            // proxy fence -> (remote) arrive -> issuer" measured ~2100 cycles, more than one k-block of MMAs (1536).
             const int ct = t - 64;                                  // 0..255
-            const uint32_t full0 = CG == 2 ? mapa(bar_full, 0) : bar_full;
+            const uint32_t lo_full0 = CG == 2 ? mapa(bar_lo_full, 0) : bar_lo_full;   // the leader's barrier counts both CTAs
             for (int it = 0; it < nkb; ++it) {
-                const int s = it % TM_STAGES;
-                const uint32_t ph = (uint32_t)((it / TM_STAGES) & 1);
+                const int s = it % TM_RAW_STAGES, l = it % TM_LO_STAGES;
+                const uint32_t phr = (uint32_t)((it / TM_RAW_STAGES) & 1), phl = (uint32_t)((it / TM_LO_STAGES) & 1);
                 const long long w0 = (tr && t == 64) ? clock64() : 0;
-                mbar_wait(bar_raw + 8 * s, ph);
-                if (tr && t == 64) tr[10] += clock64() - w0;
-                const uint32_t st = tiles + s * TM_STAGE_BYTES;
+                mbar_wait(bar_raw_full + 8 * s, phr);
+                if (tr && t == 64) { const long long w1 = clock64(); tr[10] += w1 - w0; if (it == 0 || it == 8) tr[it ? 21 : 17] = w1; }
+                const uint32_t src = tiles + s * TM_RAW_BYTES + (uint32_t)ct * 16u;
+                const uint32_t dstl = lo_ring + l * TM_RAW_BYTES + (uint32_t)ct * 16u;
+                float4 v[8];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const uint32_t src = st + (uint32_t)half * 2u * TM_PART_BYTES + (uint32_t)ct * 16u;
-                    float4 v[4];
+                for (int i = 0; i < 8; ++i)
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                 : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(src + (uint32_t)i * 4096u));
+                mbar_wait(bar_lo_empty + 8 * l, phl ^ 1u);
+                if (tr && t == 64 && it == 8) tr[24] = clock64();           // the MMAs of k-block it - TM_LO_STAGES have read this lo stage
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                     : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(src + (uint32_t)i * 4096u));
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        sts_v4(src + TM_PART_BYTES + (uint32_t)i * 4096u, tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z),
-                               tf32_lo(v[i].w));
-                }
+                for (int i = 0; i < 8; ++i)
+                    sts_v4(dstl + (uint32_t)i * 4096u, tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
                 fence_proxy_async_smem();
                 __syncwarp();
+                if (tr && t == 64 && (it == 0 || it == 8)) tr[it ? 22 : 18] = clock64();
                 if (lane == 0) {
-                    if (CG == 2) mbar_arrive_cluster(full0 + 8 * s);
-                    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8 * s) : "memory");
+                    if (CG == 2) mbar_arrive_cluster(lo_full0 + 8 * l);
+                    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_lo_full + 8 * l) : "memory");
                 }
             }
         }
@@ -440,8 +411,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
         // leave the SM, rows >= m / columns >= n are clipped by the tensor map.  Two images in flight per warp.
         // The activation / gate switches sit OUTSIDE the element loops: the first version branched per element and
         // spent 25 000 of its 28 000 epilogue cycles per tile fetching instructions (PLAGNN_TMA_TRACE).
-        const bool want_lo = direct && P.c_lo != nullptr;
-        const uint32_t stg = tiles + (uint32_t)(warp - 2) * 16384u;      // [buffer 0/1][C 4 KB | C_lo 4 KB]
+        const uint32_t stg = tiles + (uint32_t)(warp - 2) * 8192u;       // two 4 KB images per warp
         const uint32_t row_off = (uint32_t)lane * 128u;
         const int row0 = (int)(m0 + rank * 128 + lg * 32);
         const int64_t r_ld = r < P.m ? r : P.m - 1;                      // clamped row for gate loads (clipped rows are never stored)
@@ -456,6 +426,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             const int ncol = (int)((P.n - c0) < 32 ? (P.n - c0) : 32);   // valid columns of this chunk
             float v[32];
             {
+                // (reading both accumulators is what bounds the epilogue: ~7 500 cycles per tile for 2 x 128 KB of TMEM;
+                // issuing the next chunk's loads early changed nothing)
                 uint32_t acc[32], acc_small[32];
                 const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)cbase;
                 const long long e0 = (tr && t == 64) ? clock64() : 0;
@@ -504,25 +476,16 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 if (lane == 0) bulk_wait_read<1>();      // the image written two chunks ago has been read
                 __syncwarp();
                 if (tr && t == 64) tr[14] += clock64() - e1;
-                const uint32_t img = stg + (uint32_t)buf * 8192u;
+                const uint32_t img = stg + (uint32_t)buf * 4096u;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const uint32_t off = row_off + (uint32_t)((q ^ (lane & 7)) << 4);
                     sts_v4(img + off, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 }
-                if (want_lo) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t off = row_off + (uint32_t)((q ^ (lane & 7)) << 4);
-                        sts_v4(img + 4096u + off, tf32_lo(v[4 * q]), tf32_lo(v[4 * q + 1]), tf32_lo(v[4 * q + 2]),
-                               tf32_lo(v[4 * q + 3]));
-                    }
-                }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0 && P.debug != 4) {
-                    tma_store_3d(&P.map_out[0], img, (int)c0, row0, direct ? 0 : split);
-                    if (want_lo) tma_store_3d(&P.map_out[1], img + 4096u, (int)c0, row0, 0);
+                    tma_store_3d(&P.map_out, img, (int)c0, row0, direct ? 0 : split);
                     bulk_commit();
                 }
                 if (tr && t == 64) tr[15] += clock64() - e1;
@@ -530,13 +493,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             } else if (r < P.m) {
                 // unaligned destination (row pitch % 4 != 0): plain scalar stores
                 float* drow = dst + r * ldd + c0;
-                float* lrow = want_lo ? P.c_lo + r * ldd + c0 : nullptr;
 #pragma unroll 4
                 for (int j = 0; j < 32; ++j)
-                    if (j < ncol) {
-                        drow[j] = v[j];
-                        if (lrow) lrow[j] = tf32_lo(v[j]);
-                    }
+                    if (j < ncol) drow[j] = v[j];
             }
         }
         if (tr && t == 64) tr[5] = clock64();
@@ -556,7 +515,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     if (tr && t == 0) { tr[7] = clock64(); tr[11] = nkb; tr[12] = rank; }
 }
 
-// ordered reduction of split-K partials + epilogue (+ companion)
+// ordered reduction of split-K partials + epilogue
 __global__ void __launch_bounds__(256) gemm_tma_reduce_kernel(const __grid_constant__ TmParams P) {
     const int64_t total = P.m * P.n;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -566,43 +525,7 @@ __global__ void __launch_bounds__(256) gemm_tma_reduce_kernel(const __grid_const
         for (int z = 0; z < P.splits; ++z) s += q[(int64_t)z * P.m * P.ldp];
         const float v = tm_epilogue_one(P, s, r, c);
         P.c[r * P.ldc + c] = v;
-        if (P.c_lo) P.c_lo[r * P.ldc + c] = tf32_lo(v);
     }
-}
-
-// companion matrix of an fp32 matrix (same pitch conventions as the source; columns [cols, ldlo) are not touched)
-__global__ void __launch_bounds__(256) tf32_lo_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int64_t cols,
-                                                      float* __restrict__ lo, int64_t ldlo, int vec) {
-    if (vec) {
-        const int64_t c4 = cols >> 2, total = rows * c4;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-            const int64_t r = i / c4, q = i - r * c4;
-            const float4 v = ldg_f4(x + r * ldx + 4 * q);
-            *reinterpret_cast<float4*>(lo + r * ldlo + 4 * q) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
-        }
-    } else {
-        const int64_t total = rows * cols;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-            const int64_t r = i / cols, c = i - r * cols;
-            lo[r * ldlo + c] = tf32_lo(__ldg(x + r * ldx + c));
-        }
-    }
-}
-
-int tf32_lo_launch(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* lo, int64_t ldlo, cudaStream_t st) {
-    // whole padded rows when both pitches allow it: the pad columns of x are finite (zero) by the library's convention
-    int64_t c = cols;
-    const bool al = aligned16(x) && aligned16(lo) && (ldx & 3) == 0 && (ldlo & 3) == 0;
-    const int64_t c_up = (cols + 3) / 4 * 4;
-    const int vec = al && c_up <= ldx && c_up <= ldlo;
-    if (vec) c = c_up;
-    const int64_t work = vec ? rows * (c >> 2) : rows * c;
-    int64_t g = ceil_div(work, 256);
-    const int64_t cap = (int64_t)sm_count() * 16;
-    if (g > cap) g = cap;
-    if (g < 1) g = 1;
-    tf32_lo_kernel<<<(unsigned)g, 256, 0, st>>>(x, ldx, rows, c, lo, ldlo, vec);
-    return check_launch("tf32_lo");
 }
 
 // ---- host side: tensor maps ---------------------------------------------------------------------
@@ -706,14 +629,14 @@ static long long* g_trace = nullptr;
 static long long* trace_buffer(cudaStream_t st) {
     static const bool on = getenv("PLAGNN_TMA_TRACE") != nullptr;
     if (!on) return nullptr;
-    if (!g_trace && cudaMalloc(&g_trace, 64 * 16 * sizeof(long long)) != cudaSuccess) return nullptr;
-    cudaMemsetAsync(g_trace, 0, 64 * 16 * sizeof(long long), st);
+    if (!g_trace && cudaMalloc(&g_trace, 64 * 32 * sizeof(long long)) != cudaSuccess) return nullptr;
+    cudaMemsetAsync(g_trace, 0, 64 * 32 * sizeof(long long), st);
     return g_trace;
 }
-extern "C" int plagnn_tma_trace(long long* host_out /* 64 x 16 */) {
+extern "C" int plagnn_tma_trace(long long* host_out /* 64 x 32 */) {
     if (!g_trace) return -1;
     cudaDeviceSynchronize();
-    return cudaMemcpy(host_out, g_trace, 64 * 16 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+    return cudaMemcpy(host_out, g_trace, 64 * 32 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
 }
 
 // PLAGNN_TMA_CG=1 selects the single-CTA 128 x 128 tile (bring-up / cross-check); read per call so tests can flip it
@@ -758,56 +681,35 @@ size_t gemm_tma_partial_bytes(int64_t m, int64_t n, int64_t k_total) {
     return s > 1 ? align_up((size_t)s * (size_t)m * (size_t)((n + 3) / 4 * 4) * sizeof(float), 256) : 0;
 }
 
-bool gemm_tma_eligible(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair_ex* pairs) {
+bool gemm_tma_eligible(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs) {
     if (n < 16 || m < 1) return false;
     for (int p = 0; p < npairs; ++p) {
-        const plagnn_gemm_pair_ex& q = pairs[p];
+        const plagnn_gemm_pair& q = pairs[p];
         if (q.k < 8) return false;
         if ((q.lda & 3) || (q.ldb & 3) || !aligned16(q.a) || !aligned16(q.b)) return false;
-        if ((q.a_lo || q.b_lo) && ((q.lda_lo & 3) || (q.ldb_lo & 3) || !aligned16(q.a_lo) || !aligned16(q.b_lo))) return false;
         if ((q.a_trans != 0) != (pairs[0].a_trans != 0) || (q.b_trans != 0) != (pairs[0].b_trans != 0)) return false;
         if (q.k > INT_MAX - 64 || m > INT_MAX - 512 || n > INT_MAX - 512) return false;
     }
     return true;
 }
 
-// Either every pair carries its companions (a_lo / b_lo with their own pitches) or none does (lo tiles derived in-SM).
-int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair_ex* pairs, const float* bias, int act,
-                    float slope, const float* gate, int64_t ldg, int gate_act, float* c, float* c_lo, int64_t ldc,
-                    void* workspace, size_t workspace_bytes, cudaStream_t st) {
+int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs, const float* bias, int act,
+                    float slope, const float* gate, int64_t ldg, int gate_act, float* c, int64_t ldc, void* workspace,
+                    size_t workspace_bytes, cudaStream_t st) {
     TmParams P;
     memset(&P, 0, sizeof(P));
     P.m = m; P.n = n; P.npairs = npairs;
     P.total_kblocks = 0;
-    bool any_lo = false, all_lo = true;
     for (int p = 0; p < npairs; ++p) {
-        any_lo = any_lo || pairs[p].a_lo || pairs[p].b_lo;
-        all_lo = all_lo && pairs[p].a_lo && pairs[p].b_lo;
-    }
-    if (any_lo && !all_lo) return fail(PLAGNN_ERR_ARG, "gemm_tma", "companions must be given for every operand or for none");
-    P.inline_lo = any_lo ? 0 : 1;
-    for (int p = 0; p < npairs; ++p) {
-        const plagnn_gemm_pair_ex& q = pairs[p];
+        const plagnn_gemm_pair& q = pairs[p];
         P.kblocks[p] = (int)ceil_div(q.k, TM_BK);
         P.total_kblocks += P.kblocks[p];
         int rc;
-        if (!q.a_trans) {
-            if ((rc = get_map(&P.map[p][0], q.a, q.k, m, q.lda, 0))) return rc;
-            if (any_lo && (rc = get_map(&P.map[p][1], q.a_lo, q.k, m, q.lda_lo, 0))) return rc;
-        } else {
-            if ((rc = get_map(&P.map[p][0], q.a, m, q.k, q.lda, 1))) return rc;
-            if (any_lo && (rc = get_map(&P.map[p][1], q.a_lo, m, q.k, q.lda_lo, 1))) return rc;
-        }
-        if (!q.b_trans) {
-            if ((rc = get_map(&P.map[p][2], q.b, q.k, n, q.ldb, 0))) return rc;
-            if (any_lo && (rc = get_map(&P.map[p][3], q.b_lo, q.k, n, q.ldb_lo, 0))) return rc;
-        } else {
-            if ((rc = get_map(&P.map[p][2], q.b, n, q.k, q.ldb, 1))) return rc;
-            if (any_lo && (rc = get_map(&P.map[p][3], q.b_lo, n, q.k, q.ldb_lo, 1))) return rc;
-        }
+        if ((rc = q.a_trans ? get_map(&P.map[p][0], q.a, m, q.k, q.lda, 1) : get_map(&P.map[p][0], q.a, q.k, m, q.lda, 0))) return rc;
+        if ((rc = q.b_trans ? get_map(&P.map[p][1], q.b, n, q.k, q.ldb, 1) : get_map(&P.map[p][1], q.b, q.k, n, q.ldb, 0))) return rc;
     }
     P.bias = bias; P.act = act; P.slope = slope; P.gate = gate; P.ldg = ldg; P.gate_act = gate_act;
-    P.c = c; P.c_lo = c_lo; P.ldc = ldc;
+    P.c = c; P.ldc = ldc;
     { const char* e = getenv("PLAGNN_TMA_DEBUG"); P.debug = e ? atoi(e) : 0; }
     P.trace = trace_buffer(st);
     const int cg = tm_cg();
@@ -826,13 +728,10 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
             P.tma_store = 0;
         } else if (P.splits > 1) {
             P.tma_store = 1;
-            if ((rc = get_out_map(&P.map_out[0], P.partial, n, m, P.splits, P.ldp))) return rc;
-            P.map_out[1] = P.map_out[0];
-        } else if ((ldc & 3) == 0 && aligned16(c) && (!c_lo || aligned16(c_lo))) {
+            if ((rc = get_out_map(&P.map_out, P.partial, n, m, P.splits, P.ldp))) return rc;
+        } else if ((ldc & 3) == 0 && aligned16(c)) {
             P.tma_store = 1;
-            if ((rc = get_out_map(&P.map_out[0], c, n, m, 1, ldc))) return rc;
-            if (c_lo) { if ((rc = get_out_map(&P.map_out[1], c_lo, n, m, 1, ldc))) return rc; }
-            else P.map_out[1] = P.map_out[0];
+            if ((rc = get_out_map(&P.map_out, c, n, m, 1, ldc))) return rc;
         } else {
             P.tma_store = 0;
         }

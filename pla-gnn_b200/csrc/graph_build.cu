@@ -41,7 +41,9 @@ static std::atomic<int> g_prof_on{0};
 
 ProfileScope::ProfileScope(const char* name, long long t0, long long t1, long long t2, plagnn_stream_t stream)
     : slot(-1), st((cudaStream_t)stream) {
-    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    const int mode = g_prof_on.load(std::memory_order_relaxed);
+    if (!mode) return;
+    if (mode == 2 && strncmp(name, "spmm", 4) != 0) return;      // aggregation kernels only (low-overhead mode)
     ProfRec r{};
     snprintf(r.name, sizeof(r.name), "%s", name);
     r.tag[0] = t0; r.tag[1] = t1; r.tag[2] = t2;
@@ -339,7 +341,7 @@ int plagnn_profile_enable(int on) {
         for (auto& r : g_prof) { cudaEventDestroy(r.beg); cudaEventDestroy(r.end); }
         g_prof.clear();
     }
-    g_prof_on.store(on ? 1 : 0);
+    g_prof_on.store(on == 2 ? 2 : on ? 1 : 0);
     return PLAGNN_OK;
 }
 

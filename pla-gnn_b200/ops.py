@@ -52,9 +52,10 @@ class _timed:
         return False
 
 
-def profile_start() -> None:
-    """Start per-call CUDA-event timing inside the library (all entry points, C- or Python-orchestrated)."""
-    _lib.load().plagnn_profile_enable(1)
+def profile_start(aggregation_only: bool = False) -> None:
+    """Start per-call CUDA-event timing inside the library (all entry points, C- or Python-orchestrated).
+    aggregation_only: record the spmm_* entry points only (6 calls per epoch: negligible overhead)."""
+    _lib.load().plagnn_profile_enable(2 if aggregation_only else 1)
 
 
 def profile_stop() -> dict:
@@ -173,43 +174,6 @@ def gemm(m: int, n: int, pairs, bias=None, act=ACT_NONE, gate=None, gate_act=ACT
         check(lib.plagnn_gemm(m, n, len(pairs), arr, _p(bias), act, slope, _p(gate),
                               gate.stride(0) if gate is not None else 0, gate_act, _p(out), out.stride(0), _p(ws),
                               ws_bytes if ws is not None else 0, backend, _stream()), "gemm")
-    return out
-
-
-def tf32_lo(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-    """Companion matrix lo = rn_tf32(x - trunc_tf32(x)) of a row-aligned fp32 matrix (same shape and pitch)."""
-    _require_cuda_f32(x, out)
-    assert x.dim() == 2 and x.stride(1) == 1
-    if out is None:
-        out = alloc(x.shape[0], x.shape[1], x.device)
-    check(_lib.load().plagnn_tf32_lo(_p(x), x.stride(0), x.shape[0], x.shape[1], _p(out), out.stride(0), _stream()),
-          "tf32_lo")
-    return out
-
-
-def gemm_ex(m: int, n: int, pairs, bias=None, act=ACT_NONE, gate=None, gate_act=ACT_NONE, out=None, out_lo=None,
-            slope: float = LEAKY_SLOPE) -> torch.Tensor:
-    """TMA-fed contraction with caller-provided companions.  pairs: list of (a, a_lo, a_trans, b, b_lo, b_trans, k);
-    out_lo (optional, same pitch as out) receives the companion of the result."""
-    lib = _lib.load()
-    dev = pairs[0][0].device
-    arr = (_lib.GemmPairEx * len(pairs))()
-    ktot = 0
-    for i, (a, a_lo, a_trans, b, b_lo, b_trans, k) in enumerate(pairs):
-        _require_cuda_f32(a, a_lo, b, b_lo)
-        arr[i] = _lib.GemmPairEx(a.data_ptr(), a_lo.data_ptr(), a.stride(0), a_lo.stride(0), int(a_trans),
-                                 b.data_ptr(), b_lo.data_ptr(), b.stride(0), b_lo.stride(0), int(b_trans), int(k))
-        ktot += int(k)
-    if out is None:
-        out = alloc(m, n, dev)
-    _require_cuda_f32(out, out_lo, bias, gate)
-    assert out_lo is None or out_lo.stride(0) == out.stride(0)
-    ws_bytes = lib.plagnn_gemm_ex_workspace_bytes(m, n, ktot)
-    ws = workspace(ws_bytes, dev, "gemm")
-    with _timed(("gemm", m, n, ktot)):
-        check(lib.plagnn_gemm_ex(m, n, len(pairs), arr, _p(bias), act, slope, _p(gate),
-                                 gate.stride(0) if gate is not None else 0, gate_act, _p(out), _p(out_lo), out.stride(0),
-                                 _p(ws), ws_bytes if ws is not None else 0, _stream()), "gemm_ex")
     return out
 
 

@@ -43,8 +43,7 @@ def test_workspace_size_queries_are_pure_host_calls():
     assert lib.plagnn_spmm_partial_bytes(0, 503, 1) == 0
     assert lib.plagnn_spmm_partial_bytes(10, 503, 1) >= 2 * 10 * 504 * 4
     assert lib.plagnn_gemm_workspace_bytes(400, 503, 24041) > 0
-    assert lib.plagnn_gemm_ex_workspace_bytes(24041, 503, 503) == 0
-    assert lib.plagnn_gemm_ex_workspace_bytes(400, 503, 24041) > 0
+    assert lib.plagnn_gemm_workspace_bytes(24041, 503, 503) == 0
     assert lib.plagnn_bce_workspace_bytes(8000, 12) >= 32 * 12 * 8
 
 

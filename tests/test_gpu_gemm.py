@@ -137,28 +137,11 @@ def test_tcgen05_and_simt_agree_on_ppi_layer_shape(cuda):
     assert ((s - t).abs().max() / s.abs().max()).item() < TOL
 
 
-# ---- TMA-fed kernel: both tile configurations, caller-provided companions, companion of the output ----
+# ---- TMA-fed kernel: both tile configurations (CTA pair 256 x 256, single CTA 128 x 128) ----
 @pytest.fixture(params=["1", "2"], ids=["cg1", "cg2"])
 def cta_group(request, monkeypatch):
     monkeypatch.setenv("PLAGNN_TMA_CG", request.param)
     return request.param
-
-
-def tf32_lo_ref(x):
-    b = x.cpu().contiguous().view(torch.int32)
-    hi = (b & -8192).view(torch.float32)
-    d = (x.cpu() - hi).contiguous().view(torch.int32)
-    return ((d + 0x1000) & -8192).view(torch.float32)
-
-
-def test_tf32_lo_bit_exact(cuda):
-    x = ops.aligned(torch.randn(333, 503, generator=torch.Generator().manual_seed(11)).to(cuda) * 37.0)
-    lo = ops.tf32_lo(x)
-    assert torch.equal(lo.cpu()[:, :503], tf32_lo_ref(x)[:, :503])
-    # hi + lo reproduces x to 2^-21 |x| and lo is on the tf32 grid
-    hi = (x.cpu().contiguous().view(torch.int32) & -8192).view(torch.float32)
-    assert ((hi + lo.cpu() - x.cpu()).abs() <= x.cpu().abs() * 2.0 ** -21).all()
-    assert ((lo.cpu().contiguous().view(torch.int32) & 8191) == 0).all()
 
 
 @pytest.mark.parametrize("m,n,k", [(128, 128, 32), (256, 256, 64), (300, 200, 100), (1000, 503, 503), (257, 100, 200),
@@ -172,18 +155,15 @@ def test_gemm_tma_layouts_both_tile_configs(cuda, cta_group, m, n, k, at, bt):
     assert rel(got, ref_gemm(pairs, None, 0, None, 0)) < TOL
 
 
-def test_gemm_ex_companions_two_pairs_and_output_companion(cuda, cta_group):
+def test_gemm_tma_two_pairs_epilogues_both_tile_configs(cuda, cta_group):
     m, n, k1, k2 = 700, 300, 400, 200
     a1, b1 = operand(m, k1, 0, cuda, 5, True), operand(n, k1, 0, cuda, 6, True).mul_(k1 ** -0.5)
     a2, b2 = operand(m, k2, 0, cuda, 7, True), operand(n, k2, 0, cuda, 8, True).mul_(k2 ** -0.5)
     bias = torch.randn(n, device=cuda)
-    out = ops.alloc(m, n, cuda)
-    out_lo = ops.alloc(m, n, cuda)
-    ex = [(a1, ops.tf32_lo(a1), 0, b1, ops.tf32_lo(b1), 0, k1), (a2, ops.tf32_lo(a2), 0, b2, ops.tf32_lo(b2), 0, k2)]
-    ops.gemm_ex(m, n, ex, bias=bias, act=ops.ACT_LEAKY, out=out, out_lo=out_lo)
-    want = ref_gemm([(a1, 0, b1, 0, k1), (a2, 0, b2, 0, k2)], bias, ops.ACT_LEAKY, None, 0)
-    assert rel(out, want) < TOL
-    assert torch.equal(out_lo.cpu(), tf32_lo_ref(out))
+    gate = ops.aligned(torch.randn(m, n, device=cuda))
+    pairs = [(a1, 0, b1, 0, k1), (a2, 0, b2, 0, k2)]
+    got = ops.gemm(m, n, pairs, bias=bias, act=ops.ACT_LEAKY, gate=gate, gate_act=ops.ACT_LEAKY, backend=ops.GEMM_TMA)
+    assert rel(got, ref_gemm(pairs, bias, ops.ACT_LEAKY, gate, ops.ACT_LEAKY)) < TOL
 
 
 def test_gemm_tma_weight_gradient_split_k_both_tile_configs(cuda, cta_group):

@@ -1,5 +1,5 @@
-"""GEMM backends on the PPI layer shapes: old in-kernel-split tcgen05 kernel vs the TMA-fed kernel (with the companion
-pre-pass of plagnn_gemm, and through plagnn_gemm_ex with companions resident).  CUDA events, warm.
+"""GEMM backends on the PPI layer shapes: first-generation tcgen05 kernel (SIMT loader warps) vs the TMA-fed CTA-pair
+kernel.  CUDA events, warm.
     python tools/gemm_bench.py [cg]  > gpurun_out/gemm_bench.log"""
 import os
 import sys
@@ -36,22 +36,15 @@ for (m, n, k, at, bt, pr) in shapes:
     a = ops.aligned(torch.randn((k, m) if at else (m, k), device=dev))
     b = ops.aligned(torch.randn((k, n) if bt else (n, k), device=dev))
     out = ops.alloc(m, n, dev)
-    out_lo = ops.alloc(m, n, dev)
     fl = 2.0 * m * n * k * pr
     row = f"m={m:6d} n={n:5d} k={k:6d} at={at} bt={bt} pairs={pr}: "
     pairs = [(a, at, b, bt, k)] * pr
     ref = None
-    for name, be in (("tcgen05", ops.GEMM_TCGEN05), ("tma inline-lo", ops.GEMM_TMA)):
+    for name, be in (("tcgen05", ops.GEMM_TCGEN05), ("tma", ops.GEMM_TMA)):
         ms = timeit(lambda: ops.gemm(m, n, pairs, out=out, backend=be))
         row += f"{name} {ms:.4f} ms {fl / ms / 1e9:.1f} TF | "
         if ref is None:
             ref = out.clone()
         else:
             row += f"(diff {((out - ref).abs().max() / ref.abs().max()).item():.1e}) "
-    al, bl = ops.tf32_lo(a), ops.tf32_lo(b)
-    ex = [(a, al, at, b, bl, bt, k)] * pr
-    ms = timeit(lambda: ops.gemm_ex(m, n, ex, out=out, out_lo=out_lo))
-    row += f"tma companions+c_lo {ms:.4f} ms {fl / ms / 1e9:.1f} TF (diff {((out - ref).abs().max() / ref.abs().max()).item():.1e})"
-    ms = timeit(lambda: ops.tf32_lo(a, out=al))
-    row += f" | lo(A) {ms:.4f} ms"
     print(row, flush=True)

@@ -1,4 +1,4 @@
-"""One GEMM shape through plagnn_gemm_ex, timed (CUDA events) — for PLAGNN_TMA_DEBUG experiments and ncu captures.
+"""One GEMM shape through the TMA-fed backend, timed (CUDA events) — for PLAGNN_TMA_DEBUG experiments and ncu captures.
     python tools/gemm_once.py m n k at bt [reps]"""
 import os
 import sys
@@ -13,16 +13,15 @@ m, n, k, at, bt = (int(v) for v in sys.argv[1:6])
 reps = int(sys.argv[6]) if len(sys.argv) > 6 else 20
 a = ops.aligned(torch.randn((k, m) if at else (m, k), device=dev))
 b = ops.aligned(torch.randn((k, n) if bt else (n, k), device=dev))
-al, bl = ops.tf32_lo(a), ops.tf32_lo(b)
-out, out_lo = ops.alloc(m, n, dev), ops.alloc(m, n, dev)
-ex = [(a, al, at, b, bl, bt, k)]
+out = ops.alloc(m, n, dev)
+pairs = [(a, at, b, bt, k)]
 for _ in range(3):
-    ops.gemm_ex(m, n, ex, out=out, out_lo=out_lo)
+    ops.gemm(m, n, pairs, out=out, backend=ops.GEMM_TMA)
 torch.cuda.synchronize()
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s.record()
 for _ in range(reps):
-    ops.gemm_ex(m, n, ex, out=out, out_lo=out_lo)
+    ops.gemm(m, n, pairs, out=out, backend=ops.GEMM_TMA)
 e.record()
 torch.cuda.synchronize()
 ms = s.elapsed_time(e) / reps
