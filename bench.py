@@ -326,7 +326,7 @@ def run_ours(args):
         out["cpu_baseline"] = cpu_baseline(prob, train_index, args.cpu_seconds)
     print(json.dumps(out))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", f"bench_kernels_n{world}.json"), "w") as fh:
+    with open(os.path.join(ROOT, "gpurun_out", f"bench_kernels_n{world}_s{args.steps}.json"), "w") as fh:
         json.dump(kernels, fh, indent=1)
     if world > 1:
         import torch.distributed as dist

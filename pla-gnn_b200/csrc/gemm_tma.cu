@@ -45,6 +45,8 @@ constexpr int TM_MAX_CHAIN = 40;    // k-blocks per TMEM accumulation chain (see
 struct alignas(64) TmParams {
     CUtensorMap map[PLAGNN_GEMM_MAX_PAIRS][2];    // [pair][A, B]
     CUtensorMap map_out;                          // C (or the split-K partials) as {n, m, splits}, box {32, 32, 1}
+    CUtensorMap map_gate;                         // gate as {n, m}, box {32, 32} (gate_tma = 1)
+    int gate_tma;
     int tma_store;                                // 1: epilogue leaves through shared memory + TMA stores (aligned output)
     int64_t ldp;                                  // row pitch of the split-K partials
     int64_t m, n;
@@ -60,6 +62,7 @@ struct alignas(64) TmParams {
     float* c;
     int64_t ldc;
     float* partial;
+    int single_acc;     // PLAGNN_TMA_SINGLE_ACC=1 (experiment): corrections accumulate into the main accumulator
     long long* trace;   // PLAGNN_TMA_TRACE: per-CTA clock64 stamps (32 per CTA, first 64 CTAs), else null
     int debug;   // PLAGNN_TMA_DEBUG (timing experiments, results are garbage): 1 = TMA loads only for the first ring pass,
                  // 2 = no MMAs, 3 = no stores in the epilogue, 4 = shared-memory images written but not stored
@@ -93,15 +96,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
-// arrive (release at cluster scope) on a barrier given by its shared::cluster address (own or peer CTA)
+// arrive on a barrier given by its shared::cluster address (own or peer CTA).  Default semantics (release at CTA scope),
+// as CUTLASS' ClusterBarrier::arrive does: `.release.cluster` compiles to MEMBAR.ALL.GPU, which cost ~1 500 cycles per
+// k-block on the critical path.  What the peer's tensor core reads was made visible to the async proxy by
+// fence.proxy.async before this arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
@@ -243,7 +249,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     const uint32_t bar_raw_full = bars, bar_raw_empty = bars + 8 * TM_RAW_STAGES;
     const uint32_t bar_lo_full = bars + 16 * TM_RAW_STAGES, bar_lo_empty = bar_lo_full + 8 * TM_LO_STAGES;
     const uint32_t bar_acc = bar_lo_empty + 8 * TM_LO_STAGES;
-    const uint32_t tmem_slot = bar_acc + 8;
+    const uint32_t bar_gate = bar_acc + 8;                          // [TM_EPI_WARPS]: gate images of one warp landed
+    const uint32_t tmem_slot = bar_gate + 8 * TM_EPI_WARPS;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
     constexpr int TILE_M = 128 * CG, TILE_N = 128 * CG;
@@ -274,11 +281,13 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             mbar_init(bar_lo_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
+        for (int w = 0; w < TM_EPI_WARPS; ++w) mbar_init(bar_gate + 8 * w, 1);
         fence_mbar_init();
 #pragma unroll
         for (int p = 0; p < PLAGNN_GEMM_MAX_PAIRS; ++p)
             if (p < P.npairs) { prefetch_map(&P.map[p][0]); prefetch_map(&P.map[p][1]); }
         if (P.tma_store) prefetch_map(&P.map_out);
+        if (P.gate_tma) prefetch_map(&P.map_gate);
     }
     if (warp == 1) tmem_alloc<CG>(tmem_slot, TMEM_COLS);
     tc_fence_before();
@@ -348,6 +357,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     // corrections go to their own accumulator: the tensor core adds into TMEM with truncation, and the
                     // main accumulator then sees a third of the additions (gemm_tc.cu has the measurements)
                     const uint32_t acc_on = (it | kk) ? 1u : 0u;
+                    if (P.single_acc) {
+                        umma_tf32<CG>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
+                        umma_tf32<CG>(acc_main, a_lo + adv_a, b_hi + adv_b, idesc, 1u);
+                        umma_tf32<CG>(acc_main, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
+                        continue;
+                    }
                     umma_tf32<CG>(acc_corr, a_lo + adv_a, b_hi + adv_b, idesc, acc_on);
                     umma_tf32<CG>(acc_corr, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
                     umma_tf32<CG>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
@@ -415,6 +430,23 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
         const uint32_t row_off = (uint32_t)lane * 128u;
         const int row0 = (int)(m0 + rank * 128 + lg * 32);
         const int64_t r_ld = r < P.m ? r : P.m - 1;                      // clamped row for gate loads (clipped rows are never stored)
+        // gate tiles (saved activations of the backward epilogues) come in by TMA as 32 x 32 SWIZZLE_128B images, all chunks
+        // of this warp at once, while the first accumulator chunk is read (per-lane row-strided __ldg cost ~40 us per GEMM)
+        const bool gate_img_on = direct && P.gate && P.gate_tma;
+        const uint32_t gimg = tiles + 65536u + (uint32_t)(warp - 2) * 16384u;    // CHUNKS x 4 KB per warp
+        const uint32_t gbar = bar_gate + 8 * (uint32_t)(warp - 2);
+        if (gate_img_on && lane == 0) {
+            int nch = 0;
+            for (int ch = 0; ch < CHUNKS; ++ch) {
+                const int cb = (chalf * CHUNKS + ch) * 32;
+                if (cb < (int)n_eff && n0 + cb < P.n) ++nch;
+            }
+            if (nch) {
+                mbar_expect_tx(gbar, (uint32_t)nch * 4096u);
+                for (int ch = 0; ch < nch; ++ch)
+                    tma_load_2d(gimg + (uint32_t)ch * 4096u, &P.map_gate, (int)(n0 + (chalf * CHUNKS + ch) * 32), row0, gbar);
+            }
+        }
         float* dst = direct ? P.c : P.partial + (int64_t)split * P.m * P.ldp;
         const int64_t ldd = direct ? P.ldc : P.ldp;
         int buf = 0;
@@ -436,7 +468,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 tmem_ld_wait();
                 if (tr && t == 64) tr[13] += clock64() - e0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + __uint_as_float(acc_small[j]);
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + (P.single_acc ? 0.f : __uint_as_float(acc_small[j]));
             }
             if (direct) {
                 if (P.bias) {
@@ -453,7 +485,25 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
 #pragma unroll 4
                     for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
                 }
-                if (P.gate) {
+                if (gate_img_on) {
+                    if (ch == 0) mbar_wait(gbar, 0);
+                    float g[32];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(g[4 * q]), "=f"(g[4 * q + 1]), "=f"(g[4 * q + 2]), "=f"(g[4 * q + 3])
+                                     : "r"(gimg + (uint32_t)ch * 4096u + row_off + (uint32_t)((q ^ (lane & 7)) << 4)));
+                    if (P.gate_act == PLAGNN_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = g[j] > 0.f ? v[j] : 0.f;
+                    } else if (P.gate_act == PLAGNN_ACT_LEAKY) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = g[j] > 0.f ? v[j] : v[j] * P.slope;
+                    } else if (P.gate_act == PLAGNN_ACT_SIGMOID) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= g[j] * (1.f - g[j]);
+                    }
+                } else if (P.gate) {
                     const float* g = P.gate + r_ld * P.ldg + c0;
                     if (P.gate_act == PLAGNN_ACT_RELU) {
 #pragma unroll
@@ -576,12 +626,12 @@ static int get_map(CUtensorMap* out, const float* base, int64_t inner, int64_t o
     if (!enc) return fail(PLAGNN_ERR_CUDA, "gemm_tma", "cuTensorMapEncodeTiled not available");
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
     cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
-    cuuint32_t box[2] = {32u, mn_major ? 32u : 128u};
+    cuuint32_t box[2] = {32u, mn_major ? 32u : 128u};      // mn_major == 2: a 32 x 32 box of a row-major matrix (gate tiles)
     cuuint32_t estr[2] = {1, 1};
     CUtensorMap m;
     const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           mn_major == 1 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("gemm_tma: cuTensorMapEncodeTiled failed (%d) base=%p inner=%lld outer=%lld pitch=%lld", (int)r, (const void*)base,
@@ -712,6 +762,7 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
     P.c = c; P.ldc = ldc;
     { const char* e = getenv("PLAGNN_TMA_DEBUG"); P.debug = e ? atoi(e) : 0; }
     P.trace = trace_buffer(st);
+    { const char* e = getenv("PLAGNN_TMA_SINGLE_ACC"); P.single_acc = (e && e[0] == '1') ? 1 : 0; }
     const int cg = tm_cg();
     const int splits = tm_choose_splits(m, n, P.total_kblocks, cg);
     P.ldp = (n + 3) / 4 * 4;
@@ -735,6 +786,13 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
         } else {
             P.tma_store = 0;
         }
+    }
+
+    P.gate_tma = 0;
+    if (gate && P.splits == 1 && (ldg & 3) == 0 && aligned16(gate)) {
+        int rc;
+        if ((rc = get_map(&P.map_gate, gate, n, m, ldg, 2))) return rc;
+        P.gate_tma = 1;
     }
 
     using KernelFn = void (*)(const TmParams);

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_model.py -x -q > gpurun_out/pytest_gemm.log 2>&1; echo "pytest exit $?"
+tail -4 gpurun_out/pytest_gemm.log
+tools/gpu_bench_only.sh

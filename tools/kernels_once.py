@@ -17,11 +17,11 @@ if which in ("all", "gemm"):
     w = ops.aligned(torch.randn(503, 503, device=dev) * 0.05)
     b = torch.randn(503, device=dev)
     for _ in range(3):
-        ops.gemm(N, 503, [(x, 0, w, 0, 503)], bias=b, act=ops.ACT_RELU, backend=ops.GEMM_TCGEN05)
+        ops.gemm(N, 503, [(x, 0, w, 0, 503)], bias=b, act=ops.ACT_RELU, backend=ops.GEMM_AUTO)
     dz = ops.aligned(torch.randn(N, 400, device=dev))
     out = torch.empty(400, 503, device=dev)
     for _ in range(3):
-        ops.gemm(400, 503, [(dz, 1, x, 1, N)], out=out, backend=ops.GEMM_TCGEN05)
+        ops.gemm(400, 503, [(dz, 1, x, 1, N)], out=out, backend=ops.GEMM_AUTO)
 if which in ("all", "spmm"):
     prob = synth.ppi_problem(state="inter")
     g = P.graph((prob.ppi_row, prob.ppi_col), num_nodes=N).add_self_loop().to(dev)
