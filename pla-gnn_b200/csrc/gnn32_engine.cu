@@ -91,6 +91,22 @@ static Layout make_layout(const plagnn_gnn32_shape* s, void* arena) {
     return L;
 }
 
+// A weight matrix [rows x cols] as a GEMM operand: the parameter itself when its rows are 16-byte aligned (cols % 4 == 0),
+// else the row-padded copy in the arena (only the 503-wide first-layer weights need one).
+struct WeightRef {
+    const float* p;
+    int64_t ld;
+};
+static inline bool weight_in_place(const float* w, int64_t cols) { return (cols & 3) == 0 && aligned16(w); }
+static int weight_operand(const float* w, int64_t rows, int64_t cols, float* padded, bool copy, plagnn_stream_t st, WeightRef* out) {
+    if (weight_in_place(w, cols)) {
+        out->p = w; out->ld = cols;
+        return PLAGNN_OK;
+    }
+    out->p = padded; out->ld = pitch32(cols);
+    return copy ? plagnn_pad_copy(w, rows, cols, cols, padded, pitch32(cols), st) : PLAGNN_OK;
+}
+
 static int check_shape(const plagnn_gnn32_shape* s, const char* who) {
     if (!s || s->num_nodes <= 0 || s->in_feats <= 0 || s->h1 <= 0 || s->h2 <= 0 || s->h3 <= 0 || s->h4 <= 0 ||
         s->classes <= 0 || !s->indptr || !s->indices || !s->plan)
@@ -148,26 +164,27 @@ int plagnn_gnn32_forward(const plagnn_gnn32_shape* shape, const float* x, int64_
     for (int l = 0; l < 3; ++l) {
         const int64_t f = L.d[l], o = L.d[l + 1], pf = pitch32(f), po = pitch32(o);
         const float* const* P = params + 5 * l;
-        // row-padded copies of the weights (pitch % 32 == 0: aligned rows for the tensor-core loaders, also in
-        // backward where they are read MN-major)
-        TRY(plagnn_pad_copy(P[0], f, f, f, L.wp[l], pf, stream));
-        TRY(plagnn_pad_copy(P[2], o, f, f, L.ws[l], pf, stream));
-        TRY(plagnn_pad_copy(P[3], o, f, f, L.wn[l], pf, stream));
+        // weight operands: in place when rows are 16-byte aligned, else a row-padded copy (refreshed here, after Adam)
+        WeightRef wp, ws, wn;
+        TRY(weight_operand(P[0], f, f, L.wp[l], true, stream, &wp));
+        TRY(weight_operand(P[2], o, f, L.ws[l], true, stream, &ws));
+        TRY(weight_operand(P[3], o, f, L.wn[l], true, stream, &wn));
         // m = relu(h Wp^T + bp);  neigh = max over in-neighbours;  h' = leaky(h Ws^T + neigh Wn^T + b)
-        TRY(gemm1(n, f, h, ldh, 0, L.wp[l], pf, 0, f, P[1], PLAGNN_ACT_RELU, nullptr, 0, 0, L.m, pf, L, stream));
+        TRY(gemm1(n, f, h, ldh, 0, wp.p, wp.ld, 0, f, P[1], PLAGNN_ACT_RELU, nullptr, 0, 0, L.m, pf, L, stream));
         TRY(plagnn_spmm_max_fwd(shape->indptr, shape->indices, shape->plan, shape->plan_counts, n, L.m, pf, f,
                                 L.neigh[l], L.arg[l], pf, L.spmm_ws, L.spmm_ws_bytes, stream));
-        TRY(gemm2(n, o, h, ldh, L.ws[l], pf, f, L.neigh[l], pf, L.wn[l], pf, f, 0, P[4], PLAGNN_ACT_LEAKY, nullptr, 0, 0,
+        TRY(gemm2(n, o, h, ldh, ws.p, ws.ld, f, L.neigh[l], pf, wn.p, wn.ld, f, 0, P[4], PLAGNN_ACT_LEAKY, nullptr, 0, 0,
                   L.h[l], po, L, stream));
         h = L.h[l];
         ldh = po;
     }
     const int64_t d3 = L.d[3], d4 = L.d[4], c = L.d[5];
-    TRY(plagnn_pad_copy(params[15], d4, d3, d3, L.w1, pitch32(d3), stream));
-    TRY(plagnn_pad_copy(params[17], c, d4, d4, L.w2, pitch32(d4), stream));
-    TRY(gemm1(n, d4, h, ldh, 0, L.w1, pitch32(d3), 0, d3, params[16], PLAGNN_ACT_LEAKY, nullptr, 0, 0, L.h4, pitch32(d4),
+    WeightRef w1, w2;
+    TRY(weight_operand(params[15], d4, d3, L.w1, true, stream, &w1));
+    TRY(weight_operand(params[17], c, d4, L.w2, true, stream, &w2));
+    TRY(gemm1(n, d4, h, ldh, 0, w1.p, w1.ld, 0, d3, params[16], PLAGNN_ACT_LEAKY, nullptr, 0, 0, L.h4, pitch32(d4),
               L, stream));
-    TRY(gemm1(n, c, L.h4, pitch32(d4), 0, L.w2, pitch32(d4), 0, d4, params[18], PLAGNN_ACT_SIGMOID, nullptr, 0, 0, prob,
+    TRY(gemm1(n, c, L.h4, pitch32(d4), 0, w2.p, w2.ld, 0, d4, params[18], PLAGNN_ACT_SIGMOID, nullptr, 0, 0, prob,
               ldprob, L, stream));
     return PLAGNN_OK;
 }
@@ -182,27 +199,36 @@ int plagnn_gnn32_backward(const plagnn_gnn32_shape* shape, const float* x, int64
     if (arena_bytes < L.total) return fail(PLAGNN_ERR_WORKSPACE, "gnn32_backward", "arena too small");
     const int64_t n = L.n, d3 = L.d[3], d4 = L.d[4], c = L.d[5];
     const int64_t p3 = pitch32(d3), p4 = pitch32(d4), pc = pitch32(c);
+    // same operands as the forward pass (padded copies, where needed, were refreshed there)
+    WeightRef w1, w2;
+    TRY(weight_operand(params[15], d4, d3, L.w1, false, stream, &w1));
+    TRY(weight_operand(params[17], c, d4, L.w2, false, stream, &w2));
     // sigmoid, liner2, liner1
     TRY(plagnn_act_backward(dprob, lddprob, prob, ldprob, n, c, PLAGNN_ACT_SIGMOID, 0.01f, nullptr, L.dz5, pc, stream));
     TRY(gemm1(c, d4, L.dz5, pc, 1, L.h4, p4, 1, n, nullptr, 0, nullptr, 0, 0, grads[17], d4, L, stream));
     TRY(plagnn_colsum(L.dz5, n, c, pc, grads[18], L.colsum_ws, L.colsum_ws_bytes, stream));
     // input gradients read the weights [out x in] as an MN-major B operand (b_trans = 1): no transposed copies
-    TRY(gemm1(n, d4, L.dz5, pc, 0, L.w2, p4, 1, c, nullptr, 0, L.h4, p4, PLAGNN_ACT_LEAKY, L.dz4, p4, L, stream));
+    TRY(gemm1(n, d4, L.dz5, pc, 0, w2.p, w2.ld, 1, c, nullptr, 0, L.h4, p4, PLAGNN_ACT_LEAKY, L.dz4, p4, L, stream));
     const float* h3 = L.h[2];
     TRY(gemm1(d4, d3, L.dz4, p4, 1, h3, p3, 1, n, nullptr, 0, nullptr, 0, 0, grads[15], d3, L, stream));
     TRY(plagnn_colsum(L.dz4, n, d4, p4, grads[16], L.colsum_ws, L.colsum_ws_bytes, stream));
     float* drst = L.drst[0];
-    TRY(gemm1(n, d3, L.dz4, p4, 0, L.w1, p3, 1, d4, nullptr, 0, h3, p3, PLAGNN_ACT_LEAKY, drst, p3, L, stream));
+    TRY(gemm1(n, d3, L.dz4, p4, 0, w1.p, w1.ld, 1, d4, nullptr, 0, h3, p3, PLAGNN_ACT_LEAKY, drst, p3, L, stream));
     int cur = 0;
     for (int l = 2; l >= 0; --l) {
         const int64_t f = L.d[l], o = L.d[l + 1], pf = pitch32(f), po = pitch32(o);
         const float* hin = l == 0 ? x : L.h[l - 1];
         const int64_t ldin = l == 0 ? ldx : pf;
         float* const* G = grads + 5 * l;
+        const float* const* Pl = params + 5 * l;
+        WeightRef wp, ws, wn;
+        TRY(weight_operand(Pl[0], f, f, L.wp[l], false, stream, &wp));
+        TRY(weight_operand(Pl[2], o, f, L.ws[l], false, stream, &ws));
+        TRY(weight_operand(Pl[3], o, f, L.wn[l], false, stream, &wn));
         TRY(plagnn_colsum(drst, n, o, po, G[4], L.colsum_ws, L.colsum_ws_bytes, stream));
         TRY(gemm1(o, f, drst, po, 1, hin, ldin, 1, n, nullptr, 0, nullptr, 0, 0, G[2], f, L, stream));
         TRY(gemm1(o, f, drst, po, 1, L.neigh[l], pf, 1, n, nullptr, 0, nullptr, 0, 0, G[3], f, L, stream));
-        TRY(gemm1(n, f, drst, po, 0, L.wn[l], pf, 1, o, nullptr, 0, nullptr, 0, 0, L.dneigh, pf, L, stream));
+        TRY(gemm1(n, f, drst, po, 0, wn.p, wn.ld, 1, o, nullptr, 0, nullptr, 0, 0, L.dneigh, pf, L, stream));
         TRY(plagnn_spmm_max_bwd(L.dneigh, pf, L.arg[l], pf, L.neigh[l], pf, n, f, L.dm, n, pf, stream));
         TRY(gemm1(f, f, L.dm, pf, 1, hin, ldin, 1, n, nullptr, 0, nullptr, 0, 0, G[0], f, L, stream));
         TRY(plagnn_colsum(L.dm, n, f, pf, G[1], L.colsum_ws, L.colsum_ws_bytes, stream));
@@ -210,7 +236,7 @@ int plagnn_gnn32_backward(const plagnn_gnn32_shape* shape, const float* x, int64
             float* out = l > 0 ? L.drst[cur ^ 1] : dx;
             const int64_t ldo = l > 0 ? pf : lddx;
             // d(input) = drst Ws + dm Wp, times leaky'(input) when the input is the previous layer's activation
-            TRY(gemm2(n, f, drst, po, L.ws[l], pf, o, L.dm, pf, L.wp[l], pf, f, 1, nullptr, 0, l > 0 ? hin : nullptr, ldin,
+            TRY(gemm2(n, f, drst, po, ws.p, ws.ld, o, L.dm, pf, wp.p, wp.ld, f, 1, nullptr, 0, l > 0 ? hin : nullptr, ldin,
                       l > 0 ? PLAGNN_ACT_LEAKY : PLAGNN_ACT_NONE, out, ldo, L, stream));
             drst = out;
             cur ^= 1;
