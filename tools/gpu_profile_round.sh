@@ -1,0 +1,7 @@
+#!/bin/bash
+# ncu evidence for profiles/: launch list of bench.py and --set full of the hot kernels (each after its plain run exited 0)
+mkdir -p gpurun_out
+timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1; echo "plain exit $?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 700 --csv --log-file gpurun_out/launches_r1c.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1; echo "ncu launches exit $?"
+timeout 300 python tools/kernels_once.py all > gpurun_out/k1.log 2>&1; echo "kernels_once exit $?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_tma_kernel|spmm_kernel|spmm_max_scatter|spmm_combine" -o gpurun_out/prof_r1c python tools/kernels_once.py all > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"
