@@ -186,6 +186,25 @@ int plagnn_act_backward(const float* dy, int64_t lddy, const float* y, int64_t l
                         plagnn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Alteration scoring (post-training) — replaces the numpy loops of
+ *     code/main.py:15-29   scaling(logit_mat)
+ *     code/main.py:32-48   mat_merge(): mean over the 100 runs of scaling(logits)
+ *     code/main.py:80-84   diff = (inter - normal) / normal; argsort; reverse
+ * scaling: out = scaling(x) in x's precision (is_f64 = 0: float, 1: double) and/or acc += (double)scaling(x);
+ *   bit-identical to numpy (row sums in numpy's pairwise order; cols <= 128).
+ * alteration_rank: diff[r,c] = (inter - normal) / normal and order[i] = flat index r*cols + c of the i-th largest
+ *   score: NaN first, ties by descending index (= numpy stable argsort reversed).
+ * workspace >= plagnn_scoring_workspace_bytes(rows, cols) for both.
+ * ---------------------------------------------------------------------------------------- */
+size_t plagnn_scoring_workspace_bytes(int64_t rows, int64_t cols);
+int plagnn_scaling(const void* x, int is_f64, int64_t ldx, int64_t rows, int64_t cols, void* out, int64_t ldo,
+                   double* acc, int64_t ldacc, void* workspace, size_t workspace_bytes, plagnn_stream_t stream);
+int plagnn_divide_f64(double* x, int64_t ld, int64_t rows, int64_t cols, double divisor, plagnn_stream_t stream);
+int plagnn_alteration_rank(const double* normal, int64_t ldn, const double* inter, int64_t ldi, int64_t rows,
+                           int64_t cols, double* diff, int64_t ldd, int64_t* order /* rows*cols */,
+                           void* workspace, size_t workspace_bytes, plagnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * K4  loss and optimiser — replace
  *     code/train.py:89-108,203  multi_loss(logits[train_index], labels[train_index], i_weight)
  *     code/train.py:180,205     torch.optim.Adam(model.parameters(), lr).step()

@@ -17,7 +17,7 @@ What it follows in the reference (paths relative to /root/reference):
 * ``code/train.py:19-40``   protein_loc_correction (label decision).
 * ``code/train.py:43-86``   performances_record (AIM / COV / mlACC).
 * ``code/train.py:179-180,195-207`` model dims, Adam(lr) defaults, epoch order.
-* ``code/main.py:15-29``    scaling (alteration scoring pre-step).
+* ``code/main.py:15-29``    scaling (alteration scoring pre-step); ``:32-48`` mat_merge; ``:80-84`` score + ranking.
 
 Parity status
 -------------
@@ -401,6 +401,28 @@ def scaling(logit_mat: np.ndarray) -> np.ndarray:
     mat = logit_mat - logit_mat.min(0)
     mat = mat / mat.max(0)
     return mat / mat.sum(1, keepdims=True)
+
+
+def mat_merge(mats) -> np.ndarray:
+    """main.py:32-48 on in-memory matrices: float64 accumulator, += scaling(mat) per run, divided by the run count
+    (the reference divides by the literal 100, its fixed number of runs)."""
+    acc = np.zeros(np.asarray(mats[0]).shape)
+    for m in mats:
+        acc += scaling(np.asarray(m))
+    acc /= len(mats)
+    return acc
+
+
+def alteration_rank(normal_mat: np.ndarray, inter_mat: np.ndarray):
+    """main.py:80-84: scaled matrices, relative change, flat indices from the largest to the smallest score.
+    The reference uses numpy's default (unstable) argsort and reverses it: NaN first, then descending; the order inside
+    a group of equal scores is an artefact of that sort.  Here: stable argsort reversed (ties by descending index)."""
+    normal = scaling(np.asarray(normal_mat, dtype=np.float64))
+    inter = scaling(np.asarray(inter_mat, dtype=np.float64))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        diff = (inter - normal) / normal
+    order = np.argsort(diff.reshape(-1), kind="stable")[::-1].copy()
+    return normal, inter, diff, order
 
 
 # --------------------------------------------------------------------------------------

@@ -83,6 +83,12 @@ PROTOTYPES = {
     "plagnn_loc_correction_workspace_bytes": (c_size_t, [c_int64]),
     "plagnn_loc_correction": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_int64, c_void_p, c_size_t,
                                       c_void_p]),
+    "plagnn_scoring_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "plagnn_scaling": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                               c_size_t, c_void_p]),
+    "plagnn_divide_f64": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_double, c_void_p]),
+    "plagnn_alteration_rank": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
+                                       c_void_p, c_size_t, c_void_p]),
     "plagnn_gnn32_arena_bytes": (c_size_t, [POINTER(Gnn32Shape)]),
     "plagnn_gnn32_forward": (c_int, [POINTER(Gnn32Shape), c_void_p, c_int64, POINTER(c_void_p), c_void_p, c_size_t,
                                      c_void_p, c_int64, c_void_p]),

@@ -49,9 +49,17 @@ class FusedAdam(torch.optim.Optimizer):
                 dev = p.device
             if not rows:
                 continue
-            table = torch.tensor(rows, dtype=torch.int64).to(dev)
+            # The pointer table lives on the device and is re-uploaded only when a pointer changes (the caching
+            # allocator hands the gradients the same blocks every epoch).  A pageable .to(device) here would block the
+            # host until the whole epoch has drained: one stream sync per step.
+            key = tuple(rows)
+            if group.get("_table_key") != key:
+                host = torch.tensor(rows, dtype=torch.int64).pin_memory()
+                group["_table_host"] = (host, group.get("_table_host", (None,))[0])   # keep the previous one alive too
+                group["_table"] = host.to(dev, non_blocking=True)
+                group["_table_key"] = key
+            table = group["_table"]
             with torch.cuda.device(dev):
                 ops.adam_multi(table, len(rows), max_numel, group["lr"], group["betas"][0], group["betas"][1],
                                group["eps"], step)
-            group["_table_keepalive"] = table
         return loss

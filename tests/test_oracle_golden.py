@@ -51,3 +51,41 @@ def test_label_decision_and_metrics(golden_dir):
 def test_scaling(golden_dir):
     g = _g(golden_dir)
     np.testing.assert_allclose(orc.scaling(g["sc_in"]), g["sc_out"], rtol=1e-15)
+
+
+# ---- alteration scoring (tests/golden/make_golden_scoring.py ran code/main.py's own statements) ----
+def _s(golden_dir):
+    return np.load(os.path.join(golden_dir, "scoring.npz"))
+
+
+def test_scaling_float32_and_float64_bit_exact(golden_dir):
+    g = _s(golden_dir)
+    out32 = orc.scaling(g["sc32_in"])
+    assert out32.dtype == np.float32 and np.array_equal(out32, g["sc32_out"])
+    assert np.array_equal(orc.scaling(g["sc64_in"]), g["sc64_out"])
+
+
+def test_mat_merge_bit_exact(golden_dir):
+    g = _s(golden_dir)
+    assert np.array_equal(orc.mat_merge(list(g["runs"])), g["merged"])
+
+
+def check_ranking(diff_flat, order, ref_order):
+    """Same score at every rank as the reference (NaN positions included), a valid permutation, and the same index
+    wherever the score is unique."""
+    assert sorted(order.tolist()) == list(range(len(diff_flat)))
+    a, b = diff_flat[order], diff_flat[ref_order]
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+    vals, counts = np.unique(diff_flat[~np.isnan(diff_flat)], return_counts=True)
+    unique_vals = set(vals[counts == 1].tolist())
+    same = [i for i in range(len(order)) if diff_flat[ref_order[i]] in unique_vals]
+    assert np.array_equal(order[same], ref_order[same])
+
+
+def test_alteration_rank_matches_reference(golden_dir):
+    g = _s(golden_dir)
+    normal, inter, diff, order = orc.alteration_rank(g["normal_mat"], g["inter_mat"])
+    assert np.array_equal(normal, g["normal"]) and np.array_equal(inter, g["inter"])
+    assert np.array_equal(diff, g["diff"], equal_nan=True)
+    check_ranking(diff.reshape(-1), order, g["order"])
