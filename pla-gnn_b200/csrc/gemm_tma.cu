@@ -25,6 +25,19 @@
 // (TMEM -> registers -> swizzled shared-memory image -> TMA store: whole 128-byte lines, tails clipped by the map).
 #include "common.cuh"
 #include <cuda.h>
+// Diagnostics (per-CTA clock64 trace, PLAGNN_TMA_DEBUG timing modes, the single-accumulator experiment) are compiled in
+// only with -DPLAGNN_TMA_DIAG=1 (`PLAGNN_TMA_DIAG=1 python pla-gnn_b200/csrc/build.py --force`): they cost registers and
+// instruction-cache space in the production kernel.
+#ifndef PLAGNN_TMA_DIAG
+#define PLAGNN_TMA_DIAG 0
+#endif
+#if PLAGNN_TMA_DIAG
+#define TM_DEBUG(P) ((P).debug)
+#define TM_SINGLE(P) ((P).single_acc)
+#else
+#define TM_DEBUG(P) 0
+#define TM_SINGLE(P) 0
+#endif
 #include <cstdlib>
 #include <cstring>
 #include <climits>
@@ -258,7 +271,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
     const int lin_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    long long* tr = (P.trace && lin_cta < 64) ? P.trace + 32 * lin_cta : nullptr;
+#if PLAGNN_TMA_DIAG
+    long long* const tr = (P.trace && lin_cta < 64) ? P.trace + 32 * lin_cta : nullptr;
+#else
+    long long* const tr = nullptr;
+    (void)lin_cta;
+#endif
     if (tr && t == 0) tr[0] = clock64();
     // N tiles fastest in launch order: the column tiles of one row block run together, so A streams from HBM once
     const int64_t m0 = (int64_t)blockIdx.y * TILE_M, n0 = (int64_t)(blockIdx.x / CG) * TILE_N;
@@ -352,12 +370,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 const uint64_t b_lo = BT ? desc_mnmajor(sl + TM_PART_BYTES) : desc_kmajor(sl + TM_PART_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < TM_BK / 8; ++kk) {
-                    if (P.debug == 2) break;
+                    if (TM_DEBUG(P) == 2) break;
                     const uint64_t adv_a = (uint64_t)kk * a_step, adv_b = (uint64_t)kk * b_step;
                     // corrections go to their own accumulator: the tensor core adds into TMEM with truncation, and the
                     // main accumulator then sees a third of the additions (gemm_tc.cu has the measurements)
                     const uint32_t acc_on = (it | kk) ? 1u : 0u;
-                    if (P.single_acc) {
+                    if (TM_SINGLE(P)) {
                         umma_tf32<CG>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
                         umma_tf32<CG>(acc_main, a_lo + adv_a, b_hi + adv_b, idesc, 1u);
                         umma_tf32<CG>(acc_main, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
@@ -468,7 +486,15 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 tmem_ld_wait();
                 if (tr && t == 64) tr[13] += clock64() - e0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + (P.single_acc ? 0.f : __uint_as_float(acc_small[j]));
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + (TM_SINGLE(P) ? 0.f : __uint_as_float(acc_small[j]));
+                if (tr && t == 64) {
+                    // the loads are only guaranteed complete where their registers are first read: keep the sum alive
+                    float keep = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) keep += v[j];
+                    asm volatile("" ::"f"(keep));
+                    tr[25] += clock64() - e0;
+                }
             }
             if (direct) {
                 if (P.bias) {
@@ -482,7 +508,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * P.slope;
                 } else if (P.act == PLAGNN_ACT_SIGMOID) {
-#pragma unroll 4
+#pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
                 }
                 if (gate_img_on) {
@@ -520,7 +546,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     }
                 }
             }
-            if (P.debug == 3) continue;
+            if (TM_DEBUG(P) == 3) continue;
             if (P.tma_store) {
                 const long long e1 = (tr && t == 64) ? clock64() : 0;
                 if (lane == 0) bulk_wait_read<1>();      // the image written two chunks ago has been read
@@ -532,18 +558,20 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     const uint32_t off = row_off + (uint32_t)((q ^ (lane & 7)) << 4);
                     sts_v4(img + off, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 }
+                const long long e2 = (tr && t == 64) ? clock64() : 0;
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0 && P.debug != 4) {
+                const long long e3 = (tr && t == 64) ? clock64() : 0;
+                if (lane == 0 && TM_DEBUG(P) != 4) {
                     tma_store_3d(&P.map_out, img, (int)c0, row0, direct ? 0 : split);
                     bulk_commit();
                 }
-                if (tr && t == 64) tr[15] += clock64() - e1;
+                if (tr && t == 64) { const long long e4 = clock64(); tr[15] += e4 - e1; tr[26] += e2 - e1; tr[27] += e3 - e2; tr[28] += e4 - e3; }
                 buf ^= 1;
             } else if (r < P.m) {
                 // unaligned destination (row pitch % 4 != 0): plain scalar stores
                 float* drow = dst + r * ldd + c0;
-#pragma unroll 4
+#pragma unroll
                 for (int j = 0; j < 32; ++j)
                     if (j < ncol) drow[j] = v[j];
             }
