@@ -9,7 +9,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libplagnn.so")
+# PLAGNN_LIB_PATH selects another build of the same library (e.g. the diagnostics build, csrc/build.py --diag)
+LIB_PATH = os.environ.get("PLAGNN_LIB_PATH") or os.path.join(_PKG, "libplagnn.so")
 
 OK = 0
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3

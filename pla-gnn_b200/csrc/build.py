@@ -22,8 +22,11 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xcompiler", "-Wall",
          "-I", os.path.join(ROOT, "include")]
-if os.environ.get("PLAGNN_TMA_DIAG") == "1":     # diagnostics build of the TMA GEMM (tools/gemm_trace.py, PLAGNN_TMA_DEBUG)
+DIAG = "--diag" in sys.argv or os.environ.get("PLAGNN_TMA_DIAG") == "1"
+if DIAG:     # diagnostics build of the TMA GEMM (tools/gemm_trace.py, PLAGNN_TMA_DEBUG) -> libplagnn_diag.so, own objects
     FLAGS += ["-DPLAGNN_TMA_DIAG=1"]
+    OUT = os.path.join(PKG, "libplagnn_diag.so")
+    OBJ_DIR = os.path.join(HERE, "_obj_diag")
 
 
 def _stale(target: str, deps: list[str]) -> bool:

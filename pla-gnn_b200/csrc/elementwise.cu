@@ -133,6 +133,41 @@ colsum_partial_kernel(const float* __restrict__ x, int64_t rows, int cols, int64
         part[(int64_t)blockIdx.y * cols + c] = t;
     }
 }
+// Same sums (identical grouping, hence identical bits) with 16-byte loads: a lane owns 4 adjacent columns, a warp reads
+// 512 contiguous bytes per row.  Used when the rows are 16-byte aligned (the 4-byte version moved 38 MB at 2 TB/s).
+__global__ void __launch_bounds__(256)
+colsum_partial4_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ldx, double* __restrict__ part) {
+    __shared__ double red[8][32][4];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + tx) * 4;
+    const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS_PER_CHUNK;
+    const int64_t r1 = r0 + CS_ROWS_PER_CHUNK < rows ? r0 + CS_ROWS_PER_CHUNK : rows;
+    float4 v[CS_ROWS_PER_CHUNK / 8];
+    const bool on = c < cols;            // cols is rounded up to the row pitch by the caller's padding: c + 3 < ldx
+#pragma unroll
+    for (int i = 0; i < CS_ROWS_PER_CHUNK / 8; ++i) {
+        const int64_t r = r0 + ty + 8 * i;
+        v[i] = (on && r < r1) ? ldg_f4(x + r * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int w = CS_ROWS_PER_CHUNK / 16; w > 0; w >>= 1)
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            v[i].x += v[i + w].x; v[i].y += v[i + w].y; v[i].z += v[i + w].z; v[i].w += v[i + w].w;
+        }
+    red[ty][tx][0] = (double)v[0].x; red[ty][tx][1] = (double)v[0].y;
+    red[ty][tx][2] = (double)v[0].z; red[ty][tx][3] = (double)v[0].w;
+    __syncthreads();
+    if (ty < 4 && on) {                  // warp ty finishes component ty of every lane's quad
+        const int cc = c + ty;
+        if (cc < cols) {
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t += red[i][tx][ty];
+            part[(int64_t)blockIdx.y * cols + cc] = t;
+        }
+    }
+}
 // 32 columns x 8 partial-row groups per block: the per-column chain over the row chunks is split 8 ways and
 // unrolled, so 8 loads per thread are in flight (the first version walked 188 chunks with one dependent load at a
 // time: 29 us of pure L2 latency).
@@ -314,8 +349,13 @@ int plagnn_colsum(const float* x, int64_t rows, int64_t cols, int64_t ldx, float
     if (!workspace || workspace_bytes < plagnn_colsum_workspace_bytes(rows, cols))
         return fail(PLAGNN_ERR_WORKSPACE, "colsum", "workspace too small");
     const int chunks = (int)ceil_div(rows, CS_ROWS_PER_CHUNK);
-    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)chunks);
-    colsum_partial_kernel<<<grid, 256, 0, st>>>(x, rows, (int)cols, ldx, (double*)workspace);
+    if (aligned16(x) && (ldx & 3) == 0 && ceil_div(cols, 4) * 4 <= ldx) {
+        dim3 grid4((unsigned)ceil_div(cols, 128), (unsigned)chunks);
+        colsum_partial4_kernel<<<grid4, 256, 0, st>>>(x, rows, (int)cols, ldx, (double*)workspace);
+    } else {
+        dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)chunks);
+        colsum_partial_kernel<<<grid, 256, 0, st>>>(x, rows, (int)cols, ldx, (double*)workspace);
+    }
     colsum_final_kernel<<<(unsigned)ceil_div(cols, 32), 256, 0, st>>>((const double*)workspace, chunks, (int)cols, out);
     return check_launch("colsum", 2);
 }

@@ -62,6 +62,7 @@ struct alignas(64) TmParams {
     int gate_tma;
     int tma_store;                                // 1: epilogue leaves through shared memory + TMA stores (aligned output)
     int64_t ldp;                                  // row pitch of the split-K partials
+    int transpose_out;                            // split-K only: the reduction writes C^T (operands were swapped by the launcher)
     int64_t m, n;
     int npairs;
     int kblocks[PLAGNN_GEMM_MAX_PAIRS];
@@ -602,7 +603,8 @@ __global__ void __launch_bounds__(256) gemm_tma_reduce_kernel(const __grid_const
         const float* q = P.partial + r * P.ldp + c;
         for (int z = 0; z < P.splits; ++z) s += q[(int64_t)z * P.m * P.ldp];
         const float v = tm_epilogue_one(P, s, r, c);
-        P.c[r * P.ldc + c] = v;
+        if (P.transpose_out) P.c[c * P.ldc + r] = v;
+        else P.c[r * P.ldc + c] = v;
     }
 }
 
@@ -749,14 +751,21 @@ static int tm_choose_splits(int64_t m, int64_t n, int total_kblocks, int cg) {
 }
 
 size_t gemm_tma_partial_bytes(int64_t m, int64_t n, int64_t k_total) {
+    // either orientation (the launcher may compute the transpose), either tile configuration, pairs rounded up separately
     const int kb = (int)ceil_div(k_total, TM_BK);
-    int s = 1;
-    for (int cg = 1; cg <= 2; ++cg)
-        for (int extra = 0; extra <= PLAGNN_GEMM_MAX_PAIRS; ++extra) {
-            const int c = tm_choose_splits(m, n, kb + extra, cg);
-            s = c > s ? c : s;
-        }
-    return s > 1 ? align_up((size_t)s * (size_t)m * (size_t)((n + 3) / 4 * 4) * sizeof(float), 256) : 0;
+    size_t best = 0;
+    for (int o = 0; o < 2; ++o) {
+        const int64_t mm = o ? n : m, nn = o ? m : n;
+        int s = 1;
+        for (int cg = 1; cg <= 2; ++cg)
+            for (int extra = 0; extra <= PLAGNN_GEMM_MAX_PAIRS; ++extra) {
+                const int c = tm_choose_splits(mm, nn, kb + extra, cg);
+                s = c > s ? c : s;
+            }
+        const size_t b = s > 1 ? align_up((size_t)s * (size_t)mm * (size_t)((nn + 3) / 4 * 4) * sizeof(float), 256) : 0;
+        best = b > best ? b : best;
+    }
+    return best;
 }
 
 bool gemm_tma_eligible(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs) {
@@ -771,11 +780,39 @@ bool gemm_tma_eligible(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_p
     return true;
 }
 
-int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs, const float* bias, int act,
+// padded work of an m x n output in the CTA-pair tiling: 256-row tiles times the MMA widths of the column tiles
+static int64_t tm_padded_area(int64_t m, int64_t n, int cg) {
+    const int64_t tile = 128 * cg, gran = 32 * cg;
+    const int64_t full = n / tile, rem = n - full * tile;
+    return ceil_div(m, tile) * tile * (full * tile + ceil_div(rem, gran) * gran);
+}
+
+int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs_in, const float* bias, int act,
                     float slope, const float* gate, int64_t ldg, int gate_act, float* c, int64_t ldc, void* workspace,
                     size_t workspace_bytes, cudaStream_t st) {
     TmParams P;
     memset(&P, 0, sizeof(P));
+    // Split-K products without an epilogue (the weight gradients) are written by the reduction kernel, which can just as
+    // well write the transpose: compute C^T = B^T A^T when that orientation wastes less of the 256 x 256 tiles
+    // (dW[300 x 400]: 512 x 448 padded vs 512 x 320 swapped).
+    plagnn_gemm_pair swapped[PLAGNN_GEMM_MAX_PAIRS];
+    const plagnn_gemm_pair* pairs = pairs_in;
+    {
+        const int cg0 = tm_cg();
+        int tk = 0;
+        for (int p = 0; p < npairs; ++p) tk += (int)ceil_div(pairs_in[p].k, TM_BK);
+        static const bool no_swap = getenv("PLAGNN_TMA_NO_SWAP") != nullptr;
+        if (!no_swap && !bias && !gate && act == PLAGNN_ACT_NONE && m >= 16 && tm_choose_splits(m, n, tk, cg0) > 1 &&
+            tm_choose_splits(n, m, tk, cg0) > 1 && tm_padded_area(n, m, cg0) < tm_padded_area(m, n, cg0)) {
+            for (int p = 0; p < npairs; ++p) {
+                const plagnn_gemm_pair& q = pairs_in[p];
+                swapped[p] = plagnn_gemm_pair{q.b, q.ldb, q.b_trans, q.a, q.lda, q.a_trans, q.k};
+            }
+            pairs = swapped;
+            const int64_t t = m; m = n; n = t;
+            P.transpose_out = 1;
+        }
+    }
     P.m = m; P.n = n; P.npairs = npairs;
     P.total_kblocks = 0;
     for (int p = 0; p < npairs; ++p) {

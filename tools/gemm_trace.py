@@ -1,4 +1,4 @@
-"""[needs the diagnostics build: PLAGNN_TMA_DIAG=1 python pla-gnn_b200/csrc/build.py --force] Per-CTA timeline of one TMA GEMM launch (PLAGNN_TMA_TRACE=1): python tools/gemm_trace.py m n k at bt"""
+"""[needs the diagnostics build: python pla-gnn_b200/csrc/build.py --diag; run with PLAGNN_LIB_PATH=pla-gnn_b200/libplagnn_diag.so] Per-CTA timeline of one TMA GEMM launch (PLAGNN_TMA_TRACE=1): python tools/gemm_trace.py m n k at bt"""
 import ctypes, os, sys
 os.environ["PLAGNN_TMA_TRACE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
