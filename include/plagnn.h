@@ -173,6 +173,15 @@ int plagnn_gemm(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pa
                 float* c, int64_t ldc, void* workspace, size_t workspace_bytes,
                 int backend, plagnn_stream_t stream);
 
+/* Weight gradient and bias gradient of a linear layer in one pass (autograd of nn.Linear / SAGEConv fc_*,
+ * code/train.py:204):  dw[m x n] = dz^T x,  db[m] = sum over rows of dz;  dz stored [k x m], x stored [k x n] (k = nodes).
+ * On the TMA backend db is one more output column of the same split-K product (a B column that reads as 1.0);
+ * other backends run plagnn_gemm + plagnn_colsum.  workspace >= plagnn_gemm_wgrad_bias_workspace_bytes(m, n, k). */
+size_t plagnn_gemm_wgrad_bias_workspace_bytes(int64_t m, int64_t n, int64_t k);
+int plagnn_gemm_wgrad_bias(int64_t m, int64_t n, const float* dz, int64_t lddz, const float* x, int64_t ldx, int64_t k,
+                           float* dw, int64_t lddw, float* db, void* workspace, size_t workspace_bytes,
+                           plagnn_stream_t stream);
+
 /* column sums: out[j] = sum_i x[i,j]   (bias gradients). workspace >= plagnn_colsum_workspace_bytes. */
 size_t plagnn_colsum_workspace_bytes(int64_t rows, int64_t cols);
 int plagnn_colsum(const float* x, int64_t rows, int64_t cols, int64_t ldx, float* out,

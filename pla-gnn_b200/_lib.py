@@ -72,6 +72,9 @@ PROTOTYPES = {
     "plagnn_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "plagnn_gemm": (c_int, [c_int64, c_int64, c_int32, POINTER(GemmPair), c_void_p, c_int, c_float,
                             c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_size_t, c_int, c_void_p]),
+    "plagnn_gemm_wgrad_bias_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "plagnn_gemm_wgrad_bias": (c_int, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64,
+                                       c_void_p, c_void_p, c_size_t, c_void_p]),
     "plagnn_colsum_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "plagnn_colsum": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "plagnn_act_backward": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_float,

@@ -20,7 +20,7 @@ size_t gemm_tma_partial_bytes(int64_t m, int64_t n, int64_t k_total);
 bool gemm_tma_eligible(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs);
 int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs, const float* bias, int act,
                     float slope, const float* gate, int64_t ldg, int gate_act, float* c, int64_t ldc, void* workspace,
-                    size_t workspace_bytes, cudaStream_t st);
+                    size_t workspace_bytes, cudaStream_t st, float* ones_out = nullptr);
 
 static int forced_backend() {
     static const int forced = [] {
@@ -52,6 +52,34 @@ size_t plagnn_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k_total) {
     size_t w = simt > tc ? simt : tc;
     w = w > tma ? w : tma;
     return align_up(w, 256);
+}
+
+size_t plagnn_gemm_wgrad_bias_workspace_bytes(int64_t m, int64_t n, int64_t k) {
+    const size_t a = plagnn_gemm_workspace_bytes(m, n + 1, k), b = plagnn_colsum_workspace_bytes(k, m);
+    return a > b ? a : b;
+}
+
+// dW[m x n] = dZ^T X and db[m] = column sums of dZ, in one pass when the TMA kernel can take the product (the bias gradient
+// is the extra output column of a B operand whose column n reads as 1.0); otherwise plagnn_gemm + plagnn_colsum.
+int plagnn_gemm_wgrad_bias(int64_t m, int64_t n, const float* dz, int64_t lddz, const float* x, int64_t ldx, int64_t k,
+                           float* dw, int64_t lddw, float* db, void* workspace, size_t workspace_bytes,
+                           plagnn_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m <= 0 || n <= 0 || k <= 0 || !dz || !x || !dw || !db || lddz < m || ldx < n || lddw < n)
+        return fail(PLAGNN_ERR_ARG, "gemm_wgrad_bias", "bad sizes or null pointers");
+    plagnn_gemm_pair p{dz, lddz, 1, x, ldx, 1, k};
+    const size_t part = gemm_tma_partial_bytes(m, n + 1, k);
+    const int forced = forced_backend();
+    if ((forced == PLAGNN_GEMM_AUTO || forced == PLAGNN_GEMM_TMA) && part > 0 && workspace && part <= workspace_bytes &&
+        gemm_tma_eligible(m, n + 1, 1, &p)) {
+        ProfileScope prof("gemm", m, n, k, stream);
+        return gemm_tma_launch(m, n, 1, &p, nullptr, PLAGNN_ACT_NONE, 0.f, nullptr, 0, PLAGNN_ACT_NONE, dw, lddw, workspace,
+                               workspace_bytes, st, db);
+    }
+    int rc = plagnn_gemm(m, n, 1, &p, nullptr, PLAGNN_ACT_NONE, 0.f, nullptr, 0, PLAGNN_ACT_NONE, dw, lddw, workspace,
+                         workspace_bytes, PLAGNN_GEMM_AUTO, stream);
+    if (rc) return rc;
+    return plagnn_colsum(dz, k, m, lddz, db, workspace, workspace_bytes, stream);
 }
 
 int plagnn_gemm(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs, const float* bias, int act,

@@ -62,6 +62,9 @@ struct alignas(64) TmParams {
     int gate_tma;
     int tma_store;                                // 1: epilogue leaves through shared memory + TMA stores (aligned output)
     int64_t ldp;                                  // row pitch of the split-K partials
+    int ones_col;                                 // >= 0: column of the (mn-contiguous) B operand that reads as 1.0: output column
+                                                  // ones_col = sum over k of A, i.e. the bias gradient of a weight-gradient product
+    float* ones_out;                              // where the reduction writes that column (length m)
     int transpose_out;                            // split-K only: the reduction writes C^T (operands were swapped by the launcher)
     int64_t m, n;
     int npairs;
@@ -403,6 +406,18 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             // The raw ring is 4 deep (TMA latency ~2.5 us), the lo ring 3 deep: the chain "MMAs done -> commit -> split warps -> STS ->
             // proxy fence -> (remote) arrive -> issuer" measured ~2100 cycles, more than one k-block of MMAs (1536).
             const int ct = t - 64;                                  // 0..255
+            // does this thread own the piece of the B tile that holds the ones column?  MN-major box j = 32 columns,
+            // k-row ct / 8, 16-byte piece ct % 8 of the row = logical 32-byte chunk ((ct % 8) / 2) ^ (row & 3), half (ct % 8) & 1
+            int ones_piece = -1, ones_elem = 0;
+            if (BT && P.ones_col >= 0) {
+                const int64_t lc = (int64_t)P.ones_col - (n0 + rank * n_half);       // column inside this CTA's 128-wide B tile
+                if (lc >= 0 && lc < 128) {
+                    const int q = ct & 7, rr = (ct >> 3) & 3;
+                    const int cbase = (((q >> 1) ^ rr) << 3) + ((q & 1) << 2);
+                    const int c = (int)(lc & 31);
+                    if (c >= cbase && c < cbase + 4) { ones_piece = (int)(lc >> 5); ones_elem = c - cbase; }
+                }
+            }
             const uint32_t lo_full0 = CG == 2 ? mapa(bar_lo_full, 0) : bar_lo_full;   // the leader's barrier counts both CTAs
             for (int it = 0; it < nkb; ++it) {
                 const int s = it % TM_RAW_STAGES, l = it % TM_LO_STAGES;
@@ -417,6 +432,19 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 for (int i = 0; i < 8; ++i)
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                                  : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(src + (uint32_t)i * 4096u));
+                if (BT && ones_piece >= 0) {
+                    // bias-gradient column: this thread owns the 16-byte piece of B's box `ones_piece` that holds column
+                    // ones_col of k-row ct / 8: it reads as 1.0 (rows beyond K meet zero-filled rows of A, so no k test)
+#pragma unroll
+                    for (int i = 4; i < 8; ++i)
+                        if (i - 4 == ones_piece) {
+                            if (ones_elem == 0) v[i].x = 1.0f;
+                            else if (ones_elem == 1) v[i].y = 1.0f;
+                            else if (ones_elem == 2) v[i].z = 1.0f;
+                            else v[i].w = 1.0f;
+                            sts_v4(src + (uint32_t)i * 4096u, v[i].x, v[i].y, v[i].z, v[i].w);
+                        }
+                }
                 mbar_wait(bar_lo_empty + 8 * l, phl ^ 1u);
                 if (tr && t == 64 && it == 8) tr[24] = clock64();           // the MMAs of k-block it - TM_LO_STAGES have read this lo stage
 #pragma unroll
@@ -602,6 +630,10 @@ __global__ void __launch_bounds__(256) gemm_tma_reduce_kernel(const __grid_const
         const int64_t r = i / P.n, c = i - r * P.n;
         const float* q = P.partial + r * P.ldp + c;
         for (int z = 0; z < P.splits; ++z) s += q[(int64_t)z * P.m * P.ldp];
+        if (c == P.ones_col) {                 // P.n counts the extra column; it goes to the bias gradient
+            P.ones_out[r] = s;
+            continue;
+        }
         const float v = tm_epilogue_one(P, s, r, c);
         if (P.transpose_out) P.c[c * P.ldc + r] = v;
         else P.c[r * P.ldc + c] = v;
@@ -787,11 +819,20 @@ static int64_t tm_padded_area(int64_t m, int64_t n, int cg) {
     return ceil_div(m, tile) * tile * (full * tile + ceil_div(rem, gran) * gran);
 }
 
+// ones_out != nullptr: weight-gradient product with the bias gradient riding along — B (mn-contiguous, one pair) gets a
+// virtual column n that reads as 1.0, C stays m x n and ones_out[m] receives sum_k A[:, k].  Always split-K.
 int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs_in, const float* bias, int act,
                     float slope, const float* gate, int64_t ldg, int gate_act, float* c, int64_t ldc, void* workspace,
-                    size_t workspace_bytes, cudaStream_t st) {
+                    size_t workspace_bytes, cudaStream_t st, float* ones_out) {
     TmParams P;
     memset(&P, 0, sizeof(P));
+    P.ones_col = -1;
+    const int64_t n_map = n;                 // extent of B's tensor map: the virtual column is out of bounds (zero fill)
+    if (ones_out) {
+        P.ones_col = (int)n;
+        P.ones_out = ones_out;
+        n += 1;
+    }
     // Split-K products without an epilogue (the weight gradients) are written by the reduction kernel, which can just as
     // well write the transpose: compute C^T = B^T A^T when that orientation wastes less of the 256 x 256 tiles
     // (dW[300 x 400]: 512 x 448 padded vs 512 x 320 swapped).
@@ -802,7 +843,7 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
         int tk = 0;
         for (int p = 0; p < npairs; ++p) tk += (int)ceil_div(pairs_in[p].k, TM_BK);
         static const bool no_swap = getenv("PLAGNN_TMA_NO_SWAP") != nullptr;
-        if (!no_swap && !bias && !gate && act == PLAGNN_ACT_NONE && m >= 16 && tm_choose_splits(m, n, tk, cg0) > 1 &&
+        if (!no_swap && !ones_out && !bias && !gate && act == PLAGNN_ACT_NONE && m >= 16 && tm_choose_splits(m, n, tk, cg0) > 1 &&
             tm_choose_splits(n, m, tk, cg0) > 1 && tm_padded_area(n, m, cg0) < tm_padded_area(m, n, cg0)) {
             for (int p = 0; p < npairs; ++p) {
                 const plagnn_gemm_pair& q = pairs_in[p];
@@ -821,7 +862,8 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
         P.total_kblocks += P.kblocks[p];
         int rc;
         if ((rc = q.a_trans ? get_map(&P.map[p][0], q.a, m, q.k, q.lda, 1) : get_map(&P.map[p][0], q.a, q.k, m, q.lda, 0))) return rc;
-        if ((rc = q.b_trans ? get_map(&P.map[p][1], q.b, n, q.k, q.ldb, 1) : get_map(&P.map[p][1], q.b, q.k, n, q.ldb, 0))) return rc;
+        const int64_t nb = P.transpose_out ? n : n_map;   // (no virtual column when the operands were swapped)
+        if ((rc = q.b_trans ? get_map(&P.map[p][1], q.b, nb, q.k, q.ldb, 1) : get_map(&P.map[p][1], q.b, q.k, nb, q.ldb, 0))) return rc;
     }
     P.bias = bias; P.act = act; P.slope = slope; P.gate = gate; P.ldg = ldg; P.gate_act = gate_act;
     P.c = c; P.ldc = ldc;
@@ -830,6 +872,7 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
     { const char* e = getenv("PLAGNN_TMA_SINGLE_ACC"); P.single_acc = (e && e[0] == '1') ? 1 : 0; }
     const int cg = tm_cg();
     const int splits = tm_choose_splits(m, n, P.total_kblocks, cg);
+    if (ones_out && splits < 2) return fail(PLAGNN_ERR_UNSUPPORTED, "gemm_tma", "the bias-gradient column needs a split-K product");
     P.ldp = (n + 3) / 4 * 4;
     if (splits > 1 && (!workspace || !aligned16(workspace) || workspace_bytes < (size_t)splits * m * P.ldp * sizeof(float)))
         return fail(PLAGNN_ERR_WORKSPACE, "gemm_tma", "split-K workspace too small (see plagnn_gemm_workspace_bytes)");

@@ -75,12 +75,18 @@ static Layout make_layout(const plagnn_gnn32_shape* s, void* arena) {
         const size_t w = plagnn_gemm_workspace_bytes(mm, nn, kk);
         g = w > g ? w : g;
     };
+    auto updw = [&](int64_t mm, int64_t nn, int64_t kk) {
+        const size_t w = plagnn_gemm_wgrad_bias_workspace_bytes(mm, nn, kk);
+        g = w > g ? w : g;
+    };
     for (int l = 0; l < 3; ++l) {
         const int64_t f = L.d[l], o = L.d[l + 1];
         upd(n, f, f); upd(n, o, 2 * f); upd(o, f, n); upd(f, f, n); upd(n, f, o); upd(n, f, o + f);
+        updw(o, f, n); updw(f, f, n);
     }
     upd(n, L.d[4], L.d[3]); upd(n, L.d[5], L.d[4]); upd(L.d[5], L.d[4], n); upd(L.d[4], L.d[3], n);
     upd(n, L.d[4], L.d[5]); upd(n, L.d[3], L.d[4]);
+    updw(L.d[5], L.d[4], n); updw(L.d[4], L.d[3], n);
     L.gemm_ws_bytes = g;
     L.gemm_ws = b.take<char>(g);
     L.colsum_ws_bytes = plagnn_colsum_workspace_bytes(n, pitch32(fmax));
@@ -205,13 +211,12 @@ int plagnn_gnn32_backward(const plagnn_gnn32_shape* shape, const float* x, int64
     TRY(weight_operand(params[17], c, d4, L.w2, false, stream, &w2));
     // sigmoid, liner2, liner1
     TRY(plagnn_act_backward(dprob, lddprob, prob, ldprob, n, c, PLAGNN_ACT_SIGMOID, 0.01f, nullptr, L.dz5, pc, stream));
-    TRY(gemm1(c, d4, L.dz5, pc, 1, L.h4, p4, 1, n, nullptr, 0, nullptr, 0, 0, grads[17], d4, L, stream));
-    TRY(plagnn_colsum(L.dz5, n, c, pc, grads[18], L.colsum_ws, L.colsum_ws_bytes, stream));
+    // weight gradient + bias gradient of every linear map in one pass (the bias gradient is an extra output column)
+    TRY(plagnn_gemm_wgrad_bias(c, d4, L.dz5, pc, L.h4, p4, n, grads[17], d4, grads[18], L.gemm_ws, L.gemm_ws_bytes, stream));
     // input gradients read the weights [out x in] as an MN-major B operand (b_trans = 1): no transposed copies
     TRY(gemm1(n, d4, L.dz5, pc, 0, w2.p, w2.ld, 1, c, nullptr, 0, L.h4, p4, PLAGNN_ACT_LEAKY, L.dz4, p4, L, stream));
     const float* h3 = L.h[2];
-    TRY(gemm1(d4, d3, L.dz4, p4, 1, h3, p3, 1, n, nullptr, 0, nullptr, 0, 0, grads[15], d3, L, stream));
-    TRY(plagnn_colsum(L.dz4, n, d4, p4, grads[16], L.colsum_ws, L.colsum_ws_bytes, stream));
+    TRY(plagnn_gemm_wgrad_bias(d4, d3, L.dz4, p4, h3, p3, n, grads[15], d3, grads[16], L.gemm_ws, L.gemm_ws_bytes, stream));
     float* drst = L.drst[0];
     TRY(gemm1(n, d3, L.dz4, p4, 0, w1.p, w1.ld, 1, d4, nullptr, 0, h3, p3, PLAGNN_ACT_LEAKY, drst, p3, L, stream));
     int cur = 0;
@@ -225,13 +230,11 @@ int plagnn_gnn32_backward(const plagnn_gnn32_shape* shape, const float* x, int64
         TRY(weight_operand(Pl[0], f, f, L.wp[l], false, stream, &wp));
         TRY(weight_operand(Pl[2], o, f, L.ws[l], false, stream, &ws));
         TRY(weight_operand(Pl[3], o, f, L.wn[l], false, stream, &wn));
-        TRY(plagnn_colsum(drst, n, o, po, G[4], L.colsum_ws, L.colsum_ws_bytes, stream));
-        TRY(gemm1(o, f, drst, po, 1, hin, ldin, 1, n, nullptr, 0, nullptr, 0, 0, G[2], f, L, stream));
+        TRY(plagnn_gemm_wgrad_bias(o, f, drst, po, hin, ldin, n, G[2], f, G[4], L.gemm_ws, L.gemm_ws_bytes, stream));
         TRY(gemm1(o, f, drst, po, 1, L.neigh[l], pf, 1, n, nullptr, 0, nullptr, 0, 0, G[3], f, L, stream));
         TRY(gemm1(n, f, drst, po, 0, wn.p, wn.ld, 1, o, nullptr, 0, nullptr, 0, 0, L.dneigh, pf, L, stream));
         TRY(plagnn_spmm_max_bwd(L.dneigh, pf, L.arg[l], pf, L.neigh[l], pf, n, f, L.dm, n, pf, stream));
-        TRY(gemm1(f, f, L.dm, pf, 1, hin, ldin, 1, n, nullptr, 0, nullptr, 0, 0, G[0], f, L, stream));
-        TRY(plagnn_colsum(L.dm, n, f, pf, G[1], L.colsum_ws, L.colsum_ws_bytes, stream));
+        TRY(plagnn_gemm_wgrad_bias(f, f, L.dm, pf, hin, ldin, n, G[0], f, G[1], L.gemm_ws, L.gemm_ws_bytes, stream));
         if (l > 0 || dx) {
             float* out = l > 0 ? L.drst[cur ^ 1] : dx;
             const int64_t ldo = l > 0 ? pf : lddx;

@@ -177,6 +177,25 @@ def gemm(m: int, n: int, pairs, bias=None, act=ACT_NONE, gate=None, gate_act=ACT
     return out
 
 
+def gemm_wgrad_bias(dz: torch.Tensor, x: torch.Tensor, dw: torch.Tensor | None = None, db: torch.Tensor | None = None):
+    """dW[m x n] = dz^T x and db[m] = dz.sum(0) in one pass (dz: [k x m], x: [k x n], rows 16-byte aligned)."""
+    lib = _lib.load()
+    _require_cuda_f32(dz, x, dw, db)
+    k, m = dz.shape
+    n = x.shape[1]
+    assert x.shape[0] == k and dz.stride(1) == 1 and x.stride(1) == 1
+    if dw is None:
+        dw = torch.empty((m, n), device=dz.device, dtype=torch.float32)
+    if db is None:
+        db = torch.empty(m, device=dz.device, dtype=torch.float32)
+    nb = lib.plagnn_gemm_wgrad_bias_workspace_bytes(m, n, k)
+    ws = workspace(nb, dz.device, "gemm")
+    with _timed(("gemm", m, n, k)):
+        check(lib.plagnn_gemm_wgrad_bias(m, n, _p(dz), dz.stride(0), _p(x), x.stride(0), k, _p(dw), dw.stride(0), _p(db),
+                                         _p(ws), nb if ws is not None else 0, _stream()), "gemm_wgrad_bias")
+    return dw, db
+
+
 def colsum(x: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     _require_cuda_f32(x)

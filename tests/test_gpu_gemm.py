@@ -174,3 +174,20 @@ def test_gemm_tma_weight_gradient_split_k_both_tile_configs(cuda, cta_group):
     pairs = [(dz, 1, x, 1, nodes)]
     ops.gemm(o, f, pairs, out=out, backend=ops.GEMM_TMA)
     assert rel(out, ref_gemm(pairs, None, 0, None, 0)) < TOL
+
+
+@pytest.mark.parametrize("nodes,o,f", [(24041, 400, 503), (24041, 503, 503), (24041, 12, 100), (5000, 300, 400), (3000, 100, 255),
+                                       (700, 64, 31)])
+def test_gemm_wgrad_bias_one_pass(cuda, cta_group, nodes, o, f):
+    """dW = dZ^T X with the bias gradient riding along as an extra output column (B column that reads as 1.0)."""
+    g1, g2 = torch.Generator().manual_seed(21), torch.Generator().manual_seed(22)
+    dz = ops.aligned(torch.randn(nodes, o, generator=g1).to(cuda))
+    x = ops.aligned((torch.randn(nodes, f, generator=g2) + 0.5).to(cuda))
+    dw, db = ops.gemm_wgrad_bias(dz, x)
+    want_w = dz[:, :o].double().cpu().t() @ x[:, :f].double().cpu()
+    want_b = dz[:, :o].double().cpu().sum(0)
+    assert dw.shape == (o, f) and db.shape == (o,)
+    assert rel(dw, want_w) < TOL
+    assert ((db.double().cpu() - want_b).abs().max() / want_b.abs().max()).item() < TOL
+    # x must be untouched (the ones column is injected in shared memory only)
+    assert torch.equal(x, ops.aligned((torch.randn(nodes, f, generator=torch.Generator().manual_seed(22)) + 0.5).to(cuda)))
