@@ -196,7 +196,7 @@ class _EngineState:
         return torch.zeros(self.arena_bytes, dtype=torch.uint8, device=self.device)   # zero-filled once
 
     def release(self, arena):
-        if len(self.free) < 2:
+        if len(self.free) < 8:          # one arena per concurrently trained model (stream)
             self.free.append(arena)
 
 

@@ -192,3 +192,46 @@ def test_sage_mean_and_gcn_sum_family(cuda):
     for layer, lin in zip(m.layers, mo.lins):
         assert rel_err(layer.weight.grad, lin.weight.grad) < 2 * REL_TOL
         assert rel_err(layer.bias.grad, lin.bias.grad) < 2 * REL_TOL
+
+
+def test_concurrent_models_on_streams_match_sequential(cuda):
+    """Two models of the fold/seed sweep trained at the same time on two CUDA streams (one arena each) end where the same
+    two models end when trained one after the other (ordered max-pool backward, so the comparison is exact)."""
+    import copy
+    from plagnn_b200 import nn as pnn
+    prob, g, go, m0, mo = build_pair(cuda, n=1500, e=40000, dims=(3, 60, 60))
+    w = orc.weight_cal(prob.loc)
+    idx = torch.as_tensor(prob.labelled[::2], device=cuda)
+    x, y = g.ndata["feat"], g.ndata["loc"]
+    torch.manual_seed(5)
+    m1 = P.GNN32(123, 400, 300, 200, 100, 12).to(cuda)
+    seq = [copy.deepcopy(m0), copy.deepcopy(m1)]
+    par = [copy.deepcopy(m0), copy.deepcopy(m1)]
+
+    def step(model, opt):
+        opt.zero_grad()
+        loss = P.multi_loss_indexed(model(g, x), y, idx, w)
+        loss.backward()
+        opt.step()
+
+    pnn.DETERMINISTIC_BACKWARD = True
+    try:
+        for m in seq:
+            o = P.FusedAdam(m.parameters(), lr=5e-5)
+            for _ in range(3):
+                step(m, o)
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream(device=cuda) for _ in par]
+        opts = [P.FusedAdam(m.parameters(), lr=5e-5) for m in par]
+        for s in streams:
+            s.wait_stream(torch.cuda.current_stream())
+        for _ in range(3):
+            for m, o, s in zip(par, opts, streams):
+                with torch.cuda.stream(s):
+                    step(m, o)
+        torch.cuda.synchronize()
+    finally:
+        pnn.DETERMINISTIC_BACKWARD = False
+    for a, b in zip(seq, par):
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            assert torch.equal(pa, pb)
