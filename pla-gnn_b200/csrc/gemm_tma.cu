@@ -293,6 +293,31 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     const uint32_t n_eff = nrem >= TILE_N ? (uint32_t)TILE_N : (uint32_t)((nrem + 32 * CG - 1) / (32 * CG) * (32 * CG));
     const uint32_t n_half = n_eff / CG;       // rows of B this CTA stages
 
+    // raw tiles of k-block `it` of this CTA into ring stage it % TM_RAW_STAGES (executed by thread 0 only)
+    auto load_kblock = [&](int it) {
+        const int s = it % TM_RAW_STAGES;
+        int p = 0, local = kb_beg + it;
+        if (P.npairs > 1 && local >= P.kblocks[0]) { local -= P.kblocks[0]; p = 1; }
+        const int k0 = local * TM_BK;
+        const int a_row = (int)(m0 + rank * 128), b_row = (int)(n0 + rank * n_half);
+        const uint32_t st = tiles + s * TM_RAW_BYTES;
+        const uint32_t rb = bar_raw_full + 8 * s;
+        mbar_expect_tx(rb, TM_RAW_BYTES);
+        if (!AT) {
+            tma_load_2d(st, &P.map[p][0], k0, a_row, rb);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_2d(st + j * 4096, &P.map[p][0], a_row + 32 * j, k0, rb);
+        }
+        if (!BT) {
+            tma_load_2d(st + TM_PART_BYTES, &P.map[p][1], k0, b_row, rb);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_2d(st + TM_PART_BYTES + j * 4096, &P.map[p][1], b_row + 32 * j, k0, rb);
+        }
+    };
+    const int preloaded = nkb < TM_RAW_STAGES ? nkb : TM_RAW_STAGES;
+
     if (t == 0) {
         for (int s = 0; s < TM_RAW_STAGES; ++s) {
             mbar_init(bar_raw_full + 8 * s, 1);
@@ -310,6 +335,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             if (p < P.npairs) { prefetch_map(&P.map[p][0]); prefetch_map(&P.map[p][1]); }
         if (P.tma_store) prefetch_map(&P.map_out);
         if (P.gate_tma) prefetch_map(&P.map_gate);
+        // the first ring pass is requested right here, before the TMEM allocation and the CTA / cluster barriers: the loads
+        // only need this CTA's own (just initialised) barriers, and their ~3 000-cycle latency overlaps the rest of the set-up
+        for (int it = 0; it < preloaded; ++it) load_kblock(it);
     }
     if (warp == 1) tmem_alloc<CG>(tmem_slot, TMEM_COLS);
     tc_fence_before();
@@ -322,32 +350,15 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     if (warp == 0) {
         // ================= TMA producer (one elected lane): raw fp32 tiles of A and B =================
         if (lane == 0) {
-            const int a_row = (int)(m0 + rank * 128), b_row = (int)(n0 + rank * n_half);
-            for (int it = 0; it < nkb; ++it) {
+            if (tr) tr[16] = clock64();
+            for (int it = preloaded; it < nkb; ++it) {
                 const int s = it % TM_RAW_STAGES;
                 const uint32_t ph = (uint32_t)((it / TM_RAW_STAGES) & 1);
                 const long long w0 = tr ? clock64() : 0;
                 mbar_wait(bar_raw_empty + 8 * s, ph ^ 1u);
                 if (tr) tr[8] += clock64() - w0;
-                int p = 0, local = kb_beg + it;
-                if (P.npairs > 1 && local >= P.kblocks[0]) { local -= P.kblocks[0]; p = 1; }
-                const int k0 = local * TM_BK;
-                const uint32_t st = tiles + s * TM_RAW_BYTES;
-                const uint32_t rb = bar_raw_full + 8 * s;
-                mbar_expect_tx(rb, TM_RAW_BYTES);
-                if (tr && (it == 0 || it == 8)) tr[it ? 20 : 16] = clock64();
-                if (!AT) {
-                    tma_load_2d(st, &P.map[p][0], k0, a_row, rb);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) tma_load_2d(st + j * 4096, &P.map[p][0], a_row + 32 * j, k0, rb);
-                }
-                if (!BT) {
-                    tma_load_2d(st + TM_PART_BYTES, &P.map[p][1], k0, b_row, rb);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) tma_load_2d(st + TM_PART_BYTES + j * 4096, &P.map[p][1], b_row + 32 * j, k0, rb);
-                }
+                if (tr && it == 8) tr[20] = clock64();
+                load_kblock(it);
             }
         }
         __syncwarp();
