@@ -65,6 +65,8 @@ struct alignas(64) TmParams {
     int ones_col;                                 // >= 0: column of the (mn-contiguous) B operand that reads as 1.0: output column
                                                   // ones_col = sum over k of A, i.e. the bias gradient of a weight-gradient product
     float* ones_out;                              // where the reduction writes that column (length m)
+    int tiles_m, tiles_n, total_tiles;            // tile t = (split * tiles_m + row block) * tiles_n + column block
+    int persistent;                               // fewer CTA pairs than tiles: each pair walks several tiles
     int transpose_out;                            // split-K only: the reduction writes C^T (operands were swapped by the launcher)
     int64_t m, n;
     int npairs;
@@ -255,6 +257,37 @@ __device__ __forceinline__ float tm_epilogue_one(const TmParams& P, float v, int
     return v;
 }
 
+// One output tile of the launch: tile index t -> (split, row block, column block), column blocks fastest so that the
+// column tiles of one row block run together and A streams from HBM once.
+struct TmTile {
+    int64_t m0, n0;
+    int split, kb_beg, nkb;
+    uint32_t n_eff, n_half;      // MMA width of this tile / rows of B one CTA stages
+};
+template <int CG>
+__device__ __forceinline__ TmTile tm_tile(const TmParams& P, int t) {
+    constexpr int TILE = 128 * CG;
+    TmTile T;
+    const int nt = t % P.tiles_n;
+    const int rest = t / P.tiles_n;
+    const int mt = rest % P.tiles_m;
+    T.split = rest / P.tiles_m;
+    T.m0 = (int64_t)mt * TILE;
+    T.n0 = (int64_t)nt * TILE;
+    T.kb_beg = T.split * P.kblocks_per_split;
+    T.nkb = min(P.total_kblocks, T.kb_beg + P.kblocks_per_split) - T.kb_beg;
+    // columns of this tile that exist, rounded to what one MMA can produce (CG = 2: both halves multiples of 32)
+    const int64_t nrem = P.n - T.n0;
+    T.n_eff = nrem >= TILE ? (uint32_t)TILE : (uint32_t)((nrem + 32 * CG - 1) / (32 * CG) * (32 * CG));
+    T.n_half = T.n_eff / CG;
+    return T;
+}
+
+// The kernel walks a contiguous range of tiles per CTA pair.  With one
+// tile per pair that is the plain tiled launch; with fewer pairs than tiles (P.persistent) the rings simply run on across
+// tile boundaries: while warps 2..9 read out the accumulators of tile i, the producer already fills the raw ring with
+// tile i + 1, and set-up / tear-down are paid once per SM.  TMEM holds one tile (2 x 256 columns), so the MMAs of the next
+// tile start when the read-out has released it (bar_tmem_empty).
 template <int CG, bool AT, bool BT>
 __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_constant__ TmParams P) {
     using namespace tm;
@@ -266,7 +299,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     const uint32_t bar_raw_full = bars, bar_raw_empty = bars + 8 * TM_RAW_STAGES;
     const uint32_t bar_lo_full = bars + 16 * TM_RAW_STAGES, bar_lo_empty = bar_lo_full + 8 * TM_LO_STAGES;
     const uint32_t bar_acc = bar_lo_empty + 8 * TM_LO_STAGES;
-    const uint32_t bar_gate = bar_acc + 8;                          // [TM_EPI_WARPS]: gate images of one warp landed
+    const uint32_t bar_tmem_empty = bar_acc + 8;                    // accumulators read out (both CTAs): next tile may overwrite
+    const uint32_t bar_gate = bar_tmem_empty + 8;                   // [TM_EPI_WARPS]: gate images of one warp landed
     const uint32_t tmem_slot = bar_gate + 8 * TM_EPI_WARPS;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
@@ -274,32 +308,26 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     constexpr uint32_t TMEM_COLS = 2 * TILE_N;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
-    const int lin_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    // this CTA pair's tiles: a contiguous, balanced range (2 or 3 tiles when 188 tiles meet 74 pairs).  Contiguous tiles
+    // alternate over the column blocks, so every pair gets the same mix of full and ragged tiles and re-reads its rows of
+    // A while they are hot in L2 (a strided assignment gave all full-width tiles to the even pairs).
+    const int unit = blockIdx.x / CG, units = gridDim.x / CG;
+    const int first_tile = (int)((int64_t)unit * P.total_tiles / units);
+    const int end_tile = (int)((int64_t)(unit + 1) * P.total_tiles / units);
 #if PLAGNN_TMA_DIAG
-    long long* const tr = (P.trace && lin_cta < 64) ? P.trace + 32 * lin_cta : nullptr;
+    long long* const tr = (P.trace && blockIdx.x < 64) ? P.trace + 32 * blockIdx.x : nullptr;   // stamps of the FIRST tile
 #else
     long long* const tr = nullptr;
-    (void)lin_cta;
 #endif
     if (tr && t == 0) tr[0] = clock64();
-    // N tiles fastest in launch order: the column tiles of one row block run together, so A streams from HBM once
-    const int64_t m0 = (int64_t)blockIdx.y * TILE_M, n0 = (int64_t)(blockIdx.x / CG) * TILE_N;
-    const int split = blockIdx.z;
-    const int kb_beg = split * P.kblocks_per_split;
-    const int kb_end = min(P.total_kblocks, kb_beg + P.kblocks_per_split);
-    const int nkb = kb_end - kb_beg;
-    // columns of this tile that exist, rounded to what one MMA can produce (CG = 2: both halves multiples of 32)
-    const int64_t nrem = P.n - n0;
-    const uint32_t n_eff = nrem >= TILE_N ? (uint32_t)TILE_N : (uint32_t)((nrem + 32 * CG - 1) / (32 * CG) * (32 * CG));
-    const uint32_t n_half = n_eff / CG;       // rows of B this CTA stages
 
-    // raw tiles of k-block `it` of this CTA into ring stage it % TM_RAW_STAGES (executed by thread 0 only)
-    auto load_kblock = [&](int it) {
-        const int s = it % TM_RAW_STAGES;
-        int p = 0, local = kb_beg + it;
+    // raw tiles of k-block `it` of tile T into ring stage g % TM_RAW_STAGES (g = k-blocks loaded so far; thread 0 only)
+    auto load_kblock = [&](const TmTile& T, int it, int g) {
+        const int s = g % TM_RAW_STAGES;
+        int p = 0, local = T.kb_beg + it;
         if (P.npairs > 1 && local >= P.kblocks[0]) { local -= P.kblocks[0]; p = 1; }
         const int k0 = local * TM_BK;
-        const int a_row = (int)(m0 + rank * 128), b_row = (int)(n0 + rank * n_half);
+        const int a_row = (int)(T.m0 + rank * 128), b_row = (int)(T.n0 + rank * T.n_half);
         const uint32_t st = tiles + s * TM_RAW_BYTES;
         const uint32_t rb = bar_raw_full + 8 * s;
         mbar_expect_tx(rb, TM_RAW_BYTES);
@@ -316,7 +344,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             for (int j = 0; j < 4; ++j) tma_load_2d(st + TM_PART_BYTES + j * 4096, &P.map[p][1], b_row + 32 * j, k0, rb);
         }
     };
-    const int preloaded = nkb < TM_RAW_STAGES ? nkb : TM_RAW_STAGES;
+    const TmTile T0 = tm_tile<CG>(P, first_tile);
+    const int preloaded = T0.nkb < TM_RAW_STAGES ? T0.nkb : TM_RAW_STAGES;
 
     if (t == 0) {
         for (int s = 0; s < TM_RAW_STAGES; ++s) {
@@ -328,6 +357,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             mbar_init(bar_lo_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
+        mbar_init(bar_tmem_empty, (uint32_t)(CG * TM_EPI_WARPS));
         for (int w = 0; w < TM_EPI_WARPS; ++w) mbar_init(bar_gate + 8 * w, 1);
         fence_mbar_init();
 #pragma unroll
@@ -337,7 +367,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
         if (P.gate_tma) prefetch_map(&P.map_gate);
         // the first ring pass is requested right here, before the TMEM allocation and the CTA / cluster barriers: the loads
         // only need this CTA's own (just initialised) barriers, and their ~3 000-cycle latency overlaps the rest of the set-up
-        for (int it = 0; it < preloaded; ++it) load_kblock(it);
+        for (int it = 0; it < preloaded; ++it) load_kblock(T0, it, it);
     }
     if (warp == 1) tmem_alloc<CG>(tmem_slot, TMEM_COLS);
     tc_fence_before();
@@ -351,77 +381,113 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
         // ================= TMA producer (one elected lane): raw fp32 tiles of A and B =================
         if (lane == 0) {
             if (tr) tr[16] = clock64();
-            for (int it = preloaded; it < nkb; ++it) {
-                const int s = it % TM_RAW_STAGES;
-                const uint32_t ph = (uint32_t)((it / TM_RAW_STAGES) & 1);
-                const long long w0 = tr ? clock64() : 0;
-                mbar_wait(bar_raw_empty + 8 * s, ph ^ 1u);
-                if (tr) tr[8] += clock64() - w0;
-                if (tr && it == 8) tr[20] = clock64();
-                load_kblock(it);
+            int g = 0;                                   // k-blocks requested so far (all tiles)
+            for (int tile = first_tile; tile < end_tile; ++tile) {
+                const TmTile T = tm_tile<CG>(P, tile);
+                for (int it = (tile == first_tile ? preloaded : 0); it < T.nkb; ++it) {
+                    const int gg = g + it;
+                    const int s = gg % TM_RAW_STAGES;
+                    const uint32_t ph = (uint32_t)((gg / TM_RAW_STAGES) & 1);
+                    const long long w0 = tr ? clock64() : 0;
+                    mbar_wait(bar_raw_empty + 8 * s, ph ^ 1u);
+                    if (tr && tile == first_tile) tr[8] += clock64() - w0;
+                    if (tr && tile == first_tile && it == 8) tr[20] = clock64();
+                    load_kblock(T, it, gg);
+                }
+                g += T.nkb;
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer (one elected lane of the leader CTA) =================
         if (lane == 0 && rank == 0) {
-            const uint32_t idesc = make_idesc(TILE_M, n_eff, AT, BT);
             // descriptor start-address step per K = 8: 32 bytes inside a K-major row; two k-groups of 512 bytes if MN-major
             constexpr uint64_t a_step = AT ? (1024u >> 4) : 2u, b_step = BT ? (1024u >> 4) : 2u;
             const uint32_t acc_main = tmem_base, acc_corr = tmem_base + TILE_N;
-            for (int it = 0; it < nkb; ++it) {
-                const int s = it % TM_RAW_STAGES, l = it % TM_LO_STAGES;
-                const uint32_t phl = (uint32_t)((it / TM_LO_STAGES) & 1);
-                const long long w0 = tr ? clock64() : 0;
-                // the lo tiles of both CTAs are written (which also means the raw tiles have landed in both)
-                if (CG == 2) mbar_wait_cluster(bar_lo_full + 8 * l, phl);
-                else mbar_wait(bar_lo_full + 8 * l, phl);
-                tc_fence_after();
-                if (tr) { const long long w1 = clock64(); tr[9] += w1 - w0; if (it == 0) tr[2] = w1; if (it == 0 || it == 8) tr[it ? 23 : 19] = w1; }
-                const uint32_t st = tiles + s * TM_RAW_BYTES, sl = lo_ring + l * TM_RAW_BYTES;
-                const uint64_t a_hi = AT ? desc_mnmajor(st) : desc_kmajor(st);
-                const uint64_t a_lo = AT ? desc_mnmajor(sl) : desc_kmajor(sl);
-                const uint64_t b_hi = BT ? desc_mnmajor(st + TM_PART_BYTES) : desc_kmajor(st + TM_PART_BYTES);
-                const uint64_t b_lo = BT ? desc_mnmajor(sl + TM_PART_BYTES) : desc_kmajor(sl + TM_PART_BYTES);
-#pragma unroll
-                for (int kk = 0; kk < TM_BK / 8; ++kk) {
-                    if (TM_DEBUG(P) == 2) break;
-                    const uint64_t adv_a = (uint64_t)kk * a_step, adv_b = (uint64_t)kk * b_step;
-                    // corrections go to their own accumulator: the tensor core adds into TMEM with truncation, and the
-                    // main accumulator then sees a third of the additions (gemm_tc.cu has the measurements)
-                    const uint32_t acc_on = (it | kk) ? 1u : 0u;
-                    if (TM_SINGLE(P)) {
-                        umma_tf32<CG>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
-                        umma_tf32<CG>(acc_main, a_lo + adv_a, b_hi + adv_b, idesc, 1u);
-                        umma_tf32<CG>(acc_main, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
-                        continue;
-                    }
-                    umma_tf32<CG>(acc_corr, a_lo + adv_a, b_hi + adv_b, idesc, acc_on);
-                    umma_tf32<CG>(acc_corr, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
-                    umma_tf32<CG>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
+            int g = 0, tile_iter = 0;
+            for (int tile = first_tile; tile < end_tile; ++tile, ++tile_iter) {
+                const TmTile T = tm_tile<CG>(P, tile);
+                const uint32_t idesc = make_idesc(TILE_M, T.n_eff, AT, BT);
+                if (tile_iter > 0) {                     // the previous tile's accumulators have been read out in both CTAs
+                    mbar_wait(bar_tmem_empty, (uint32_t)((tile_iter - 1) & 1));
+                    tc_fence_after();
                 }
-                // both rings are released (in both CTAs) when the MMAs issued so far have read them
-                umma_commit<CG>(bar_lo_empty + 8 * l);
-                umma_commit<CG>(bar_raw_empty + 8 * s);
+                for (int it = 0; it < T.nkb; ++it, ++g) {
+                    const int s = g % TM_RAW_STAGES, l = g % TM_LO_STAGES;
+                    const uint32_t phl = (uint32_t)((g / TM_LO_STAGES) & 1);
+                    const long long w0 = tr ? clock64() : 0;
+                    // the lo tiles of both CTAs are written (which also means the raw tiles have landed in both)
+                    mbar_wait(bar_lo_full + 8 * l, phl);
+                    tc_fence_after();
+                    if (tr && tile_iter == 0) {
+                        const long long w1 = clock64();
+                        tr[9] += w1 - w0;
+                        if (it == 0) tr[2] = w1;
+                        if (it == 0 || it == 8) tr[it ? 23 : 19] = w1;
+                    }
+                    const uint32_t st = tiles + s * TM_RAW_BYTES, sl = lo_ring + l * TM_RAW_BYTES;
+                    const uint64_t a_hi = AT ? desc_mnmajor(st) : desc_kmajor(st);
+                    const uint64_t a_lo = AT ? desc_mnmajor(sl) : desc_kmajor(sl);
+                    const uint64_t b_hi = BT ? desc_mnmajor(st + TM_PART_BYTES) : desc_kmajor(st + TM_PART_BYTES);
+                    const uint64_t b_lo = BT ? desc_mnmajor(sl + TM_PART_BYTES) : desc_kmajor(sl + TM_PART_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < TM_BK / 8; ++kk) {
+                        if (TM_DEBUG(P) == 2) break;
+                        const uint64_t adv_a = (uint64_t)kk * a_step, adv_b = (uint64_t)kk * b_step;
+                        // corrections go to their own accumulator: the tensor core adds into TMEM with truncation, and the
+                        // main accumulator then sees a third of the additions (gemm_tc.cu has the measurements)
+                        const uint32_t acc_on = (it | kk) ? 1u : 0u;
+                        if (TM_SINGLE(P)) {
+                            umma_tf32<CG>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
+                            umma_tf32<CG>(acc_main, a_lo + adv_a, b_hi + adv_b, idesc, 1u);
+                            umma_tf32<CG>(acc_main, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
+                            continue;
+                        }
+                        umma_tf32<CG>(acc_corr, a_lo + adv_a, b_hi + adv_b, idesc, acc_on);
+                        umma_tf32<CG>(acc_corr, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
+                        umma_tf32<CG>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
+                    }
+                    // both rings are released (in both CTAs) when the MMAs issued so far have read them
+                    umma_commit<CG>(bar_lo_empty + 8 * l);
+                    umma_commit<CG>(bar_raw_empty + 8 * s);
+                }
+                umma_commit<CG>(bar_acc);               // accumulators of this tile complete (both CTAs)
+                if (tr && tile_iter == 0) tr[3] = clock64();
             }
-            umma_commit<CG>(bar_acc);                   // accumulators complete (both CTAs)
-            if (tr) tr[3] = clock64();
         }
         __syncwarp();
     } else {
-        {
-            // ================= hi/lo split in shared memory (warps 2..9) =================
-            // The tensor core reads the raw fp32 tile as the hi operand (it drops the low 13 bits itself); the lo tile has
-            // the same swizzled layout, so the pass is purely elementwise: lo[i] = rn_tf32(x[i] - trunc_tf32(x[i])).
-            // Tensor-core operand reads do not compete with LDS/STS for bandwidth (tools/mma_probe.cu, "contend").
-            // The raw ring is 4 deep (TMA latency ~2.5 us), the lo ring 3 deep: the chain "MMAs done -> commit -> split warps -> STS ->
-            // proxy fence -> (remote) arrive -> issuer" measured ~2100 cycles, more than one k-block of MMAs (1536).
-            const int ct = t - 64;                                  // 0..255
+        // ================= warps 2..9: hi/lo split in shared memory, then the read-out of the tile =================
+        // The tensor core reads the raw fp32 tile as the hi operand (it drops the low 13 bits itself); the lo tile has
+        // the same swizzled layout, so the pass is purely elementwise: lo[i] = rn_tf32(x[i] - trunc_tf32(x[i])).
+        // Tensor-core operand reads do not compete with LDS/STS for bandwidth (tools/mma_probe.cu, "contend").
+        // The raw ring is 4 deep (TMA latency ~2.5 us), the lo ring 3 deep: the chain "MMAs done -> commit -> split warps
+        // -> STS -> proxy fence -> (remote) arrive -> issuer" is longer than one k-block of MMAs (1536 cycles).
+        const int ct = t - 64;                                  // 0..255
+        const uint32_t lo_full0 = CG == 2 ? mapa(bar_lo_full, 0) : bar_lo_full;   // the leader's barriers count both CTAs
+        const uint32_t tmem_empty0 = CG == 2 ? mapa(bar_tmem_empty, 0) : bar_tmem_empty;
+        const int lg = warp & 3;                        // TMEM lane group this warp may read (warp % 4)
+        const int chalf = (warp - 2) >> 2;              // column half of the tile
+        const bool direct = P.splits == 1;
+        constexpr int CHUNKS = TILE_N / 32 / 2;
+        // staging images of the read-out: in the raw ring for a single tile per CTA (everything is free by then); with
+        // several tiles per CTA the raw ring is being refilled for the next tile, so they live in the lo ring, which is
+        // idle until these same warps start splitting again (no gate images there: P.persistent excludes a gate)
+        const uint32_t stg = (P.persistent ? lo_ring : tiles) + (uint32_t)(warp - 2) * 8192u;      // two 4 KB images per warp
+        const uint32_t gimg = tiles + 65536u + (uint32_t)(warp - 2) * 16384u;                      // CHUNKS x 4 KB per warp
+        const uint32_t gbar = bar_gate + 8 * (uint32_t)(warp - 2);
+        const uint32_t row_off = (uint32_t)lane * 128u;
+        int g = 0, tile_iter = 0, buf = 0;
+        for (int tile = first_tile; tile < end_tile; ++tile, ++tile_iter) {
+            const TmTile T = tm_tile<CG>(P, tile);
+            const int64_t m0 = T.m0, n0 = T.n0;
+            const uint32_t n_eff = T.n_eff;
+            const int split = T.split;
             // does this thread own the piece of the B tile that holds the ones column?  MN-major box j = 32 columns,
             // k-row ct / 8, 16-byte piece ct % 8 of the row = logical 32-byte chunk ((ct % 8) / 2) ^ (row & 3), half (ct % 8) & 1
             int ones_piece = -1, ones_elem = 0;
             if (BT && P.ones_col >= 0) {
-                const int64_t lc = (int64_t)P.ones_col - (n0 + rank * n_half);       // column inside this CTA's 128-wide B tile
+                const int64_t lc = (int64_t)P.ones_col - (n0 + rank * T.n_half);     // column inside this CTA's 128-wide B tile
                 if (lc >= 0 && lc < 128) {
                     const int q = ct & 7, rr = (ct >> 3) & 3;
                     const int cbase = (((q >> 1) ^ rr) << 3) + ((q & 1) << 2);
@@ -429,13 +495,16 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     if (c >= cbase && c < cbase + 4) { ones_piece = (int)(lc >> 5); ones_elem = c - cbase; }
                 }
             }
-            const uint32_t lo_full0 = CG == 2 ? mapa(bar_lo_full, 0) : bar_lo_full;   // the leader's barrier counts both CTAs
-            for (int it = 0; it < nkb; ++it) {
-                const int s = it % TM_RAW_STAGES, l = it % TM_LO_STAGES;
-                const uint32_t phr = (uint32_t)((it / TM_RAW_STAGES) & 1), phl = (uint32_t)((it / TM_LO_STAGES) & 1);
+            for (int it = 0; it < T.nkb; ++it, ++g) {
+                const int s = g % TM_RAW_STAGES, l = g % TM_LO_STAGES;
+                const uint32_t phr = (uint32_t)((g / TM_RAW_STAGES) & 1), phl = (uint32_t)((g / TM_LO_STAGES) & 1);
                 const long long w0 = (tr && t == 64) ? clock64() : 0;
                 mbar_wait(bar_raw_full + 8 * s, phr);
-                if (tr && t == 64) { const long long w1 = clock64(); tr[10] += w1 - w0; if (it == 0 || it == 8) tr[it ? 21 : 17] = w1; }
+                if (tr && t == 64 && tile_iter == 0) {
+                    const long long w1 = clock64();
+                    tr[10] += w1 - w0;
+                    if (it == 0 || it == 8) tr[it ? 21 : 17] = w1;
+                }
                 const uint32_t src = tiles + s * TM_RAW_BYTES + (uint32_t)ct * 16u;
                 const uint32_t dstl = lo_ring + l * TM_RAW_BYTES + (uint32_t)ct * 16u;
                 float4 v[8];
@@ -456,181 +525,187 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                             sts_v4(src + (uint32_t)i * 4096u, v[i].x, v[i].y, v[i].z, v[i].w);
                         }
                 }
-                mbar_wait(bar_lo_empty + 8 * l, phl ^ 1u);
-                if (tr && t == 64 && it == 8) tr[24] = clock64();           // the MMAs of k-block it - TM_LO_STAGES have read this lo stage
+                mbar_wait(bar_lo_empty + 8 * l, phl ^ 1u);      // the MMAs of k-block g - TM_LO_STAGES have read this lo stage
+                if (tr && t == 64 && tile_iter == 0 && it == 8) tr[24] = clock64();
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     sts_v4(dstl + (uint32_t)i * 4096u, tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (tr && t == 64 && (it == 0 || it == 8)) tr[it ? 22 : 18] = clock64();
+                if (tr && t == 64 && tile_iter == 0 && (it == 0 || it == 8)) tr[it ? 22 : 18] = clock64();
                 if (lane == 0) {
                     if (CG == 2) mbar_arrive_cluster(lo_full0 + 8 * l);
                     else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_lo_full + 8 * l) : "memory");
                 }
             }
-        }
-        // ================= epilogue: TMEM -> registers -> global =================
-        mbar_wait(bar_acc, 0);
-        tc_fence_after();
-        if (tr && t == 64) tr[4] = clock64();
-        const int lg = warp & 3;                        // TMEM lane group this warp may read (warp % 4)
-        const int chalf = (warp - 2) >> 2;              // column half of the tile
-        const int64_t r = m0 + rank * 128 + lg * 32 + lane;
-        const bool direct = P.splits == 1;
-        constexpr int CHUNKS = TILE_N / 32 / 2;
-        // Shared-memory path: each warp turns its 32 rows x 32 columns into a 4 KB SWIZZLE_128B image (the pipeline
-        // stages are free: every MMA has completed) and one lane stores it with a bulk tensor copy: whole 128-byte lines
-        // leave the SM, rows >= m / columns >= n are clipped by the tensor map.  Two images in flight per warp.
-        // The activation / gate switches sit OUTSIDE the element loops: the first version branched per element and
-        // spent 25 000 of its 28 000 epilogue cycles per tile fetching instructions (PLAGNN_TMA_TRACE).
-        const uint32_t stg = tiles + (uint32_t)(warp - 2) * 8192u;       // two 4 KB images per warp
-        const uint32_t row_off = (uint32_t)lane * 128u;
-        const int row0 = (int)(m0 + rank * 128 + lg * 32);
-        const int64_t r_ld = r < P.m ? r : P.m - 1;                      // clamped row for gate loads (clipped rows are never stored)
-        // gate tiles (saved activations of the backward epilogues) come in by TMA as 32 x 32 SWIZZLE_128B images, all chunks
-        // of this warp at once, while the first accumulator chunk is read (per-lane row-strided __ldg cost ~40 us per GEMM)
-        const bool gate_img_on = direct && P.gate && P.gate_tma;
-        const uint32_t gimg = tiles + 65536u + (uint32_t)(warp - 2) * 16384u;    // CHUNKS x 4 KB per warp
-        const uint32_t gbar = bar_gate + 8 * (uint32_t)(warp - 2);
-        if (gate_img_on && lane == 0) {
-            int nch = 0;
-            for (int ch = 0; ch < CHUNKS; ++ch) {
-                const int cb = (chalf * CHUNKS + ch) * 32;
-                if (cb < (int)n_eff && n0 + cb < P.n) ++nch;
+
+            // ---------------- read-out: TMEM -> registers -> swizzled image -> TMA store ----------------
+            mbar_wait(bar_acc, (uint32_t)(tile_iter & 1));
+            tc_fence_after();
+            if (tr && t == 64 && tile_iter == 0) tr[4] = clock64();
+            const int64_t r = m0 + rank * 128 + lg * 32 + lane;
+            // Each warp turns its 32 rows x 32 columns into a 4 KB SWIZZLE_128B image and one lane stores it with a bulk
+            // tensor copy: whole 128-byte lines leave the SM, rows >= m / columns >= n are clipped by the tensor map; two
+            // images in flight per warp.  The activation / gate switches sit OUTSIDE the element loops (the first version
+            // branched per element and spent 25 000 of its 28 000 epilogue cycles per tile fetching instructions), and the
+            // loops are fully unrolled so that the 32 outputs of a thread stay in registers.
+            const int row0 = (int)(m0 + rank * 128 + lg * 32);
+            const int64_t r_ld = r < P.m ? r : P.m - 1;                  // clamped row for gate loads (clipped rows are never stored)
+            // gate tiles (saved activations of the backward epilogues) come in by TMA as 32 x 32 SWIZZLE_128B images, all
+            // chunks of this warp at once, while the first accumulator chunk is read
+            const bool gate_img_on = direct && P.gate && P.gate_tma;
+            if (gate_img_on && lane == 0) {
+                int nch = 0;
+                for (int ch = 0; ch < CHUNKS; ++ch) {
+                    const int cb = (chalf * CHUNKS + ch) * 32;
+                    if (cb < (int)n_eff && n0 + cb < P.n) ++nch;
+                }
+                if (nch) {
+                    mbar_expect_tx(gbar, (uint32_t)nch * 4096u);
+                    for (int ch = 0; ch < nch; ++ch)
+                        tma_load_2d(gimg + (uint32_t)ch * 4096u, &P.map_gate, (int)(n0 + (chalf * CHUNKS + ch) * 32), row0, gbar);
+                }
             }
-            if (nch) {
-                mbar_expect_tx(gbar, (uint32_t)nch * 4096u);
-                for (int ch = 0; ch < nch; ++ch)
-                    tma_load_2d(gimg + (uint32_t)ch * 4096u, &P.map_gate, (int)(n0 + (chalf * CHUNKS + ch) * 32), row0, gbar);
-            }
-        }
-        float* dst = direct ? P.c : P.partial + (int64_t)split * P.m * P.ldp;
-        const int64_t ldd = direct ? P.ldc : P.ldp;
-        int buf = 0;
+            float* dst = direct ? P.c : P.partial + (int64_t)split * P.m * P.ldp;
+            const int64_t ldd = direct ? P.ldc : P.ldp;
 #pragma unroll 1
-        for (int ch = 0; ch < CHUNKS; ++ch) {
-            const int cbase = (chalf * CHUNKS + ch) * 32;
-            if (cbase >= (int)n_eff || n0 + cbase >= P.n) break;     // warp-uniform
-            const int64_t c0 = n0 + cbase;
-            const int ncol = (int)((P.n - c0) < 32 ? (P.n - c0) : 32);   // valid columns of this chunk
-            float v[32];
-            {
-                // (reading both accumulators is what bounds the epilogue: ~7 500 cycles per tile for 2 x 128 KB of TMEM;
-                // issuing the next chunk's loads early changed nothing)
-                uint32_t acc[32], acc_small[32];
-                const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)cbase;
-                const long long e0 = (tr && t == 64) ? clock64() : 0;
-                tmem_ld32(ta, acc);
-                tmem_ld32(ta + TILE_N, acc_small);
-                tmem_ld_wait();
-                if (tr && t == 64) tr[13] += clock64() - e0;
+            for (int ch = 0; ch < CHUNKS; ++ch) {
+                const int cbase = (chalf * CHUNKS + ch) * 32;
+                if (cbase >= (int)n_eff || n0 + cbase >= P.n) break;     // warp-uniform
+                const int64_t c0 = n0 + cbase;
+                const int ncol = (int)((P.n - c0) < 32 ? (P.n - c0) : 32);   // valid columns of this chunk
+                float v[32];
+                {
+                    uint32_t acc[32], acc_small[32];
+                    const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)cbase;
+                    const long long e0 = (tr && t == 64) ? clock64() : 0;
+                    tmem_ld32(ta, acc);
+                    tmem_ld32(ta + TILE_N, acc_small);
+                    tmem_ld_wait();
+                    if (tr && t == 64 && tile_iter == 0) tr[13] += clock64() - e0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + (TM_SINGLE(P) ? 0.f : __uint_as_float(acc_small[j]));
-                if (tr && t == 64) {
-                    // the loads are only guaranteed complete where their registers are first read: keep the sum alive
-                    float keep = 0.f;
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + (TM_SINGLE(P) ? 0.f : __uint_as_float(acc_small[j]));
+                    if (tr && t == 64 && tile_iter == 0) {
+                        // the loads are only guaranteed complete where their registers are first read: keep the sum alive
+                        float keep = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) keep += v[j];
-                    asm volatile("" ::"f"(keep));
-                    tr[25] += clock64() - e0;
-                }
-            }
-            if (direct) {
-                if (P.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += __ldg(P.bias + c0 + (j < ncol ? j : 0));
-                }
-                if (P.act == PLAGNN_ACT_RELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
-                } else if (P.act == PLAGNN_ACT_LEAKY) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * P.slope;
-                } else if (P.act == PLAGNN_ACT_SIGMOID) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
-                }
-                if (gate_img_on) {
-                    if (ch == 0) mbar_wait(gbar, 0);
-                    float g[32];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                     : "=f"(g[4 * q]), "=f"(g[4 * q + 1]), "=f"(g[4 * q + 2]), "=f"(g[4 * q + 3])
-                                     : "r"(gimg + (uint32_t)ch * 4096u + row_off + (uint32_t)((q ^ (lane & 7)) << 4)));
-                    if (P.gate_act == PLAGNN_ACT_RELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = g[j] > 0.f ? v[j] : 0.f;
-                    } else if (P.gate_act == PLAGNN_ACT_LEAKY) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = g[j] > 0.f ? v[j] : v[j] * P.slope;
-                    } else if (P.gate_act == PLAGNN_ACT_SIGMOID) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= g[j] * (1.f - g[j]);
+                        for (int j = 0; j < 32; ++j) keep += v[j];
+                        asm volatile("" ::"f"(keep));
+                        tr[25] += clock64() - e0;
                     }
-                } else if (P.gate) {
-                    const float* g = P.gate + r_ld * P.ldg + c0;
-                    if (P.gate_act == PLAGNN_ACT_RELU) {
+                }
+                if (direct) {
+                    if (P.bias) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __ldg(g + (j < ncol ? j : 0)) > 0.f ? v[j] : 0.f;
-                    } else if (P.gate_act == PLAGNN_ACT_LEAKY) {
+                        for (int j = 0; j < 32; ++j) v[j] += __ldg(P.bias + c0 + (j < ncol ? j : 0));
+                    }
+                    if (P.act == PLAGNN_ACT_RELU) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __ldg(g + (j < ncol ? j : 0)) > 0.f ? v[j] : v[j] * P.slope;
-                    } else if (P.gate_act == PLAGNN_ACT_SIGMOID) {
+                        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
+                    } else if (P.act == PLAGNN_ACT_LEAKY) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float y = __ldg(g + (j < ncol ? j : 0));
-                            v[j] *= y * (1.f - y);
+                        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * P.slope;
+                    } else if (P.act == PLAGNN_ACT_SIGMOID) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+                    }
+                    if (gate_img_on) {
+                        if (ch == 0) mbar_wait(gbar, (uint32_t)(tile_iter & 1));
+                        float gt[32];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                         : "=f"(gt[4 * q]), "=f"(gt[4 * q + 1]), "=f"(gt[4 * q + 2]), "=f"(gt[4 * q + 3])
+                                         : "r"(gimg + (uint32_t)ch * 4096u + row_off + (uint32_t)((q ^ (lane & 7)) << 4)));
+                        if (P.gate_act == PLAGNN_ACT_RELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = gt[j] > 0.f ? v[j] : 0.f;
+                        } else if (P.gate_act == PLAGNN_ACT_LEAKY) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = gt[j] > 0.f ? v[j] : v[j] * P.slope;
+                        } else if (P.gate_act == PLAGNN_ACT_SIGMOID) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] *= gt[j] * (1.f - gt[j]);
+                        }
+                    } else if (P.gate) {
+                        const float* gp = P.gate + r_ld * P.ldg + c0;
+                        if (P.gate_act == PLAGNN_ACT_RELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __ldg(gp + (j < ncol ? j : 0)) > 0.f ? v[j] : 0.f;
+                        } else if (P.gate_act == PLAGNN_ACT_LEAKY) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __ldg(gp + (j < ncol ? j : 0)) > 0.f ? v[j] : v[j] * P.slope;
+                        } else if (P.gate_act == PLAGNN_ACT_SIGMOID) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float y = __ldg(gp + (j < ncol ? j : 0));
+                                v[j] *= y * (1.f - y);
+                            }
                         }
                     }
                 }
-            }
-            if (TM_DEBUG(P) == 3) continue;
-            if (P.tma_store) {
-                const long long e1 = (tr && t == 64) ? clock64() : 0;
-                if (lane == 0) bulk_wait_read<1>();      // the image written two chunks ago has been read
-                __syncwarp();
-                if (tr && t == 64) tr[14] += clock64() - e1;
-                const uint32_t img = stg + (uint32_t)buf * 4096u;
+                if (TM_DEBUG(P) == 3) continue;
+                if (P.tma_store) {
+                    const long long e1 = (tr && t == 64) ? clock64() : 0;
+                    if (lane == 0) bulk_wait_read<1>();      // the image written two chunks ago has been read
+                    __syncwarp();
+                    if (tr && t == 64 && tile_iter == 0) tr[14] += clock64() - e1;
+                    const uint32_t img = stg + (uint32_t)buf * 4096u;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const uint32_t off = row_off + (uint32_t)((q ^ (lane & 7)) << 4);
-                    sts_v4(img + off, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                }
-                const long long e2 = (tr && t == 64) ? clock64() : 0;
-                fence_proxy_async_smem();
-                __syncwarp();
-                const long long e3 = (tr && t == 64) ? clock64() : 0;
-                if (lane == 0 && TM_DEBUG(P) != 4) {
-                    tma_store_3d(&P.map_out, img, (int)c0, row0, direct ? 0 : split);
-                    bulk_commit();
-                }
-                if (tr && t == 64) { const long long e4 = clock64(); tr[15] += e4 - e1; tr[26] += e2 - e1; tr[27] += e3 - e2; tr[28] += e4 - e3; }
-                buf ^= 1;
-            } else if (r < P.m) {
-                // unaligned destination (row pitch % 4 != 0): plain scalar stores
-                float* drow = dst + r * ldd + c0;
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t off = row_off + (uint32_t)((q ^ (lane & 7)) << 4);
+                        sts_v4(img + off, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                    const long long e2 = (tr && t == 64) ? clock64() : 0;
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    const long long e3 = (tr && t == 64) ? clock64() : 0;
+                    if (lane == 0 && TM_DEBUG(P) != 4) {
+                        tma_store_3d(&P.map_out, img, (int)c0, row0, direct ? 0 : split);
+                        bulk_commit();
+                    }
+                    if (tr && t == 64 && tile_iter == 0) {
+                        const long long e4 = clock64();
+                        tr[15] += e4 - e1; tr[26] += e2 - e1; tr[27] += e3 - e2; tr[28] += e4 - e3;
+                    }
+                    buf ^= 1;
+                } else if (r < P.m) {
+                    // unaligned destination (row pitch % 4 != 0): plain scalar stores
+                    float* drow = dst + r * ldd + c0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < ncol) drow[j] = v[j];
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncol) drow[j] = v[j];
+                }
             }
+            if (tr && t == 64 && tile_iter == 0) tr[5] = clock64();
+            // the accumulators of this tile are in registers / on their way out: the next tile may overwrite TMEM
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(tmem_empty0);
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tmem_empty) : "memory");
+            }
+            if (tile + 1 < end_tile) {
+                // the staging images live in the lo ring, which these warps are about to refill: every warp's stores must
+                // have been read out of shared memory first
+                if (P.tma_store && lane == 0) bulk_wait_read<0>();
+                asm volatile("bar.sync 1, %0;" ::"n"(TM_EPI_WARPS * 32) : "memory");
+            }
+            if (tr && t == 64 && tile_iter == 0) tr[6] = clock64();
         }
-        if (tr && t == 64) tr[5] = clock64();
         if (P.tma_store) {
             if (lane == 0) bulk_wait_all();
             __syncwarp();
         }
-        if (tr && t == 64) tr[6] = clock64();
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (CG == 2) cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<CG>(tmem_base, TMEM_COLS);
     }
-    if (tr && t == 0) { tr[7] = clock64(); tr[11] = nkb; tr[12] = rank; }
+    if (tr && t == 0) { tr[7] = clock64(); tr[11] = T0.nkb; tr[12] = rank; }
 }
 
 // ordered reduction of split-K partials + epilogue
@@ -933,8 +1008,19 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
     }
     const int kidx = (cg == 2 ? 4 : 0) + (pairs[0].a_trans ? 2 : 0) + (pairs[0].b_trans ? 1 : 0);
     const int64_t tile = 128 * cg;
+    P.tiles_m = (int)ceil_div(m, tile);
+    P.tiles_n = (int)ceil_div(n, tile);
+    const int64_t total_tiles = (int64_t)P.tiles_m * P.tiles_n * P.splits;
+    if (total_tiles >= ((int64_t)1 << 30)) return fail(PLAGNN_ERR_UNSUPPORTED, "gemm_tma", "too many tiles");
+    P.total_tiles = (int)total_tiles;
+    // more tiles than CTA pairs fit at once: each pair walks several tiles (set-up once, next tile's loads overlap the
+    // read-out).  Not with a gate (its images need the shared memory the next tile's loads would use).
+    static const bool allow_persistent = [] { const char* e = getenv("PLAGNN_TMA_PERSISTENT"); return !e || e[0] != '0'; }();
+    const int64_t units = sm_count() / cg;
+    P.persistent = (allow_persistent && !gate && total_tiles > units) ? 1 : 0;
+    const int64_t launched = P.persistent ? units : total_tiles;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(ceil_div(n, tile) * cg), (unsigned)ceil_div(m, tile), (unsigned)P.splits);
+    cfg.gridDim = dim3((unsigned)(launched * cg), 1u, 1u);
     cfg.blockDim = dim3(TM_THREADS);
     cfg.dynamicSmemBytes = TM_SMEM_BYTES;
     cfg.stream = st;

@@ -191,3 +191,35 @@ def test_gemm_wgrad_bias_one_pass(cuda, cta_group, nodes, o, f):
     assert ((db.double().cpu() - want_b).abs().max() / want_b.abs().max()).item() < TOL
     # x must be untouched (the ones column is injected in shared memory only)
     assert torch.equal(x, ops.aligned((torch.randn(nodes, f, generator=torch.Generator().manual_seed(22)) + 0.5).to(cuda)))
+
+
+@pytest.mark.parametrize("persistent", ["1", "0"], ids=["persistent", "one-tile-per-pair"])
+def test_gemm_tma_many_tiles_per_cta_pair(cuda, monkeypatch, persistent):
+    """More output tiles than CTA pairs: each pair walks several tiles (rings run on across tile boundaries, TMEM is handed
+    back by the read-out); same results as the one-tile-per-pair launch, for plain, two-pair + epilogue and split-K products."""
+    monkeypatch.setenv("PLAGNN_TMA_PERSISTENT", persistent)
+    # plain product with bias + ReLU, 188 tiles
+    a, b = operand(24041, 503, 0, cuda, 31, True), operand(503, 503, 0, cuda, 32, True).mul_(503 ** -0.5)
+    bias = torch.randn(503, device=cuda)
+    pairs = [(a, 0, b, 0, 503)]
+    got = ops.gemm(24041, 503, pairs, bias=bias, act=ops.ACT_RELU, backend=ops.GEMM_TMA)
+    assert rel(got, ref_gemm(pairs, bias, ops.ACT_RELU, None, 0)) < TOL
+    # two pairs, MN-major B (the input-gradient shape without its gate), 188 tiles of 22 k-blocks
+    a1, b1 = operand(24041, 400, 0, cuda, 33, True), operand(503, 400, 1, cuda, 34, True).mul_(400 ** -0.5)
+    a2, b2 = operand(24041, 300, 0, cuda, 35, True), operand(503, 300, 1, cuda, 36, True).mul_(300 ** -0.5)
+    pairs2 = [(a1, 0, b1, 1, 400), (a2, 0, b2, 1, 300)]
+    got2 = ops.gemm(24041, 503, pairs2, act=ops.ACT_LEAKY, backend=ops.GEMM_TMA)
+    assert rel(got2, ref_gemm(pairs2, None, ops.ACT_LEAKY, None, 0)) < TOL
+    # split-K with more (tile, split) units than pairs: 3 x 3 tiles x 44 splits
+    a3, b3 = operand(700, 56000, 1, cuda, 37, True), operand(600, 56000, 1, cuda, 38, True)
+    pairs3 = [(a3, 1, b3, 1, 56000)]
+    got3 = ops.gemm(700, 600, pairs3, backend=ops.GEMM_TMA)
+    assert rel(got3, ref_gemm(pairs3, None, 0, None, 0)) < TOL
+    # ragged last column tile (n = 300 -> 256 + 64) and a gate (gated launches stay one tile per pair)
+    a4, b4 = operand(24041, 200, 0, cuda, 39, True), operand(300, 200, 0, cuda, 40, True).mul_(200 ** -0.5)
+    gate = ops.aligned(torch.randn(24041, 300, device=cuda))
+    pairs4 = [(a4, 0, b4, 0, 200)]
+    got4 = ops.gemm(24041, 300, pairs4, backend=ops.GEMM_TMA)
+    assert rel(got4, ref_gemm(pairs4, None, 0, None, 0)) < TOL
+    got5 = ops.gemm(24041, 300, pairs4, gate=gate, gate_act=ops.ACT_LEAKY, backend=ops.GEMM_TMA)
+    assert rel(got5, ref_gemm(pairs4, None, 0, gate, ops.ACT_LEAKY)) < TOL
