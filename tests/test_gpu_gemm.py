@@ -177,7 +177,7 @@ def test_gemm_tma_weight_gradient_split_k_both_tile_configs(cuda, cta_group):
 
 
 @pytest.mark.parametrize("nodes,o,f", [(24041, 400, 503), (24041, 503, 503), (24041, 12, 100), (5000, 300, 400), (3000, 100, 255),
-                                       (700, 64, 31)])
+                                       (700, 64, 31), (20000, 700, 600)])     # last: more (tile, split) units than CTA pairs
 def test_gemm_wgrad_bias_one_pass(cuda, cta_group, nodes, o, f):
     """dW = dZ^T X with the bias gradient riding along as an extra output column (B column that reads as 1.0)."""
     g1, g2 = torch.Generator().manual_seed(21), torch.Generator().manual_seed(22)
