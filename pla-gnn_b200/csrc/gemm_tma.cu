@@ -151,6 +151,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
+// one lane of a converged warp.  The issuing warps run their loops with all 32 lanes (warp-uniform control flow and
+// operands, which the compiler keeps in uniform registers) and predicate only the tcgen05 / TMA instructions with this:
+// inside an `if (lane == 0)` region every UTCHMMA / UTMALDG cost an ELECT + 6 x R2UR.BROADCAST + branch loop (12-17
+// instructions per MMA, i.e. the single issuing thread became a co-bottleneck of the main loop).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -378,9 +387,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     if (tr && t == 0) tr[1] = clock64();
 
     if (warp == 0) {
-        // ================= TMA producer (one elected lane): raw fp32 tiles of A and B =================
-        if (lane == 0) {
-            if (tr) tr[16] = clock64();
+        // ================= TMA producer (whole warp, loads issued by one elected lane): raw fp32 tiles of A and B =========
+        {
+            if (tr && lane == 0) tr[16] = clock64();
             int g = 0;                                   // k-blocks requested so far (all tiles)
             for (int tile = first_tile; tile < end_tile; ++tile) {
                 const TmTile T = tm_tile<CG>(P, tile);
@@ -390,17 +399,17 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     const uint32_t ph = (uint32_t)((gg / TM_RAW_STAGES) & 1);
                     const long long w0 = tr ? clock64() : 0;
                     mbar_wait(bar_raw_empty + 8 * s, ph ^ 1u);
-                    if (tr && tile == first_tile) tr[8] += clock64() - w0;
-                    if (tr && tile == first_tile && it == 8) tr[20] = clock64();
-                    load_kblock(T, it, gg);
+                    if (tr && lane == 0 && tile == first_tile) tr[8] += clock64() - w0;
+                    if (tr && lane == 0 && tile == first_tile && it == 8) tr[20] = clock64();
+                    if (elect_one()) load_kblock(T, it, gg);
+                    __syncwarp();
                 }
                 g += T.nkb;
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        // ================= MMA issuer (one elected lane of the leader CTA) =================
-        if (lane == 0 && rank == 0) {
+        // ================= MMA issuer (leader CTA; whole warp, instructions issued by one elected lane) =================
+        if (rank == 0) {
             // descriptor start-address step per K = 8: 32 bytes inside a K-major row; two k-groups of 512 bytes if MN-major
             constexpr uint64_t a_step = AT ? (1024u >> 4) : 2u, b_step = BT ? (1024u >> 4) : 2u;
             const uint32_t acc_main = tmem_base, acc_corr = tmem_base + TILE_N;
@@ -419,7 +428,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     // the lo tiles of both CTAs are written (which also means the raw tiles have landed in both)
                     mbar_wait(bar_lo_full + 8 * l, phl);
                     tc_fence_after();
-                    if (tr && tile_iter == 0) {
+                    if (tr && lane == 0 && tile_iter == 0) {
                         const long long w1 = clock64();
                         tr[9] += w1 - w0;
                         if (it == 0) tr[2] = w1;
@@ -430,29 +439,33 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     const uint64_t a_lo = AT ? desc_mnmajor(sl) : desc_kmajor(sl);
                     const uint64_t b_hi = BT ? desc_mnmajor(st + TM_PART_BYTES) : desc_kmajor(st + TM_PART_BYTES);
                     const uint64_t b_lo = BT ? desc_mnmajor(sl + TM_PART_BYTES) : desc_kmajor(sl + TM_PART_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < TM_BK / 8; ++kk) {
-                        if (TM_DEBUG(P) == 2) break;
-                        const uint64_t adv_a = (uint64_t)kk * a_step, adv_b = (uint64_t)kk * b_step;
-                        // corrections go to their own accumulator: the tensor core adds into TMEM with truncation, and the
-                        // main accumulator then sees a third of the additions (gemm_tc.cu has the measurements)
-                        const uint32_t acc_on = (it | kk) ? 1u : 0u;
-                        if (TM_SINGLE(P)) {
+                        for (int kk = 0; kk < TM_BK / 8; ++kk) {
+                            if (TM_DEBUG(P) == 2) break;
+                            const uint64_t adv_a = (uint64_t)kk * a_step, adv_b = (uint64_t)kk * b_step;
+                            // corrections go to their own accumulator: the tensor core adds into TMEM with truncation, and the
+                            // main accumulator then sees a third of the additions (gemm_tc.cu has the measurements)
+                            const uint32_t acc_on = (it | kk) ? 1u : 0u;
+                            if (TM_SINGLE(P)) {
+                                umma_tf32<CG>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
+                                umma_tf32<CG>(acc_main, a_lo + adv_a, b_hi + adv_b, idesc, 1u);
+                                umma_tf32<CG>(acc_main, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
+                                continue;
+                            }
+                            umma_tf32<CG>(acc_corr, a_lo + adv_a, b_hi + adv_b, idesc, acc_on);
+                            umma_tf32<CG>(acc_corr, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
                             umma_tf32<CG>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
-                            umma_tf32<CG>(acc_main, a_lo + adv_a, b_hi + adv_b, idesc, 1u);
-                            umma_tf32<CG>(acc_main, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
-                            continue;
                         }
-                        umma_tf32<CG>(acc_corr, a_lo + adv_a, b_hi + adv_b, idesc, acc_on);
-                        umma_tf32<CG>(acc_corr, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
-                        umma_tf32<CG>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
+                        // both rings are released (in both CTAs) when the MMAs issued so far have read them
+                        umma_commit<CG>(bar_lo_empty + 8 * l);
+                        umma_commit<CG>(bar_raw_empty + 8 * s);
                     }
-                    // both rings are released (in both CTAs) when the MMAs issued so far have read them
-                    umma_commit<CG>(bar_lo_empty + 8 * l);
-                    umma_commit<CG>(bar_raw_empty + 8 * s);
+                    __syncwarp();
                 }
-                umma_commit<CG>(bar_acc);               // accumulators of this tile complete (both CTAs)
-                if (tr && tile_iter == 0) tr[3] = clock64();
+                if (elect_one()) umma_commit<CG>(bar_acc);       // accumulators of this tile complete (both CTAs)
+                __syncwarp();
+                if (tr && lane == 0 && tile_iter == 0) tr[3] = clock64();
             }
         }
         __syncwarp();
