@@ -356,27 +356,33 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     const TmTile T0 = tm_tile<CG>(P, first_tile);
     const int preloaded = T0.nkb < TM_RAW_STAGES ? T0.nkb : TM_RAW_STAGES;
 
-    if (t == 0) {
-        for (int s = 0; s < TM_RAW_STAGES; ++s) {
-            mbar_init(bar_raw_full + 8 * s, 1);
-            mbar_init(bar_raw_empty + 8 * s, 1);
-        }
-        for (int s = 0; s < TM_LO_STAGES; ++s) {
-            mbar_init(bar_lo_full + 8 * s, (uint32_t)(CG * TM_EPI_WARPS));   // one arrival per splitting warp of the pair
-            mbar_init(bar_lo_empty + 8 * s, 1);
-        }
-        mbar_init(bar_acc, 1);
-        mbar_init(bar_tmem_empty, (uint32_t)(CG * TM_EPI_WARPS));
-        for (int w = 0; w < TM_EPI_WARPS; ++w) mbar_init(bar_gate + 8 * w, 1);
-        fence_mbar_init();
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int s = 0; s < TM_RAW_STAGES; ++s) {
+                mbar_init(bar_raw_full + 8 * s, 1);
+                mbar_init(bar_raw_empty + 8 * s, 1);
+            }
+            for (int s = 0; s < TM_LO_STAGES; ++s) {
+                mbar_init(bar_lo_full + 8 * s, (uint32_t)(CG * TM_EPI_WARPS));   // one arrival per splitting warp of the pair
+                mbar_init(bar_lo_empty + 8 * s, 1);
+            }
+            mbar_init(bar_acc, 1);
+            mbar_init(bar_tmem_empty, (uint32_t)(CG * TM_EPI_WARPS));
+            for (int w = 0; w < TM_EPI_WARPS; ++w) mbar_init(bar_gate + 8 * w, 1);
+            fence_mbar_init();
 #pragma unroll
-        for (int p = 0; p < PLAGNN_GEMM_MAX_PAIRS; ++p)
-            if (p < P.npairs) { prefetch_map(&P.map[p][0]); prefetch_map(&P.map[p][1]); }
-        if (P.tma_store) prefetch_map(&P.map_out);
-        if (P.gate_tma) prefetch_map(&P.map_gate);
+            for (int p = 0; p < PLAGNN_GEMM_MAX_PAIRS; ++p)
+                if (p < P.npairs) { prefetch_map(&P.map[p][0]); prefetch_map(&P.map[p][1]); }
+            if (P.tma_store) prefetch_map(&P.map_out);
+            if (P.gate_tma) prefetch_map(&P.map_gate);
+        }
+        __syncwarp();
         // the first ring pass is requested right here, before the TMEM allocation and the CTA / cluster barriers: the loads
         // only need this CTA's own (just initialised) barriers, and their ~3 000-cycle latency overlaps the rest of the set-up
-        for (int it = 0; it < preloaded; ++it) load_kblock(T0, it, it);
+        for (int it = 0; it < preloaded; ++it) {
+            if (elect_one()) load_kblock(T0, it, it);
+            __syncwarp();
+        }
     }
     if (warp == 1) tmem_alloc<CG>(tmem_slot, TMEM_COLS);
     tc_fence_before();
@@ -673,7 +679,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     fence_proxy_async_smem();
                     __syncwarp();
                     const long long e3 = (tr && t == 64) ? clock64() : 0;
-                    if (lane == 0 && TM_DEBUG(P) != 4) {
+                    if (TM_DEBUG(P) != 4 && lane == 0) {     // (bulk groups belong to the issuing thread: always lane 0)
                         tma_store_3d(&P.map_out, img, (int)c0, row0, direct ? 0 : split);
                         bulk_commit();
                     }
