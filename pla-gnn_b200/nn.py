@@ -50,8 +50,12 @@ def sage_pool_backward(g, saved, w_pool, w_self, w_neigh, drst, has_bias, need_d
     n, f = x.shape
     o = w_self.shape[0]
     drst = ops.aligned(drst)
-    db = ops.colsum(drst) if has_bias else None
-    d_ws = ops.gemm(o, f, [(drst, 1, x, 1, n)], out=torch.empty_like(w_self))
+    # weight gradient and bias gradient in one split-K product (the bias gradient is an extra output column)
+    if has_bias:
+        d_ws, db = ops.gemm_wgrad_bias(drst, x, dw=torch.empty_like(w_self))
+    else:
+        db = None
+        d_ws = ops.gemm(o, f, [(drst, 1, x, 1, n)], out=torch.empty_like(w_self))
     d_wn = ops.gemm(o, f, [(drst, 1, neigh, 1, n)], out=torch.empty_like(w_neigh))
     # input gradients read the weight [o x f] as an MN-major B operand (b_trans = 1): no transposed copy needed
     dneigh = ops.gemm(n, f, [(drst, 0, ops.aligned(w_neigh), 1, o)])
@@ -62,8 +66,7 @@ def sage_pool_backward(g, saved, w_pool, w_self, w_neigh, drst, has_bias, need_d
     else:
         dm = ops.spmm_max_bwd(dneigh, arg, neigh, n)    # relu' folded in through neigh > 0
     del dneigh
-    d_wp = ops.gemm(f, f, [(dm, 1, x, 1, n)], out=torch.empty_like(w_pool))
-    d_bp = ops.colsum(dm)
+    d_wp, d_bp = ops.gemm_wgrad_bias(dm, x, dw=torch.empty_like(w_pool))
     dx = None
     if need_dx:
         dx = ops.gemm(n, f, [(drst, 0, ops.aligned(w_self), 1, o), (dm, 0, ops.aligned(w_pool), 1, f)], gate=gate,
@@ -81,8 +84,10 @@ def linear_backward(x, w, dz, has_bias, need_dx, gate=None, gate_act=ACT_NONE):
     n, k = x.shape
     o = w.shape[0]
     dz = ops.aligned(dz)
-    d_w = ops.gemm(o, k, [(dz, 1, x, 1, n)], out=torch.empty_like(w))
-    d_b = ops.colsum(dz) if has_bias else None
+    if has_bias:
+        d_w, d_b = ops.gemm_wgrad_bias(dz, x, dw=torch.empty_like(w))
+    else:
+        d_w, d_b = ops.gemm(o, k, [(dz, 1, x, 1, n)], out=torch.empty_like(w)), None
     dx = None
     if need_dx:
         dx = ops.gemm(n, k, [(dz, 0, ops.aligned(w), 1, o)], gate=gate, gate_act=gate_act)
