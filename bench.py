@@ -372,6 +372,7 @@ def run_ours(args):
                  "measured_in": "second pass with per-call events (ms_per_step_profiled)"},
         "ms_per_step_profiled": ms_profiled / args.steps,
         "spmm": {"ms_per_step": spmm_all_ms},
+        "roofline_gemm": roofline_gemm(prof, args.steps, flops_epoch, gemm_ms, tf_peak, peak_src),
         "kernels": kernels[:10],
     }
     if not args.no_cpu_baseline and world == 1:
@@ -383,6 +384,28 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def roofline_gemm(prof, steps, flops_epoch, gemm_ms, bf16_peak, peak_src):
+    """Tensor-pipe roofline of the dense contraction (K3): every fp32 product costs three tf32 MMAs (hi*hi, lo*hi, hi*lo), so
+    the tensor work issued is 3 x the algorithmic flops; dense tf32 runs at half the bf16 rate, hence peak = measured bf16 / 2."""
+    if not gemm_ms:
+        return None
+    peak = bf16_peak / 2.0
+    best = None
+    for k, (c, t) in prof.items():
+        if k[0] != "gemm" or min(k[1], k[2], k[3]) < 64:
+            continue
+        tf = 3.0 * 2.0 * k[1] * k[2] * k[3] * c / (t * 1e-3) / 1e12
+        if best is None or tf > best[1]:
+            best = ("gemm/%d/%d/%d" % (k[1], k[2], k[3]), tf, t / c)
+    all_tf = 3.0 * flops_epoch / (gemm_ms * 1e-3) / 1e12
+    return {"kernel": "gemm_tma_kernel (all 23 products of the epoch)", "bound": "tensor", "achieved": all_tf, "peak": peak,
+            "unit": "TFLOP/s", "frac": all_tf / peak, "traffic": None,
+            "peak_source": peak_src + ": sustained dense bf16 / 2 (tf32 rate)",
+            "note": "achieved = 3 tf32 MMAs per fp32 product x algorithmic flops / event time (second, fully instrumented pass)",
+            "best_product": None if best is None else {"kernel": best[0], "achieved": best[1], "frac": best[1] / peak,
+                                                      "avg_ms": best[2]}}
 
 
 def dense_flops(n, f_in):
