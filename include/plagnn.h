@@ -40,7 +40,7 @@ enum {
 };
 
 enum { PLAGNN_ACT_NONE = 0, PLAGNN_ACT_RELU = 1, PLAGNN_ACT_LEAKY = 2, PLAGNN_ACT_SIGMOID = 3 };
-enum { PLAGNN_GEMM_AUTO = 0, PLAGNN_GEMM_SIMT = 1, PLAGNN_GEMM_TCGEN05 = 2, PLAGNN_GEMM_TMA = 3 };
+enum { PLAGNN_GEMM_AUTO = 0, PLAGNN_GEMM_SIMT = 1, PLAGNN_GEMM_TCGEN05 = 2, PLAGNN_GEMM_TMA = 3, PLAGNN_GEMM_NARROW = 4 };
 enum { PLAGNN_REDUCE_SUM = 0, PLAGNN_REDUCE_MAX = 1 };
 
 int plagnn_version(void);
@@ -157,7 +157,9 @@ int plagnn_dropout_scale(float* grad, int64_t rows, int64_t feat, int64_t ld, fl
  *   written in terms of the saved forward OUTPUT (relu/leaky: sign test, sigmoid: y(1-y)).
  *   Up to PLAGNN_GEMM_MAX_PAIRS pairs accumulate into one tile (fc_self + fc_neigh in one pass).
  *   backend: AUTO picks PLAGNN_GEMM_TMA (TMA-fed tcgen05 on CTA pairs, 3xTF32 split, fp32-level accuracy) when the
- *   operands have 16-byte aligned rows, else TCGEN05 (first-generation kernel) / SIMT (exact fp32 FFMA).
+ *   operands have 16-byte aligned rows, else TCGEN05 (first-generation kernel) / SIMT (exact fp32 FFMA); products with
+ *   n <= 16 or a contraction of at most 32 (the 12-class head, code/model.py:17,28) go to PLAGNN_GEMM_NARROW, streaming
+ *   FFMA kernels without tile padding.
  * ---------------------------------------------------------------------------------------- */
 #define PLAGNN_GEMM_MAX_PAIRS 2
 typedef struct {
@@ -176,7 +178,8 @@ int plagnn_gemm(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pa
 /* Weight gradient and bias gradient of a linear layer in one pass (autograd of nn.Linear / SAGEConv fc_*,
  * code/train.py:204):  dw[m x n] = dz^T x,  db[m] = sum over rows of dz;  dz stored [k x m], x stored [k x n] (k = nodes).
  * On the TMA backend db is one more output column of the same split-K product (a B column that reads as 1.0);
- * other backends run plagnn_gemm + plagnn_colsum.  workspace >= plagnn_gemm_wgrad_bias_workspace_bytes(m, n, k). */
+ * m <= 16 (the class dimension) takes a streaming FFMA kernel with the same extra column; other backends run
+ * plagnn_gemm + plagnn_colsum.  workspace >= plagnn_gemm_wgrad_bias_workspace_bytes(m, n, k). */
 size_t plagnn_gemm_wgrad_bias_workspace_bytes(int64_t m, int64_t n, int64_t k);
 int plagnn_gemm_wgrad_bias(int64_t m, int64_t n, const float* dz, int64_t lddz, const float* x, int64_t ldx, int64_t k,
                            float* dw, int64_t lddw, float* db, void* workspace, size_t workspace_bytes,
@@ -223,7 +226,8 @@ int plagnn_alteration_rank(const double* normal, int64_t ldn, const double* inte
  *   BCE exactly in fp32 (p, 1-p, clamp, log) and writes
  *     loss[0]            = sum_i -(1/R) sum_r [...]            (fp32)
  *     dprob[N x C]       = d loss / d p  on the selected rows, 0 elsewhere (if dprob != NULL)
- *   grad_scale multiplies dprob (upstream gradient of the scalar loss).
+ *   grad_scale multiplies dprob (upstream gradient of the scalar loss).  Negative indices count from the end, as in
+ *   torch; an index outside [-N, N) (IndexError in the reference) makes loss[0] NaN.
  * ---------------------------------------------------------------------------------------- */
 size_t plagnn_bce_workspace_bytes(int64_t num_index, int64_t classes);
 int plagnn_bce_weighted(const float* prob, int64_t ldp, const float* target, int64_t ldt,

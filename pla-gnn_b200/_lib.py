@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("PLAGNN_LIB_PATH") or os.path.join(_PKG, "libplagnn.so
 
 OK = 0
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
-GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_TMA = 0, 1, 2, 3
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_TMA, GEMM_NARROW = 0, 1, 2, 3, 4
 REDUCE_SUM, REDUCE_MAX = 0, 1
 GEMM_MAX_PAIRS = 2
 

@@ -18,47 +18,61 @@ __global__ void __launch_bounds__(BCE_THREADS)
 bce_kernel(const float* __restrict__ prob, int64_t ldp, const float* __restrict__ target, int64_t ldt,
            const int64_t* __restrict__ index, int64_t num_index, int64_t num_rows, int classes,
            const float* __restrict__ cw, const float* __restrict__ cwp1, float grad_scale,
-           double* __restrict__ block_part, float* __restrict__ dprob, int64_t lddp, int* __restrict__ bad) {
+           double* __restrict__ block_part, float* __restrict__ dprob, int64_t lddp) {
     __shared__ double red[BCE_THREADS / 32][BCE_MAX_CLASSES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i = (int64_t)blockIdx.x * BCE_THREADS + threadIdx.x;
     int64_t row = -1;
+    int bad = 0;
     if (i < num_index) {
         row = index ? index[i] : i;
         if (row < 0) row += num_rows;            // python-style negative index
-        if (row < 0 || row >= num_rows) { atomicOr(bad, 1); row = -1; }
+        if (row < 0 || row >= num_rows) { bad = 1; row = -1; }
     }
     const float inv_r = -1.0f / (float)num_index;   // grad of  -(sum)/R  w.r.t. sum
-    for (int c = 0; c < classes; ++c) {
-        double term = 0.0;
-        if (row >= 0) {
-            const float p = prob[row * ldp + c];
-            const float t = target[row * ldt + c];
-            const float w = cw[c], wp1 = cwp1[c];
-            const float q = 1.0f - p;
-            const float pc = fminf(fmaxf(p, 1e-9f), 10.0f);
-            const float qc = fminf(fmaxf(q, 1e-9f), 10.0f);
-            const float pos = t * logf(pc) * w;
-            const float neg = (1.0f - t) * logf(qc);
-            term = (double)((pos + neg) / wp1 * 2.0f);
-            if (dprob) {
-                const float g2 = (inv_r * grad_scale * 2.0f) / wp1;
-                float g = 0.f;
-                if (p >= 1e-9f && p <= 10.0f) g += ((g2 * w) * t) / pc;
-                if (q >= 1e-9f && q <= 10.0f) g -= (g2 * (1.0f - t)) / qc;
-                atomicAdd(dprob + row * lddp + c, g);
-            }
+    constexpr int CU = 4;                            // classes whose loads are in flight together
+    for (int c0 = 0; c0 < classes; c0 += CU) {
+        float pv[CU], tv[CU];
+#pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            const bool on = row >= 0 && c0 + u < classes;
+            pv[u] = on ? prob[row * ldp + c0 + u] : 0.5f;
+            tv[u] = on ? target[row * ldt + c0 + u] : 0.f;
         }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) term += __shfl_xor_sync(0xffffffffu, term, d);
-        if (lane == 0) red[warp][c] = term;
+        for (int u = 0; u < CU; ++u) {
+            const int c = c0 + u;
+            if (c >= classes) break;
+            double term = 0.0;
+            if (row >= 0) {
+                const float p = pv[u], t = tv[u];
+                const float w = cw[c], wp1 = cwp1[c];
+                const float q = 1.0f - p;
+                const float pc = fminf(fmaxf(p, 1e-9f), 10.0f);
+                const float qc = fminf(fmaxf(q, 1e-9f), 10.0f);
+                const float pos = t * logf(pc) * w;
+                const float neg = (1.0f - t) * logf(qc);
+                term = (double)((pos + neg) / wp1 * 2.0f);
+                if (dprob) {
+                    const float g2 = (inv_r * grad_scale * 2.0f) / wp1;
+                    float g = 0.f;
+                    if (p >= 1e-9f && p <= 10.0f) g += ((g2 * w) * t) / pc;
+                    if (q >= 1e-9f && q <= 10.0f) g -= (g2 * (1.0f - t)) / qc;
+                    atomicAdd(dprob + row * lddp + c, g);
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) term += __shfl_xor_sync(0xffffffffu, term, d);
+            if (lane == 0) red[warp][c] = term;
+        }
     }
-    __syncthreads();
+    // an index outside [-num_rows, num_rows) (torch raises IndexError there) poisons the loss: NaN, never a silent skip
+    const int any_bad = __syncthreads_or(bad);
     if (threadIdx.x < classes) {
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < BCE_THREADS / 32; ++w) s += red[w][threadIdx.x];
-        block_part[(int64_t)blockIdx.x * classes + threadIdx.x] = s;
+        block_part[(int64_t)blockIdx.x * classes + threadIdx.x] = any_bad ? (double)NAN : s;
     }
 }
 
@@ -312,11 +326,9 @@ int plagnn_bce_weighted(const float* prob, int64_t ldp, const float* target, int
     ProfileScope prof("bce_weighted", num_index, classes, 0, stream);
     const int blocks = (int)ceil_div(num_index, BCE_THREADS);
     double* part = (double*)workspace;
-    int* bad = (int*)((char*)workspace + need - 256);
-    PLAGNN_CUDA_TRY(cudaMemsetAsync(bad, 0, sizeof(int), st));
     if (dprob) PLAGNN_CUDA_TRY(cudaMemset2DAsync(dprob, lddp * sizeof(float), 0, classes * sizeof(float), num_rows, st));
     bce_kernel<<<blocks, BCE_THREADS, 0, st>>>(prob, ldp, target, ldt, index, num_index, num_rows, (int)classes,
-                                                class_weight, class_weight_plus1, grad_scale, part, dprob, lddp, bad);
+                                                class_weight, class_weight_plus1, grad_scale, part, dprob, lddp);
     bce_finalize_kernel<<<1, BCE_MAX_CLASSES, 0, st>>>(part, blocks, (int)classes, num_index, loss);
     return check_launch("bce_weighted", 2);
 }

@@ -21,12 +21,20 @@ bool gemm_tma_eligible(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_p
 int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs, const float* bias, int act,
                     float slope, const float* gate, int64_t ldg, int gate_act, float* c, int64_t ldc, void* workspace,
                     size_t workspace_bytes, cudaStream_t st, float* ones_out = nullptr);
+// gemm_narrow.cu
+bool gemm_narrow_eligible(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs);
+int gemm_narrow_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs, const float* bias, int act,
+                       float slope, const float* gate, int64_t ldg, int gate_act, float* c, int64_t ldc, cudaStream_t st);
+size_t gemm_narrow_wgrad_bytes(int64_t m, int64_t n, int64_t k);
+int gemm_narrow_wgrad_launch(int64_t m, int64_t n, const float* dz, int64_t lddz, const float* x, int64_t ldx, int64_t k,
+                             float* dw, int64_t lddw, float* db, void* workspace, cudaStream_t st);
 
 static int forced_backend() {
     static const int forced = [] {
         const char* e = getenv("PLAGNN_GEMM");
         if (!e) return (int)PLAGNN_GEMM_AUTO;
         if (e[0] == 's' || e[0] == 'S') return (int)PLAGNN_GEMM_SIMT;
+        if (e[0] == 'w' || e[0] == 'W') return -1;      // "wide": AUTO without the narrow kernels (A/B measurements)
         if (e[0] == 't' || e[0] == 'T') return (e[1] == 'm' || e[1] == 'M') ? (int)PLAGNN_GEMM_TMA : (int)PLAGNN_GEMM_TCGEN05;
         return (int)PLAGNN_GEMM_AUTO;
     }();
@@ -56,7 +64,8 @@ size_t plagnn_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k_total) {
 
 size_t plagnn_gemm_wgrad_bias_workspace_bytes(int64_t m, int64_t n, int64_t k) {
     const size_t a = plagnn_gemm_workspace_bytes(m, n + 1, k), b = plagnn_colsum_workspace_bytes(k, m);
-    return a > b ? a : b;
+    const size_t c = gemm_narrow_wgrad_bytes(m, n, k);
+    return (a > b ? a : b) > c ? (a > b ? a : b) : c;
 }
 
 // dW[m x n] = dZ^T X and db[m] = column sums of dZ, in one pass when the TMA kernel can take the product (the bias gradient
@@ -69,7 +78,13 @@ int plagnn_gemm_wgrad_bias(int64_t m, int64_t n, const float* dz, int64_t lddz, 
         return fail(PLAGNN_ERR_ARG, "gemm_wgrad_bias", "bad sizes or null pointers");
     plagnn_gemm_pair p{dz, lddz, 1, x, ldx, 1, k};
     const size_t part = gemm_tma_partial_bytes(m, n + 1, k);
-    const int forced = forced_backend();
+    int forced = forced_backend();
+    const size_t narrow = gemm_narrow_wgrad_bytes(m, n, k);
+    if (forced == PLAGNN_GEMM_AUTO && narrow > 0 && workspace && narrow <= workspace_bytes) {
+        ProfileScope prof("gemm", m, n, k, stream);
+        return gemm_narrow_wgrad_launch(m, n, dz, lddz, x, ldx, k, dw, lddw, db, workspace, st);
+    }
+    if (forced < 0) forced = PLAGNN_GEMM_AUTO;
     if ((forced == PLAGNN_GEMM_AUTO || forced == PLAGNN_GEMM_TMA) && part > 0 && workspace && part <= workspace_bytes &&
         gemm_tma_eligible(m, n + 1, 1, &p)) {
         ProfileScope prof("gemm", m, n, k, stream);
@@ -100,7 +115,15 @@ int plagnn_gemm(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pa
         if (q.lda < (q.a_trans ? m : q.k) || q.ldb < (q.b_trans ? n : q.k))
             return fail(PLAGNN_ERR_ARG, "gemm", "operand pitch too small");
     }
-    if (backend == PLAGNN_GEMM_AUTO) backend = forced_backend();
+    bool narrow_ok = gemm_narrow_eligible(m, n, npairs, pairs);
+    if (backend == PLAGNN_GEMM_AUTO) {
+        backend = forced_backend();
+        if (backend < 0) { backend = PLAGNN_GEMM_AUTO; narrow_ok = false; }
+    }
+    if (backend == PLAGNN_GEMM_NARROW && !narrow_ok)
+        return fail(PLAGNN_ERR_UNSUPPORTED, "gemm", "narrow backend needs n <= 16 (k <= 4096) or a contraction of at most 32");
+    if (backend == PLAGNN_GEMM_NARROW || (backend == PLAGNN_GEMM_AUTO && narrow_ok))
+        return gemm_narrow_launch(m, n, npairs, pairs, bias, act, slope, gate, ldg, gate_act, c, ldc, st);
     const bool tc_ok = gemm_tc_eligible(m, n, npairs, pairs);
     const size_t part_bytes = gemm_tma_partial_bytes(m, n, ktot);
     const bool tma_ok = tc_ok && gemm_tma_eligible(m, n, npairs, pairs) &&

@@ -59,13 +59,34 @@ __device__ __forceinline__ float4 sum_epilogue(float4 a, const SpmmEpilogue& ep,
     return make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// if (v > acc) { acc = v; arg = u; } with the work spread over two pipes.  Written in C the compiler emits FSETP + FSEL + SEL,
+// three ALU-pipe instructions per gathered element, and the max reducer is bound by that pipe (ncu: ALU 76 %, FMA 16 %).
+// Here the value moves with a predicated FFMA on the FMA pipe: acc = v * 1.0f + (-0.0f), exact for every v (the two
+// constants arrive as kernel arguments so that ptxas cannot fold the multiply-add back into a select).
+__device__ __forceinline__ void max_update(float& acc, int& arg, const float v, const int u, const float one, const float nzero) {
+    float na;
+    int ng;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %2, %3;\n\tmov.f32 %0, %3;\n\t@p fma.rn.f32 %0, %2, %5, %6;\n\tselp.b32 %1, %4, %7, p;\n\t}"
+        : "=&f"(na), "=r"(ng)
+        : "f"(v), "f"(acc), "r"(u), "f"(one), "f"(nzero), "r"(arg));
+    acc = na;
+    arg = ng;
+}
+
+// base + u * pitch_bytes as one IMAD.WIDE.U32 (u: node id >= 0)
+__device__ __forceinline__ const float* row_ptr(const float* base, int u, unsigned pitch_bytes) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"((unsigned)u), "r"(pitch_bytes), "l"((unsigned long long)base));
+    return reinterpret_cast<const float*>(r);
+}
+
 template <int MODE>
-__device__ __forceinline__ void reduce_one(float4& acc, int4& arg, const float4 v, const int u) {
+__device__ __forceinline__ void reduce_one(float4& acc, int4& arg, const float4 v, const int u, const float one, const float nzero) {
     if (MODE == MODE_MAX) {
-        if (v.x > acc.x) { acc.x = v.x; arg.x = u; }
-        if (v.y > acc.y) { acc.y = v.y; arg.y = u; }
-        if (v.z > acc.z) { acc.z = v.z; arg.z = u; }
-        if (v.w > acc.w) { acc.w = v.w; arg.w = u; }
+        max_update(acc.x, arg.x, v.x, u, one, nzero);
+        max_update(acc.y, arg.y, v.y, u, one, nzero);
+        max_update(acc.z, arg.z, v.z, u, one, nzero);
+        max_update(acc.w, arg.w, v.w, u, one, nzero);
     } else {
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
@@ -75,14 +96,17 @@ __device__ __forceinline__ void reduce_one(float4& acc, int4& arg, const float4 
 // MODE_SUM  : x = features,  optional edge weights, epilogue
 // MODE_MATCH: x = dz (rows = destinations v of the out-edge u->v), argm = arg[v,:], zfwd = z[v,:] (nullable);
 //             acc[u,f] += (argm[v,f]==u && z>0) ? dz[v,f] : 0
+// The max reducer runs at the L2 -> SM bandwidth cap once enough warps are resident (measured: 24 warps/SM at 80
+// registers 0.198 ms, 16 warps at 110 registers 0.322 ms for F = 503), so its default variants are held to 3 blocks per SM.
 template <int MODE, int VEC, int NB>
-__global__ void __launch_bounds__(SPMM_WARPS * 32)
+__global__ void __launch_bounds__(SPMM_WARPS * 32, (MODE == MODE_MAX && NB * VEC <= 8) ? 3 : 1)
 spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int32_t* __restrict__ eids,
             const float* __restrict__ ew, const int32_t* __restrict__ plan_hdr, const int32_t* __restrict__ item_ptr,
             const int32_t* __restrict__ slot_ptr, const int32_t* __restrict__ item_row, int item_begin, int n_items,
             const float* __restrict__ x, int64_t ldx, int feat, const int32_t* __restrict__ argm, int64_t ldarg,
             const float* __restrict__ zfwd, int64_t ldzf, float* __restrict__ out, int32_t* __restrict__ arg_out, int64_t ldo,
-            float* __restrict__ part_val, int32_t* __restrict__ part_arg, int part_ld, SpmmEpilogue ep) {
+            float* __restrict__ part_val, int32_t* __restrict__ part_arg, int part_ld, SpmmEpilogue ep, float one,
+            float nzero) {
     const int lane = threadIdx.x & 31;
     const int item = item_begin + blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
@@ -95,13 +119,19 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
     const int beg = rbeg + k * chunk;
     const int end = min(rend, beg + chunk);
 
+    // Column groups (float4) of this block's slab are dealt to the lanes with stride S = ceil(groups / VEC): lane l owns
+    // groups l, l + S, l + 2S, ...  For F = 400 (100 groups, VEC 4) that is 26 lanes x 3 full groups + 22 lanes; only the last
+    // group of a lane can fall outside the slab.  Lanes >= S shadow lane 0 (same addresses, nothing stored).
     const int col0 = blockIdx.y * (128 * VEC);   // first column of this block's slab
+    const int groups = min((feat + 3) / 4 - blockIdx.y * (32 * VEC), 32 * VEC);
+    const int S = min(32, ((groups + VEC - 1) / VEC + 1) & ~1);   // even: every request covers whole 32-byte sectors
+    const int lane_c = (lane < S && lane < groups) ? lane : 0;
     int col[VEC];
     bool cok[VEC];
 #pragma unroll
     for (int q = 0; q < VEC; ++q) {
-        col[q] = col0 + 4 * (lane + 32 * q);
-        cok[q] = col[q] < feat;
+        cok[q] = lane < S && lane_c + S * q < groups;
+        col[q] = col0 + 4 * (lane_c + S * (lane_c + S * q < groups ? q : 0));   // clamped: always a readable column
     }
 
     float4 acc[VEC];
@@ -113,6 +143,42 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
         arg[q] = make_int4(-1, -1, -1, -1);
     }
 
+    if (MODE == MODE_MAX) {
+        // Unmasked inner loop: a slot past the end of the chunk repeats the chunk's last neighbour and a lane without
+        // columns re-reads lane 0's — a repeated value never beats the running maximum (strict >), so neither needs
+        // a select, and the loads carry no predicates.  One IMAD.WIDE per load forms the address.
+        const float* xq[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) xq[q] = x + col[q];
+        const unsigned ldx_bytes = (unsigned)ldx * 4u;      // host checks ldx < 2^30
+        // neighbour ids: every lane reads the same word (one broadcast request, L1-resident after the first touch of a
+        // sector) one step ahead of the rows it addresses — no shuffles, so no divergence side path in the loop
+        if (beg < end) {
+            const int last = end - 1;
+            int u[NB];
+#pragma unroll
+            for (int t = 0; t < NB; ++t) u[t] = __ldg(indices + min(beg + t, last));
+#ifdef PLAGNN_SPMM_UNROLL1
+#pragma unroll 1
+#endif
+            for (int j = beg; j < end; j += NB) {
+                int un[NB];
+                float4 v[NB][VEC];
+#pragma unroll
+                for (int t = 0; t < NB; ++t) {
+                    un[t] = __ldg(indices + min(j + NB + t, last));
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) v[t][q] = ldg_f4(row_ptr(xq[q], u[t], ldx_bytes));
+                }
+#pragma unroll
+                for (int t = 0; t < NB; ++t)
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) reduce_one<MODE>(acc[q], arg[q], v[t][q], u[t], one, nzero);
+#pragma unroll
+                for (int t = 0; t < NB; ++t) u[t] = un[t];
+            }
+        }
+    } else {
     for (int base = beg; base < end; base += 32) {
         const int cnt = min(32, end - base);
         int my_u = 0;
@@ -167,10 +233,11 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
                         val.x = a.x == row ? g.x : 0.f; val.y = a.y == row ? g.y : 0.f;
                         val.z = a.z == row ? g.z : 0.f; val.w = a.w == row ? g.w : 0.f;
                     }
-                    reduce_one<MODE>(acc[q], arg[q], val, u[t]);
+                    reduce_one<MODE>(acc[q], arg[q], val, u[t], one, nzero);
                 }
             }
         }
+    }
     }
 
     // ---- write: final result for unsplit rows, ordered partial otherwise --------------------
@@ -319,7 +386,7 @@ static void launch_main(const SpmmArgs& a, const int32_t* item_ptr, const int32_
     dim3 grid((unsigned)ceil_div(n_items - item_begin, SPMM_WARPS), (unsigned)ceil_div((a.feat + 3) / 4, 32 * VEC));
     spmm_kernel<MODE, VEC, NB><<<grid, SPMM_WARPS * 32, 0, st>>>(
         a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, item_begin, n_items, a.x, a.ldx,
-        (int)a.feat, a.argm, a.ldarg, a.zfwd, a.ldzf, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep);
+        (int)a.feat, a.argm, a.ldarg, a.zfwd, a.ldzf, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep, 1.0f, -0.0f);
 }
 
 template <int MODE>

@@ -11,7 +11,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_TMA, REDUCE_MAX,
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, GEMM_AUTO, GEMM_NARROW, GEMM_SIMT, GEMM_TCGEN05, GEMM_TMA, REDUCE_MAX,
                    REDUCE_SUM, GemmPair, check)
 
 LEAKY_SLOPE = 0.01          # F.leaky_relu default, code/model.py:21,23,25,27

@@ -119,6 +119,55 @@ def test_gemm_weight_gradient_shape_split_k(cuda, backend):
     assert torch.equal(out, out2)                      # ordered split-K reduction: bit-stable
 
 
+# ---- narrow products (one tiny dimension): streaming FFMA kernels, the 12-class head of the network ----
+@pytest.mark.parametrize("m,n,k", [(24041, 12, 100), (500, 12, 100), (1000, 16, 300), (777, 5, 37), (64, 1, 1), (65, 9, 129),
+                                   (24041, 100, 12), (2500, 400, 12), (333, 503, 7), (100, 2047, 4), (50, 255, 32)])
+@pytest.mark.parametrize("at,bt", [(0, 0), (0, 1), (1, 1), (1, 0)])
+def test_gemm_narrow_layouts(cuda, m, n, k, at, bt):
+    a = operand(m, k, at, cuda, 11, pad=True)
+    b = operand(n, k, bt, cuda, 12, pad=True)
+    pairs = [(a, at, b, bt, k)]
+    got = ops.gemm(m, n, pairs, backend=ops.GEMM_NARROW)
+    assert rel(got, ref_gemm(pairs, None, 0, None, 0)) < TOL
+    auto = ops.gemm(m, n, pairs)                      # AUTO takes the same kernel for these shapes
+    assert torch.equal(got, auto)
+
+
+@pytest.mark.parametrize("n,k1,k2", [(12, 100, 60), (100, 12, 8), (101, 20, 12)])
+@pytest.mark.parametrize("act,gate_act", [(ops.ACT_SIGMOID, 0), (ops.ACT_LEAKY, 0), (ops.ACT_RELU, 0), (0, ops.ACT_LEAKY),
+                                          (0, ops.ACT_SIGMOID)])
+def test_gemm_narrow_two_pairs_and_epilogues(cuda, n, k1, k2, act, gate_act):
+    m = 3001
+    a1, b1 = operand(m, k1, 0, cuda, 5, True), operand(n, k1, 0, cuda, 6, True).mul_(k1 ** -0.5)
+    a2, b2 = operand(m, k2, 0, cuda, 7, True), operand(n, k2, 0, cuda, 8, True).mul_(k2 ** -0.5)
+    bias = torch.randn(n, device=cuda)
+    gate = None
+    if gate_act:
+        gate = torch.randn(m, n, device=cuda)
+        if gate_act == ops.ACT_SIGMOID:
+            gate = torch.sigmoid(gate)
+        gate = ops.aligned(gate) if n % 2 == 0 else gate.contiguous()      # odd n: unaligned gate and output pitch
+    pairs = [(a1, 0, b1, 0, k1), (a2, 0, b2, 0, k2)]
+    out = None if n % 2 == 0 else torch.empty(m, n, device=cuda)
+    got = ops.gemm(m, n, pairs, bias=bias, act=act, gate=gate, gate_act=gate_act, out=out, backend=ops.GEMM_NARROW)
+    assert rel(got, ref_gemm(pairs, bias, act, gate, gate_act)) < TOL
+
+
+def test_gemm_narrow_rejects_wide_products(cuda):
+    import plagnn_b200 as P
+    a, b = operand(500, 100, 0, cuda, 1, True), operand(100, 100, 0, cuda, 2, True)
+    with pytest.raises(P.PlagnnError):
+        ops.gemm(500, 100, [(a, 0, b, 0, 100)], backend=ops.GEMM_NARROW)
+
+
+def test_gemm_narrow_wgrad_bias_is_bit_stable(cuda):
+    dz = ops.aligned(torch.randn(24041, 12, generator=torch.Generator().manual_seed(5)).to(cuda))
+    x = ops.aligned(torch.randn(24041, 100, generator=torch.Generator().manual_seed(6)).to(cuda))
+    dw1, db1 = ops.gemm_wgrad_bias(dz, x)
+    dw2, db2 = ops.gemm_wgrad_bias(dz, x)
+    assert torch.equal(dw1, dw2) and torch.equal(db1, db2)
+
+
 def test_gemm_tiny_n_falls_to_simt_in_auto(cuda):
     a, b = operand(500, 100, 0, cuda, 1, True), operand(12, 100, 0, cuda, 2, True)
     pairs = [(a, 0, b, 0, 100)]
@@ -177,7 +226,8 @@ def test_gemm_tma_weight_gradient_split_k_both_tile_configs(cuda, cta_group):
 
 
 @pytest.mark.parametrize("nodes,o,f", [(24041, 400, 503), (24041, 503, 503), (24041, 12, 100), (5000, 300, 400), (3000, 100, 255),
-                                       (700, 64, 31), (20000, 700, 600)])     # last: more (tile, split) units than CTA pairs
+                                       (700, 64, 31), (20000, 700, 600),      # more (tile, split) units than CTA pairs
+                                       (1000, 5, 503), (300, 16, 7), (129, 1, 130), (128, 13, 127)])   # narrow kernel (o <= 16)
 def test_gemm_wgrad_bias_one_pass(cuda, cta_group, nodes, o, f):
     """dW = dZ^T X with the bias gradient riding along as an extra output column (B column that reads as 1.0)."""
     g1, g2 = torch.Generator().manual_seed(21), torch.Generator().manual_seed(22)

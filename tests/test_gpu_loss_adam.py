@@ -43,6 +43,27 @@ def test_bce_indexed_equals_gather_then_loss(cuda):
     assert (pc.grad.cpu()[~torch.isin(torch.arange(n), idx)] == 0).all()
 
 
+def test_bce_negative_and_out_of_range_indices(cuda):
+    """Negative indices count from the end (torch indexing); an index outside [-N, N) — IndexError in the reference —
+    must not be skipped silently: the loss comes back NaN."""
+    torch.manual_seed(1)
+    n, c = 700, 12
+    prob = P.ops.aligned(torch.sigmoid(torch.randn(n, c)).to(cuda))
+    tgt = (torch.rand(n, c) < 0.3).float().to(cuda)
+    w = torch.rand(c, dtype=torch.float64) * 5 + 1
+    cw, cwp1 = w.float().to(cuda), (w + 1.0).float().to(cuda)
+    pos = torch.tensor([0, 5, 699, 300, 5], device=cuda)                  # a duplicate too
+    neg = torch.tensor([-700, -695, -1, -400, -695], device=cuda)
+    l_pos, g_pos = P.ops.bce_weighted(prob, tgt, pos, cw, cwp1)
+    l_neg, g_neg = P.ops.bce_weighted(prob, tgt, neg, cw, cwp1)
+    assert torch.equal(l_pos, l_neg) and torch.equal(g_pos, g_neg) and torch.isfinite(l_pos).all()
+    for bad in (n, -n - 1):
+        l_bad, _ = P.ops.bce_weighted(prob, tgt, torch.tensor([0, bad, 3], device=cuda), cw, cwp1)
+        assert torch.isnan(l_bad).all()
+    l_again, _ = P.ops.bce_weighted(prob, tgt, pos, cw, cwp1)              # no state left behind by the failed call
+    assert torch.equal(l_again, l_pos)
+
+
 def test_fused_adam_tracks_torch_adam(cuda):
     torch.manual_seed(1)
     shapes = [(503, 503), (503,), (400, 503), (400,), (12, 100), (12,)]

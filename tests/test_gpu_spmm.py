@@ -24,7 +24,7 @@ def make(cuda, n, e, seed, loops=True, chunk=128, **kw):
     return g, orc.OracleGraph(so, do, n)
 
 
-@pytest.mark.parametrize("f", [1, 12, 100, 128, 200, 300, 400, 503, 1024])
+@pytest.mark.parametrize("f", [1, 3, 5, 12, 100, 128, 129, 200, 260, 300, 385, 400, 503, 513, 600, 1024])
 def test_spmm_max_forward_bit_exact(cuda, f):
     g, go = make(cuda, 900, 20000, f, loops=False, hubs=3, hub_deg=700, isolated=5)
     x = torch.randn(900, f, generator=torch.Generator().manual_seed(f))
