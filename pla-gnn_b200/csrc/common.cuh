@@ -54,7 +54,33 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
 
+// Programmatic dependent launch: every kernel of the epoch is launched with the stream-serialisation attribute relaxed, so
+// the next grid's CTAs are placed (and run their set-up: barrier init, TMEM allocation, descriptor prefetch) while the
+// previous grid drains.  Kernels call pdl_trigger() on entry and pdl_wait() before their first access to global memory;
+// pdl_wait() returns once the preceding grid has completed and its writes are visible.  PLAGNN_PDL=0 restores plain
+// stream order (the device-side instructions are then no-ops).
+bool pdl_enabled();
+
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 // ---- device helpers ------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// entry sequence of a kernel without set-up work worth overlapping
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {

@@ -20,6 +20,7 @@ bce_kernel(const float* __restrict__ prob, int64_t ldp, const float* __restrict_
            const float* __restrict__ cw, const float* __restrict__ cwp1, float grad_scale,
            double* __restrict__ block_part, float* __restrict__ dprob, int64_t lddp) {
     __shared__ double red[BCE_THREADS / 32][BCE_MAX_CLASSES];
+    pdl_enter();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i = (int64_t)blockIdx.x * BCE_THREADS + threadIdx.x;
     int64_t row = -1;
@@ -79,6 +80,7 @@ bce_kernel(const float* __restrict__ prob, int64_t ldp, const float* __restrict_
 __global__ void bce_finalize_kernel(const double* __restrict__ block_part, int num_blocks, int classes,
                                     int64_t num_index, float* __restrict__ loss) {
     __shared__ float per_class[BCE_MAX_CLASSES];
+    pdl_enter();
     if (threadIdx.x < classes) {
         double s = 0.0;
         for (int b = 0; b < num_blocks; ++b) s += block_part[(int64_t)b * classes + threadIdx.x];
@@ -97,6 +99,7 @@ __global__ void bce_finalize_kernel(const double* __restrict__ block_part, int n
 __global__ void __launch_bounds__(256)
 adam_kernel(const plagnn_adam_tensor* __restrict__ tensors, float lerp_w, float beta2, float one_minus_beta2,
             float eps, float step_size, float bc2_sqrt) {
+    pdl_enter();
     const plagnn_adam_tensor T = tensors[blockIdx.y];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T.numel; i += (int64_t)gridDim.x * blockDim.x) {
         const float g = T.grad[i];
@@ -276,6 +279,7 @@ __global__ void loc_decide_kernel(const float* __restrict__ p, int64_t ldp, int6
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pad_copy_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t lds, float* __restrict__ dst, int64_t ldd) {
+    pdl_enter();
     const int64_t total = rows * ldd;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / ldd;
@@ -327,9 +331,9 @@ int plagnn_bce_weighted(const float* prob, int64_t ldp, const float* target, int
     const int blocks = (int)ceil_div(num_index, BCE_THREADS);
     double* part = (double*)workspace;
     if (dprob) PLAGNN_CUDA_TRY(cudaMemset2DAsync(dprob, lddp * sizeof(float), 0, classes * sizeof(float), num_rows, st));
-    bce_kernel<<<blocks, BCE_THREADS, 0, st>>>(prob, ldp, target, ldt, index, num_index, num_rows, (int)classes,
+    launch_pdl(bce_kernel, dim3(blocks), dim3(BCE_THREADS), 0, st, prob, ldp, target, ldt, index, num_index, num_rows, (int)classes,
                                                 class_weight, class_weight_plus1, grad_scale, part, dprob, lddp);
-    bce_finalize_kernel<<<1, BCE_MAX_CLASSES, 0, st>>>(part, blocks, (int)classes, num_index, loss);
+    launch_pdl(bce_finalize_kernel, dim3(1), dim3(BCE_MAX_CLASSES), 0, st, part, blocks, (int)classes, num_index, loss);
     return check_launch("bce_weighted", 2);
 }
 
@@ -344,7 +348,7 @@ int plagnn_adam_multi(const plagnn_adam_tensor* tensors, int32_t count, int64_t 
     const float lerp_w = (float)(1.0 - beta1);
     const float omb2 = (float)(1.0 - beta2);
     dim3 grid((unsigned)capped_grid(max_numel, 256, 4), (unsigned)count);
-    adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tensors, lerp_w, (float)beta2, omb2, (float)eps, step_size,
+    launch_pdl(adam_kernel, grid, dim3(256), 0, (cudaStream_t)stream, tensors, lerp_w, (float)beta2, omb2, (float)eps, step_size,
                                                         (float)bias_correction2_sqrt);
     return check_launch("adam_multi");
 }
@@ -394,7 +398,7 @@ int plagnn_pad_copy(const float* src, int64_t rows, int64_t cols, int64_t lds, f
                     plagnn_stream_t stream) {
     if (!src || !dst || rows <= 0 || cols <= 0 || lds < cols || ldd < cols) return fail(PLAGNN_ERR_ARG, "pad_copy", "bad arguments");
     ProfileScope prof("pad_copy", rows, cols, 0, stream);
-    pad_copy_kernel<<<capped_grid(rows * ldd, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, rows, (int)cols, lds, dst, ldd);
+    launch_pdl(pad_copy_kernel, dim3(capped_grid(rows * ldd, 256, 8)), dim3(256), 0, (cudaStream_t)stream, src, rows, (int)cols, lds, dst, ldd);
     return check_launch("pad_copy");
 }
 
@@ -416,6 +420,7 @@ __global__ void __launch_bounds__(256)
 act_backward_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ y, int64_t ldy, int64_t rows,
                     int cols, int act, float slope, const float* __restrict__ row_scale, float* __restrict__ dz,
                     int64_t lddz) {
+    pdl_enter();
     const int64_t total = rows * cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / cols;
@@ -435,7 +440,7 @@ extern "C" int plagnn_act_backward(const float* dy, int64_t lddy, const float* y
     if (!dy || !dz || rows <= 0 || cols <= 0 || lddy < cols || (y && ldy < cols) || lddz < cols)
         return fail(PLAGNN_ERR_ARG, "act_backward", "bad arguments");
     ProfileScope prof("act_backward", rows, cols, 0, stream);
-    act_backward_kernel<<<capped_grid(rows * cols, 256, 8), 256, 0, (cudaStream_t)stream>>>(dy, lddy, y, ldy, rows,
+    launch_pdl(act_backward_kernel, dim3(capped_grid(rows * cols, 256, 8)), dim3(256), 0, (cudaStream_t)stream, dy, lddy, y, ldy, rows,
                                                                                           (int)cols, act, slope, row_scale, dz, lddz);
     return check_launch("act_backward");
 }

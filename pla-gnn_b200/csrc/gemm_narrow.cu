@@ -33,6 +33,7 @@ constexpr int NW_ROWS = 64;     // narrow_n: output rows per block
 constexpr int NW_KC = 128;      // narrow_n: k chunk staged in shared memory
 constexpr int NK_MAX_K = 32;    // narrow_k: longest contraction
 constexpr int NK_MAX_B = 8192;  // narrow_k: floats of B kept in shared memory
+constexpr int NK_ROWS = 64;     // narrow_k: output rows per block step
 constexpr int WG_ROWS = 128;    // narrow_wgrad: contraction rows per block
 constexpr int WG_COLS = 128;    // narrow_wgrad: output columns per block
 
@@ -46,6 +47,7 @@ __device__ __forceinline__ float narrow_epilogue(float v, const NarrowParams& P,
 // thread (r, g) of a 64-row block owns row r and columns g, g+4, ..., g+4(CG-1)
 template <int CG>
 __global__ void __launch_bounds__(NW_THREADS) narrow_n_kernel(const NarrowParams P) {
+    pdl_enter();
     __shared__ float As[NW_ROWS][NW_KC + 1];
     __shared__ float Bs[NW_MAX][NW_KC + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(NW_THREADS) narrow_n_kernel(const NarrowParams
 
 // one thread per (row, 4 output columns); the whole B operand ([sum k] x n, n contiguous) sits in shared memory
 __global__ void __launch_bounds__(NW_THREADS) narrow_k_kernel(const NarrowParams P, int vec_io) {
+    pdl_enter();
     extern __shared__ __align__(16) float Bsh[];
     const int n = (int)P.n, n4 = (n + 3) >> 2, npad = n4 * 4;
     int koff = 0;
@@ -161,10 +164,14 @@ __global__ void __launch_bounds__(NW_THREADS) narrow_k_kernel(const NarrowParams
         koff += k;
     }
     __syncthreads();
-    const int64_t total = P.m * n4;
-    for (int64_t idx = (int64_t)blockIdx.x * NW_THREADS + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NW_THREADS) {
-        const int64_t row = idx / n4;
-        const int j = (int)(idx - row * n4) * 4;
+    // blocks stride over groups of NK_ROWS rows; inside a group the (row, column quad) index is 32-bit (one cheap division)
+    const unsigned per_group = (unsigned)(NK_ROWS * n4);
+    for (int64_t r0 = (int64_t)blockIdx.x * NK_ROWS; r0 < P.m; r0 += (int64_t)gridDim.x * NK_ROWS)
+    for (unsigned it = threadIdx.x; it < per_group; it += NW_THREADS) {
+        const unsigned rr = it / (unsigned)n4;
+        const int64_t row = r0 + rr;
+        if (row >= P.m) break;
+        const int j = (int)(it - rr * (unsigned)n4) * 4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int ko = 0;
         for (int p = 0; p < P.npairs; ++p) {
@@ -211,6 +218,7 @@ template <int MM>
 __global__ void __launch_bounds__(NW_THREADS)
 narrow_wgrad_kernel(const float* __restrict__ dz, int64_t lddz, const float* __restrict__ x, int64_t ldx, int64_t k, int m,
                     int n, float* __restrict__ part) {
+    pdl_enter();
     __shared__ __align__(16) float dzs[WG_ROWS][NW_MAX];
     __shared__ float red[MM][WG_COLS];
     const int tid = threadIdx.x, cl = tid & (WG_COLS - 1), half = tid >> 7;
@@ -265,6 +273,7 @@ narrow_wgrad_kernel(const float* __restrict__ dz, int64_t lddz, const float* __r
 __global__ void __launch_bounds__(NW_THREADS)
 narrow_wgrad_reduce_kernel(const float* __restrict__ part, int nblocks, int m, int n, float* __restrict__ dw, int64_t lddw,
                            float* __restrict__ db) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int e = blockIdx.x * (NW_THREADS / 32) + (threadIdx.x >> 5);
     if (e >= m * (n + 1)) return;
@@ -300,20 +309,20 @@ int gemm_narrow_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_p
     if (narrow_n_shape(n, ktot)) {
         const unsigned grid = (unsigned)ceil_div(m, NW_ROWS);
         switch ((n + 3) / 4) {
-            case 1: narrow_n_kernel<1><<<grid, NW_THREADS, 0, st>>>(P); break;
-            case 2: narrow_n_kernel<2><<<grid, NW_THREADS, 0, st>>>(P); break;
-            case 3: narrow_n_kernel<3><<<grid, NW_THREADS, 0, st>>>(P); break;
-            default: narrow_n_kernel<4><<<grid, NW_THREADS, 0, st>>>(P); break;
+            case 1: launch_pdl(narrow_n_kernel<1>, dim3(grid), dim3(NW_THREADS), 0, st, P); break;
+            case 2: launch_pdl(narrow_n_kernel<2>, dim3(grid), dim3(NW_THREADS), 0, st, P); break;
+            case 3: launch_pdl(narrow_n_kernel<3>, dim3(grid), dim3(NW_THREADS), 0, st, P); break;
+            default: launch_pdl(narrow_n_kernel<4>, dim3(grid), dim3(NW_THREADS), 0, st, P); break;
         }
         return check_launch("gemm(narrow n)");
     }
     if (!narrow_k_shape(n, ktot)) return fail(PLAGNN_ERR_UNSUPPORTED, "gemm", "narrow backend needs n <= 16 or a contraction <= 32");
     const int64_t n4 = (n + 3) / 4;
     const int vec_io = (ldc & 3) == 0 && aligned16(c) && (!gate || ((ldg & 3) == 0 && aligned16(gate)));
-    const int64_t blocks = ceil_div(m * n4, NW_THREADS);
+    const int64_t blocks = ceil_div(m, NK_ROWS);
     const int64_t cap = (int64_t)sm_count() * 8;
     const size_t smem = (size_t)ktot * n4 * 4 * sizeof(float);
-    narrow_k_kernel<<<(unsigned)(blocks < cap ? blocks : cap), NW_THREADS, smem, st>>>(P, vec_io);
+    launch_pdl(narrow_k_kernel, dim3((unsigned)(blocks < cap ? blocks : cap)), dim3(NW_THREADS), smem, st, P, vec_io);
     return check_launch("gemm(narrow k)");
 }
 
@@ -328,14 +337,14 @@ int gemm_narrow_wgrad_launch(int64_t m, int64_t n, const float* dz, int64_t lddz
     float* part = (float*)workspace;
     dim3 grid((unsigned)nblocks, (unsigned)ceil_div(n + 1, WG_COLS));
     switch ((m + 3) / 4) {
-        case 1: narrow_wgrad_kernel<4><<<grid, NW_THREADS, 0, st>>>(dz, lddz, x, ldx, k, (int)m, (int)n, part); break;
-        case 2: narrow_wgrad_kernel<8><<<grid, NW_THREADS, 0, st>>>(dz, lddz, x, ldx, k, (int)m, (int)n, part); break;
-        case 3: narrow_wgrad_kernel<12><<<grid, NW_THREADS, 0, st>>>(dz, lddz, x, ldx, k, (int)m, (int)n, part); break;
-        default: narrow_wgrad_kernel<16><<<grid, NW_THREADS, 0, st>>>(dz, lddz, x, ldx, k, (int)m, (int)n, part); break;
+        case 1: launch_pdl(narrow_wgrad_kernel<4>, grid, dim3(NW_THREADS), 0, st, dz, lddz, x, ldx, k, (int)m, (int)n, part); break;
+        case 2: launch_pdl(narrow_wgrad_kernel<8>, grid, dim3(NW_THREADS), 0, st, dz, lddz, x, ldx, k, (int)m, (int)n, part); break;
+        case 3: launch_pdl(narrow_wgrad_kernel<12>, grid, dim3(NW_THREADS), 0, st, dz, lddz, x, ldx, k, (int)m, (int)n, part); break;
+        default: launch_pdl(narrow_wgrad_kernel<16>, grid, dim3(NW_THREADS), 0, st, dz, lddz, x, ldx, k, (int)m, (int)n, part); break;
     }
     const int64_t elems = m * (n + 1);
-    narrow_wgrad_reduce_kernel<<<(unsigned)ceil_div(elems, NW_THREADS / 32), NW_THREADS, 0, st>>>(part, nblocks, (int)m, (int)n, dw,
-                                                                                               lddw, db);
+    launch_pdl(narrow_wgrad_reduce_kernel, dim3((unsigned)ceil_div(elems, NW_THREADS / 32)), dim3(NW_THREADS), 0, st, part, nblocks,
+               (int)m, (int)n, dw, lddw, db);
     return check_launch("gemm_wgrad_bias(narrow)", 2);
 }
 

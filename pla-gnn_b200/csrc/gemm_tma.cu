@@ -300,6 +300,7 @@ __device__ __forceinline__ TmTile tm_tile(const TmParams& P, int t) {
 template <int CG, bool AT, bool BT>
 __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_constant__ TmParams P) {
     using namespace tm;
+    pdl_trigger();      // the next grid may be placed as SMs free up; it holds at its own pdl_wait() until this one is done
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;                  // 1024-byte aligned (swizzle atoms)
@@ -377,6 +378,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             if (P.gate_tma) prefetch_map(&P.map_gate);
         }
         __syncwarp();
+        pdl_wait();     // barrier init and descriptor prefetch above overlap the previous grid's tail; operands are read below
         // the first ring pass is requested right here, before the TMEM allocation and the CTA / cluster barriers: the loads
         // only need this CTA's own (just initialised) barriers, and their ~3 000-cycle latency overlaps the rest of the set-up
         for (int it = 0; it < preloaded; ++it) {
@@ -385,6 +387,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
         }
     }
     if (warp == 1) tmem_alloc<CG>(tmem_slot, TMEM_COLS);
+    pdl_wait();         // every thread, before bias / gate reads and output stores
     tc_fence_before();
     __syncthreads();
     if (CG == 2) cluster_sync_all();
@@ -729,6 +732,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
 
 // ordered reduction of split-K partials + epilogue
 __global__ void __launch_bounds__(256) gemm_tma_reduce_kernel(const __grid_constant__ TmParams P) {
+    pdl_enter();
     const int64_t total = P.m * P.n;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         float s = 0.f;
@@ -1043,10 +1047,12 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
     cfg.blockDim = dim3(TM_THREADS);
     cfg.dynamicSmemBytes = TM_SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 2;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernels[kidx], P);
     if (e != cudaSuccess) {
         set_error("gemm_tma: launch: %s", cudaGetErrorString(e));
@@ -1055,7 +1061,7 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
     if (P.splits > 1) {
         const int64_t total = m * n;
         const int g = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 8 ? ceil_div(total, 256) : (int64_t)sm_count() * 8);
-        gemm_tma_reduce_kernel<<<g, 256, 0, st>>>(P);
+        launch_pdl(gemm_tma_reduce_kernel, dim3(g), dim3(256), 0, st, P);
     }
     return check_launch("gemm_tma", P.splits > 1 ? 2 : 1);
 }

@@ -8,6 +8,7 @@
 // All of this is HBM-bound integer work: coalesced streaming reads, shared-memory digit counters,
 // grids sized by the input (set-up code, runs once per graph).
 #include "common.cuh"
+#include <cstdlib>
 #include <cstdarg>
 #include <cstring>
 #include <atomic>
@@ -57,6 +58,11 @@ ProfileScope::~ProfileScope() {
     if (slot < 0) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].end, st);
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("PLAGNN_PDL"); return !e || e[0] != '0'; }();
+    return on;
 }
 
 int sm_count() {

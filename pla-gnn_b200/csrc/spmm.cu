@@ -107,9 +107,11 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
             const float* __restrict__ zfwd, int64_t ldzf, float* __restrict__ out, int32_t* __restrict__ arg_out, int64_t ldo,
             float* __restrict__ part_val, int32_t* __restrict__ part_arg, int part_ld, SpmmEpilogue ep, float one,
             float nzero) {
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int item = item_begin + blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
+    pdl_wait();
     const int chunk = __ldg(plan_hdr);
     const int row = __ldg(item_row + item);
     const int first = __ldg(item_ptr + row);
@@ -275,9 +277,11 @@ spmm_combine_kernel(const int32_t* __restrict__ item_ptr, const int32_t* __restr
                     const float* __restrict__ part_val,
                     const int32_t* __restrict__ part_arg, int part_ld, float* __restrict__ out,
                     int32_t* __restrict__ arg_out, int64_t ldo, SpmmEpilogue ep) {
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int h = hub_begin + blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
     if (h >= n_hubs) return;
+    pdl_wait();
     const int col = blockIdx.y * 128 + lane * 4;
     if (col >= feat) return;
     const int row = __ldg(hub_rows + h);
@@ -327,6 +331,7 @@ __global__ void __launch_bounds__(256)
 spmm_max_scatter_kernel(const float* __restrict__ dz, int64_t lddz, const int32_t* __restrict__ arg, int64_t ldarg,
                         const float* __restrict__ z, int64_t ldz, int64_t n_rows, int feat, float* __restrict__ dx,
                         int64_t lddx) {
+    pdl_enter();
     const int f4 = (feat + 3) >> 2;
     const int64_t total = n_rows * f4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -345,6 +350,7 @@ spmm_max_scatter_kernel(const float* __restrict__ dz, int64_t lddz, const int32_
 
 __global__ void __launch_bounds__(256)
 dropout_scale_kernel(float* __restrict__ g, int64_t rows, int feat, int64_t ld, float p, unsigned long long seed) {
+    pdl_enter();
     const int64_t total = rows * feat;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / feat;
@@ -384,7 +390,7 @@ static void launch_main(const SpmmArgs& a, const int32_t* item_ptr, const int32_
     const int n_items = a.range ? (int)a.range[1] : (int)a.counts[0];
     if (n_items <= item_begin) return;
     dim3 grid((unsigned)ceil_div(n_items - item_begin, SPMM_WARPS), (unsigned)ceil_div((a.feat + 3) / 4, 32 * VEC));
-    spmm_kernel<MODE, VEC, NB><<<grid, SPMM_WARPS * 32, 0, st>>>(
+    launch_pdl(spmm_kernel<MODE, VEC, NB>, grid, dim3(SPMM_WARPS * 32), 0, st,
         a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, item_begin, n_items, a.x, a.ldx,
         (int)a.feat, a.argm, a.ldarg, a.zfwd, a.ldzf, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep, 1.0f, -0.0f);
 }
@@ -392,7 +398,7 @@ static void launch_main(const SpmmArgs& a, const int32_t* item_ptr, const int32_
 template <int MODE>
 static int spmm_dispatch(const SpmmArgs& a, const char* name, cudaStream_t st) {
     if (!a.indptr || !a.indices || !a.plan || !a.counts || !a.x || !a.out) return fail(PLAGNN_ERR_ARG, name, "null pointer");
-    if (a.n_rows <= 0 || a.feat <= 0) return fail(PLAGNN_ERR_ARG, name, "bad sizes");
+    if (a.n_rows <= 0 || a.feat <= 0 || a.ldx >= ((int64_t)1 << 30)) return fail(PLAGNN_ERR_ARG, name, "bad sizes");
     const int64_t f4 = (a.feat + 3) / 4 * 4;
     if (a.ldx < f4 || a.ldo < f4 || (a.ldx & 3) || (a.ldo & 3) || !aligned16(a.x) || !aligned16(a.out) ||
         (a.arg_out && !aligned16(a.arg_out)))
@@ -432,7 +438,7 @@ static int spmm_dispatch(const SpmmArgs& a, const char* name, cudaStream_t st) {
         return fail(PLAGNN_ERR_ARG, name, "row range outside the plan");
     if (hub_end > hub_begin) {
         dim3 grid((unsigned)ceil_div(hub_end - hub_begin, SPMM_WARPS), (unsigned)ceil_div(a.feat, 128));
-        spmm_combine_kernel<MODE><<<grid, SPMM_WARPS * 32, 0, st>>>(item_ptr, slot_ptr, hub_rows, (int)hub_begin, (int)hub_end, (int)a.feat,
+        launch_pdl(spmm_combine_kernel<MODE>, grid, dim3(SPMM_WARPS * 32), 0, st, item_ptr, slot_ptr, hub_rows, (int)hub_begin, (int)hub_end, (int)a.feat,
                                                                      pv, pa, pld, a.out, a.arg_out, a.ldo, a.ep);
     }
     return check_launch(name, hub_end > hub_begin ? 2 : 1);
@@ -472,7 +478,7 @@ int plagnn_spmm_max_bwd(const float* dz, int64_t lddz, const int32_t* arg, int64
     PLAGNN_CUDA_TRY(cudaMemset2DAsync(dx, lddx * sizeof(float), 0, (size_t)(lddx < f4 ? feat : f4) * sizeof(float), n_src, st));
     const int64_t total = num_rows * (f4 / 4);
     const int grid = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 16 ? ceil_div(total, 256) : (int64_t)sm_count() * 16);
-    spmm_max_scatter_kernel<<<grid, 256, 0, st>>>(dz, lddz, arg, ldarg, z, ldz, num_rows, (int)feat, dx, lddx);
+    launch_pdl(spmm_max_scatter_kernel, dim3(grid), dim3(256), 0, st, dz, lddz, arg, ldarg, z, ldz, num_rows, (int)feat, dx, lddx);
     return check_launch("spmm_max_bwd");
 }
 
@@ -537,7 +543,7 @@ int plagnn_dropout_scale(float* grad, int64_t rows, int64_t feat, int64_t ld, fl
     if (dropout_p == 0.f) return PLAGNN_OK;
     const int64_t total = rows * feat;
     const int grid = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 16 ? ceil_div(total, 256) : (int64_t)sm_count() * 16);
-    dropout_scale_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(grad, rows, (int)feat, ld, dropout_p,
+    launch_pdl(dropout_scale_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, grad, rows, (int)feat, ld, dropout_p,
                                                                  (unsigned long long)dropout_seed);
     return check_launch("dropout_scale");
 }

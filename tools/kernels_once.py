@@ -22,6 +22,15 @@ if which in ("all", "gemm"):
     out = torch.empty(400, 503, device=dev)
     for _ in range(3):
         ops.gemm(400, 503, [(dz, 1, x, 1, N)], out=out, backend=ops.GEMM_AUTO)
+if which in ("all", "narrow"):
+    h4 = ops.aligned(torch.randn(N, 100, device=dev))
+    w2 = ops.aligned(torch.randn(12, 100, device=dev) * 0.1)
+    b2 = torch.randn(12, device=dev)
+    dz5 = ops.aligned(torch.randn(N, 12, device=dev))
+    for _ in range(3):
+        ops.gemm(N, 12, [(h4, 0, w2, 0, 100)], bias=b2, act=ops.ACT_SIGMOID)                 # narrow_n_kernel
+        ops.gemm(N, 100, [(dz5, 0, w2, 1, 12)], gate=h4, gate_act=ops.ACT_LEAKY)             # narrow_k_kernel
+        ops.gemm_wgrad_bias(dz5, h4)                                                         # narrow_wgrad_kernel + reduce
 if which in ("all", "spmm"):
     prob = synth.ppi_problem(state="inter")
     g = P.graph((prob.ppi_row, prob.ppi_col), num_nodes=N).add_self_loop().to(dev)
