@@ -348,6 +348,16 @@ spmm_max_scatter_kernel(const float* __restrict__ dz, int64_t lddz, const int32_
     }
 }
 
+// dx[0..rows) x [0..4*w4) = 0 with 16-byte stores: the clear before the scatter, as a kernel so that it stays in the
+// launch chain (a memset node would break it) — one block per row step, threads over the row's float4 groups
+__global__ void __launch_bounds__(128)
+zero_rows_kernel(float* __restrict__ dx, int64_t ld, int64_t rows, int w4) {
+    pdl_enter();
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x)
+        for (int c = threadIdx.x; c < w4; c += 128) *reinterpret_cast<float4*>(dx + r * ld + 4 * c) = z;
+}
+
 __global__ void __launch_bounds__(256)
 dropout_scale_kernel(float* __restrict__ g, int64_t rows, int feat, int64_t ld, float p, unsigned long long seed) {
     pdl_enter();
@@ -475,11 +485,18 @@ int plagnn_spmm_max_bwd(const float* dz, int64_t lddz, const int32_t* arg, int64
     if (lddz < f4 || (lddz & 3) || ldarg < f4 || (ldarg & 3) || lddx < feat || !aligned16(dz) || !aligned16(arg) ||
         (z && (!aligned16(z) || ldz < f4 || (ldz & 3))))
         return fail(PLAGNN_ERR_ALIGN, "spmm_max_bwd", "dz/arg/z need 16-byte aligned rows");
-    PLAGNN_CUDA_TRY(cudaMemset2DAsync(dx, lddx * sizeof(float), 0, (size_t)(lddx < f4 ? feat : f4) * sizeof(float), n_src, st));
+    int launched = 1;
+    if (lddx >= f4 && (lddx & 3) == 0 && aligned16(dx)) {
+        const int64_t zgrid = n_src < (int64_t)sm_count() * 16 ? n_src : (int64_t)sm_count() * 16;
+        launch_pdl(zero_rows_kernel, dim3((unsigned)zgrid), dim3(128), 0, st, dx, lddx, n_src, (int)(f4 / 4));
+        launched = 2;
+    } else {
+        PLAGNN_CUDA_TRY(cudaMemset2DAsync(dx, lddx * sizeof(float), 0, (size_t)feat * sizeof(float), n_src, st));
+    }
     const int64_t total = num_rows * (f4 / 4);
     const int grid = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 16 ? ceil_div(total, 256) : (int64_t)sm_count() * 16);
     launch_pdl(spmm_max_scatter_kernel, dim3(grid), dim3(256), 0, st, dz, lddz, arg, ldarg, z, ldz, num_rows, (int)feat, dx, lddx);
-    return check_launch("spmm_max_bwd");
+    return check_launch("spmm_max_bwd", launched);
 }
 
 int plagnn_spmm_max_bwd_gather(const int32_t* out_indptr, const int32_t* out_indices, const void* out_plan,
