@@ -323,6 +323,7 @@ def run_ours(args):
     for _ in range(SETTLE_EPOCHS):
         epoch()
     # ---- device-resident timed region (value) ------------------------------------------------------
+    barrier()                  # communicator set-up (N > 1) happens here, not inside the sampled window
     if sampler:
         sampler.start()
     launches0 = ops.launch_count()

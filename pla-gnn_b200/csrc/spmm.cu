@@ -97,9 +97,10 @@ __device__ __forceinline__ void reduce_one(float4& acc, int4& arg, const float4 
 // MODE_MATCH: x = dz (rows = destinations v of the out-edge u->v), argm = arg[v,:], zfwd = z[v,:] (nullable);
 //             acc[u,f] += (argm[v,f]==u && z>0) ? dz[v,f] : 0
 // The max reducer runs at the L2 -> SM bandwidth cap once enough warps are resident (measured: 24 warps/SM at 80
-// registers 0.198 ms, 16 warps at 110 registers 0.322 ms for F = 503), so its default variants are held to 3 blocks per SM.
+// registers 0.198 ms, 16 warps at 110 registers 0.322 ms for F = 503), so its default variants are held to 3 blocks per SM;
+// the sum reducer (no arg registers) to 4 blocks = 32 warps (weighted 100 M-edge graph: 55.7 ms at 64 registers, 71.3 at 72).
 template <int MODE, int VEC, int NB>
-__global__ void __launch_bounds__(SPMM_WARPS * 32, (MODE == MODE_MAX && NB * VEC <= 8) ? 3 : 1)
+__global__ void __launch_bounds__(SPMM_WARPS * 32, NB * VEC > 8 ? 1 : MODE == MODE_MAX ? 3 : MODE == MODE_SUM ? 4 : 1)
 spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int32_t* __restrict__ eids,
             const float* __restrict__ ew, const int32_t* __restrict__ plan_hdr, const int32_t* __restrict__ item_ptr,
             const int32_t* __restrict__ slot_ptr, const int32_t* __restrict__ item_row, int item_begin, int n_items,
@@ -126,14 +127,21 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
     // group of a lane can fall outside the slab.  Lanes >= S shadow lane 0 (same addresses, nothing stored).
     const int col0 = blockIdx.y * (128 * VEC);   // first column of this block's slab
     const int groups = min((feat + 3) / 4 - blockIdx.y * (32 * VEC), 32 * VEC);
-    const int S = min(32, ((groups + VEC - 1) / VEC + 1) & ~1);   // even: every request covers whole 32-byte sectors
-    const int lane_c = (lane < S && lane < groups) ? lane : 0;
+    // max reducer: runtime stride, clamped columns (its loads are unconditional); the other reducers keep the fixed
+    // stride of 32 with compile-time column offsets from one row pointer and guard their loads with cok[]
+    const int S = MODE == MODE_MAX ? min(32, ((groups + VEC - 1) / VEC + 1) & ~1) : 32;   // even: whole 32-byte sectors
+    const int lane_c = MODE == MODE_MAX ? ((lane < S && lane < groups) ? lane : 0) : lane;
     int col[VEC];
     bool cok[VEC];
 #pragma unroll
     for (int q = 0; q < VEC; ++q) {
-        cok[q] = lane < S && lane_c + S * q < groups;
-        col[q] = col0 + 4 * (lane_c + S * (lane_c + S * q < groups ? q : 0));   // clamped: always a readable column
+        if (MODE == MODE_MAX) {
+            cok[q] = lane < S && lane_c + S * q < groups;
+            col[q] = col0 + 4 * (lane_c + S * (lane_c + S * q < groups ? q : 0));   // clamped: always a readable column
+        } else {
+            col[q] = col0 + 4 * (lane + 32 * q);
+            cok[q] = col[q] < feat;
+        }
     }
 
     float4 acc[VEC];
