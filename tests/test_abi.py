@@ -47,6 +47,25 @@ def test_workspace_size_queries_are_pure_host_calls():
     assert lib.plagnn_bce_workspace_bytes(8000, 12) >= 32 * 12 * 8
 
 
+def test_python_constants_equal_the_header_enums():
+    """Backend / activation / reducer codes of `_lib.py` are the header's (a drifted constant would pick another kernel)."""
+    import re
+    from plagnn_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "plagnn.h")).read()
+    enums = dict((k, int(v)) for k, v in re.findall(r"(PLAGNN_[A-Z0-9_]+)\s*=\s*(-?\d+)", hdr))
+    for name in ("GEMM_AUTO", "GEMM_SIMT", "GEMM_TCGEN05", "GEMM_TMA", "GEMM_NARROW", "ACT_NONE", "ACT_RELU", "ACT_LEAKY",
+                 "ACT_SIGMOID", "REDUCE_MAX", "REDUCE_SUM"):
+        assert getattr(_lib, name) == enums["PLAGNN_" + name], name
+
+
+def test_weight_gradient_workspace_covers_the_narrow_kernel():
+    from plagnn_b200 import _lib
+    lib = _lib.load()
+    # m <= 16: one 12 x 101 partial per 128-row block of the contraction
+    assert lib.plagnn_gemm_wgrad_bias_workspace_bytes(12, 100, 24041) >= 188 * 12 * 101 * 4
+    assert lib.plagnn_gemm_wgrad_bias_workspace_bytes(400, 503, 24041) >= lib.plagnn_gemm_workspace_bytes(400, 504, 24041)
+
+
 def test_product_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "pla-gnn_b200")
     for dirpath, _, files in os.walk(pkg):
