@@ -7,9 +7,11 @@
 // Shape of the kernel (HBM / L2 bound, no tensor cores):
 //   * one warp owns one work item = (destination row, chunk of <= `chunk` in-edges) from the plan
 //     built in graph_build.cu, so power-law hubs are spread over many warps;
-//   * a lane owns VEC float4 column groups (lane, lane+32, ...): every neighbour row is read with
-//     fully coalesced 512-byte LDG.128 requests; NB neighbour rows are in flight per lane;
-//   * neighbour ids are read 32 at a time (one coalesced load) and broadcast with shuffles;
+//   * a lane owns VEC float4 column groups (lane, lane+S, ...): every neighbour row is read with
+//     fully coalesced LDG.128 requests; NB neighbour rows are in flight per lane;
+//   * sum / match reducers read neighbour ids 32 at a time and broadcast them with shuffles and mask the
+//     slots past the end; the max reducer (the PLA-GNN path) reads them as broadcast loads one step ahead
+//     and needs no masks at all (see the comment in the kernel);
 //   * rows split over several chunks write (value,arg) partials that a second small kernel folds
 //     in chunk order, which keeps "first maximum wins" and makes sums order-stable.
 #include "common.cuh"
