@@ -170,9 +170,6 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
             int u[NB];
 #pragma unroll
             for (int t = 0; t < NB; ++t) u[t] = __ldg(indices + min(beg + t, last));
-#ifdef PLAGNN_SPMM_UNROLL1
-#pragma unroll 1
-#endif
             for (int j = beg; j < end; j += NB) {
                 int un[NB];
                 float4 v[NB][VEC];
