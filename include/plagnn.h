@@ -287,6 +287,42 @@ int plagnn_gnn32_backward(const plagnn_gnn32_shape* shape, const float* x, int64
                           const float* prob, int64_t ldprob, const float* dprob, int64_t lddprob,
                           float* const* grads /* host[19] */, float* dx, int64_t lddx, plagnn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Preprocessing (offline stage) — replaces the Python loops / dense numpy passes of
+ *     code/data_preprocess.py:175-214   edge_clustering_coefficients(ppi_net, epsilon=0)
+ *     code/data_preprocess.py:217-257   modify_network_topology(ppi_net, pcc_nor, pcc_inter, thr)
+ * ecc: input = the PPI matrix as CSR with strictly ascending columns per row (what ppi_net.tocsr() gives for a simple
+ *   0/1 matrix).  For every stored entry (i, j) with j > i, in row-major order (rank u): COO entries 2u = (i, j, v),
+ *   2u+1 = (j, i, v) with v = |N(i) & N(j)| / (min(deg i, deg j) - 1), or epsilon when the denominator is 0 — the order
+ *   and the float64 values of the reference's lists.  *n_out (device) = number of COO entries (2 x #upper entries);
+ *   capacity = allocated entries (2*nnz always suffices).  *status (device, int32): 0 ok, bit 0 = a row is unsorted or
+ *   holds a duplicate, bit 1 = column id out of range, bit 2 = capacity too small.
+ * diff_moments: mean_std[0] = mean, mean_std[1] = population standard deviation of (inter - normal) over rows x cols
+ *   (np.mean / np.std of code/data_preprocess.py:243-244; two passes, fixed summation tree: equal to numpy's pairwise
+ *   sums to rounding, not bit for bit).
+ * adj_bitmask: mask[r * words_per_row + c / 32] bit (c % 32) = 1 for every COO entry (r, c); the mask is cleared first.
+ * rewire: new_mask = mask with (r, c) cleared where inter - normal < l_threshold and set where inter - normal >
+ *   r_threshold (code/data_preprocess.py:250-253; the differences and comparisons are exact, so the result is
+ *   bit-identical for given thresholds); rowptr[N+1] = CSR row pointer of new_mask, *n_out (device) = its entry count.
+ * bitmask_to_coo: the set bits of mask in row-major order (= coo_matrix(dense), code/data_preprocess.py:255).
+ * ---------------------------------------------------------------------------------------- */
+size_t plagnn_ecc_workspace_bytes(int64_t num_nodes);
+int plagnn_ecc(const int32_t* indptr, const int32_t* indices, int64_t num_nodes, int64_t nnz, double epsilon,
+               int32_t* ecc_row, int32_t* ecc_col, double* ecc_data, int64_t capacity, int64_t* n_out /* device */,
+               int32_t* status /* device */, void* workspace, size_t workspace_bytes, plagnn_stream_t stream);
+size_t plagnn_diff_moments_workspace_bytes(void);
+int plagnn_diff_moments(const double* normal, int64_t ldn, const double* inter, int64_t ldi, int64_t rows, int64_t cols,
+                        double* mean_std /* device[2] */, void* workspace, size_t workspace_bytes, plagnn_stream_t stream);
+int plagnn_adj_bitmask(const int32_t* row, const int32_t* col, int64_t nnz, int64_t num_nodes, uint32_t* mask,
+                       int64_t words_per_row, int32_t* status /* device */, plagnn_stream_t stream);
+size_t plagnn_rewire_workspace_bytes(int64_t num_nodes);
+int plagnn_rewire(const double* normal, int64_t ldn, const double* inter, int64_t ldi, int64_t num_nodes,
+                  const uint32_t* mask, uint32_t* new_mask, int64_t words_per_row, double l_threshold, double r_threshold,
+                  int32_t* rowptr /* N+1 */, int64_t* n_out /* device */, void* workspace, size_t workspace_bytes,
+                  plagnn_stream_t stream);
+int plagnn_bitmask_to_coo(const uint32_t* mask, int64_t words_per_row, int64_t num_nodes, const int32_t* rowptr,
+                          int32_t* out_row, int32_t* out_col, plagnn_stream_t stream);
+
 /* small utilities used by the host layer */
 int plagnn_pad_copy(const float* src, int64_t rows, int64_t cols, int64_t lds, float* dst, int64_t ldd,
                     plagnn_stream_t stream); /* dst[:, :cols] = src; dst[:, cols:ldd] = 0 */

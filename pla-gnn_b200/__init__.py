@@ -7,6 +7,7 @@ Public surface (mirrors what the reference's train loop touches)
     FusedAdam                  fused optimiser (optim.py)
     protein_loc_correction     on-device label decision (metrics.py)
     scoring                    alteration scoring after training: scaling / mat_merge / alteration_rank (scoring.py)
+    preprocess                 offline stage on the device: edge_clustering_coefficients / modify_network_topology (preprocess.py)
 The kernels live in libplagnn.so (csrc/, C ABI in include/plagnn.h); importing this package does not
 need a GPU, calling any kernel does.
 """
@@ -19,6 +20,7 @@ from .optim import FusedAdam
 from .metrics import protein_loc_correction, performances_record
 from .utils import create_graph
 from . import scoring
+from . import preprocess
 
 __all__ = ["GNN32", "SAGEConv", "GraphConvSum", "GCN", "Graph", "Csr", "graph", "add_self_loop", "build_csr",
            "create_graph", "multi_loss", "multi_loss_indexed", "weight_cal", "FusedAdam", "protein_loc_correction",

@@ -93,6 +93,17 @@ PROTOTYPES = {
     "plagnn_divide_f64": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_double, c_void_p]),
     "plagnn_alteration_rank": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
                                        c_void_p, c_size_t, c_void_p]),
+    "plagnn_ecc_workspace_bytes": (c_size_t, [c_int64]),
+    "plagnn_ecc": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                           c_void_p, c_void_p, c_size_t, c_void_p]),
+    "plagnn_diff_moments_workspace_bytes": (c_size_t, []),
+    "plagnn_diff_moments": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_size_t,
+                                    c_void_p]),
+    "plagnn_adj_bitmask": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "plagnn_rewire_workspace_bytes": (c_size_t, [c_int64]),
+    "plagnn_rewire": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_double, c_double,
+                              c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "plagnn_bitmask_to_coo": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "plagnn_gnn32_arena_bytes": (c_size_t, [POINTER(Gnn32Shape)]),
     "plagnn_gnn32_forward": (c_int, [POINTER(Gnn32Shape), c_void_p, c_int64, POINTER(c_void_p), c_void_p, c_size_t,
                                      c_void_p, c_int64, c_void_p]),

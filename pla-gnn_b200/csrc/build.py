@@ -17,7 +17,7 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "libplagnn.so")
 OBJ_DIR = os.path.join(HERE, "_obj")
-SOURCES = ["graph_build.cu", "spmm.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tma.cu", "gemm_narrow.cu", "gemm_api.cu", "elementwise.cu", "scoring.cu", "gnn32_engine.cu"]
+SOURCES = ["graph_build.cu", "spmm.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tma.cu", "gemm_narrow.cu", "gemm_api.cu", "elementwise.cu", "scoring.cu", "preprocess.cu", "gnn32_engine.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xcompiler", "-Wall",
