@@ -44,13 +44,28 @@ cases = {
     "path_isolated": (sym_graph(9, [(1, 2), (2, 3), (5, 6)]), 7.5),                   # denominators 0 -> epsilon; isolated nodes
     "empty": (coo_matrix((5, 5), dtype=np.int64), 0),
 }
+
+
+def with_diagonal(g, nodes):
+    """self-interactions kept on the diagonal: not edges of the loop (`neighbors > i`, :195) but counted in the degree and
+    in the row overlap"""
+    r = np.concatenate([g.row, np.array(nodes, dtype=np.int32)])
+    c = np.concatenate([g.col, np.array(nodes, dtype=np.int32)])
+    return coo_matrix((np.ones(r.size, dtype=np.int64), (r, c)), shape=g.shape)
+
 out = {}
-for name, (g, eps) in cases.items():
+
+
+def record_ecc(name, g, eps):
     ecc = ref.edge_clustering_coefficients(g, epsilon=eps)
     out[f"ecc_{name}_in_row"], out[f"ecc_{name}_in_col"] = g.row.astype(np.int32), g.col.astype(np.int32)
     out[f"ecc_{name}_n"], out[f"ecc_{name}_eps"] = np.int64(g.shape[0]), np.float64(eps)
     out[f"ecc_{name}_row"], out[f"ecc_{name}_col"] = ecc.row.astype(np.int32), ecc.col.astype(np.int32)
     out[f"ecc_{name}_data"] = ecc.data.astype(np.float64)
+
+
+for name, (g, eps) in cases.items():
+    record_ecc(name, g, eps)
     # (when every value is the integer epsilon, e.g. the star, scipy infers int64 for the list; values are what is pinned)
 
 
@@ -77,6 +92,9 @@ for name, n, m, thr in (("a", 70, 420, 1.0), ("b", 45, 150, 2.0), ("c", 33, 60, 
     out[f"mod_{name}_row"], out[f"mod_{name}_col"] = res.row.astype(np.int32), res.col.astype(np.int32)
     out[f"mod_{name}_data"] = res.data
     print(name, "edges", g.nnz, "->", res.nnz, "dtype", res.data.dtype)
+
+# drawn last so that the generator state of the cases above does not depend on it
+record_ecc("diagonal", with_diagonal(sym_graph(40, powerlaw_pairs(40, 160)), [0, 1, 2, 5, 17, 39]), 0)
 
 np.savez_compressed(os.path.join(OUT, "preprocess.npz"), **out)
 print("wrote", os.path.join(OUT, "preprocess.npz"), os.path.getsize(os.path.join(OUT, "preprocess.npz")), "bytes")

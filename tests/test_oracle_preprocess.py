@@ -11,6 +11,9 @@ from oracle import preprocess_oracle as po
 
 ECC_CASES = ("powerlaw", "powerlaw_eps", "star", "k6", "path_isolated", "empty")
 MOD_CASES = ("a", "b", "c")
+# fixtures added after the last GPU run of round 1: checked against the oracle here, to be added to the GPU list (ECC_CASES,
+# which tests/test_gpu_preprocess.py imports) with the next GPU run
+ECC_CASES_ORACLE_ONLY = ("diagonal",)
 
 
 def ppi_of(g, prefix):
@@ -24,7 +27,7 @@ def g(golden_dir):
     return np.load(os.path.join(golden_dir, "preprocess.npz"))
 
 
-@pytest.mark.parametrize("name", ECC_CASES)
+@pytest.mark.parametrize("name", ECC_CASES + ECC_CASES_ORACLE_ONLY)
 def test_ecc_oracle_equals_reference(g, name):
     e = po.edge_clustering_coefficients(ppi_of(g, f"ecc_{name}"), float(g[f"ecc_{name}_eps"]))
     assert np.array_equal(e.row, g[f"ecc_{name}_row"]) and np.array_equal(e.col, g[f"ecc_{name}_col"])
@@ -46,6 +49,52 @@ def test_rewiring_oracle_equals_reference(g, name):
     assert np.array_equal(res.row, g[f"mod_{name}_row"]) and np.array_equal(res.col, g[f"mod_{name}_col"])
     assert res.data.dtype == np.int64 and np.array_equal(res.data, g[f"mod_{name}_data"])
     assert np.array_equal(np.array(po.diff_moments(g[f"mod_{name}_pcc_nor"], g[f"mod_{name}_pcc_inter"])), g[f"mod_{name}_mean_std"])
+
+
+def brute_force_ecc(adj, epsilon):
+    """the definition on a dense 0/1 matrix, one edge at a time (small n only)"""
+    n = adj.shape[0]
+    deg = adj.sum(axis=1)
+    rows, cols, vals = [], [], []
+    for i in range(n):
+        for j in range(i + 1, n):
+            if adj[i, j]:
+                den = min(deg[i], deg[j]) - 1
+                v = float(epsilon) if den == 0 else int(np.count_nonzero(adj[i] & adj[j])) / int(den)
+                rows += [i, j]
+                cols += [j, i]
+                vals += [v, v]
+    return np.array(rows, dtype=np.int32), np.array(cols, dtype=np.int32), np.array(vals, dtype=np.float64)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_ecc_oracle_equals_dense_definition(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2, 40))
+    adj = rng.random((n, n)) < rng.uniform(0.05, 0.6)
+    adj = np.triu(adj, 1)
+    adj = (adj | adj.T).astype(np.int64)
+    if seed % 2:
+        adj[np.arange(0, n, 3), np.arange(0, n, 3)] = 1          # some self-interactions
+    r, c = np.nonzero(adj)
+    perm = rng.permutation(r.size)
+    m = coo_matrix((np.ones(r.size, dtype=np.int64), (r[perm].astype(np.int32), c[perm].astype(np.int32))), shape=(n, n))
+    e = po.edge_clustering_coefficients(m, 0.5)
+    br, bc, bv = brute_force_ecc(adj, 0.5)
+    assert np.array_equal(e.row, br) and np.array_equal(e.col, bc) and np.array_equal(e.data, bv)
+
+
+def test_rewiring_thresholds_are_strict(g):
+    """a difference equal to a threshold changes nothing (`<` and `>` at code/data_preprocess.py:250-251)"""
+    n = 4
+    ppi = coo_matrix((np.ones(2, dtype=np.int64), ([0, 1], [1, 0])), shape=(n, n))
+    nor = np.zeros((n, n))
+    inter = np.zeros((n, n))
+    inter[0, 1] = inter[1, 0] = -0.5          # existing edge at the left threshold: kept
+    inter[2, 3] = inter[3, 2] = 0.5           # missing edge at the right threshold: not added
+    inter[0, 2] = 0.75                        # missing, above: added (one direction only, as the reference would)
+    res = po.modify_network_topology(ppi, nor, inter, 0.0, l_threshold=-0.5, r_threshold=0.5)
+    assert sorted(zip(res.row.tolist(), res.col.tolist())) == [(0, 1), (0, 2), (1, 0)]
 
 
 def test_rewiring_changes_both_ways(g):
