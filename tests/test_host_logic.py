@@ -70,3 +70,27 @@ def test_weight_cal_matches_oracle():
 
 def test_import_shim_and_package_dir():
     assert os.path.basename(os.path.dirname(P.__file__)) == "pla-gnn_b200"
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: no module of the package (nor the drop-ins, nor tools the product imports) may
+    import it — a product path routed through the CPU restatement would void every parity claim."""
+    import ast
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "pla-gnn_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            path = os.path.join(dirpath, f)
+            for node in ast.walk(ast.parse(open(path).read(), path)):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                if any(n == "oracle" or n.startswith("oracle.") for n in names):
+                    offenders.append(os.path.relpath(path, root))
+    assert not offenders, offenders
