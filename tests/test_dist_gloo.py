@@ -1,4 +1,4 @@
-"""N > 1 host logic on CPU: world_size-2 gloo run of the row-partitioned GCN choreography with a CPU compute backend
+"""N > 1 host logic on CPU: world_size-2 and -3 gloo runs of the row-partitioned GCN choreography with a CPU compute backend
 (oracle kernels), compared with the single-process oracle model.  No CUDA involved."""
 import os
 
@@ -149,16 +149,27 @@ def test_block_bounds_and_plan_cover_every_edge_once():
     assert abs(plans[0].num_local_edges - plans[1].num_local_edges) < 0.25 * sg.src.numel()
 
 
-def test_two_rank_gloo_matches_single_process_oracle(tmp_path):
-    world, port = 2, 29500 + os.getpid() % 2000
+def _run_world(world, tmp_path):
+    port = 29500 + (os.getpid() * 7 + world) % 2000
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")
     # spawn, not fork: the parent already runs OpenMP / MKL threads
     mp.start_processes(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
     out_ref, grads_ref = _reference()
     parts = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
+    assert [p["r0"] for p in parts][0] == 0 and parts[-1]["r1"] == out_ref.shape[0]
     out = torch.cat([p["out"] for p in parts])
     assert torch.allclose(out, out_ref, rtol=1e-5, atol=1e-6)
     for r in range(world):                                   # replicated, all-reduced gradients agree on every rank
         for g, gr in zip(parts[r]["grads"], grads_ref):
             assert torch.allclose(g, gr, rtol=1e-4, atol=1e-7)
+
+
+def test_two_rank_gloo_matches_single_process_oracle(tmp_path):
+    _run_world(2, tmp_path)
+
+
+def test_three_rank_gloo_uneven_blocks(tmp_path):
+    """403 rows over 3 ranks: blocks of different in-edge counts, padded slabs and a chunk count that does not divide the
+    block — the exchange must still deliver every source row exactly once."""
+    _run_world(3, tmp_path)
