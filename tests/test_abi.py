@@ -80,3 +80,20 @@ def test_no_cpu_fallback_raises_without_cuda_tensor():
     import plagnn_b200 as P
     with pytest.raises(P.PlagnnError):
         P.ops.aligned(torch.zeros(4, 4))
+
+
+def test_argument_validation_is_host_side():
+    """Entry points reject bad arguments before any CUDA call (return code + message, no exception, no GPU needed)."""
+    from plagnn_b200 import _lib
+    lib = _lib.load()
+    ERR_ARG = -1
+    assert lib.plagnn_ecc(None, None, 10, 5, 0.0, None, None, None, 10, None, None, None, 0, None) == ERR_ARG
+    assert b"ecc" in lib.plagnn_last_error()
+    assert lib.plagnn_diff_moments(None, 4, None, 4, 4, 4, None, None, 0, None) == ERR_ARG
+    assert b"diff_moments" in lib.plagnn_last_error()
+    assert lib.plagnn_adj_bitmask(None, None, 3, 40, None, 1, None, None) == ERR_ARG
+    assert lib.plagnn_rewire(None, 8, None, 8, 8, None, None, 1, -1.0, 1.0, None, None, None, 0, None) == ERR_ARG
+    assert b"rewire" in lib.plagnn_last_error()
+    assert lib.plagnn_bitmask_to_coo(None, 1, 8, None, None, None, None) == ERR_ARG
+    assert lib.plagnn_scaling(None, 0, 12, 10, 12, None, 12, None, 12, None, 0, None) == ERR_ARG
+    assert lib.plagnn_divide_f64(None, 12, 10, 12, 100.0, None) == ERR_ARG
