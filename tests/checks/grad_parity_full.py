@@ -1,6 +1,6 @@
 """Full-size (N = 24 041) gradient parity: GPU vs the fp32 oracle and vs the float64 oracle, per parameter tensor."""
 import os, sys, copy
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import plagnn_b200 as P
 from plagnn_b200 import synth

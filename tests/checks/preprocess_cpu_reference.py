@@ -1,7 +1,7 @@
 """Times the REFERENCE's own `edge_clustering_coefficients` / `modify_network_topology` (code/data_preprocess.py, imported
 unchanged from /root/reference — build container only) on the synthetic PPI-shaped inputs that tools/preprocess_time.py
 gives the device kernels, and checks on the way that the oracle restatement returns the same matrices.
-    python tools/preprocess_cpu_reference.py [--nodes N --edges E --dense-nodes M]"""
+    python tests/checks/preprocess_cpu_reference.py [--nodes N --edges E --dense-nodes M]"""
 import argparse
 import json
 import os
@@ -11,7 +11,7 @@ import time
 import numpy as np
 from scipy.sparse import coo_matrix
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference/code")
 import data_preprocess as ref  # noqa: E402
