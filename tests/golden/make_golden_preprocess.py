@@ -96,5 +96,15 @@ for name, n, m, thr in (("a", 70, 420, 1.0), ("b", 45, 150, 2.0), ("c", 33, 60, 
 # drawn last so that the generator state of the cases above does not depend on it
 record_ecc("diagonal", with_diagonal(sym_graph(40, powerlaw_pairs(40, 160)), [0, 1, 2, 5, 17, 39]), 0)
 
+# the rewired network can be asymmetric in a few entries (ECC is applied to it at code/data_preprocess.py:327): entries
+# (i, j) without (j, i), one of them pointing at a node whose own row is empty (denominator -1 -> value -0.0)
+g_asym = sym_graph(30, powerlaw_pairs(30, 90))
+keep = ~(((g_asym.row == 7) & (g_asym.col < 7)) | ((g_asym.row == 12) & (g_asym.col < 12)))
+extra_r, extra_c = np.array([3, 4], dtype=np.int32), np.array([29, 29], dtype=np.int32)
+sel = keep & (g_asym.row != 29) & (g_asym.col != 29)
+g_asym = coo_matrix((np.ones(sel.sum() + 2, dtype=np.int64), (np.concatenate([g_asym.row[sel], extra_r]),
+                                                              np.concatenate([g_asym.col[sel], extra_c]))), shape=(30, 30))
+record_ecc("asymmetric", g_asym, 0)
+
 np.savez_compressed(os.path.join(OUT, "preprocess.npz"), **out)
 print("wrote", os.path.join(OUT, "preprocess.npz"), os.path.getsize(os.path.join(OUT, "preprocess.npz")), "bytes")

@@ -13,7 +13,7 @@ ECC_CASES = ("powerlaw", "powerlaw_eps", "star", "k6", "path_isolated", "empty")
 MOD_CASES = ("a", "b", "c")
 # fixtures added after the last GPU run of round 1: checked against the oracle here, to be added to the GPU list (ECC_CASES,
 # which tests/test_gpu_preprocess.py imports) with the next GPU run
-ECC_CASES_ORACLE_ONLY = ("diagonal",)
+ECC_CASES_ORACLE_ONLY = ("diagonal", "asymmetric")
 
 
 def ppi_of(g, prefix):
@@ -32,6 +32,7 @@ def test_ecc_oracle_equals_reference(g, name):
     e = po.edge_clustering_coefficients(ppi_of(g, f"ecc_{name}"), float(g[f"ecc_{name}_eps"]))
     assert np.array_equal(e.row, g[f"ecc_{name}_row"]) and np.array_equal(e.col, g[f"ecc_{name}_col"])
     assert e.data.dtype == np.float64 and np.array_equal(e.data, g[f"ecc_{name}_data"])
+    assert np.array_equal(np.signbit(e.data), np.signbit(g[f"ecc_{name}_data"]))      # 0 / -1 = -0.0 in the asymmetric case
 
 
 def test_ecc_known_answers(g):
@@ -60,7 +61,7 @@ def brute_force_ecc(adj, epsilon):
         for j in range(i + 1, n):
             if adj[i, j]:
                 den = min(deg[i], deg[j]) - 1
-                v = float(epsilon) if den == 0 else int(np.count_nonzero(adj[i] & adj[j])) / int(den)
+                v = float(epsilon) if den == 0 else np.float64(np.count_nonzero(adj[i] & adj[j])) / np.float64(den)
                 rows += [i, j]
                 cols += [j, i]
                 vals += [v, v]
@@ -76,6 +77,8 @@ def test_ecc_oracle_equals_dense_definition(seed):
     adj = (adj | adj.T).astype(np.int64)
     if seed % 2:
         adj[np.arange(0, n, 3), np.arange(0, n, 3)] = 1          # some self-interactions
+    if seed >= 3:
+        adj[rng.random((n, n)) < 0.05] = 0                        # a few one-directional entries (rewired networks)
     r, c = np.nonzero(adj)
     perm = rng.permutation(r.size)
     m = coo_matrix((np.ones(r.size, dtype=np.int64), (r[perm].astype(np.int32), c[perm].astype(np.int32))), shape=(n, n))
