@@ -214,6 +214,7 @@ class GNN32EngineFunction(torch.autograd.Function):
     """GNN32 forward / backward through the two whole-network C calls (plagnn_gnn32_forward / _backward)."""
 
     @staticmethod
+    @ops.on_tensor_device
     def forward(ctx, state, x, *params):
         lib = ops._lib.load()
         xa = ops.aligned(x.detach())
@@ -233,6 +234,7 @@ class GNN32EngineFunction(torch.autograd.Function):
         return prob
 
     @staticmethod
+    @ops.on_tensor_device
     def backward(ctx, dprob):
         lib = ops._lib.load()
         params = ctx.saved_tensors
@@ -386,6 +388,24 @@ class GNN32(nn.Module):
         if self.engine == "c" and not DETERMINISTIC_BACKWARD:
             return GNN32EngineFunction.apply(self._engine_state(g), in_feat, *self.hot_path_parameters())
         return GNN32Function.apply(g, in_feat, *self.hot_path_parameters())
+
+    def discrete_decisions(self, g, in_feat):
+        """The pieces of the piecewise-linear network this forward pass selects: per conv layer the arg-max source ids of
+        the max-pool (DGL's argU), the sign of the pooled value (relu'), and the leaky_relu branch of conv1..3 / liner1
+        outputs.  Same kernels in the same order as forward(); host tensors.  Parity tests hand these to the oracle so
+        that gradients are compared on the same piece (tests/test_gpu_model.py)."""
+        dec = {"arg": [], "pool_pos": [], "act": []}
+        h = in_feat
+        with torch.no_grad():
+            for c in (self.conv1, self.conv2, self.conv3):
+                h, (_, neigh, arg) = sage_pool_forward(g, h, c.fc_pool.weight, c.fc_pool.bias, c.fc_self.weight,
+                                                       c.fc_neigh.weight, c.bias, ACT_LEAKY)
+                dec["arg"].append(arg.cpu())
+                dec["pool_pos"].append((neigh > 0).cpu())
+                dec["act"].append((h > 0).cpu())
+            h4, _ = linear_forward(h, self.liner1.weight, self.liner1.bias, ACT_LEAKY)
+            dec["act"].append((h4 > 0).cpu())
+        return dec
 
     def forward_layerwise(self, g, in_feat):
         """Same arithmetic through the per-layer Functions (used by tests to cross-check the fused path)."""

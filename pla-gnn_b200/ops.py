@@ -6,6 +6,7 @@ libplagnn.so on the current CUDA stream.  All functions raise on failure (no fal
 from __future__ import annotations
 
 import ctypes
+import functools
 import math
 
 import torch
@@ -80,6 +81,44 @@ def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _device_of(obj, depth: int = 0):
+    """CUDA device of the first tensor found in obj (tensor, object with .indptr, or a short list / tuple of those)."""
+    if isinstance(obj, torch.Tensor):
+        return obj.device if obj.is_cuda else None
+    ip = getattr(obj, "indptr", None)
+    if isinstance(ip, torch.Tensor):
+        return ip.device if ip.is_cuda else None
+    if depth < 2 and isinstance(obj, (list, tuple)):
+        for o in obj:
+            d = _device_of(o, depth + 1)
+            if d is not None:
+                return d
+    return None
+
+
+def on_tensor_device(fn):
+    """Runs the wrapped entry point with the CUDA device of its tensor arguments current, so that the stream handed to the
+    library, the kernels' context and the cached TMA tensor maps belong to the GPU that holds the data — the reference's
+    `-d cuda:1` (code/main_normal.py:30,66: g.to(device), model.to(device)) while device 0 is current."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in args:
+            dev = _device_of(a)
+            if dev is not None:
+                break
+        if dev is None:
+            for a in kwargs.values():
+                dev = _device_of(a)
+                if dev is not None:
+                    break
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 def _p(t: torch.Tensor | None) -> ctypes.c_void_p | None:
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -110,6 +149,7 @@ def _require_cuda_f32(*ts: torch.Tensor) -> None:
             raise _lib.PlagnnError(f"expected float32, got {t.dtype}")
 
 
+@on_tensor_device
 def aligned(x: torch.Tensor) -> torch.Tensor:
     """Returns x if its rows are 16-byte aligned, else a padded copy made by plagnn_pad_copy."""
     _require_cuda_f32(x)
@@ -123,6 +163,7 @@ def aligned(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@on_tensor_device
 def transpose(x: torch.Tensor) -> torch.Tensor:
     """x^T as a new row-aligned matrix (used for the K-contiguous weight operand of the input-gradient GEMMs)."""
     _require_cuda_f32(x)
@@ -153,6 +194,7 @@ def workspace(nbytes: int, device, tag: str = "ws") -> torch.Tensor | None:
 # ------------------------------------------------------------------------------------------------
 # K3 dense contraction
 # ------------------------------------------------------------------------------------------------
+@on_tensor_device
 def gemm(m: int, n: int, pairs, bias=None, act=ACT_NONE, gate=None, gate_act=ACT_NONE, out=None,
          slope: float = LEAKY_SLOPE, backend: int = GEMM_AUTO) -> torch.Tensor:
     """C[m x n] = epilogue(sum_p op(A_p) op(B_p)).  pairs: list of (a, a_trans, b, b_trans, k)."""
@@ -177,6 +219,7 @@ def gemm(m: int, n: int, pairs, bias=None, act=ACT_NONE, gate=None, gate_act=ACT
     return out
 
 
+@on_tensor_device
 def gemm_wgrad_bias(dz: torch.Tensor, x: torch.Tensor, dw: torch.Tensor | None = None, db: torch.Tensor | None = None):
     """dW[m x n] = dz^T x and db[m] = dz.sum(0) in one pass (dz: [k x m], x: [k x n], rows 16-byte aligned)."""
     lib = _lib.load()
@@ -196,6 +239,7 @@ def gemm_wgrad_bias(dz: torch.Tensor, x: torch.Tensor, dw: torch.Tensor | None =
     return dw, db
 
 
+@on_tensor_device
 def colsum(x: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     _require_cuda_f32(x)
@@ -207,6 +251,7 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@on_tensor_device
 def act_backward(dy: torch.Tensor, y: torch.Tensor | None, act: int, slope: float = LEAKY_SLOPE,
                  row_scale: torch.Tensor | None = None) -> torch.Tensor:
     """dz = dy * act'(y) * row_scale[:, None]   (y / row_scale optional)."""
@@ -227,6 +272,7 @@ def row_scale(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # K2 aggregation
 # ------------------------------------------------------------------------------------------------
+@on_tensor_device
 def spmm_max_fwd(csc, x: torch.Tensor):
     """csc: graph.Csr (in-edge structure + plan).  Returns (out, arg) with x's row pitch."""
     lib = _lib.load()
@@ -242,6 +288,7 @@ def spmm_max_fwd(csc, x: torch.Tensor):
     return out, arg
 
 
+@on_tensor_device
 def spmm_max_bwd(dz: torch.Tensor, arg: torch.Tensor, z: torch.Tensor | None, n_src: int) -> torch.Tensor:
     """dx[arg[v,f], f] += dz[v,f] (* (z>0) when z is given)."""
     lib = _lib.load()
@@ -255,6 +302,7 @@ def spmm_max_bwd(dz: torch.Tensor, arg: torch.Tensor, z: torch.Tensor | None, n_
     return dx
 
 
+@on_tensor_device
 def spmm_max_bwd_gather(csr, dz: torch.Tensor, arg: torch.Tensor, z: torch.Tensor | None) -> torch.Tensor:
     """Ordered twin of spmm_max_bwd over the out-edge structure `csr` (graph must have no duplicate edges)."""
     lib = _lib.load()
@@ -271,6 +319,7 @@ def spmm_max_bwd_gather(csr, dz: torch.Tensor, arg: torch.Tensor, z: torch.Tenso
     return dx
 
 
+@on_tensor_device
 def spmm_sum(csx, x: torch.Tensor, w=None, scale=None, bias=None, act=ACT_NONE, dropout_p: float = 0.0,
              dropout_seed: int = 0, slope: float = LEAKY_SLOPE) -> torch.Tensor:
     lib = _lib.load()
@@ -287,6 +336,7 @@ def spmm_sum(csx, x: torch.Tensor, w=None, scale=None, bias=None, act=ACT_NONE, 
     return out
 
 
+@on_tensor_device
 def plan_range(csx, row_begin: int, row_end: int):
     """Host handle (ctypes int64[4]) for aggregating only rows [row_begin, row_end) of `csx` (set-up call)."""
     rng = (ctypes.c_int64 * 4)()
@@ -294,6 +344,7 @@ def plan_range(csx, row_begin: int, row_end: int):
     return rng
 
 
+@on_tensor_device
 def spmm_sum_rows(csx, rng, x: torch.Tensor, out: torch.Tensor, w=None, scale=None, bias=None, act=ACT_NONE,
                   slope: float = LEAKY_SLOPE) -> torch.Tensor:
     """Row-range aggregation into the rows of a preallocated `out` (other rows untouched)."""
@@ -307,6 +358,7 @@ def spmm_sum_rows(csx, rng, x: torch.Tensor, out: torch.Tensor, w=None, scale=No
     return out
 
 
+@on_tensor_device
 def dropout_scale_(grad: torch.Tensor, p: float, seed: int) -> torch.Tensor:
     check(_lib.load().plagnn_dropout_scale(_p(grad), grad.shape[0], grad.shape[1], grad.stride(0), float(p), int(seed),
                                            _stream()), "dropout_scale")
@@ -316,6 +368,7 @@ def dropout_scale_(grad: torch.Tensor, p: float, seed: int) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # K4 loss / optimiser / label decision
 # ------------------------------------------------------------------------------------------------
+@on_tensor_device
 def bce_weighted(prob: torch.Tensor, target: torch.Tensor, index: torch.Tensor | None, cw: torch.Tensor,
                  cwp1: torch.Tensor, want_grad: bool = True, grad_scale: float = 1.0):
     """Returns (loss[1], dprob[N x C] or None).  index: int64 device tensor of selected rows or None."""
@@ -334,6 +387,7 @@ def bce_weighted(prob: torch.Tensor, target: torch.Tensor, index: torch.Tensor |
     return loss, dprob
 
 
+@on_tensor_device
 def loc_correction(prob: torch.Tensor, alpha: float) -> torch.Tensor:
     lib = _lib.load()
     _require_cuda_f32(prob)
@@ -346,6 +400,7 @@ def loc_correction(prob: torch.Tensor, alpha: float) -> torch.Tensor:
     return pred
 
 
+@on_tensor_device
 def adam_multi(table: torch.Tensor, count: int, max_numel: int, lr: float, beta1: float, beta2: float, eps: float,
                step: int) -> None:
     bc1 = 1.0 - beta1 ** step

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 from ._lib import check
-from .ops import _p, _stream, workspace
+from .ops import _p, _stream, on_tensor_device, workspace
 
 
 def _as_matrix(x: torch.Tensor) -> torch.Tensor:
@@ -24,6 +24,7 @@ def _as_matrix(x: torch.Tensor) -> torch.Tensor:
     return x if x.stride(1) == 1 else x.contiguous()
 
 
+@on_tensor_device
 def scaling(logit_mat: torch.Tensor) -> torch.Tensor:
     """code/main.py:15-29 — column min-max, then rows divided by their sum, in the input's precision."""
     x = _as_matrix(logit_mat.detach())
@@ -37,6 +38,7 @@ def scaling(logit_mat: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@on_tensor_device
 def mat_merge(mats) -> torch.Tensor:
     """code/main.py:32-48 — mean over the runs of scaling(mat); float64 accumulator like ``np.zeros((N, 12))``."""
     mats = [_as_matrix(m.detach()) for m in mats]
@@ -54,6 +56,7 @@ def mat_merge(mats) -> torch.Tensor:
     return acc
 
 
+@on_tensor_device
 def alteration_rank(normal_mat: torch.Tensor, inter_mat: torch.Tensor):
     """code/main.py:80-84 — returns (normal, inter, diff, order): the two scaled matrices, the relative change
     ``(inter - normal) / normal`` and the flat indices of its entries from the largest to the smallest score

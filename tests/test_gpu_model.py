@@ -39,6 +39,31 @@ def epoch_cuda(model, opt, g, features, labels, train_index, i_weight):
     return logits, loss
 
 
+def assert_gradients_match_on_shared_decisions(m, g, mo, go, idx, w, tag):
+    """Gradient bar of the north_star (1e-5 relative, every tensor) with the oracle evaluated on the CUDA path's own
+    discrete decisions; every decision that differs from the oracle's own must be a near-tie in the oracle's numbers and
+    every arg id a real in-edge (oracle.forward_with_decisions)."""
+    dec = m.discrete_decisions(g, g.ndata["feat"])
+    mo.zero_grad()
+    lo, rep = orc.forward_with_decisions(mo, go, go.ndata["feat"], dec)
+    orc.multi_loss(lo[idx], go.ndata["loc"][idx], w).backward()
+    lines = [f"{tag}: decisions differing from the fp32 oracle's own: arg {rep['arg_diff']} (gap {rep['arg_gap']:.1e}), "
+             f"pool sign {rep['pool_diff']} ({rep['pool_gap']:.1e}), leaky branch {rep['act_diff']} ({rep['act_gap']:.1e}) "
+             f"of {rep['entries']} pooled entries; arg ids that are not in-edges: {rep['bad_edges']}"]
+    bad = []
+    for (name, pc), po in zip(m.named_parameters(), mo.parameters()):
+        e = rel_err(pc.grad, po.grad)
+        lines.append(f"{name:24s} cuda-vs-oracle32 (shared decisions) {e:.2e}")
+        if not e <= REL_TOL:
+            bad.append((name, e))
+    print("\n".join(lines))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/grad_parity_shared_{tag}.txt", "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    assert rep["near_ties_only"], rep
+    assert not bad, f"gradient parity (shared decisions) failed: {bad}"
+
+
 def test_same_init_as_oracle_given_the_seed():
     torch.manual_seed(5)
     a = P.GNN32(43, 400, 300, 200, 100, 12)
@@ -67,26 +92,18 @@ def test_forward_backward_parity(cuda, backend, monkeypatch):
     loss_c.backward()
     assert rel_err(lc, lo) < REL_TOL, "logits"
     assert abs(loss_c.item() - loss_o.item()) <= REL_TOL * abs(loss_o.item()), "loss"
-    # Gradients: two fp32 implementations of an ill-conditioned sum (e.g. a bias gradient = a column sum with
-    # heavy cancellation) can differ from each other by more than 1e-5 while both are equally close to the exact
-    # result.  The float64 oracle arbitrates: the CUDA gradient must be within 1e-5 of the fp32 oracle, or at
-    # least as close to the float64 result as the fp32 oracle itself is (factor 3 of slack).
-    m64 = orc.GNN32Ref(go.ndata["feat"].shape[1], 400, 300, 200, 100, 12, use_c=False).double()
-    m64.load_state_dict({k: v.double() for k, v in mo.state_dict().items()})
-    l64 = m64(go, go.ndata["feat"].double())
-    orc.multi_loss(l64[idx], go.ndata["loc"][idx].double(), w).backward()
-    report, bad = [], []
-    for (name, pc), (_, po), (_, p64) in zip(m.named_parameters(), mo.named_parameters(), m64.named_parameters()):
-        e_co, e_c64, e_o64 = rel_err(pc.grad, po.grad), rel_err(pc.grad, p64.grad), rel_err(po.grad, p64.grad)
-        report.append(f"{name:24s} cuda-vs-oracle32 {e_co:.2e}  cuda-vs-f64 {e_c64:.2e}  oracle32-vs-f64 {e_o64:.2e}")
-        if not (e_co < REL_TOL or e_c64 <= max(REL_TOL, 3 * e_o64)):
-            bad.append(name)
-    print("\n".join(report))
+    # Gradients, 1e-5 on every tensor.  GNN32 is piecewise linear and max-pool / leaky_relu are discontinuous in their
+    # choice of piece: two fp32 pipelines that agree to 2e-6 on every activation still resolve a handful of near-ties
+    # (relative gap < 1e-6) differently, and ONE re-routed entry moves a weight gradient by ~1e-4 (CPU-side proof with
+    # the fp32 and float64 oracles: tests/test_oracle_consistency.py).  So the oracle's backward runs on the CUDA path's
+    # decisions, each checked to be a near-tie in the oracle's own numbers; what is compared is then the arithmetic.
+    plain = [f"{name:24s} cuda-vs-oracle32 (own decisions) {rel_err(pc.grad, po.grad):.2e}"
+             for (name, pc), po in zip(m.named_parameters(), mo.parameters())]
     os.makedirs("gpurun_out", exist_ok=True)
     with open(f"gpurun_out/grad_parity_{backend}.txt", "w") as fh:
-        fh.write(f"logits rel err {rel_err(lc, lo):.3e}  loss rel err {abs(loss_c.item() - loss_o.item()) / abs(loss_o.item()):.3e}"
-                 f"  logits cuda-vs-f64 {rel_err(lc, l64):.3e}  oracle32-vs-f64 {rel_err(lo, l64):.3e}\n" + "\n".join(report) + "\n")
-    assert not bad, f"gradient parity failed for {bad}"
+        fh.write(f"logits rel err {rel_err(lc, lo):.3e}  loss rel err {abs(loss_c.item() - loss_o.item()) / abs(loss_o.item()):.3e}\n"
+                 + "\n".join(plain) + "\n")
+    assert_gradients_match_on_shared_decisions(m, g, mo, go, idx, w, backend)
     pred_c = P.protein_loc_correction(lc, 0.1).cpu()
     pred_o = orc.protein_loc_correction(lo.detach(), 0.1)
     assert (pred_c != pred_o).float().mean().item() < 1e-4          # identical labels up to fp32 near-ties
@@ -240,10 +257,7 @@ def test_concurrent_models_on_streams_match_sequential(cuda):
 def test_full_size_ppi_epoch_parity(cuda):
     """One epoch at BASELINE.json's full size (N = 24 041, E = 1.4 M + self-loops, F = 503) against the oracle: logits and
     loss within 1e-5 relative, predicted localisation labels identical up to fp32 near-ties (<= 1e-4 of the entries).
-    Gradients are arbitrated by the float64 oracle: at this size the fp32 oracle itself is 3e-5 .. 3e-3 away from float64
-    (sums over 24 041 rows cancel heavily), so the bar is: at most 2e-5 from float64, or closer to float64 than 1.5 x the
-    fp32 oracle is (measured: 17 of 19 tensors are closer than the fp32 oracle; liner2.weight is at 1.1e-5, the forward
-    difference of 3e-6 amplified by the cancellation; see DESIGN.md section 5, numerics)."""
+    All 19 gradient tensors within 1e-5 of the fp32 oracle evaluated on the CUDA path's discrete decisions (near-ties only)."""
     import copy
     prob = synth.ppi_problem(state="inter")
     n = prob.num_nodes
@@ -270,9 +284,31 @@ def test_full_size_ppi_epoch_parity(cuda):
     pred_c = P.protein_loc_correction(lc, 0.1).cpu()
     pred_o = orc.protein_loc_correction(lo.detach(), 0.1)
     assert (pred_c != pred_o).double().mean().item() <= 1e-4
-    loss_o.backward()
-    loss_d.backward()
     loss_c.backward()
-    for (name, pc), po, pd in zip(m.named_parameters(), mo.parameters(), md.parameters()):
-        e_gpu, e_f32 = rel_err(pc.grad, pd.grad), rel_err(po.grad, pd.grad)
-        assert e_gpu <= max(2e-5, 1.5 * e_f32), (name, e_gpu, e_f32)
+    assert_gradients_match_on_shared_decisions(m, g, mo, go, idx, w, "full_size")
+
+
+def test_model_on_second_gpu_while_device_zero_is_current(cuda):
+    """The reference's `-d cuda:1` (code/main_normal.py:30,66): graph and model moved to GPU 1 while the process's current
+    device stays 0.  Every wrapper must run its kernels (and take its stream) on the device that holds the tensors."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    dev1 = torch.device("cuda:1")
+    assert torch.cuda.current_device() == 0
+    prob, g0, go, m0, mo = build_pair(cuda, n=800, e=16000, dims=(3, 20, 20))
+    ids = list(range(prob.num_nodes))
+    g1 = P.create_graph(prob.scipy_ppi(), prob.ecc, prob.gcn, prob.scipy_loc(), prob.expr, ids).to(dev1)
+    import copy
+    m1 = copy.deepcopy(m0).to(dev1)
+    w = orc.weight_cal(prob.loc)
+    idx = [int(i) for i in prob.labelled[::2]]
+    outs = []
+    for g, m in ((g0, m0), (g1, m1)):
+        opt = P.FusedAdam(m.parameters(), lr=5e-5)
+        lc, loss = epoch_cuda(m, opt, g, g.ndata["feat"], g.ndata["loc"], idx, w)
+        pred = P.protein_loc_correction(lc, 0.1)
+        outs.append((lc.detach().cpu(), loss.item(), pred.cpu(), [p.grad.cpu() for p in m.parameters()]))
+    assert torch.cuda.current_device() == 0
+    assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1] and torch.equal(outs[0][2], outs[1][2])
+    for a, b in zip(outs[0][3], outs[1][3]):
+        assert rel_err(a, b) < 1e-5                     # the scatter's fp32 reductions are unordered
