@@ -52,6 +52,10 @@ def parse():
     ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--concurrent-models", type=int, default=4)
+    ap.add_argument("--no-partitioned", action="store_true", help="skip the configs[3] partitioned block")
+    ap.add_argument("--partitioned-steps", type=int, default=10)
+    ap.add_argument("--partitioned-nodes", type=int, default=1_000_000)
+    ap.add_argument("--partitioned-edges", type=int, default=100_000_000)
     return ap.parse_args()
 
 
@@ -387,6 +391,14 @@ def run_ours(args):
     ops.profile_start()
     ms_profiled = timed(epoch, args.steps)
     prof = ops.profile_stop()
+    # ---- BASELINE configs[3]: the partitioned synthetic graph on the same N GPUs (reported beside `value`) ---------------
+    partitioned = None
+    if not args.no_partitioned:
+        from plagnn_b200 import dist_bench
+        torch.cuda.empty_cache()
+        partitioned = dist_bench.run_partitioned(args.partitioned_nodes, args.partitioned_edges, args.feat, args.partitioned_steps,
+                                                 3, rank, world, dev, modes=("rows",) if world == 1 else ("rows", "cols"))
+        torch.cuda.empty_cache()
     # ---- device-resident timed region (value): the LAST leg of the process, W warm-up steps right before it --------------
     # (the legs above — end-to-end, concurrent models, per-kernel breakdown — are timed regions of their own, each with
     # its own warm-up; running them first also means the clocks are up when this one starts)
@@ -438,13 +450,14 @@ def run_ours(args):
                    "l2": "no explicit flush: one step touches >1 GB of distinct activations/gradients (> 126 MB L2); the "
                          "aggregation input is produced by the preceding GEMM, as in the real loop",
                    "legs": "in process order: end-to-end (3 warm-up + K), concurrent models (3 + K), per-kernel breakdown "
-                           "(3 + K), then W warm-up + K timed steps = `value`",
+                           "(3 + K), partitioned configs[3] block, then W warm-up + K timed steps = `value`",
                    "train_rows": int(len(train_index)), "lr": LR},
         "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": int(feat_h.numel() * 4 + loc_h.numel() * 4 + idx_h.numel() * 8),
                 "d2h_bytes_per_step": int(4 + logits_h.numel() * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "concurrent_models": conc,
+        "partitioned": partitioned,
         "clocks": clocks,
         "roofline": {"kernel": f"spmm_max_fwd F={f_in} (layer-1 aggregation)", "bound": "hbm",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

@@ -121,7 +121,8 @@ int plagnn_spmm_max_bwd_gather(const int32_t* out_indptr, const int32_t* out_ind
 
 /* sum family (copy_u / u_mul_e + sum, optional per-destination scale = mean / right norm):
  *   out[v,:] = act( scale[v] * sum_{e in in(v)} w[eids[e]] * x[src(e),:] + bias ) [* dropout mask]
- * eids/w/scale/bias may be NULL.  dropout_p == 0 disables dropout (the reference never applies
+ * eids/w/scale/bias may be NULL; w without eids is read in CSR order (w[e]: weights permuted once at set-up, no
+ * indirection in the kernel).  dropout_p == 0 disables dropout (the reference never applies
  * any: code/model.py:11 accepts and ignores `dropout`).  The same call on the out-edge CSR is the
  * exact transpose used by backward. */
 int plagnn_spmm_sum(const int32_t* indptr, const int32_t* indices, const int32_t* eids, const void* plan,
@@ -322,6 +323,43 @@ int plagnn_rewire(const double* normal, int64_t ldn, const double* inter, int64_
                   plagnn_stream_t stream);
 int plagnn_bitmask_to_coo(const uint32_t* mask, int64_t words_per_row, int64_t num_nodes, const int32_t* rowptr,
                           int32_t* out_row, int32_t* out_col, plagnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Exchange steps of the partitioned aggregation (BASELINE.json configs[3]).
+ * The reference is single-process (code/main_normal.py:30,66: one `-d` device), so there is no reference
+ * call site to replace: these wrap NCCL for the two ways the scaled synthetic graph is split over GPUs.
+ *   row partition     : plagnn_nccl_allgather_rows (forward: projected rows of every rank),
+ *                       plagnn_nccl_reducescatter_rows (backward: partial source gradients);
+ *   feature partition : plagnn_cols_pack -> plagnn_nccl_alltoall_blocks -> (aggregate all rows x my columns)
+ *                       -> plagnn_nccl_alltoall_blocks -> plagnn_cols_unpack;
+ *   both              : plagnn_nccl_allreduce of the weight gradients, once per step.
+ * `comm` is an ncclComm_t (the caller's own, or one made by plagnn_nccl_comm_init from an id that rank 0 obtained with
+ * plagnn_nccl_get_unique_id and distributed by any means).  NCCL is resolved at run time (dlopen of the libnccl.so.2 already
+ * in the process, else PLAGNN_NCCL_LIB); without it these return PLAGNN_ERR_UNSUPPORTED.  Calls enqueue on `stream`.
+ * Matrices are exchanged with their row pitch (count = rows * pitch floats), so padded buffers go as they are.
+ * ---------------------------------------------------------------------------------------- */
+typedef void* plagnn_nccl_comm_t; /* an ncclComm_t */
+#define PLAGNN_NCCL_UNIQUE_ID_BYTES 128
+int plagnn_nccl_available(void);
+int plagnn_nccl_get_unique_id(void* id_out /* host, 128 bytes */);
+int plagnn_nccl_comm_init(const void* id /* host, 128 bytes */, int rank, int world,
+                          int max_ctas /* > 0: cap NCCL's CTAs (ncclConfig_t.maxCTAs) so the exchange leaves the SMs to the aggregation */,
+                          plagnn_nccl_comm_t* comm_out);
+int plagnn_nccl_comm_destroy(plagnn_nccl_comm_t comm);
+/* recv[world * rows x pitch] = concatenation over ranks of send[rows x pitch] */
+int plagnn_nccl_allgather_rows(const float* send, float* recv, int64_t rows, int64_t pitch, plagnn_nccl_comm_t comm,
+                               plagnn_stream_t stream);
+/* recv[rows x pitch] = sum over ranks of their send[rank * rows ... (rank + 1) * rows) */
+int plagnn_nccl_reducescatter_rows(const float* send, float* recv, int64_t rows, int64_t pitch, plagnn_nccl_comm_t comm,
+                                   plagnn_stream_t stream);
+int plagnn_nccl_allreduce(float* buf /* in place */, int64_t count, plagnn_nccl_comm_t comm, plagnn_stream_t stream);
+/* block q of send goes to rank q, block q of recv comes from rank q (grouped send / recv) */
+int plagnn_nccl_alltoall_blocks(const float* send, float* recv, int64_t block_elems, int world, plagnn_nccl_comm_t comm,
+                                plagnn_stream_t stream);
+/* x[rows x feat] (pitch ldx) <-> blocks[world][rows][feat / world] (block q = columns [q * feat/world, (q+1) * feat/world));
+ * feat % (4 * world) == 0 */
+int plagnn_cols_pack(const float* x, int64_t ldx, int64_t rows, int64_t feat, int world, float* blocks, plagnn_stream_t stream);
+int plagnn_cols_unpack(const float* blocks, int64_t rows, int64_t feat, int world, float* x, int64_t ldx, plagnn_stream_t stream);
 
 /* small utilities used by the host layer */
 int plagnn_pad_copy(const float* src, int64_t rows, int64_t cols, int64_t lds, float* dst, int64_t ldd,

@@ -110,6 +110,16 @@ PROTOTYPES = {
     "plagnn_gnn32_backward": (c_int, [POINTER(Gnn32Shape), c_void_p, c_int64, POINTER(c_void_p), c_void_p, c_size_t,
                                       c_void_p, c_int64, c_void_p, c_int64, POINTER(c_void_p), c_void_p, c_int64,
                                       c_void_p]),
+    "plagnn_nccl_available": (c_int, []),
+    "plagnn_nccl_get_unique_id": (c_int, [c_void_p]),
+    "plagnn_nccl_comm_init": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "plagnn_nccl_comm_destroy": (c_int, [c_void_p]),
+    "plagnn_nccl_allgather_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "plagnn_nccl_reducescatter_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "plagnn_nccl_allreduce": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "plagnn_nccl_alltoall_blocks": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "plagnn_cols_pack": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "plagnn_cols_unpack": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "plagnn_pad_copy": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "plagnn_transpose": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
 }

@@ -17,11 +17,28 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "libplagnn.so")
 OBJ_DIR = os.path.join(HERE, "_obj")
-SOURCES = ["graph_build.cu", "spmm.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tma.cu", "gemm_narrow.cu", "gemm_api.cu", "elementwise.cu", "scoring.cu", "preprocess.cu", "gnn32_engine.cu"]
+SOURCES = ["graph_build.cu", "spmm.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tma.cu", "gemm_narrow.cu", "gemm_api.cu", "elementwise.cu", "scoring.cu", "preprocess.cu", "gnn32_engine.cu", "dist_comm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xcompiler", "-Wall",
          "-I", os.path.join(ROOT, "include")]
+
+
+def _nccl_include() -> str:
+    """nccl.h of the NCCL that PyTorch bundles (types only: the library is resolved with dlopen at run time)."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations or []) if spec else []:
+            inc = os.path.join(loc, "include")
+            if os.path.exists(os.path.join(inc, "nccl.h")):
+                return inc
+    except Exception:
+        pass
+    return "/usr/include"
+
+
+FLAGS += ["-I", _nccl_include()]
 DIAG = "--diag" in sys.argv or os.environ.get("PLAGNN_TMA_DIAG") == "1"
 if DIAG:     # diagnostics build of the TMA GEMM (tools/gemm_trace.py, PLAGNN_TMA_DEBUG) -> libplagnn_diag.so, own objects
     FLAGS += ["-DPLAGNN_TMA_DIAG=1"]
@@ -60,7 +77,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {cmd[-3]}")
     if force or jobs or _stale(OUT, objs):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -1,0 +1,240 @@
+// Exchange steps of the partitioned aggregation (SURVEY.md 8b "nccl_* wrappers taking an ncclComm_t", 8e).
+//
+// The reference has no distributed code (single process, one `-d` device: code/main_normal.py:30,66); these entry points
+// exist for BASELINE.json configs[3] only (1 M nodes / 100 M weighted edges across 2 / 4 / 8 GPUs):
+//   * row partition     : all-gather of projected rows (forward), reduce-scatter of source gradients (backward);
+//   * feature partition : all-to-all between "my rows x all columns" and "all rows x my columns" around the aggregation,
+//                         with the pack / unpack kernels below doing the column-block transposition on the device;
+//   * both              : one all-reduce of the weight gradients per step.
+// NCCL is resolved at run time from the libnccl the process already has (the one PyTorch loaded), so libplagnn.so carries
+// no link-time dependency on it and still loads on a machine without NCCL (the ABI tests run there).
+#include "common.cuh"
+#include <dlfcn.h>
+#include <nccl.h>
+#include <cstdlib>
+#include <cstring>
+
+namespace plagnn {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+static NcclApi& nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        const char* env = getenv("PLAGNN_NCCL_LIB");
+        // the copy already mapped into the process first (two NCCL versions in one process do not mix)
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h && env && env[0]) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return a;
+        a.handle = h;
+#define PLAGNN_NCCL_SYM(field, name) a.field = reinterpret_cast<decltype(a.field)>(dlsym(h, name))
+        PLAGNN_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+        PLAGNN_NCCL_SYM(CommInitRankConfig, "ncclCommInitRankConfig");
+        PLAGNN_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+        PLAGNN_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+        PLAGNN_NCCL_SYM(AllGather, "ncclAllGather");
+        PLAGNN_NCCL_SYM(ReduceScatter, "ncclReduceScatter");
+        PLAGNN_NCCL_SYM(AllReduce, "ncclAllReduce");
+        PLAGNN_NCCL_SYM(Send, "ncclSend");
+        PLAGNN_NCCL_SYM(Recv, "ncclRecv");
+        PLAGNN_NCCL_SYM(GroupStart, "ncclGroupStart");
+        PLAGNN_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+        PLAGNN_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef PLAGNN_NCCL_SYM
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.ReduceScatter && a.AllReduce && a.Send &&
+               a.Recv && a.GroupStart && a.GroupEnd;
+        return a;
+    }();
+    return api;
+}
+
+static int nccl_fail(const char* who, ncclResult_t r) {
+    NcclApi& a = nccl_api();
+    set_error("%s: NCCL error %d (%s)", who, (int)r, a.GetErrorString ? a.GetErrorString(r) : "?");
+    return PLAGNN_ERR_CUDA;
+}
+
+#define PLAGNN_NCCL_TRY(who, expr)                        \
+    do {                                                  \
+        ncclResult_t _r = (expr);                         \
+        if (_r != ncclSuccess) return nccl_fail(who, _r); \
+    } while (0)
+
+static int need_nccl(const char* who) {
+    if (!nccl_api().ok) return fail(PLAGNN_ERR_UNSUPPORTED, who, "libnccl.so.2 could not be resolved (set PLAGNN_NCCL_LIB)");
+    return PLAGNN_OK;
+}
+
+// x[rows x feat] (row pitch ldx) -> out[world][rows][fc], fc = feat / world: block q holds columns [q*fc, (q+1)*fc).
+// One float4 per thread, consecutive threads walk a row of the SOURCE (coalesced reads; writes are fc*4-byte runs).
+__global__ void __launch_bounds__(256) cols_pack_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int feat, int fc,
+                                                        float* __restrict__ out) {
+    pdl_enter();
+    const int f4 = feat >> 2, fc4 = fc >> 2;
+    const int64_t total = rows * f4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / f4;
+        const int c4 = (int)(i - r * f4);
+        const int q = c4 / fc4, j4 = c4 - q * fc4;
+        const float4 v = ldg_f4(x + r * ldx + 4 * c4);
+        *reinterpret_cast<float4*>(out + ((int64_t)q * rows + r) * fc + 4 * j4) = v;
+    }
+}
+
+// in[world][rows][fc] -> x[rows x feat] (row pitch ldx): consecutive threads walk a row of the DESTINATION
+__global__ void __launch_bounds__(256) cols_unpack_kernel(const float* __restrict__ in, int64_t rows, int feat, int fc,
+                                                          float* __restrict__ x, int64_t ldx) {
+    pdl_enter();
+    const int f4 = feat >> 2, fc4 = fc >> 2;
+    const int64_t total = rows * f4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / f4;
+        const int c4 = (int)(i - r * f4);
+        const int q = c4 / fc4, j4 = c4 - q * fc4;
+        const float4 v = ldg_f4(in + ((int64_t)q * rows + r) * fc + 4 * j4);
+        *reinterpret_cast<float4*>(x + r * ldx + 4 * c4) = v;
+    }
+}
+
+static int check_cols(const char* who, const void* a, const void* b, int64_t ld, int64_t rows, int64_t feat, int world) {
+    if (!a || !b || rows <= 0 || feat <= 0 || world <= 0) return fail(PLAGNN_ERR_ARG, who, "bad arguments");
+    if (feat % (4 * (int64_t)world)) return fail(PLAGNN_ERR_ARG, who, "feat must be a multiple of 4 * world");
+    if (ld < feat || (ld & 3) || !aligned16(a) || !aligned16(b)) return fail(PLAGNN_ERR_ALIGN, who, "16-byte aligned rows needed");
+    return PLAGNN_OK;
+}
+
+}  // namespace plagnn
+
+using namespace plagnn;
+
+extern "C" {
+
+int plagnn_nccl_available(void) { return nccl_api().ok ? 1 : 0; }
+
+int plagnn_nccl_get_unique_id(void* id_out) {
+    if (!id_out) return fail(PLAGNN_ERR_ARG, "nccl_get_unique_id", "null pointer");
+    int rc = need_nccl("nccl_get_unique_id");
+    if (rc) return rc;
+    ncclUniqueId id;
+    PLAGNN_NCCL_TRY("nccl_get_unique_id", nccl_api().GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == PLAGNN_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    memcpy(id_out, &id, sizeof(id));
+    return PLAGNN_OK;
+}
+
+int plagnn_nccl_comm_init(const void* id, int rank, int world, int max_ctas, plagnn_nccl_comm_t* comm_out) {
+    if (!id || !comm_out || world <= 0 || rank < 0 || rank >= world) return fail(PLAGNN_ERR_ARG, "nccl_comm_init", "bad arguments");
+    int rc = need_nccl("nccl_comm_init");
+    if (rc) return rc;
+    NcclApi& a = nccl_api();
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclComm_t comm = nullptr;
+    if (max_ctas > 0 && a.CommInitRankConfig) {
+        // fewer NCCL CTAs: the exchange runs beside the aggregation, which needs the SMs and the HBM bandwidth more
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.maxCTAs = max_ctas;
+        cfg.minCTAs = 1;
+        PLAGNN_NCCL_TRY("nccl_comm_init", a.CommInitRankConfig(&comm, world, uid, rank, &cfg));
+    } else {
+        PLAGNN_NCCL_TRY("nccl_comm_init", a.CommInitRank(&comm, world, uid, rank));
+    }
+    *comm_out = (plagnn_nccl_comm_t)comm;
+    return PLAGNN_OK;
+}
+
+int plagnn_nccl_comm_destroy(plagnn_nccl_comm_t comm) {
+    if (!comm) return PLAGNN_OK;
+    int rc = need_nccl("nccl_comm_destroy");
+    if (rc) return rc;
+    PLAGNN_NCCL_TRY("nccl_comm_destroy", nccl_api().CommDestroy((ncclComm_t)comm));
+    return PLAGNN_OK;
+}
+
+int plagnn_nccl_allgather_rows(const float* send, float* recv, int64_t rows, int64_t pitch, plagnn_nccl_comm_t comm,
+                               plagnn_stream_t stream) {
+    if (!send || !recv || !comm || rows <= 0 || pitch <= 0) return fail(PLAGNN_ERR_ARG, "nccl_allgather_rows", "bad arguments");
+    int rc = need_nccl("nccl_allgather_rows");
+    if (rc) return rc;
+    ProfileScope prof("nccl_allgather", rows, pitch, 0, stream);
+    PLAGNN_NCCL_TRY("nccl_allgather_rows", nccl_api().AllGather(send, recv, (size_t)(rows * pitch), ncclFloat, (ncclComm_t)comm,
+                                                                (cudaStream_t)stream));
+    return PLAGNN_OK;
+}
+
+int plagnn_nccl_reducescatter_rows(const float* send, float* recv, int64_t rows, int64_t pitch, plagnn_nccl_comm_t comm,
+                                   plagnn_stream_t stream) {
+    if (!send || !recv || !comm || rows <= 0 || pitch <= 0) return fail(PLAGNN_ERR_ARG, "nccl_reducescatter_rows", "bad arguments");
+    int rc = need_nccl("nccl_reducescatter_rows");
+    if (rc) return rc;
+    ProfileScope prof("nccl_reducescatter", rows, pitch, 0, stream);
+    PLAGNN_NCCL_TRY("nccl_reducescatter_rows", nccl_api().ReduceScatter(send, recv, (size_t)(rows * pitch), ncclFloat, ncclSum,
+                                                                        (ncclComm_t)comm, (cudaStream_t)stream));
+    return PLAGNN_OK;
+}
+
+int plagnn_nccl_allreduce(float* buf, int64_t count, plagnn_nccl_comm_t comm, plagnn_stream_t stream) {
+    if (!buf || !comm || count <= 0) return fail(PLAGNN_ERR_ARG, "nccl_allreduce", "bad arguments");
+    int rc = need_nccl("nccl_allreduce");
+    if (rc) return rc;
+    ProfileScope prof("nccl_allreduce", count, 0, 0, stream);
+    PLAGNN_NCCL_TRY("nccl_allreduce", nccl_api().AllReduce(buf, buf, (size_t)count, ncclFloat, ncclSum, (ncclComm_t)comm,
+                                                           (cudaStream_t)stream));
+    return PLAGNN_OK;
+}
+
+int plagnn_nccl_alltoall_blocks(const float* send, float* recv, int64_t block_elems, int world, plagnn_nccl_comm_t comm,
+                                plagnn_stream_t stream) {
+    if (!send || !recv || !comm || block_elems <= 0 || world <= 0) return fail(PLAGNN_ERR_ARG, "nccl_alltoall_blocks", "bad arguments");
+    int rc = need_nccl("nccl_alltoall_blocks");
+    if (rc) return rc;
+    NcclApi& a = nccl_api();
+    ProfileScope prof("nccl_alltoall", block_elems, world, 0, stream);
+    PLAGNN_NCCL_TRY("nccl_alltoall_blocks", a.GroupStart());
+    for (int q = 0; q < world; ++q) {
+        PLAGNN_NCCL_TRY("nccl_alltoall_blocks", a.Send(send + (int64_t)q * block_elems, (size_t)block_elems, ncclFloat, q,
+                                                        (ncclComm_t)comm, (cudaStream_t)stream));
+        PLAGNN_NCCL_TRY("nccl_alltoall_blocks", a.Recv(recv + (int64_t)q * block_elems, (size_t)block_elems, ncclFloat, q,
+                                                        (ncclComm_t)comm, (cudaStream_t)stream));
+    }
+    PLAGNN_NCCL_TRY("nccl_alltoall_blocks", a.GroupEnd());
+    return PLAGNN_OK;
+}
+
+int plagnn_cols_pack(const float* x, int64_t ldx, int64_t rows, int64_t feat, int world, float* out, plagnn_stream_t stream) {
+    int rc = check_cols("cols_pack", x, out, ldx, rows, feat, world);
+    if (rc) return rc;
+    ProfileScope prof("cols_pack", rows, feat, world, stream);
+    const int64_t total = rows * (feat / 4);
+    const int grid = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 16 ? ceil_div(total, 256) : (int64_t)sm_count() * 16);
+    launch_pdl(cols_pack_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, ldx, rows, (int)feat, (int)(feat / world), out);
+    return check_launch("cols_pack");
+}
+
+int plagnn_cols_unpack(const float* in, int64_t rows, int64_t feat, int world, float* x, int64_t ldx, plagnn_stream_t stream) {
+    int rc = check_cols("cols_unpack", in, x, ldx, rows, feat, world);
+    if (rc) return rc;
+    ProfileScope prof("cols_unpack", rows, feat, world, stream);
+    const int64_t total = rows * (feat / 4);
+    const int grid = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 16 ? ceil_div(total, 256) : (int64_t)sm_count() * 16);
+    launch_pdl(cols_unpack_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, in, rows, (int)feat, (int)(feat / world), x, ldx);
+    return check_launch("cols_unpack");
+}
+
+}  // extern "C"

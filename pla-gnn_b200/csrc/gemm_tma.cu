@@ -54,6 +54,13 @@ constexpr int TM_SMEM_BYTES = (TM_RAW_STAGES + TM_LO_STAGES) * TM_RAW_BYTES + 10
 constexpr int TM_EPI_WARPS = 8;
 constexpr int TM_THREADS = (2 + TM_EPI_WARPS) * 32;
 constexpr int TM_MAX_CHAIN = 40;    // k-blocks per TMEM accumulation chain (see gemm_tc.cu: truncating accumulate)
+// Long contractions (the weight gradients: K = number of nodes) get shorter chains.  The tensor core truncates when it adds
+// into the fp32 accumulator, so one chain's error grows with its length (~0.5 ulp per MMA for same-sign data); the gradient
+// sums then cancel and amplify it ~3x.  Measured at K = 24 041 on shared decisions (tests/test_gpu_model.py, full size):
+// chains of 40 k-blocks leave the weight gradients 1.0e-5 .. 1.5e-5 from the fp32 oracle, above the 1e-5 bar.  More, shorter
+// chains also tile better: 47 x 4 tiles on 74 CTA pairs is 3 waves of 20 k-blocks instead of 2 waves of 44.
+constexpr int TM_LONG_K_BLOCKS = 64;   // contractions of at least this many k-blocks (K >= 2048) ...
+constexpr int TM_LONG_CHAIN = 16;      // ... are cut into chains of at most this many
 
 struct alignas(64) TmParams {
     CUtensorMap map[PLAGNN_GEMM_MAX_PAIRS][2];    // [pair][A, B]
@@ -735,10 +742,11 @@ __global__ void __launch_bounds__(256) gemm_tma_reduce_kernel(const __grid_const
     pdl_enter();
     const int64_t total = P.m * P.n;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        float s = 0.f;
+        double sd = 0.0;                       // the partials are few and exact to fp32: fold them without further rounding
         const int64_t r = i / P.n, c = i - r * P.n;
         const float* q = P.partial + r * P.ldp + c;
-        for (int z = 0; z < P.splits; ++z) s += q[(int64_t)z * P.m * P.ldp];
+        for (int z = 0; z < P.splits; ++z) sd += (double)q[(int64_t)z * P.m * P.ldp];
+        const float s = (float)sd;
         if (c == P.ones_col) {                 // P.n counts the extra column; it goes to the bias gradient
             P.ones_out[r] = s;
             continue;
@@ -866,6 +874,12 @@ static int tm_cg() {
     return (e && e[0] == '1') ? 1 : 2;
 }
 
+// PLAGNN_TMA_LONG_CHAIN overrides TM_LONG_CHAIN (accuracy / speed experiments); read once
+static int tm_long_chain() {
+    static const int v = [] { const char* e = getenv("PLAGNN_TMA_LONG_CHAIN"); const int x = e ? atoi(e) : 0; return x >= 4 && x <= 64 ? x : TM_LONG_CHAIN; }();
+    return v;
+}
+
 static int tm_choose_splits(int64_t m, int64_t n, int total_kblocks, int cg) {
     const int64_t tile = 128 * cg;
     const int64_t tiles = ceil_div(m, tile) * ceil_div(n, tile);
@@ -874,10 +888,10 @@ static int tm_choose_splits(int64_t m, int64_t n, int total_kblocks, int cg) {
     if (tiles < units && total_kblocks >= 8) {
         s = units / tiles;
         if (s > total_kblocks / 4) s = total_kblocks / 4;
-        if (s > 64) s = 64;
+        if (s > 128) s = 128;
         if (s < 1) s = 1;
     }
-    const int64_t for_accuracy = ceil_div(total_kblocks, TM_MAX_CHAIN);
+    const int64_t for_accuracy = ceil_div(total_kblocks, total_kblocks >= TM_LONG_K_BLOCKS ? tm_long_chain() : TM_MAX_CHAIN);
     int64_t s0 = s > for_accuracy ? s : for_accuracy;
     if (s0 > 1) {
         int64_t best = s0, best_cost = INT64_MAX;

@@ -1,32 +1,40 @@
-"""1-D row partition of the aggregation across GPUs (BASELINE.json configs[3]).
+"""Partitioned aggregation across GPUs (BASELINE.json configs[3]).
 
 The reference has no distributed code at all (single process, one ``-d`` device string,
 ``code/main_normal.py:30,66``); the PPI graph fits one GPU, so partitioning is used only for the scaled
-synthetic graph.  One process per GPU, ``torch.distributed`` (NCCL over NVLink / NVSwitch) for the exchange:
+synthetic graph.  One process per GPU; the exchange steps go through the C ABI's NCCL wrappers
+(``plagnn_nccl_*``, NVLink / NVSwitch) on the GPU and through ``torch.distributed`` (gloo) in the CPU tests.
 
-* destination rows are split into ``world`` equal contiguous blocks (node ids are shuffled by the generator, so
-  rows and in-edges balance together); rank p owns ``x[rows_p]``, the in-edge CSR of its rows with source ids in
-  the gathered numbering, its loss rows and a full replica of the weights;
-* forward, per layer:  t_p = h_p W^T (local GEMM)  ->  all-gather t  ->  out_p = act(scale * A_p t + b) (local SpMM);
-* backward, per layer: dt = A_p^T (scale * dz_p) over ALL source rows (local transposed SpMM)  ->  reduce-scatter
-  ->  dt_p;  dW = dt_p^T h_p  ->  one all-reduce per step with the other weight gradients.
+Two ways to split the aggregation, two reducers each (weighted sum = the north_star's ``u_mul_e`` + ``sum`` with right
+normalisation; max = the reference's SAGEConv 'pool'):
 
-Overlap.  Every rank's block is cut into ``chunks`` row chunks and gathered matrices are laid out CHUNK-MAJOR
-(gathered row = chunk * world * cr + rank * cr + row_in_chunk), so the all-gather of local chunk c fills one
-contiguous slab and the reduce-scatter of slab c yields local chunk c.  Forward: while chunk c of layer l+1 is
-being gathered, the aggregation (layer l) and projection (layer l+1) of chunk c+1 run on the compute stream
-(row-range SpMM launches, ``plagnn_spmm_sum_rows``).  Backward: the transposed aggregation produces slab c+1 while
-slab c is being reduce-scattered.  Only the first layer's gather and the last chunk of each exchange stay exposed.
+**Row partition** (``mode="rows"``, north_star: "1D row partitioning with a halo feature all-gather"):
+  destination rows are split into ``world`` contiguous blocks (equal, or balanced by in-edge count); rank p owns
+  ``x[rows_p]``, the in-edge CSR of its rows with source ids in the gathered numbering, its loss rows and a replica of the
+  weights.  Per layer: local GEMM -> all-gather of the projected rows -> local SpMM; backward: local transposed SpMM (or
+  arg-scatter) over ALL source rows -> reduce-scatter.  Every rank receives the whole N x F matrix per layer and direction.
+  Overlap: a rank's block is cut into ``chunks`` row chunks, gathered matrices are CHUNK-MAJOR (gathered row = chunk *
+  world * cr + rank * cr + row_in_chunk), so the all-gather of local chunk c fills one contiguous slab and the
+  reduce-scatter of slab c yields local chunk c; the aggregation / projection of chunk c+1 run while chunk c is in flight.
 
-Halo pruning (sending only referenced rows) is pointless here: at ~100 in-edges per node on a power-law graph
-every rank references essentially every source row, so the exchange is a plain all-gather; fetching neighbour
-rows from peer memory inside the SpMM would move each remote row E/(N*world) ~ 12x instead of once.
+**Feature partition** (``mode="cols"``): the aggregation is independent per feature column, so rank p aggregates ALL rows
+  but only columns [p F/P, (p+1) F/P) over a replica of the graph structure; the dense products stay row-partitioned.
+  Around every aggregation one all-to-all turns "my rows x all columns" into "all rows x my columns" and one turns it
+  back.  Each moves N F (P-1)/P^2 floats per GPU — P times less than the all-gather (112 MB instead of 0.9 GB at P = 8,
+  F = 256) — the max reducer's backward needs no reduction across ranks at all (a rank holds every row of its columns),
+  and at P = 8 the N x 32 slice a rank gathers from (128 MB) is L2-sized.  Costs: the structure is replicated (0.8 GB
+  per direction at 100 M edges — nothing against 180 GB) and narrow rows (128 bytes at P = 8) need the sub-warp kernel.
 
-The choreography is separated from the compute backend so that the N > 1 path runs on CPU with gloo in the tests
+Halo pruning (sending only referenced rows) is pointless here: at ~100 in-edges per node on a power-law graph every rank
+references essentially every source row; fetching neighbour rows from peer memory inside the SpMM would move each remote
+row E/(N*world) ~ 12x instead of once.
+
+The choreography is separated from the compute backend so that the N > 1 paths run on CPU with gloo in the tests
 (they inject a CPU backend with the same method names; the product uses the CUDA kernels + NCCL).
 """
 from __future__ import annotations
 
+import ctypes
 import math
 
 import torch
@@ -39,12 +47,35 @@ def block_bounds(num_nodes: int, world: int):
     return per, [min(p * per, num_nodes) for p in range(world + 1)]
 
 
-class RowPartitionPlan:
-    """Pure index arithmetic (any device, no kernels): which edges a rank owns and how they are renumbered."""
+def block_bounds_by_edges(in_degree: torch.Tensor, world: int):
+    """Contiguous row blocks balanced by in-edge count (power-law => balance edges, not nodes):
+    (largest block, [r0_0, ..., r0_world]).  Block p ends at the first row where the running in-edge count reaches
+    (p + 1) E / world."""
+    n = int(in_degree.numel())
+    csum = torch.cumsum(in_degree.to(torch.int64), 0)
+    total = int(csum[-1]) if n else 0
+    targets = torch.tensor([(p * total + world - 1) // world for p in range(1, world)], dtype=torch.int64, device=csum.device)
+    cuts = (torch.searchsorted(csum, targets, right=False) + 1).clamp(max=n).tolist() if world > 1 else []
+    bounds = [0] + cuts + [n]
+    for i in range(1, len(bounds)):                       # monotone even for degenerate inputs
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    per = max(bounds[i + 1] - bounds[i] for i in range(world))
+    return per, bounds
 
-    def __init__(self, src: torch.Tensor, dst: torch.Tensor, num_nodes: int, rank: int, world: int, chunks: int = 1):
+
+class RowPartitionPlan:
+    """Pure index arithmetic (any device, no kernels): which edges a rank owns and how they are renumbered.
+    balance = "rows" (equal blocks; node ids are shuffled by the generator, so rows and in-edges balance together)
+    or "edges" (blocks of equal in-edge count)."""
+
+    def __init__(self, src: torch.Tensor, dst: torch.Tensor, num_nodes: int, rank: int, world: int, chunks: int = 1,
+                 balance: str = "rows"):
         self.num_nodes, self.rank, self.world, self.chunks = int(num_nodes), int(rank), int(world), int(chunks)
-        self.per_raw, self.bounds = block_bounds(num_nodes, world)
+        if balance == "edges":
+            self.per_raw, self.bounds = block_bounds_by_edges(torch.bincount(dst, minlength=num_nodes), world)
+        else:
+            self.per_raw, self.bounds = block_bounds(num_nodes, world)
+        self._bounds_t = torch.tensor(self.bounds, dtype=torch.int64)
         self.cr = (self.per_raw + chunks - 1) // chunks       # rows per chunk
         self.per = self.cr * chunks                           # padded rows per rank
         self.r0, self.r1 = self.bounds[rank], self.bounds[rank + 1]
@@ -59,8 +90,9 @@ class RowPartitionPlan:
 
     def gathered_id(self, g: torch.Tensor) -> torch.Tensor:
         """Global node id -> row of a chunk-major gathered matrix."""
-        owner = g // self.per_raw
-        i = g - owner * self.per_raw
+        b = self._bounds_t.to(g.device)
+        owner = torch.searchsorted(b[1:], g, right=True).clamp(max=self.world - 1)
+        i = g - b[owner]
         return (i // self.cr) * (self.world * self.cr) + owner * self.cr + (i % self.cr)
 
     def local_rows(self, c: int):
@@ -74,8 +106,44 @@ class RowPartitionPlan:
         return int(self.edge_ids.numel())
 
 
+class FeaturePartitionPlan:
+    """Index arithmetic of the feature partition: rank p owns rows [r0, r1) for the dense products and columns
+    [p F/P, (p+1) F/P) of every aggregated matrix.  The whole graph is kept by every rank with node ids in the gathered
+    numbering (owner * per + row_in_block), so the all-to-all's receive buffer IS the all-rows matrix."""
+
+    def __init__(self, src: torch.Tensor, dst: torch.Tensor, num_nodes: int, rank: int, world: int, balance: str = "rows"):
+        self.num_nodes, self.rank, self.world, self.chunks = int(num_nodes), int(rank), int(world), 1
+        if balance == "edges":
+            self.per_raw, self.bounds = block_bounds_by_edges(torch.bincount(dst, minlength=num_nodes), world)
+        else:
+            self.per_raw, self.bounds = block_bounds(num_nodes, world)
+        self._bounds_t = torch.tensor(self.bounds, dtype=torch.int64)
+        self.per = self.cr = self.per_raw
+        self.r0, self.r1 = self.bounds[rank], self.bounds[rank + 1]
+        self.n_local = self.r1 - self.r0
+        self.n_padded = self.per * world
+        self.src_gathered = self.gathered_id(src)
+        self.dst_gathered = self.gathered_id(dst)
+        in_deg = torch.bincount(self.dst_gathered, minlength=self.n_padded).to(torch.float32)
+        self.scale_full = 1.0 / in_deg.clamp(min=1.0)
+        self.scale_local = self.scale_full[rank * self.per:(rank + 1) * self.per]
+
+    def gathered_id(self, g: torch.Tensor) -> torch.Tensor:
+        b = self._bounds_t.to(g.device)
+        owner = torch.searchsorted(b[1:], g, right=True).clamp(max=self.world - 1)
+        return owner * self.per + (g - b[owner])
+
+    def col_range(self, feat: int):
+        fc = feat // self.world
+        return self.rank * fc, (self.rank + 1) * fc
+
+    @property
+    def num_local_edges(self):
+        return int(self.src_gathered.numel())
+
+
 class DistGCN(torch.nn.Module):
-    """L-layer weighted-sum GCN over a row partition.  Parameters are replicated (same seed on every rank)."""
+    """L-layer weighted-sum GCN over a partition.  Parameters are replicated (same seed on every rank)."""
 
     def __init__(self, dims, seed: int = 0):
         super().__init__()
@@ -88,29 +156,89 @@ class DistGCN(torch.nn.Module):
             self.biases.append(torch.nn.Parameter(torch.zeros(dims[i + 1])))
         self.dims = list(dims)
 
+    def grad_order(self):
+        return [p for pair in zip(self.weights, self.biases) for p in pair]
+
+
+class DistSAGEPool(torch.nn.Module):
+    """L SAGEConv('pool') layers over a partition (the reference's layer, code/model.py:13-15, on the scaled graph):
+    rst = h Ws^T + max_{u in in(v)} relu(h Wp^T + bp)[u] Wn^T + b, leaky_relu between layers, none after the last.
+    Parameters replicated; per layer in the order fc_pool.weight, fc_pool.bias, fc_self.weight, fc_neigh.weight, bias."""
+
+    def __init__(self, dims, seed: int = 0):
+        super().__init__()
+        gen = torch.Generator().manual_seed(seed)
+
+        def uni(o, i):
+            return torch.nn.Parameter((torch.rand(o, i, generator=gen) * 2 - 1) / math.sqrt(i))
+
+        self.w_pool, self.b_pool, self.w_self, self.w_neigh, self.bias = (torch.nn.ParameterList() for _ in range(5))
+        for i in range(len(dims) - 1):
+            f, o = dims[i], dims[i + 1]
+            self.w_pool.append(uni(f, f))
+            self.b_pool.append(torch.nn.Parameter((torch.rand(f, generator=gen) * 2 - 1) / math.sqrt(f)))
+            self.w_self.append(uni(o, f))
+            self.w_neigh.append(uni(o, f))
+            self.bias.append(torch.nn.Parameter(torch.zeros(o)))
+        self.dims = list(dims)
+
+    def grad_order(self):
+        out = []
+        for i in range(len(self.dims) - 1):
+            out += [self.w_pool[i], self.b_pool[i], self.w_self[i], self.w_neigh[i], self.bias[i]]
+        return out
+
 
 class PartitionedGraph:
-    """Device structures of one rank: in-edge CSR of the owned rows (gathered source ids) and its transpose."""
+    """Device structures of one rank.  Row partition: in-edge CSR of the owned rows (gathered source ids) and its
+    transpose.  Feature partition: in-edge and out-edge CSR of the whole graph in the gathered numbering.  Edge weights
+    are stored once per direction in that direction's CSR order (no edge-id indirection in the kernel)."""
 
-    def __init__(self, plan: RowPartitionPlan, weight_global: torch.Tensor | None, build_csr, device):
+    def __init__(self, plan, weight_global: torch.Tensor | None, build_csr, device, transposed: bool = True):
         self.plan = plan
-        s = plan.src_gathered.to(device=device, dtype=torch.int32)
-        d = plan.dst_local.to(device=device, dtype=torch.int32)
-        # rows = padded local rows (per), entries = rows of the gathered matrix
-        self.csc = build_csr(d, s, plan.per, False, num_other=plan.n_padded)
-        # transpose: rows = gathered (source) rows, entries = local destination rows
-        self.csr_t = build_csr(s, d, plan.n_padded, False, num_other=plan.per)
-        self.edge_weight = None if weight_global is None else weight_global[plan.edge_ids.to(weight_global.device)].to(device)
-        self.scale = plan.scale_local.to(device)
+        self.mode = "cols" if isinstance(plan, FeaturePartitionPlan) else "rows"
+        if self.mode == "rows":
+            s = plan.src_gathered.to(device=device, dtype=torch.int32)
+            d = plan.dst_local.to(device=device, dtype=torch.int32)
+            n_dst, w = plan.per, None if weight_global is None else weight_global[plan.edge_ids.to(weight_global.device)].to(device)
+            self.scale = plan.scale_local.to(device)
+        else:
+            s = plan.src_gathered.to(device=device, dtype=torch.int32)
+            d = plan.dst_gathered.to(device=device, dtype=torch.int32)
+            n_dst, w = plan.n_padded, None if weight_global is None else weight_global.to(device)
+            self.scale = plan.scale_local.to(device)
+            self.scale_full = plan.scale_full.to(device)
+        # rows = destination rows, entries = rows of the gathered matrix
+        self.csc = build_csr(d, s, n_dst, False, num_other=plan.n_padded)
+        self.w_csc = None if w is None else w[self.csc.eids.long()].contiguous()
+        # transpose: rows = gathered (source) rows, entries = destination rows (only the sum reducer's backward walks it)
+        self.csr_t = self.w_csr_t = None
+        if transposed:
+            self.csr_t = build_csr(s, d, plan.n_padded, False, num_other=n_dst)
+            self.w_csr_t = None if w is None else w[self.csr_t.eids.long()].contiguous()
+        self.edge_weight = w
 
 
+def _mask_padded_rows(plan, d_out):
+    """Rows past n_local are padding: they carry act(bias) in the forward pass and must not reach any gradient."""
+    if plan.n_local < d_out.shape[0]:
+        d_out[plan.n_local:] = 0
+    return d_out
+
+
+# ======================================================================================================================
+# row partition
+# ======================================================================================================================
 def dist_gcn_forward_backward(model: DistGCN, pg, h0_local, backend, group=None, loss_grad_fn=None, act_leaky=True):
-    """One forward + backward of the partitioned GCN.  h0_local: [per, F0] (rows past n_local are zero).
+    """One forward + backward of the row-partitioned weighted-sum GCN.  h0_local: [per, F0] (rows past n_local are zero).
     Returns (out_local, grads) with grads = [W0, b0, W1, b1, ...] already summed over ranks."""
+    if getattr(pg, "mode", "rows") == "cols":
+        return _gcn_cols_forward_backward(model, pg, h0_local, backend, group, loss_grad_fn, act_leaky)
     plan = pg.plan
     world, chunks = plan.world, plan.chunks
     n_layers = len(model.weights)
     dims = model.dims
+    w_csc, w_csr_t = getattr(pg, "w_csc", pg.edge_weight), getattr(pg, "w_csr_t", pg.edge_weight)
     hs = [h0_local]                  # layer inputs (local rows)
     outs = []                        # layer outputs (local rows)
     t_full_prev = None
@@ -125,7 +253,7 @@ def dist_gcn_forward_backward(model: DistGCN, pg, h0_local, backend, group=None,
         for c in range(chunks):
             a, b = plan.local_rows(c)
             if li > 0:   # aggregation of the previous layer for this row chunk, then this layer's projection
-                backend.spmm_rows(pg.csc, ("csc", c), a, b, t_full_prev, out_prev, pg.edge_weight, pg.scale,
+                backend.spmm_rows(pg.csc, ("csc", c), a, b, t_full_prev, out_prev, w_csc, pg.scale,
                                   model.biases[li - 1].detach(), act=act_leaky)
                 h_c = backend.rows(out_prev, a, b)
             else:
@@ -139,11 +267,12 @@ def dist_gcn_forward_backward(model: DistGCN, pg, h0_local, backend, group=None,
             hs.append(out_prev)
         t_full_prev = t_full
     out_last = backend.alloc(plan.per, dims[-1])
-    backend.spmm_rows(pg.csc, ("csc", -1), 0, plan.per, t_full_prev, out_last, pg.edge_weight, pg.scale,
+    backend.spmm_rows(pg.csc, ("csc", -1), 0, plan.per, t_full_prev, out_last, w_csc, pg.scale,
                       model.biases[-1].detach(), act=False)
     outs.append(out_last)
     # ---------------- backward ----------------
     d_out = loss_grad_fn(out_last) if loss_grad_fn is not None else torch.ones_like(out_last)
+    d_out = _mask_padded_rows(plan, d_out)
     grads = [None] * (2 * n_layers)
     dz = d_out
     for li in reversed(range(n_layers)):
@@ -157,7 +286,7 @@ def dist_gcn_forward_backward(model: DistGCN, pg, h0_local, backend, group=None,
         pending = []
         for c in range(chunks):
             sa, sb = plan.slab_rows(c)
-            backend.spmm_rows(pg.csr_t, ("csr_t", c), sa, sb, dzs, dt_partial, pg.edge_weight, None, None, act=False)
+            backend.spmm_rows(pg.csr_t, ("csr_t", c), sa, sb, dzs, dt_partial, w_csr_t, None, None, act=False)
             a, b = plan.local_rows(c)
             pending.append(backend.reduce_scatter_chunk(backend.rows(dt_local, a, b), backend.rows(dt_partial, sa, sb),
                                                         world, group))
@@ -168,18 +297,179 @@ def dist_gcn_forward_backward(model: DistGCN, pg, h0_local, backend, group=None,
     return out_last, backend.all_reduce_grads(grads, world, group)
 
 
-class CudaBackend:
-    """Compute + collectives on the CUDA kernels / NCCL.  (Tests use a CPU twin with the same method names.)"""
+def dist_pool_forward_backward(model: DistSAGEPool, pg, h0_local, backend, group=None, loss_grad_fn=None):
+    """One forward + backward of the partitioned SAGEConv-pool stack (either partition).  Returns (out_local, grads) with
+    grads in DistSAGEPool.grad_order(), summed over ranks.
 
-    def __init__(self, pg: PartitionedGraph):
-        from . import ops
-        self.ops = ops
+    Row partition: all-gather of m = relu(h Wp^T + bp) (chunk by chunk behind the projection), local max with arg over the
+    gathered rows; backward: arg-scatter into a full-height partial dm, reduce-scatter slab by slab while the two
+    weight-gradient products that do not need dm run."""
+    cols = getattr(pg, "mode", "rows") == "cols"
+    plan = pg.plan
+    world, chunks = plan.world, plan.chunks
+    n_layers = len(model.w_pool)
+    dims = model.dims
+    saved = []
+    h = h0_local
+    # ---------------- forward ----------------
+    for li in range(n_layers):
+        last = li + 1 == n_layers
+        wp, bp, ws, wn, b = (model.w_pool[li].detach(), model.b_pool[li].detach(), model.w_self[li].detach(),
+                             model.w_neigh[li].detach(), model.bias[li].detach())
+        f = dims[li]
+        if cols:
+            m_local = backend.alloc(plan.per, f)
+            backend.gemm_nt_bias_relu_into(h, wp, bp, m_local)
+            m_col = backend.to_cols(m_local, world, group)
+            neigh_col, arg = backend.spmm_max(pg.csc, m_col)
+            neigh = backend.to_rows(neigh_col, f, world, group)
+            ctx = (neigh_col, arg)
+        else:
+            m_local = backend.alloc(plan.per, f)
+            m_full = backend.alloc(plan.n_padded, f)
+            pending = []
+            for c in range(chunks):
+                a, e = plan.local_rows(c)
+                backend.gemm_nt_bias_relu_into(backend.rows(h, a, e), wp, bp, backend.rows(m_local, a, e))
+                sa, sb = plan.slab_rows(c)
+                pending.append(backend.all_gather_chunk(backend.rows(m_full, sa, sb), backend.rows(m_local, a, e), world, group))
+            backend.wait(pending)
+            neigh, arg = backend.spmm_max(pg.csc, m_full)
+            ctx = (neigh, arg)
+        out = backend.gemm2_nt(h, ws, neigh, wn, b, leaky=not last)
+        saved.append((h, neigh, ctx, out))
+        h = out
+    out_last = h
+    # ---------------- backward ----------------
+    d_out = loss_grad_fn(out_last) if loss_grad_fn is not None else torch.ones_like(out_last)
+    dz = _mask_padded_rows(plan, d_out)
+    grads = [None] * (5 * n_layers)
+    for li in reversed(range(n_layers)):
+        last = li + 1 == n_layers
+        wp, ws, wn = model.w_pool[li].detach(), model.w_self[li].detach(), model.w_neigh[li].detach()
+        h, neigh, (neigh_agg, arg), out = saved[li]
+        f = dims[li]
+        drst = backend.act_backward(dz, None if last else out, None)
+        dneigh = backend.gemm_nn(drst, wn)                                       # [per, F]
+        if cols:
+            dneigh_col = backend.to_cols(dneigh, world, group)
+            dm_col = backend.max_scatter(dneigh_col, arg, neigh_agg, plan.n_padded)   # complete: every row of my columns
+            grads[5 * li + 4] = backend.colsum(drst)
+            grads[5 * li + 2] = backend.gemm_tn(drst, h)
+            grads[5 * li + 3] = backend.gemm_tn(drst, neigh)
+            dm_local = backend.to_rows(dm_col, f, world, group)
+        else:
+            dm_partial = backend.max_scatter(dneigh, arg, neigh_agg, plan.n_padded)   # relu' folded in: pooled value > 0
+            dm_local = backend.alloc(plan.per, f)
+            pending = []
+            for c in range(chunks):
+                sa, sb = plan.slab_rows(c)
+                a, e = plan.local_rows(c)
+                pending.append(backend.reduce_scatter_chunk(backend.rows(dm_local, a, e), backend.rows(dm_partial, sa, sb),
+                                                            world, group))
+            # these do not need dm: they run while the reduce-scatter is in flight
+            grads[5 * li + 4] = backend.colsum(drst)
+            grads[5 * li + 2] = backend.gemm_tn(drst, h)
+            grads[5 * li + 3] = backend.gemm_tn(drst, neigh)
+            backend.wait(pending)
+        grads[5 * li + 0] = backend.gemm_tn(dm_local, h)
+        grads[5 * li + 1] = backend.colsum(dm_local)
+        if li > 0:
+            dz = backend.gemm_nn2(drst, ws, dm_local, wp)                        # d h = drst Ws + dm Wp
+    return out_last, backend.all_reduce_grads(grads, world, group)
+
+
+# ======================================================================================================================
+# feature partition, weighted sum
+# ======================================================================================================================
+def _gcn_cols_forward_backward(model: DistGCN, pg, h0_local, backend, group, loss_grad_fn, act_leaky):
+    plan = pg.plan
+    world = plan.world
+    n_layers = len(model.weights)
+    dims = model.dims
+    hs, outs = [h0_local], []
+    h = h0_local
+    for li in range(n_layers):
+        last = li + 1 == n_layers
+        o = dims[li + 1]
+        t_local = backend.alloc(plan.per, o)
+        backend.gemm_nt_into(h, model.weights[li].detach(), t_local)
+        t_col = backend.to_cols(t_local, world, group)
+        c0, c1 = plan.col_range(o)
+        out_col = backend.spmm_cols(pg.csc, "csc", t_col, pg.w_csc, pg.scale_full, model.biases[li].detach()[c0:c1],
+                                    act=act_leaky and not last)
+        h = backend.to_rows(out_col, o, world, group)
+        outs.append(h)
+        if not last:
+            hs.append(h)
+    out_last = h
+    d_out = loss_grad_fn(out_last) if loss_grad_fn is not None else torch.ones_like(out_last)
+    dz = _mask_padded_rows(plan, d_out)
+    grads = [None] * (2 * n_layers)
+    for li in reversed(range(n_layers)):
+        last = li + 1 == n_layers
+        o = dims[li + 1]
+        dzb = backend.act_backward(dz, outs[li] if (not last and act_leaky) else None, None)
+        grads[2 * li + 1] = backend.colsum(dzb)
+        dzs = backend.act_backward(dzb, None, pg.scale)
+        dzs_col = backend.to_cols(dzs, world, group)
+        dt_col = backend.spmm_cols(pg.csr_t, "csr_t", dzs_col, pg.w_csr_t, None, None, act=False)
+        dt_local = backend.to_rows(dt_col, o, world, group)
+        grads[2 * li] = backend.gemm_tn(dt_local, hs[li])
+        if li > 0:
+            dz = backend.gemm_nn(dt_local, model.weights[li].detach())
+    return out_last, backend.all_reduce_grads(grads, world, group)
+
+
+# ======================================================================================================================
+# CUDA backend: the library's kernels + its NCCL wrappers
+# ======================================================================================================================
+class NcclComm:
+    """An NCCL communicator of the library's own (plagnn_nccl_comm_init).  The 128-byte id travels from rank 0 through
+    the already initialised torch.distributed group (any backend); after that the data path does not touch
+    torch.distributed.  max_ctas > 0 caps the CTAs NCCL may use (the exchange runs beside the aggregation)."""
+
+    def __init__(self, rank: int, world: int, device, max_ctas: int = 0):
+        from . import _lib
+        lib = _lib.load()
+        self.rank, self.world = rank, world
+        idbuf = (ctypes.c_ubyte * 128)()
+        if rank == 0:
+            _lib.check(lib.plagnn_nccl_get_unique_id(idbuf), "nccl_get_unique_id")
+        box = [bytes(idbuf)]
+        dist.broadcast_object_list(box, src=0)
+        idbuf = (ctypes.c_ubyte * 128).from_buffer_copy(box[0])
+        comm = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.plagnn_nccl_comm_init(idbuf, rank, world, int(max_ctas), ctypes.byref(comm)), "nccl_comm_init")
+        self.handle = comm
+        self._lib = lib
+
+    def destroy(self):
+        if self.handle:
+            self._lib.plagnn_nccl_comm_destroy(self.handle)
+            self.handle = None
+
+
+class CudaBackend:
+    """Compute + collectives on the CUDA kernels / NCCL wrappers.  (Tests use a CPU twin with the same method names.)
+    comm: NcclComm or None (world 1).  skip_comm = True leaves every collective out (timing of the compute alone: the
+    difference to the full step is the exposed exchange time; results are then meaningless)."""
+
+    def __init__(self, pg: PartitionedGraph, comm: NcclComm | None = None):
+        from . import _lib, ops
+        self.ops, self._lib, self.lib = ops, _lib, _lib.load()
+        self.comm = comm
+        self.skip_comm = False
+        self.comm_stream = torch.cuda.Stream() if comm is not None else None
         plan = pg.plan
         self.ranges = {}
-        for c in range(plan.chunks):
-            self.ranges[("csc", c)] = ops.plan_range(pg.csc, *plan.local_rows(c))
-            self.ranges[("csr_t", c)] = ops.plan_range(pg.csr_t, *plan.slab_rows(c))
-        self.ranges[("csc", -1)] = ops.plan_range(pg.csc, 0, plan.per)
+        if pg.mode == "rows":
+            for c in range(plan.chunks):
+                self.ranges[("csc", c)] = ops.plan_range(pg.csc, *plan.local_rows(c))
+                if pg.csr_t is not None:
+                    self.ranges[("csr_t", c)] = ops.plan_range(pg.csr_t, *plan.slab_rows(c))
+            self.ranges[("csc", -1)] = ops.plan_range(pg.csc, 0, plan.per)
 
     def alloc(self, rows, cols):
         return self.ops.alloc(rows, cols, torch.cuda.current_device())
@@ -188,31 +478,38 @@ class CudaBackend:
     def rows(t, a, b):
         return t[a:b]
 
-    @staticmethod
-    def _padded(t):
-        """The row-padded storage behind a [rows, cols] view (contiguous: what NCCL gets)."""
-        return t.as_strided((t.shape[0], t.stride(0)), (t.stride(0), 1), t.storage_offset())
-
+    # ---- dense ----------------------------------------------------------------------------------------------------
     def gemm_nt_into(self, a, w, out):
         ops = self.ops
         a = ops.aligned(a)
         ops.gemm(a.shape[0], w.shape[0], [(a, 0, ops.aligned(w), 0, a.shape[1])], out=out)
+
+    def gemm_nt_bias_relu_into(self, a, w, bias, out):
+        ops = self.ops
+        a = ops.aligned(a)
+        ops.gemm(a.shape[0], w.shape[0], [(a, 0, ops.aligned(w), 0, a.shape[1])], bias=bias, act=ops.ACT_RELU, out=out)
+
+    def gemm2_nt(self, h, ws, neigh, wn, bias, leaky):
+        ops = self.ops
+        h, neigh = ops.aligned(h), ops.aligned(neigh)
+        return ops.gemm(h.shape[0], ws.shape[0], [(h, 0, ops.aligned(ws), 0, h.shape[1]), (neigh, 0, ops.aligned(wn), 0, h.shape[1])],
+                        bias=bias, act=ops.ACT_LEAKY if leaky else ops.ACT_NONE)
 
     def gemm_nn(self, a, w):
         ops = self.ops
         a = ops.aligned(a)
         return ops.gemm(a.shape[0], w.shape[1], [(a, 0, ops.aligned(w), 1, a.shape[1])])
 
+    def gemm_nn2(self, a0, w0, a1, w1):
+        ops = self.ops
+        a0, a1 = ops.aligned(a0), ops.aligned(a1)
+        return ops.gemm(a0.shape[0], w0.shape[1], [(a0, 0, ops.aligned(w0), 1, a0.shape[1]), (a1, 0, ops.aligned(w1), 1, a1.shape[1])])
+
     def gemm_tn(self, a, b):
         ops = self.ops
         a, b = ops.aligned(a), ops.aligned(b)
         out = torch.empty((a.shape[1], b.shape[1]), device=a.device, dtype=torch.float32)
         return ops.gemm(a.shape[1], b.shape[1], [(a, 1, b, 1, a.shape[0])], out=out)
-
-    def spmm_rows(self, csx, key, a, b, x, out, w, scale, bias, act):
-        ops = self.ops
-        ops.spmm_sum_rows(csx, self.ranges[key], x, out, w=w, scale=scale, bias=bias,
-                          act=ops.ACT_LEAKY if act else ops.ACT_NONE)
 
     def act_backward(self, dy, y, scale):
         ops = self.ops
@@ -223,30 +520,110 @@ class CudaBackend:
     def colsum(self, x):
         return self.ops.colsum(self.ops.aligned(x))
 
+    # ---- aggregation ----------------------------------------------------------------------------------------------
+    def spmm_rows(self, csx, key, a, b, x, out, w, scale, bias, act):
+        ops = self.ops
+        ops.spmm_sum_rows(csx, self.ranges[key], x, out, w=w, scale=scale, bias=bias,
+                          act=ops.ACT_LEAKY if act else ops.ACT_NONE, w_in_csr_order=True)
+
+    def spmm_cols(self, csx, key, x_col, w, scale, bias, act):
+        ops = self.ops
+        return ops.spmm_sum(csx, x_col, w=w, scale=scale, bias=bias, act=ops.ACT_LEAKY if act else ops.ACT_NONE,
+                            w_in_csr_order=True)
+
+    def spmm_max(self, csc, x):
+        return self.ops.spmm_max_fwd(csc, x)
+
+    def max_scatter(self, dneigh, arg, neigh, n_src):
+        return self.ops.spmm_max_bwd(dneigh, arg, neigh, n_src)
+
+    # ---- exchange -------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _pitch(t):
+        return t.stride(0)
+
+    def _on_comm_stream(self, fn):
+        """Runs fn(stream_ptr) on the exchange stream after everything enqueued so far on the compute stream; returns the
+        event the compute stream must wait for before it touches the result."""
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.comm_stream.wait_event(ready)
+        fn(ctypes.c_void_p(self.comm_stream.cuda_stream))
+        done = torch.cuda.Event()
+        done.record(self.comm_stream)
+        return done
+
     def all_gather_chunk(self, slab, local_chunk, world, group):
         if world == 1:
             slab.copy_(local_chunk)
             return None
-        return dist.all_gather_into_tensor(self._padded(slab), self._padded(local_chunk), group=group, async_op=True)
+        if self.skip_comm:
+            return None
+        assert self._pitch(slab) == self._pitch(local_chunk)
+        rows, pitch = local_chunk.shape[0], self._pitch(local_chunk)
+        return self._on_comm_stream(lambda st: self._lib.check(self.lib.plagnn_nccl_allgather_rows(
+            local_chunk.data_ptr(), slab.data_ptr(), rows, pitch, self.comm.handle, st), "nccl_allgather_rows"))
 
     def reduce_scatter_chunk(self, out_chunk, slab, world, group):
         if world == 1:
             out_chunk.copy_(slab)
             return None
-        return dist.reduce_scatter_tensor(self._padded(out_chunk), self._padded(slab), op=dist.ReduceOp.SUM, group=group,
-                                          async_op=True)
+        if self.skip_comm:
+            return None
+        assert self._pitch(slab) == self._pitch(out_chunk)
+        rows, pitch = out_chunk.shape[0], self._pitch(out_chunk)
+        return self._on_comm_stream(lambda st: self._lib.check(self.lib.plagnn_nccl_reducescatter_rows(
+            slab.data_ptr(), out_chunk.data_ptr(), rows, pitch, self.comm.handle, st), "nccl_reducescatter_rows"))
 
     @staticmethod
     def wait(pending):
-        for h in pending:
-            if h is not None:
-                h.wait()              # the compute stream waits for the NCCL stream; the host does not block
+        cur = torch.cuda.current_stream()
+        for ev in pending:
+            if ev is not None:
+                cur.wait_event(ev)        # the compute stream waits for the exchange stream; the host does not block
+
+    def to_cols(self, x_local, world, group):
+        """[per x F] (my rows, all columns) -> [world * per x F / world] (all rows, my columns)."""
+        ops = self.ops
+        x_local = ops.aligned(x_local)
+        rows, feat = x_local.shape
+        fc = feat // world
+        st = ops._stream()
+        send = torch.empty((world * rows, fc), device=x_local.device, dtype=torch.float32)
+        self._lib.check(self.lib.plagnn_cols_pack(x_local.data_ptr(), x_local.stride(0), rows, feat, world, send.data_ptr(), st),
+                        "cols_pack")
+        if world == 1 or self.skip_comm:
+            return send
+        recv = torch.empty_like(send)
+        self._lib.check(self.lib.plagnn_nccl_alltoall_blocks(send.data_ptr(), recv.data_ptr(), rows * fc, world,
+                                                             self.comm.handle, st), "nccl_alltoall_blocks")
+        return recv
+
+    def to_rows(self, x_col, feat, world, group):
+        """[world * per x F / world] (all rows, my columns) -> [per x F] (my rows, all columns)."""
+        ops = self.ops
+        fc = feat // world
+        rows = x_col.shape[0] // world
+        st = ops._stream()
+        if x_col.stride(0) != fc:
+            x_col = x_col.contiguous()
+        recv = x_col
+        if world > 1 and not self.skip_comm:
+            recv = torch.empty((world * rows, fc), device=x_col.device, dtype=torch.float32)
+            self._lib.check(self.lib.plagnn_nccl_alltoall_blocks(x_col.data_ptr(), recv.data_ptr(), rows * fc, world,
+                                                                 self.comm.handle, st), "nccl_alltoall_blocks")
+        out = ops.alloc(rows, feat, x_col.device)
+        self._lib.check(self.lib.plagnn_cols_unpack(recv.data_ptr(), rows, feat, world, out.data_ptr(), out.stride(0), st),
+                        "cols_unpack")
+        return out
 
     def all_reduce_grads(self, grads, world, group):
-        if world == 1:
+        if world == 1 or self.skip_comm:
             return grads
         flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        self._lib.check(self.lib.plagnn_nccl_allreduce(flat.data_ptr(), flat.numel(), self.comm.handle, self.ops._stream()),
+                        "nccl_allreduce")
         out, off = [], 0
         for g in grads:
             out.append(flat[off:off + g.numel()].view_as(g))

@@ -321,7 +321,8 @@ def spmm_max_bwd_gather(csr, dz: torch.Tensor, arg: torch.Tensor, z: torch.Tenso
 
 @on_tensor_device
 def spmm_sum(csx, x: torch.Tensor, w=None, scale=None, bias=None, act=ACT_NONE, dropout_p: float = 0.0,
-             dropout_seed: int = 0, slope: float = LEAKY_SLOPE) -> torch.Tensor:
+             dropout_seed: int = 0, slope: float = LEAKY_SLOPE, w_in_csr_order: bool = False) -> torch.Tensor:
+    """w: one weight per edge, indexed by edge id (DGL's convention) or, with w_in_csr_order, by position in csx."""
     lib = _lib.load()
     x = aligned(x)
     n, f = csx.num_rows, x.shape[1]
@@ -329,7 +330,7 @@ def spmm_sum(csx, x: torch.Tensor, w=None, scale=None, bias=None, act=ACT_NONE, 
     nb = lib.plagnn_spmm_partial_bytes(csx.counts[2], f, REDUCE_SUM)
     part = workspace(nb, x.device, "spmm_partial")
     with _timed(("spmm_sum", f)):
-        check(lib.plagnn_spmm_sum(_p(csx.indptr), _p(csx.indices), _p(csx.eids) if w is not None else None,
+        check(lib.plagnn_spmm_sum(_p(csx.indptr), _p(csx.indices), _p(csx.eids) if (w is not None and not w_in_csr_order) else None,
                                   _p(csx.plan), csx.counts_c, n, _p(w), _p(scale), _p(x), x.stride(0), f, _p(bias), act,
                                   slope, float(dropout_p), int(dropout_seed), _p(out), out.stride(0), _p(part), nb,
                                   _stream()), "spmm_sum")
@@ -346,13 +347,13 @@ def plan_range(csx, row_begin: int, row_end: int):
 
 @on_tensor_device
 def spmm_sum_rows(csx, rng, x: torch.Tensor, out: torch.Tensor, w=None, scale=None, bias=None, act=ACT_NONE,
-                  slope: float = LEAKY_SLOPE) -> torch.Tensor:
+                  slope: float = LEAKY_SLOPE, w_in_csr_order: bool = False) -> torch.Tensor:
     """Row-range aggregation into the rows of a preallocated `out` (other rows untouched)."""
     lib = _lib.load()
     f = x.shape[1]
     nb = lib.plagnn_spmm_partial_bytes(csx.counts[2], f, REDUCE_SUM)
     part = workspace(nb, x.device, "spmm_partial")
-    check(lib.plagnn_spmm_sum_rows(_p(csx.indptr), _p(csx.indices), _p(csx.eids) if w is not None else None, _p(csx.plan),
+    check(lib.plagnn_spmm_sum_rows(_p(csx.indptr), _p(csx.indices), _p(csx.eids) if (w is not None and not w_in_csr_order) else None, _p(csx.plan),
                                    csx.counts_c, rng, csx.num_rows, _p(w), _p(scale), _p(x), x.stride(0), f, _p(bias), act,
                                    slope, _p(out), out.stride(0), _p(part), nb, _stream()), "spmm_sum_rows")
     return out

@@ -1,5 +1,6 @@
-"""N > 1 host logic on CPU: world_size-2 and -3 gloo runs of the row-partitioned GCN choreography with a CPU compute backend
-(oracle kernels), compared with the single-process oracle model.  No CUDA involved."""
+"""N > 1 host logic on CPU: world_size-2 and -3 gloo runs of the partitioned choreographies (row partition and feature
+partition, weighted-sum and max-pool reducers) with a CPU compute backend (oracle kernels), compared with the
+single-process oracle model.  No CUDA involved."""
 import os
 
 import numpy as np
@@ -9,7 +10,8 @@ import torch.multiprocessing as mp
 
 from oracle import plagnn_oracle as orc
 from plagnn_b200 import synth
-from plagnn_b200.dist import DistGCN, RowPartitionPlan, block_bounds, dist_gcn_forward_backward
+from plagnn_b200.dist import (DistGCN, DistSAGEPool, FeaturePartitionPlan, RowPartitionPlan, block_bounds,
+                              block_bounds_by_edges, dist_gcn_forward_backward, dist_pool_forward_backward)
 
 
 class _Csx:
@@ -29,8 +31,42 @@ class CpuBackend:
     def gemm_tn(self, a, b): return a.t() @ b
     def colsum(self, x): return x.sum(0)
 
+    def gemm_nt_bias_relu_into(self, a, w, bias, out): out.copy_(torch.relu(a @ w.t() + bias))
+    def gemm_nn2(self, a0, w0, a1, w1): return a0 @ w0 + a1 @ w1
+
+    def gemm2_nt(self, h, ws, neigh, wn, bias, leaky):
+        r = h @ ws.t() + neigh @ wn.t() + bias
+        return torch.nn.functional.leaky_relu(r) if leaky else r
+
+    def spmm_max(self, csc, x):
+        return orc.spmm_max_c(csc.indptr, csc.indices, x.contiguous())
+
+    def max_scatter(self, dneigh, arg, neigh, n_src):
+        return orc.spmm_max_bwd_c(arg, (dneigh * (neigh > 0)).contiguous(), n_src)
+
+    def spmm_cols(self, csx, key, x_col, w, scale, bias, act):
+        r = orc.spmm_sum_c(csx.indptr, csx.indices, x_col.contiguous(), eids=None, w=w, scale=scale)
+        if bias is not None:
+            r = r + bias
+        return torch.nn.functional.leaky_relu(r) if act else r
+
+    def to_cols(self, x_local, world, group):
+        rows, feat = x_local.shape
+        fc = feat // world
+        send = x_local.reshape(rows, world, fc).permute(1, 0, 2).contiguous()      # [world][rows][fc]
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=group)
+        return recv.reshape(world * rows, fc)
+
+    def to_rows(self, x_col, feat, world, group):
+        fc = feat // world
+        rows = x_col.shape[0] // world
+        recv = torch.empty(world, rows, fc)
+        dist.all_to_all_single(recv, x_col.contiguous().reshape(world, rows, fc), group=group)
+        return recv.permute(1, 0, 2).reshape(rows, feat).contiguous()
+
     def spmm_rows(self, csx, key, a, b, x, out, w, scale, bias, act):
-        r = orc.spmm_sum_c(csx.indptr[a:b + 1], csx.indices, x.contiguous(), eids=csx.eids if w is not None else None, w=w,
+        r = orc.spmm_sum_c(csx.indptr[a:b + 1], csx.indices, x.contiguous(), eids=None, w=w,
                            scale=None if scale is None else scale[a:b].contiguous())
         if bias is not None:
             r = r + bias
@@ -70,11 +106,21 @@ class CpuBackend:
 
 
 class _PG:
+    """CPU twin of plagnn_b200.dist.PartitionedGraph (weights stored per direction in CSR order)."""
+
     def __init__(self, plan, weight):
         self.plan = plan
-        self.csc = _Csx(plan.dst_local, plan.src_gathered, plan.per)
-        self.csr_t = _Csx(plan.src_gathered, plan.dst_local, plan.n_padded)
-        self.edge_weight = weight[plan.edge_ids]
+        self.mode = "cols" if isinstance(plan, FeaturePartitionPlan) else "rows"
+        if self.mode == "rows":
+            d, n_dst, w = plan.dst_local, plan.per, weight[plan.edge_ids]
+        else:
+            d, n_dst, w = plan.dst_gathered, plan.n_padded, weight
+            self.scale_full = plan.scale_full
+        self.csc = _Csx(d, plan.src_gathered, n_dst)
+        self.csr_t = _Csx(plan.src_gathered, d, plan.n_padded)
+        self.w_csc = w[torch.as_tensor(self.csc.eids, dtype=torch.long)].contiguous()
+        self.w_csr_t = w[torch.as_tensor(self.csr_t.eids, dtype=torch.long)].contiguous()
+        self.edge_weight = w
         self.scale = plan.scale_local
 
 
@@ -84,38 +130,93 @@ def _problem(n=403, e=6000, f=24):
     return sg, x
 
 
-def _worker(rank, world, port, out_dir):
+DIMS = [24, 24, 12]            # every width a multiple of 4 * world for world in (2, 3)
+
+
+def _make_plan(sg, n, rank, world, mode, balance):
+    if mode == "cols":
+        return FeaturePartitionPlan(sg.src, sg.dst, n, rank, world, balance=balance)
+    return RowPartitionPlan(sg.src, sg.dst, n, rank, world, chunks=3, balance=balance)
+
+
+def _worker(rank, world, port, out_dir, mode, reducer, balance):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sg, x = _problem()
     n, f = sg.num_nodes, x.shape[1]
-    plan = RowPartitionPlan(sg.src, sg.dst, n, rank, world, chunks=3)
+    plan = _make_plan(sg, n, rank, world, mode, balance)
     pg = _PG(plan, sg.weight)
-    model = DistGCN([f, 16, 8], seed=3)
     h0 = torch.zeros(plan.per, f)
     h0[:plan.n_local] = x[plan.r0:plan.r1]
-    mask = (torch.arange(plan.per) < plan.n_local).float().unsqueeze(1)
-    out, grads = dist_gcn_forward_backward(model, pg, h0, CpuBackend(), None, lambda o: o * mask / n)
+    # no row mask here: padded rows (act(bias) in the forward pass) must be kept out of the gradients by the library
+    if reducer == "sum":
+        model = DistGCN(DIMS, seed=3)
+        with torch.no_grad():
+            for b in model.biases:
+                b.add_(0.05)                      # non-zero biases: padded rows are not zero after the first layer
+        out, grads = dist_gcn_forward_backward(model, pg, h0, CpuBackend(), None, lambda o: o / n)
+    else:
+        model = DistSAGEPool(DIMS, seed=3)
+        with torch.no_grad():
+            for b in model.bias:
+                b.add_(0.05)
+        out, grads = dist_pool_forward_backward(model, pg, h0, CpuBackend(), None, lambda o: o / n)
     torch.save({"out": out[:plan.n_local], "grads": grads, "r0": plan.r0, "r1": plan.r1},
                os.path.join(out_dir, f"rank{rank}.pt"))
     dist.destroy_process_group()
 
 
-def _reference():
+class _PoolStackRef(torch.nn.Module):
+    """The oracle's SAGEConv-pool layers stacked like DistSAGEPool (leaky_relu between layers, none after the last)."""
+
+    def __init__(self, model: DistSAGEPool):
+        super().__init__()
+        self.convs = torch.nn.ModuleList()
+        for i in range(len(model.dims) - 1):
+            c = orc.SAGEConvPoolRef(model.dims[i], model.dims[i + 1], "pool")
+            with torch.no_grad():
+                c.fc_pool.weight.copy_(model.w_pool[i]); c.fc_pool.bias.copy_(model.b_pool[i])
+                c.fc_self.weight.copy_(model.w_self[i]); c.fc_neigh.weight.copy_(model.w_neigh[i]); c.bias.copy_(model.bias[i])
+            self.convs.append(c)
+
+    def forward(self, g, x):
+        h = x
+        for i, c in enumerate(self.convs):
+            h = c(g, h)
+            if i + 1 < len(self.convs):
+                h = torch.nn.functional.leaky_relu(h)
+        return h
+
+    def grads(self):
+        out = []
+        for c in self.convs:
+            out += [c.fc_pool.weight.grad, c.fc_pool.bias.grad, c.fc_self.weight.grad, c.fc_neigh.weight.grad, c.bias.grad]
+        return out
+
+
+def _reference(reducer="sum"):
     sg, x = _problem()
     n, f = sg.num_nodes, x.shape[1]
     g = orc.OracleGraph(sg.src.numpy(), sg.dst.numpy(), n)
-    model = DistGCN([f, 16, 8], seed=3)
-    ref = orc.GCNSumRef([f, 16, 8])
+    if reducer == "sum":
+        model = DistGCN(DIMS, seed=3)
+        ref = orc.GCNSumRef(DIMS)
+        with torch.no_grad():
+            for lin, w, b in zip(ref.lins, model.weights, model.biases):
+                lin.weight.copy_(w); lin.bias.copy_(b + 0.05)
+        scale = 1.0 / torch.bincount(sg.dst, minlength=n).clamp(min=1).float()
+        out = ref(g, x, sg.weight, scale)
+        (0.5 * (out ** 2).sum() / n).backward()
+        return out.detach(), [t.grad for lin in ref.lins for t in (lin.weight, lin.bias)]
+    model = DistSAGEPool(DIMS, seed=3)
     with torch.no_grad():
-        for lin, w, b in zip(ref.lins, model.weights, model.biases):
-            lin.weight.copy_(w); lin.bias.copy_(b)
-    scale = 1.0 / torch.bincount(sg.dst, minlength=n).clamp(min=1).float()
-    out = ref(g, x, sg.weight, scale)
+        for b in model.bias:
+            b.add_(0.05)
+    ref = _PoolStackRef(model)
+    out = ref(g, x)
     (0.5 * (out ** 2).sum() / n).backward()
-    grads = [t.grad for lin in ref.lins for t in (lin.weight, lin.bias)]
-    return out.detach(), grads
+    return out.detach(), ref.grads()
 
 
 def test_block_bounds_and_plan_cover_every_edge_once():
@@ -149,13 +250,37 @@ def test_block_bounds_and_plan_cover_every_edge_once():
     assert abs(plans[0].num_local_edges - plans[1].num_local_edges) < 0.25 * sg.src.numel()
 
 
-def _run_world(world, tmp_path):
-    port = 29500 + (os.getpid() * 7 + world) % 2000
+def test_edge_balanced_bounds():
+    sg, _ = _problem()
+    n = sg.num_nodes
+    deg = torch.bincount(sg.dst, minlength=n)
+    for world in (1, 2, 3, 8):
+        per, b = block_bounds_by_edges(deg, world)
+        assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(world))
+        assert per == max(b[i + 1] - b[i] for i in range(world))
+        counts = [int(deg[b[i]:b[i + 1]].sum()) for i in range(world)]
+        assert sum(counts) == int(deg.sum())
+        assert max(counts) - min(counts) <= 2 * int(deg.max())          # within one (hub) row of the ideal cut
+        seen = torch.zeros(sg.src.numel(), dtype=torch.int32)
+        gathered = []
+        for r in range(world):
+            plan = RowPartitionPlan(sg.src, sg.dst, n, r, world, chunks=2, balance="edges")
+            seen[plan.edge_ids] += 1
+            gathered.append(plan.gathered_id(torch.arange(plan.r0, plan.r1)))
+            fp = FeaturePartitionPlan(sg.src, sg.dst, n, r, world, balance="edges")
+            assert torch.equal(fp.gathered_id(torch.arange(fp.r0, fp.r1)), r * fp.per + torch.arange(fp.n_local))
+        gathered = torch.cat(gathered)
+        assert (seen == 1).all() and torch.unique(gathered).numel() == n and gathered.max() < plan.n_padded
+
+
+def _run_world(world, tmp_path, mode="rows", reducer="sum", balance="rows"):
+    port = 29500 + (os.getpid() * 7 + world + 11 * len(mode + reducer + balance)) % 2000
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")
     # spawn, not fork: the parent already runs OpenMP / MKL threads
-    mp.start_processes(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
-    out_ref, grads_ref = _reference()
+    mp.start_processes(_worker, args=(world, port, str(tmp_path), mode, reducer, balance), nprocs=world, join=True,
+                       start_method="spawn")
+    out_ref, grads_ref = _reference(reducer)
     parts = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
     assert [p["r0"] for p in parts][0] == 0 and parts[-1]["r1"] == out_ref.shape[0]
     out = torch.cat([p["out"] for p in parts])
@@ -171,5 +296,24 @@ def test_two_rank_gloo_matches_single_process_oracle(tmp_path):
 
 def test_three_rank_gloo_uneven_blocks(tmp_path):
     """403 rows over 3 ranks: blocks of different in-edge counts, padded slabs and a chunk count that does not divide the
-    block — the exchange must still deliver every source row exactly once."""
+    block — the exchange must still deliver every source row exactly once; padded rows stay out of the gradients."""
     _run_world(3, tmp_path)
+
+
+def test_row_partition_max_pool_two_ranks(tmp_path):
+    """SAGEConv-pool over the row partition: all-gather of the pooled projections, arg-scatter into a full-height partial,
+    reduce-scatter."""
+    _run_world(2, tmp_path, reducer="max")
+
+
+def test_row_partition_edge_balanced_three_ranks(tmp_path):
+    _run_world(3, tmp_path, reducer="max", balance="edges")
+
+
+def test_feature_partition_weighted_sum_two_and_three_ranks(tmp_path):
+    _run_world(2, tmp_path, mode="cols")
+    _run_world(3, tmp_path, mode="cols", balance="edges")
+
+
+def test_feature_partition_max_pool_three_ranks(tmp_path):
+    _run_world(3, tmp_path, mode="cols", reducer="max")
