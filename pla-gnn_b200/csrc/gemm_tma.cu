@@ -54,13 +54,14 @@ constexpr int TM_SMEM_BYTES = (TM_RAW_STAGES + TM_LO_STAGES) * TM_RAW_BYTES + 10
 constexpr int TM_EPI_WARPS = 8;
 constexpr int TM_THREADS = (2 + TM_EPI_WARPS) * 32;
 constexpr int TM_MAX_CHAIN = 40;    // k-blocks per TMEM accumulation chain (see gemm_tc.cu: truncating accumulate)
-// Long contractions (the weight gradients: K = number of nodes) get shorter chains.  The tensor core truncates when it adds
-// into the fp32 accumulator, so one chain's error grows with its length (~0.5 ulp per MMA for same-sign data); the gradient
-// sums then cancel and amplify it ~3x.  Measured at K = 24 041 on shared decisions (tests/test_gpu_model.py, full size):
-// chains of 40 k-blocks leave the weight gradients 1.0e-5 .. 1.5e-5 from the fp32 oracle, above the 1e-5 bar.  More, shorter
-// chains also tile better: 47 x 4 tiles on 74 CTA pairs is 3 waves of 20 k-blocks instead of 2 waves of 44.
+// Long contractions (the weight gradients: K = number of nodes) can be cut into shorter chains (PLAGNN_TMA_LONG_CHAIN).  The
+// tensor core truncates when it adds into the fp32 accumulator, so one chain's error grows with its length.  Measured at
+// K = 24 041 on shared decisions (tests/test_gpu_model.py, full size, worst of the 19 gradient tensors against the fp32
+// oracle): chains of 40 / 16 / 8 k-blocks -> 1.49e-5 / 1.23e-5 / 1.21e-5, and the PPI epoch 2.25 / 2.44 ms for 40 / 16 (more
+// partials to write and fold).  What remains comes from the FORWARD products (K = 503 / 1006, one chain each), whose
+// truncation bias the gradient sums amplify ~3.5x — so the default stays at TM_MAX_CHAIN.
 constexpr int TM_LONG_K_BLOCKS = 64;   // contractions of at least this many k-blocks (K >= 2048) ...
-constexpr int TM_LONG_CHAIN = 16;      // ... are cut into chains of at most this many
+constexpr int TM_LONG_CHAIN = 40;      // ... are cut into chains of at most this many
 
 struct alignas(64) TmParams {
     CUtensorMap map[PLAGNN_GEMM_MAX_PAIRS][2];    // [pair][A, B]

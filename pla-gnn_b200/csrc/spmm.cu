@@ -16,6 +16,7 @@
 //     in chunk order, which keeps "first maximum wins" and makes sums order-stable.
 #include "common.cuh"
 #include <math.h>
+#include <climits>
 #include <cstdlib>
 
 namespace plagnn {
@@ -276,6 +277,115 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
     }
 }
 
+// Narrow rows (feat <= 64: the column slice of one GPU in the feature partition, 128 or 256 bytes per row).  With one
+// float4 per lane a row needs only G = 8 or 16 lanes, so the warp's S = 32 / G lane groups each take a different in-edge of
+// the same work item: edge e of a batch of 32 goes to group e % S.  Every LDG.128 of the warp then fetches S neighbour rows
+// (512 bytes per request, as in the wide kernel, instead of 128), and the S partial results are folded with shuffles at the
+// end.  The max reducer keeps "first maximum in in-edge order wins" across the groups by carrying the winning edge position.
+template <int MODE, int G>
+__global__ void __launch_bounds__(SPMM_WARPS * 32, 4)
+spmm_narrow_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int32_t* __restrict__ eids,
+                   const float* __restrict__ ew, const int32_t* __restrict__ plan_hdr, const int32_t* __restrict__ item_ptr,
+                   const int32_t* __restrict__ slot_ptr, const int32_t* __restrict__ item_row, int item_begin, int n_items,
+                   const float* __restrict__ x, int64_t ldx, int feat, float* __restrict__ out, int32_t* __restrict__ arg_out,
+                   int64_t ldo, float* __restrict__ part_val, int32_t* __restrict__ part_arg, int part_ld, SpmmEpilogue ep) {
+    static_assert(MODE == MODE_MAX || MODE == MODE_SUM, "narrow kernel: max and sum reducers");
+    constexpr int S = 32 / G;          // lane groups = in-edges in flight per load instruction
+    constexpr int U = 4;               // rounds unrolled: U rows in flight per lane (32 warps x 32 lanes x 4 x 16 B = 64 KB per SM)
+    pdl_trigger();
+    const int lane = threadIdx.x & 31;
+    const int item = item_begin + blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+    if (item >= n_items) return;
+    pdl_wait();
+    const int chunk = __ldg(plan_hdr);
+    const int row = __ldg(item_row + item);
+    const int first = __ldg(item_ptr + row);
+    const int nch = __ldg(item_ptr + row + 1) - first;
+    const int k = item - first;
+    const int rbeg = __ldg(indptr + row), rend = __ldg(indptr + row + 1);
+    const int beg = rbeg + k * chunk;
+    const int end = min(rend, beg + chunk);
+    const int sub = lane / G, gl = lane % G;
+    const int col = 4 * gl;
+    const bool cok = col < feat;
+    const float* xc = x + (cok ? col : 0);                  // lanes past the last column re-read column 0 (nothing stored)
+    const float init = MODE == MODE_MAX ? -INFINITY : 0.f;
+    float4 acc = make_float4(init, init, init, init);
+    int4 arg = make_int4(-1, -1, -1, -1);
+    int4 pos = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
+
+    for (int base = beg; base < end; base += 32) {
+        const int cnt = min(32, end - base);
+        int my_u = 0;
+        float my_w = 1.f;
+        if (lane < cnt) {
+            my_u = __ldg(indices + base + lane);
+            if (MODE == MODE_SUM && ew) my_w = __ldg(ew + (eids ? __ldg(eids + base + lane) : base + lane));
+        }
+        for (int t = 0; t * S < cnt; t += U) {
+            int u[U];
+            float w[U];
+            float4 v[U];
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                const int e = min((t + i) * S + sub, 31);
+                u[i] = __shfl_sync(0xffffffffu, my_u, e);
+                if (MODE == MODE_SUM) w[i] = __shfl_sync(0xffffffffu, my_w, e);
+                const bool live = (t + i) * S + sub < cnt;
+                v[i] = live ? ldg_f4(xc + (int64_t)u[i] * ldx) : make_float4(init, init, init, init);
+            }
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                if (MODE == MODE_MAX) {
+                    const int p = base + (t + i) * S + sub;
+                    if (v[i].x > acc.x) { acc.x = v[i].x; arg.x = u[i]; pos.x = p; }
+                    if (v[i].y > acc.y) { acc.y = v[i].y; arg.y = u[i]; pos.y = p; }
+                    if (v[i].z > acc.z) { acc.z = v[i].z; arg.z = u[i]; pos.z = p; }
+                    if (v[i].w > acc.w) { acc.w = v[i].w; arg.w = u[i]; pos.w = p; }
+                } else {
+                    const float ww = ew ? w[i] : 1.f;
+                    acc.x = fmaf(ww, v[i].x, acc.x); acc.y = fmaf(ww, v[i].y, acc.y);
+                    acc.z = fmaf(ww, v[i].z, acc.z); acc.w = fmaf(ww, v[i].w, acc.w);
+                }
+            }
+        }
+    }
+    // fold the S lane groups (group 0 ends up with the result)
+#pragma unroll
+    for (int off = G; off < 32; off <<= 1) {
+        const float ox = __shfl_xor_sync(0xffffffffu, acc.x, off), oy = __shfl_xor_sync(0xffffffffu, acc.y, off);
+        const float oz = __shfl_xor_sync(0xffffffffu, acc.z, off), ow = __shfl_xor_sync(0xffffffffu, acc.w, off);
+        if (MODE == MODE_MAX) {
+            const int ax = __shfl_xor_sync(0xffffffffu, arg.x, off), ay = __shfl_xor_sync(0xffffffffu, arg.y, off);
+            const int az = __shfl_xor_sync(0xffffffffu, arg.z, off), aw = __shfl_xor_sync(0xffffffffu, arg.w, off);
+            const int px = __shfl_xor_sync(0xffffffffu, pos.x, off), py = __shfl_xor_sync(0xffffffffu, pos.y, off);
+            const int pz = __shfl_xor_sync(0xffffffffu, pos.z, off), pw = __shfl_xor_sync(0xffffffffu, pos.w, off);
+            if (ox > acc.x || (ox == acc.x && px < pos.x)) { acc.x = ox; arg.x = ax; pos.x = px; }
+            if (oy > acc.y || (oy == acc.y && py < pos.y)) { acc.y = oy; arg.y = ay; pos.y = py; }
+            if (oz > acc.z || (oz == acc.z && pz < pos.z)) { acc.z = oz; arg.z = az; pos.z = pz; }
+            if (ow > acc.w || (ow == acc.w && pw < pos.w)) { acc.w = ow; arg.w = aw; pos.w = pw; }
+        } else {
+            acc.x += ox; acc.y += oy; acc.z += oz; acc.w += ow;
+        }
+    }
+    if (sub != 0 || !cok) return;
+    if (nch == 1) {
+        float4 r = acc;
+        if (MODE == MODE_MAX) {
+            r.x = arg.x < 0 ? 0.f : r.x; r.y = arg.y < 0 ? 0.f : r.y;
+            r.z = arg.z < 0 ? 0.f : r.z; r.w = arg.w < 0 ? 0.f : r.w;
+            *reinterpret_cast<int4*>(arg_out + (int64_t)row * ldo + col) = arg;
+        } else {
+            r = sum_epilogue(r, ep, row, col, feat);
+        }
+        *reinterpret_cast<float4*>(out + (int64_t)row * ldo + col) = r;
+    } else {
+        const int64_t slot = (int64_t)__ldg(slot_ptr + row) + k;
+        *reinterpret_cast<float4*>(part_val + slot * part_ld + col) = acc;
+        if (MODE == MODE_MAX) *reinterpret_cast<int4*>(part_arg + slot * part_ld + col) = arg;
+    }
+}
+
 // folds the partials of split rows in chunk order: one warp per (split row, 128-column group)
 template <int MODE>
 __global__ void __launch_bounds__(SPMM_WARPS * 32)
@@ -412,6 +522,18 @@ static void launch_main(const SpmmArgs& a, const int32_t* item_ptr, const int32_
         (int)a.feat, a.argm, a.ldarg, a.zfwd, a.ldzf, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep, 1.0f, -0.0f);
 }
 
+template <int MODE, int G>
+static void launch_narrow(const SpmmArgs& a, const int32_t* item_ptr, const int32_t* slot_ptr, const int32_t* item_row,
+                          float* pv, int32_t* pa, cudaStream_t st) {
+    const int item_begin = a.range ? (int)a.range[0] : 0;
+    const int n_items = a.range ? (int)a.range[1] : (int)a.counts[0];
+    if (n_items <= item_begin) return;
+    dim3 grid((unsigned)ceil_div(n_items - item_begin, SPMM_WARPS));
+    launch_pdl(spmm_narrow_kernel<MODE, G>, grid, dim3(SPMM_WARPS * 32), 0, st,
+        a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, item_begin, n_items, a.x, a.ldx,
+        (int)a.feat, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep);
+}
+
 template <int MODE>
 static int spmm_dispatch(const SpmmArgs& a, const char* name, cudaStream_t st) {
     if (!a.indptr || !a.indices || !a.plan || !a.counts || !a.x || !a.out) return fail(PLAGNN_ERR_ARG, name, "null pointer");
@@ -439,7 +561,13 @@ static int spmm_dispatch(const SpmmArgs& a, const char* name, cudaStream_t st) {
     // NB = 4 -> 0.2174 ms (128 registers, lower occupancy); the deeper variant only wins for chunks >= 1024 and stays
     // opt-in (PLAGNN_SPMM_DEEP=1).
     static const int deep = [] { const char* e = getenv("PLAGNN_SPMM_DEEP"); return e ? atoi(e) : 0; }();
-    if (MODE == MODE_MATCH || !deep) {
+    // rows of <= 64 floats: several in-edges per load instruction (PLAGNN_SPMM_NARROW=0: the wide kernel, for A/B runs)
+    static const bool narrow_ok = [] { const char* e = getenv("PLAGNN_SPMM_NARROW"); return !e || e[0] != '0'; }();
+    if (MODE != MODE_MATCH && narrow_ok && groups <= 16) {
+        constexpr int NM = MODE == MODE_MATCH ? MODE_SUM : MODE;     // (MATCH never gets here; keeps the template instantiable)
+        if (groups <= 8) launch_narrow<NM, 8>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
+        else launch_narrow<NM, 16>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
+    } else if (MODE == MODE_MATCH || !deep) {
         if (groups <= 32) launch_main<MODE, 1, 8>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
         else if (groups <= 64) launch_main<MODE, 2, 4>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
         else if (groups <= 96) launch_main<MODE, 3, 2>(a, item_ptr, slot_ptr, item_row, pv, pa, st);

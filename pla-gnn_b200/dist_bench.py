@@ -161,19 +161,72 @@ def measure_variant(v: Variant, steps, warmup, rank, world, dev, reference=None)
     return res
 
 
+def probe_collectives(comm, n, f, world, dev, reps=5):
+    """The exchange steps alone (nothing else on the GPU), at the sizes one layer of the workload moves: what NCCL delivers on
+    this box through the library's wrappers.  GB/s = bytes a rank receives from its peers / time (max over ranks)."""
+    from . import _lib
+    lib = _lib.load()
+    per = (n + world - 1) // world
+    st = torch.cuda.current_stream().cuda_stream
+    local = torch.randn(per, f, device=dev)
+    full = torch.empty(world * per, f, device=dev)
+    blocks = torch.empty(world * per, f // world, device=dev)
+    blocks2 = torch.empty_like(blocks)
+    calls = {
+        "allgather_rows": (lambda: lib.plagnn_nccl_allgather_rows(local.data_ptr(), full.data_ptr(), per, f, comm.handle, st),
+                           4.0 * per * f * (world - 1)),
+        "reducescatter_rows": (lambda: lib.plagnn_nccl_reducescatter_rows(full.data_ptr(), local.data_ptr(), per, f, comm.handle, st),
+                               4.0 * per * f * (world - 1)),
+        "alltoall_blocks": (lambda: lib.plagnn_nccl_alltoall_blocks(blocks.data_ptr(), blocks2.data_ptr(), per * (f // world), world,
+                                                                    comm.handle, st), 4.0 * per * (f // world) * (world - 1)),
+    }
+    out = {}
+    for name, (fn, nbytes) in calls.items():
+        for _ in range(2):
+            _lib.check(fn(), name)
+        dist.barrier()
+        torch.cuda.synchronize()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        for _ in range(reps):
+            _lib.check(fn(), name)
+        e_.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([s_.elapsed_time(e_) / reps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name] = {"ms": round(t.item(), 4), "received_gb_per_s": round(nbytes / (t.item() * 1e-3) / 1e9, 1)}
+    return out
+
+
 def run_partitioned(n, e, f, steps, warmup, rank, world, dev, modes=("rows", "cols"), reducers=("sum", "max"), chunks=None,
                     balance="edges", max_ctas=None):
     """All requested variants on the same generated graph.  Returns (dict for the JSON line on rank 0, None elsewhere)."""
     from . import synth
     from .dist import NcclComm
     t0 = time.perf_counter()
-    sg = synth.scaled_graph(n, e, seed=1234, device=dev)                  # identical on every rank (seeded)
-    gen = torch.Generator(device=dev).manual_seed(100)
-    h0_global = torch.randn(n, f, generator=gen, device=dev)
+    # Generated on rank 0's GPU and broadcast: device-side generation (randperm / unique over 1e8 keys) is not guaranteed
+    # to be bit-identical from one GPU to the next, and a rank working on a slightly different graph was what the first
+    # N = 2 run of the in-run check caught (a few output rows off by percents, gradients by 1e-4).
+    if rank == 0 or world == 1:
+        sg = synth.scaled_graph(n, e, seed=1234, device=dev)
+        gen = torch.Generator(device=dev).manual_seed(100)
+        h0_global = torch.randn(n, f, generator=gen, device=dev)
+        num_e = torch.tensor([sg.src.numel()], device=dev, dtype=torch.int64)
+    else:
+        sg, h0_global, num_e = None, torch.empty((n, f), device=dev), torch.zeros(1, device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.broadcast(num_e, 0)
+        if rank != 0:
+            ne = int(num_e.item())
+            sg = synth.ScaledGraph(torch.empty(ne, dtype=torch.int64, device=dev), torch.empty(ne, dtype=torch.int64, device=dev),
+                                   torch.empty(ne, dtype=torch.float32, device=dev), n)
+        for t in (sg.src, sg.dst, sg.weight, h0_global):
+            dist.broadcast(t, 0)
     t_gen = time.perf_counter() - t0
     chunks = chunks or int(os.environ.get("PLAGNN_DIST_CHUNKS", "2" if world > 1 else "1"))
-    max_ctas = int(os.environ.get("PLAGNN_NCCL_MAX_CTAS", "16")) if max_ctas is None else max_ctas
+    max_ctas = int(os.environ.get("PLAGNN_NCCL_MAX_CTAS", "0")) if max_ctas is None else max_ctas
     comm = NcclComm(rank, world, dev, max_ctas=max_ctas) if world > 1 else None
+    probe = probe_collectives(comm, n, f, world, dev) if world > 1 else None
     results = []
     single_ms = {}
     for reducer in reducers:
@@ -229,7 +282,7 @@ def run_partitioned(n, e, f, steps, warmup, rank, world, dev, modes=("rows", "co
     return {"workload": f"BASELINE configs[3]: power-law graph N={n}, E={e} directed weighted edges, F={f}; 2-layer weighted-sum GCN "
                         "(u_mul_e + sum, right-normalised, bias + leaky_relu fused) and 2-layer SAGEConv-pool stack (max reducer); "
                         "step = forward + backward + weight-gradient all-reduce + Adam", "scaling": "strong", "n_gpus": world,
-            "balance": balance, "nccl_max_ctas": max_ctas, "generate_seconds": round(t_gen, 2),
+            "balance": balance, "nccl_max_ctas": max_ctas, "generate_seconds": round(t_gen, 2), "nccl_alone": probe,
             "variants": results,
             "winner": {k: {"mode": v["mode"], "ms_per_step": v["ms_per_step"], "edges_per_s": v["edges_per_s"],
                            "strong_scaling_efficiency": v.get("strong_scaling_efficiency")} for k, v in best.items()},

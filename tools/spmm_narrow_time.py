@@ -1,0 +1,42 @@
+"""Aggregation over the WHOLE 1 M-node / 100 M-edge graph on a column slice of F/P columns (what one GPU of the feature
+partition runs): weighted sum and max reducer at F/P = 32, 64, 128, 256, event-timed.  Run once with PLAGNN_SPMM_NARROW=0
+and once with =1 to compare the wide kernel with the sub-warp kernel on the narrow slices."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+import plagnn_b200 as P
+from plagnn_b200 import ops, synth
+
+dev = torch.device("cuda:0")
+n, e = 1_000_000, 100_000_000
+sg = synth.scaled_graph(n, e, seed=1234, device=dev)
+csc = P.build_csr(sg.dst.to(torch.int32), sg.src.to(torch.int32), n, False)
+w = sg.weight[csc.eids.long()].contiguous()
+scale = (1.0 / csc.degrees.clamp(min=1).float()).contiguous()
+del sg
+out = {"narrow": os.environ.get("PLAGNN_SPMM_NARROW", "1"), "edges": int(csc.num_edges)}
+for f in (32, 64, 128, 256):
+    x = ops.alloc(n, f, dev)
+    x.copy_(torch.randn(n, f, device=dev))
+    bias = torch.zeros(f, device=dev)
+    for name, fn in (("sum", lambda: ops.spmm_sum(csc, x, w=w, scale=scale, bias=bias, act=ops.ACT_LEAKY, w_in_csr_order=True)),
+                     ("max", lambda: ops.spmm_max_fwd(csc, x))):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(5):
+            fn()
+        t.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(t) / 5
+        alg = 4 * f * csc.num_edges + 4 * csc.num_edges * (2 if name == "sum" else 1) + 4 * f * n * (1 if name == "sum" else 2)
+        out[f"{name}/{f}"] = {"ms": round(ms, 3), "algorithmic_gb_per_s": round(alg / ms / 1e6, 0)}
+    del x
+print(json.dumps(out))
