@@ -320,29 +320,6 @@ def run_ours(args):
         sampler.prepare()
     for _ in range(3):
         epoch()
-    # ---- end-to-end timed region (host buffers in, loss + logits out) ------------------------------
-    for _ in range(3):
-        epoch_e2e()
-
-    def timed_e2e(steps):
-        barrier()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(steps):
-            epoch_e2e()
-        torch.cuda.current_stream().wait_stream(copy_stream)   # the last step's results must have reached the host
-        e.record()
-        barrier()
-        ms = s.elapsed_time(e)
-        if world > 1:
-            import torch.distributed as dist
-            tt = torch.tensor([ms], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms = tt.item()
-        return ms
-
-    ms_e2e = timed_e2e(args.steps)
-
     # ---- several models of the fold/seed sweep at once on this GPU, one CUDA stream each (reported beside `value`) ----
     # The reference trains 100 independent models per condition one after the other (code/train.py:162-180); their
     # kernels can share the GPU: the aggregation of one model fills the SMs a GEMM tail wave of another leaves idle.
@@ -391,6 +368,23 @@ def run_ours(args):
     ops.profile_start()
     ms_profiled = timed(epoch, args.steps)
     prof = ops.profile_stop()
+    # ---- the same epoch as one CUDA-graph replay (plagnn_b200.TrainStep: no autograd, no host work per launch) -----------
+    graph_leg = None
+    try:
+        torch.manual_seed(70)
+        m_g = P.GNN32(features.shape[1], *HIDDEN).to(dev)
+        ts = P.TrainStep(m_g, g, features, labels, idx_d, i_weight, lr=LR)
+        for _ in range(3):
+            ts.step()
+        ms_graph = timed(ts.step, args.steps)
+        graph_leg = {"value": world * args.steps / (ms_graph * 1e-3), "unit": UNIT, "ms_per_step": ms_graph / args.steps,
+                     "launches_per_step": ts.launches_per_epoch, "loss_after": float(ts.loss.item()),
+                     "note": "forward + indexed loss + backward + Adam (step count on the device) as four C-ABI calls captured "
+                             "once and replayed; every node is a library kernel, PDL edges kept; `value` above stays the "
+                             "autograd-driven loop the unchanged train.py runs"}
+        del ts, m_g
+    except Exception as ex:                    # a capture problem must not take the headline measurement down
+        graph_leg = {"value": None, "error": repr(ex)[:300]}
     # ---- BASELINE configs[3]: the partitioned synthetic graph on the same N GPUs (reported beside `value`) ---------------
     partitioned = None
     if not args.no_partitioned:
@@ -399,9 +393,33 @@ def run_ours(args):
         partitioned = dist_bench.run_partitioned(args.partitioned_nodes, args.partitioned_edges, args.feat, args.partitioned_steps,
                                                  3, rank, world, dev, modes=("rows",) if world == 1 else ("rows", "cols"))
         torch.cuda.empty_cache()
+    # ---- end-to-end timed region (host buffers in, loss + logits out) ------------------------------
+    for _ in range(3):
+        epoch_e2e()
+
+    def timed_e2e(steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            epoch_e2e()
+        torch.cuda.current_stream().wait_stream(copy_stream)   # the last step's results must have reached the host
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            import torch.distributed as dist
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = tt.item()
+        return ms
+
+    ms_e2e = timed_e2e(args.steps)
+
     # ---- device-resident timed region (value): the LAST leg of the process, W warm-up steps right before it --------------
-    # (the legs above — end-to-end, concurrent models, per-kernel breakdown — are timed regions of their own, each with
-    # its own warm-up; running them first also means the clocks are up when this one starts)
+    # (the legs above are timed regions of their own, each with its own warm-up; the two headline legs — end to end and
+    # this one — come last, when the process has been launching kernels for seconds and the clocks are up: a first run of
+    # this order with the end-to-end leg first measured it at 5.9 ms per step instead of 2.3)
     warm = max(args.warmup, 3)
     for _ in range(warm):
         epoch()
@@ -449,14 +467,15 @@ def run_ours(args):
                    "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one graph/model per GPU)",
                    "l2": "no explicit flush: one step touches >1 GB of distinct activations/gradients (> 126 MB L2); the "
                          "aggregation input is produced by the preceding GEMM, as in the real loop",
-                   "legs": "in process order: end-to-end (3 warm-up + K), concurrent models (3 + K), per-kernel breakdown "
-                           "(3 + K), partitioned configs[3] block, then W warm-up + K timed steps = `value`",
+                   "legs": "in process order: concurrent models (3 warm-up + K), per-kernel breakdown (3 + K), graph replay (3 + K), partitioned "
+                           "configs[3] block, end-to-end (3 + K), then W warm-up + K timed steps = `value`",
                    "train_rows": int(len(train_index)), "lr": LR},
         "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": int(feat_h.numel() * 4 + loc_h.numel() * 4 + idx_h.numel() * 8),
                 "d2h_bytes_per_step": int(4 + logits_h.numel() * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "concurrent_models": conc,
+        "graph_replay": graph_leg,
         "partitioned": partitioned,
         "clocks": clocks,
         "roofline": {"kernel": f"spmm_max_fwd F={f_in} (layer-1 aggregation)", "bound": "hbm",

@@ -238,6 +238,11 @@ int plagnn_bce_weighted(const float* prob, int64_t ldp, const float* target, int
                         float grad_scale, float* loss, float* dprob, int64_t lddp,
                         void* workspace, size_t workspace_bytes, plagnn_stream_t stream);
 
+/* dst[rows x cols] = src * (*scalar), scalar on the device: the product of the saved loss gradient with autograd's incoming
+ * gradient of the scalar loss (code/train.py:204 `train_loss.backward()`), without a host read of that scalar. */
+int plagnn_scale_by_device_scalar(const float* src, int64_t lds, int64_t rows, int64_t cols, const float* scalar /* device */,
+                                  float* dst, int64_t ldd, plagnn_stream_t stream);
+
 /* multi-tensor Adam (betas, eps, no weight decay, no amsgrad — torch.optim.Adam defaults).
  * tensors: DEVICE array of `count` descriptors.  bias_correction1 = 1-beta1^t and
  * bias_correction2_sqrt = sqrt(1-beta2^t) are computed by the host in double, as torch does. */
@@ -247,6 +252,13 @@ typedef struct {
 int plagnn_adam_multi(const plagnn_adam_tensor* tensors /* device */, int32_t count, int64_t max_numel,
                       double lr, double beta1, double beta2, double eps,
                       double bias_correction1, double bias_correction2_sqrt, plagnn_stream_t stream);
+/* The same step with the step count held on the DEVICE, so that the call can sit inside a CUDA graph that is replayed once
+ * per epoch (code/train.py:195-205 runs 200 epochs of fixed shape per model): `step_count` (device int64, starts at 0) is
+ * incremented by the call; the bias corrections 1-beta1^t, sqrt(1-beta2^t) are formed from it on the device in double and
+ * rounded once to fp32, like the host version.  `scalars`: device float[4] scratch owned by the caller. */
+int plagnn_adam_multi_devstep(const plagnn_adam_tensor* tensors /* device */, int32_t count, int64_t max_numel,
+                              double lr, double beta1, double beta2, double eps,
+                              int64_t* step_count /* device */, float* scalars /* device float[4] */, plagnn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * next-1: label decision on device — replaces the Python row loop of

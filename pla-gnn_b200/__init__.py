@@ -5,6 +5,7 @@ Public surface (mirrors what the reference's train loop touches)
     create_graph, Graph, graph, add_self_loop    utils.py / dgl drop-ins (utils.py, graph.py)
     multi_loss, multi_loss_indexed, weight_cal   fused loss (loss.py)
     FusedAdam                  fused optimiser (optim.py)
+    TrainStep                  the epoch body (forward, loss, backward, Adam) as one CUDA graph replay (epoch.py)
     protein_loc_correction     on-device label decision (metrics.py)
     scoring                    alteration scoring after training: scaling / mat_merge / alteration_rank (scoring.py)
     preprocess                 offline stage on the device: edge_clustering_coefficients / modify_network_topology (preprocess.py)
@@ -17,11 +18,12 @@ from .graph import Graph, Csr, graph, add_self_loop, build_csr
 from .nn import GNN32, SAGEConv, GraphConvSum, GCN
 from .loss import multi_loss, multi_loss_indexed, weight_cal
 from .optim import FusedAdam
+from .epoch import TrainStep
 from .metrics import protein_loc_correction, performances_record
 from .utils import create_graph
 from . import scoring
 from . import preprocess
 
 __all__ = ["GNN32", "SAGEConv", "GraphConvSum", "GCN", "Graph", "Csr", "graph", "add_self_loop", "build_csr",
-           "create_graph", "multi_loss", "multi_loss_indexed", "weight_cal", "FusedAdam", "protein_loc_correction",
+           "create_graph", "multi_loss", "multi_loss_indexed", "weight_cal", "FusedAdam", "TrainStep", "protein_loc_correction",
            "performances_record", "PlagnnError", "LIB_PATH"]

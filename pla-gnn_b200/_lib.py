@@ -84,6 +84,9 @@ PROTOTYPES = {
                                     c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "plagnn_adam_multi": (c_int, [c_void_p, c_int32, c_int64, c_double, c_double, c_double, c_double, c_double, c_double,
                                   c_void_p]),
+    "plagnn_scale_by_device_scalar": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
+    "plagnn_adam_multi_devstep": (c_int, [c_void_p, c_int32, c_int64, c_double, c_double, c_double, c_double, c_void_p, c_void_p,
+                                          c_void_p]),
     "plagnn_loc_correction_workspace_bytes": (c_size_t, [c_int64]),
     "plagnn_loc_correction": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_int64, c_void_p, c_size_t,
                                       c_void_p]),

@@ -77,6 +77,21 @@ bce_kernel(const float* __restrict__ prob, int64_t ldp, const float* __restrict_
     }
 }
 
+// dst[r, c] = src ? src[r, c] * (*scalar) : 0 for c < cols: the clear of the loss gradient before bce_kernel's reductions and the
+// product with autograd's incoming gradient (a device scalar), both as kernels so that they stay in the launch chain
+__global__ void __launch_bounds__(256)
+scale_or_zero_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols, const float* __restrict__ scalar,
+                     float* __restrict__ dst, int64_t ldd) {
+    pdl_enter();
+    const float s = scalar ? *scalar : 1.f;
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols;
+        const int c = (int)(i - r * cols);
+        dst[r * ldd + c] = src ? src[r * lds + c] * s : 0.f;
+    }
+}
+
 __global__ void bce_finalize_kernel(const double* __restrict__ block_part, int num_blocks, int classes,
                                     int64_t num_index, float* __restrict__ loss) {
     __shared__ float per_class[BCE_MAX_CLASSES];
@@ -96,10 +111,27 @@ __global__ void bce_finalize_kernel(const double* __restrict__ block_part, int n
 }
 
 // ---------------------------------------------------------------------------------------------
+// step count on the device (graph-replayable Adam): t = ++(*step_count); scalars[0] = lr / (1 - beta1^t), scalars[1] =
+// sqrt(1 - beta2^t), both formed in double and rounded once
+__global__ void adam_step_scalars_kernel(int64_t* __restrict__ step_count, float* __restrict__ scalars, double lr, double beta1,
+                                         double beta2) {
+    pdl_enter();
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int64_t t = *step_count + 1;
+        *step_count = t;
+        scalars[0] = (float)(lr / (1.0 - pow(beta1, (double)t)));
+        scalars[1] = (float)sqrt(1.0 - pow(beta2, (double)t));
+    }
+}
+
 __global__ void __launch_bounds__(256)
 adam_kernel(const plagnn_adam_tensor* __restrict__ tensors, float lerp_w, float beta2, float one_minus_beta2,
-            float eps, float step_size, float bc2_sqrt) {
+            float eps, float step_size, float bc2_sqrt, const float* __restrict__ dev_scalars) {
     pdl_enter();
+    if (dev_scalars) {
+        step_size = dev_scalars[0];
+        bc2_sqrt = dev_scalars[1];
+    }
     const plagnn_adam_tensor T = tensors[blockIdx.y];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T.numel; i += (int64_t)gridDim.x * blockDim.x) {
         const float g = T.grad[i];
@@ -330,11 +362,22 @@ int plagnn_bce_weighted(const float* prob, int64_t ldp, const float* target, int
     ProfileScope prof("bce_weighted", num_index, classes, 0, stream);
     const int blocks = (int)ceil_div(num_index, BCE_THREADS);
     double* part = (double*)workspace;
-    if (dprob) PLAGNN_CUDA_TRY(cudaMemset2DAsync(dprob, lddp * sizeof(float), 0, classes * sizeof(float), num_rows, st));
+    if (dprob)
+        launch_pdl(scale_or_zero_kernel, dim3((unsigned)capped_grid(num_rows * classes, 256, 8)), dim3(256), 0, st, (const float*)nullptr,
+                   (int64_t)0, num_rows, (int)classes, (const float*)nullptr, dprob, lddp);
     launch_pdl(bce_kernel, dim3(blocks), dim3(BCE_THREADS), 0, st, prob, ldp, target, ldt, index, num_index, num_rows, (int)classes,
                                                 class_weight, class_weight_plus1, grad_scale, part, dprob, lddp);
     launch_pdl(bce_finalize_kernel, dim3(1), dim3(BCE_MAX_CLASSES), 0, st, part, blocks, (int)classes, num_index, loss);
-    return check_launch("bce_weighted", 2);
+    return check_launch("bce_weighted", dprob ? 3 : 2);
+}
+
+int plagnn_scale_by_device_scalar(const float* src, int64_t lds, int64_t rows, int64_t cols, const float* scalar, float* dst,
+                                  int64_t ldd, plagnn_stream_t stream) {
+    if (!src || !dst || !scalar || rows <= 0 || cols <= 0 || lds < cols || ldd < cols)
+        return fail(PLAGNN_ERR_ARG, "scale_by_device_scalar", "bad arguments");
+    launch_pdl(scale_or_zero_kernel, dim3((unsigned)capped_grid(rows * cols, 256, 8)), dim3(256), 0, (cudaStream_t)stream, src, lds, rows,
+               (int)cols, scalar, dst, ldd);
+    return check_launch("scale_by_device_scalar");
 }
 
 int plagnn_adam_multi(const plagnn_adam_tensor* tensors, int32_t count, int64_t max_numel, double lr, double beta1,
@@ -349,8 +392,20 @@ int plagnn_adam_multi(const plagnn_adam_tensor* tensors, int32_t count, int64_t 
     const float omb2 = (float)(1.0 - beta2);
     dim3 grid((unsigned)capped_grid(max_numel, 256, 4), (unsigned)count);
     launch_pdl(adam_kernel, grid, dim3(256), 0, (cudaStream_t)stream, tensors, lerp_w, (float)beta2, omb2, (float)eps, step_size,
-                                                        (float)bias_correction2_sqrt);
+                                                        (float)bias_correction2_sqrt, (const float*)nullptr);
     return check_launch("adam_multi");
+}
+
+int plagnn_adam_multi_devstep(const plagnn_adam_tensor* tensors, int32_t count, int64_t max_numel, double lr, double beta1,
+                              double beta2, double eps, int64_t* step_count, float* scalars, plagnn_stream_t stream) {
+    if (!tensors || count <= 0 || max_numel <= 0 || !step_count || !scalars)
+        return fail(PLAGNN_ERR_ARG, "adam_multi_devstep", "bad arguments");
+    ProfileScope prof("adam_multi", count, max_numel, 1, stream);
+    launch_pdl(adam_step_scalars_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, step_count, scalars, lr, beta1, beta2);
+    dim3 grid((unsigned)capped_grid(max_numel, 256, 4), (unsigned)count);
+    launch_pdl(adam_kernel, grid, dim3(256), 0, (cudaStream_t)stream, tensors, (float)(1.0 - beta1), (float)beta2,
+               (float)(1.0 - beta2), (float)eps, 0.f, 1.f, (const float*)scalars);
+    return check_launch("adam_multi_devstep", 2);
 }
 
 size_t plagnn_colsum_workspace_bytes(int64_t rows, int64_t cols) {

@@ -461,7 +461,9 @@ class CudaBackend:
         self.ops, self._lib, self.lib = ops, _lib, _lib.load()
         self.comm = comm
         self.skip_comm = False
-        self.comm_stream = torch.cuda.Stream() if comm is not None else None
+        # highest priority: when an SM slot frees up, the exchange kernel's CTAs are placed before the pending CTAs of the
+        # aggregation launched ahead of it — otherwise the collective only starts once that whole grid has been scheduled
+        self.comm_stream = torch.cuda.Stream(priority=-1) if comm is not None else None
         plan = pg.plan
         self.ranges = {}
         if pg.mode == "rows":

@@ -48,7 +48,8 @@ class _BCEFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        return ctx.dprob * grad_out, None, None, None, None
+        # d loss / d prob was formed by the loss kernel; times the incoming gradient of the scalar loss (a device scalar)
+        return ops.scale_by_device_scalar(ctx.dprob, grad_out), None, None, None, None
 
 
 def multi_loss(input, target, i_weight):

@@ -389,6 +389,17 @@ def bce_weighted(prob: torch.Tensor, target: torch.Tensor, index: torch.Tensor |
 
 
 @on_tensor_device
+def scale_by_device_scalar(x: torch.Tensor, scalar: torch.Tensor) -> torch.Tensor:
+    """x * scalar with the scalar read on the device (0-dim or 1-element fp32 CUDA tensor)."""
+    _require_cuda_f32(x, scalar)
+    assert x.dim() == 2 and x.stride(1) == 1 and scalar.numel() == 1
+    out = alloc(x.shape[0], x.shape[1], x.device)
+    check(_lib.load().plagnn_scale_by_device_scalar(_p(x), x.stride(0), x.shape[0], x.shape[1], _p(scalar), _p(out), out.stride(0),
+                                                    _stream()), "scale_by_device_scalar")
+    return out
+
+
+@on_tensor_device
 def loc_correction(prob: torch.Tensor, alpha: float) -> torch.Tensor:
     lib = _lib.load()
     _require_cuda_f32(prob)
