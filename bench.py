@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--concurrent-models", type=int, default=4)
     ap.add_argument("--no-partitioned", action="store_true", help="skip the configs[3] partitioned block")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the configs[1] end-to-end pipeline sample")
+    ap.add_argument("--pipeline-models", type=int, default=2)
+    ap.add_argument("--pipeline-epochs", type=int, default=25)
     ap.add_argument("--partitioned-steps", type=int, default=10)
     ap.add_argument("--partitioned-nodes", type=int, default=1_000_000)
     ap.add_argument("--partitioned-edges", type=int, default=100_000_000)
@@ -385,6 +388,30 @@ def run_ours(args):
         del ts, m_g
     except Exception as ex:                    # a capture problem must not take the headline measurement down
         graph_leg = {"value": None, "error": repr(ex)[:300]}
+    # ---- BASELINE configs[1] end to end: control + perturbation state trained, merged, scored, ranked (bounded sample) ----
+    config2 = None
+    if rank == 0 and not args.no_pipeline:
+        try:
+            from plagnn_b200 import pipeline, synth
+            prob_n = synth.ppi_problem(n, len(prob.ppi_row), "normal", seed=70)
+            g_n = P.create_graph(prob_n.scipy_ppi(), prob_n.ecc, prob_n.gcn, prob_n.scipy_loc(), prob_n.expr, ids).to(dev)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rec, _, _ = pipeline.alteration_pipeline(g_n, g, prob.labelled, prob.loc, lr=LR, fold_num=10, epoch_num=args.pipeline_epochs,
+                                                     fold_seeds=(12,), model_seed=70, max_models=args.pipeline_models)
+            top_rows = rec["row"][:5].tolist()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            config2 = {"seconds": dt, "models_per_state": args.pipeline_models, "epochs_per_model": args.pipeline_epochs,
+                       "epochs_total": 2 * args.pipeline_models * args.pipeline_epochs, "ranked_entries": int(rec["row"].numel()),
+                       "top_rows": top_rows, "full_sweep_extrapolated_hours": dt / (2 * args.pipeline_models * args.pipeline_epochs)
+                                                                                * (2 * 100 * 200) / 3600.0,
+                       "note": "wall clock incl. graph capture per model and KFold on the host: train control and TSA state "
+                               "(TrainStep), mat_merge of each, (inter - normal) / normal, rank; the reference's full sweep is 100 "
+                               "models x 200 epochs per state (code/train.py:162-205, code/main.py:32-48,80-84)"}
+            del g_n, rec
+        except Exception as ex:
+            config2 = {"seconds": None, "error": repr(ex)[:300]}
     # ---- BASELINE configs[3]: the partitioned synthetic graph on the same N GPUs (reported beside `value`) ---------------
     partitioned = None
     if not args.no_partitioned:
@@ -452,11 +479,13 @@ def run_ours(args):
     flops_epoch = dense_flops(n, f_in)
     sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
     l2_cap = 6300.0 * sm_mhz * 1e6 / 1e9 if sm_mhz else None
-    traffic = None
+    traffic = lts = None
     tpath = os.path.join(ROOT, "profiles", "r1_spmm_traffic.json")
     if n == 24041 and os.path.exists(tpath):          # dram__bytes_read + write of this kernel from the committed ncu capture
         tj = json.load(open(tpath))
         traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        lts = tj.get("lts_sectors_read_by_sm")
+    rg = roofline_gemm(prof, args.steps, flops_epoch, gemm_ms, tf_peak, peak_src)
     out = {
         "metric": METRIC, "value": world * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps,
@@ -476,26 +505,33 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "concurrent_models": conc,
         "graph_replay": graph_leg,
+        "config2_pipeline": config2,
         "partitioned": partitioned,
         "clocks": clocks,
-        "roofline": {"kernel": f"spmm_max_fwd F={f_in} (layer-1 aggregation)", "bound": "hbm",
-                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": traffic, "traffic_source": "ncu --set full capture committed under profiles/ (per launch)" if traffic else None,
-                     "peak_source": peak_src, "algorithmic_bytes": alg, "avg_ms": spmm_ms,
-                     "edges_per_s": e_prime / (spmm_ms * 1e-3),
-                     "l2_cap": l2_cap, "l2_cap_unit": "GB/s", "frac_of_l2_cap": achieved / l2_cap if l2_cap else None,
-                     "l2_cap_source": "B300_MICROARCH.md: L2 -> SM throughput cap ~6300 B/clk full chip, x the SM clock sampled "
-                                      "in this run; the gather is served by L2 (L1 hit rate 14 % under ncu), so this is the "
-                                      "bound that applies",
-                     "note": "achieved = SURVEY 8(d) algorithmic bytes (every gathered neighbour row counted) / event time; the 49 MB "
-                             "feature matrix is L2-resident, so frac > 1 against the HBM peak and DRAM traffic is ~20x below the "
-                             "algorithmic bytes; the kernel runs at the L2 -> SM bandwidth cap (frac_of_l2_cap)"},
+        # dominant kernel of the step (61 % of the epoch): the dense contraction, bounded by the tensor pipe
+        "roofline": rg,
+        # the aggregation (north_star kernel 2).  On this workload its input (49 MB) is L2-resident, so the SURVEY 8(d)
+        # algorithmic bytes do not go through HBM: the fraction against the HBM peak is formed from the DRAM traffic ncu
+        # measured for this kernel, the fraction against the L2 -> SM fabric from the sectors ncu counted.
+        "roofline_aggregation": {"kernel": f"spmm_max_fwd F={f_in} (layer-1 aggregation)", "bound": "l2 (L2 -> SM fabric; input L2-resident)",
+                                 "algorithmic_bytes": alg, "avg_ms": spmm_ms, "algorithmic_gb_per_s": achieved,
+                                 "edges_per_s": e_prime / (spmm_ms * 1e-3),
+                                 "traffic": traffic, "lts_sectors_read": lts,
+                                 "traffic_source": "ncu --set full capture committed under profiles/ (per launch)" if traffic else None,
+                                 "frac_dram": (traffic / (spmm_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
+                                 "hbm_peak": hbm_peak, "peak_source": peak_src,
+                                 "frac_l2": (lts * 32 / (spmm_ms * 1e-3) / 1e9 / l2_cap) if (lts and l2_cap) else None,
+                                 "l2_cap": l2_cap, "l2_cap_unit": "GB/s",
+                                 "l2_cap_source": "B300_MICROARCH.md: L2 -> SM throughput cap ~6300 B/clk full chip x the SM clock "
+                                                  "sampled in this run",
+                                 "note": "the >= 70 % of HBM target is judged on the graph that is NOT L2-resident: "
+                                         "`partitioned` (configs[3]) -> aggregation_frac_of_hbm_peak, ncu DRAM bytes for that kernel in "
+                                         "profiles/"},
         "gemm": {"ms_per_step": gemm_ms, "tflops_fp32_equiv": flops_epoch / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
                  "flops_per_step": flops_epoch, "backend": os.environ.get("PLAGNN_GEMM", "auto (TMA-fed tcgen05, CTA pairs, 3xTF32)"),
                  "measured_in": "second pass with per-call events (ms_per_step_profiled)"},
         "ms_per_step_profiled": ms_profiled / args.steps,
         "spmm": {"ms_per_step": spmm_all_ms},
-        "roofline_gemm": roofline_gemm(prof, args.steps, flops_epoch, gemm_ms, tf_peak, peak_src),
         "kernels": kernels[:10],
     }
     if not args.no_cpu_baseline and world == 1:

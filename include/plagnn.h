@@ -135,12 +135,26 @@ int plagnn_spmm_sum(const int32_t* indptr, const int32_t* indices, const int32_t
  * the previous chunk is in flight).  plagnn_spmm_plan_range (set-up call, synchronises) turns a row range into the
  * host[4] = {item_begin, item_end, hub_begin, hub_end} handle that plagnn_spmm_sum_rows takes. */
 int plagnn_spmm_plan_range(const void* plan, int64_t num_rows, int64_t row_begin, int64_t row_end,
-                           int64_t* host_range /* [4] */, plagnn_stream_t stream);
+                           int64_t* host_range /* host[4] */, plagnn_stream_t stream);
 int plagnn_spmm_sum_rows(const int32_t* indptr, const int32_t* indices, const int32_t* eids, const void* plan,
                          const int64_t* plan_counts /* host[3] */, const int64_t* row_range /* host[4] */,
                          int64_t num_rows, const float* w, const float* scale,
                          const float* x, int64_t ldx, int64_t feat, const float* bias, int act, float slope,
                          float* out, int64_t ldo, void* partial, size_t partial_bytes, plagnn_stream_t stream);
+/* Source-slab passes of the same reducers for NARROW rows (feat <= 64: the column slice of one GPU in the feature partition of
+ * BASELINE.json configs[3]).  The caller splits the in-edges by SOURCE range into several CSR structures (one per slab of the
+ * feature matrix small enough to stay in L2) and calls once per slab, in slab order: each call continues from `prev*` (the
+ * result so far; NULL for the first slab; may alias the outputs) and the call with last != 0 applies the epilogue (sum) or the
+ * "row without in-edges = 0" rule (max).  Max reducer: on equal values the earlier slab wins, inside a slab the first in-edge. */
+int plagnn_spmm_sum_slab(const int32_t* indptr, const int32_t* indices, const int32_t* eids, const void* plan,
+                         const int64_t* plan_counts /* host[3] */, int64_t num_rows, const float* w, const float* scale,
+                         const float* x, int64_t ldx, int64_t feat, const float* bias, int act, float slope,
+                         const float* prev, int64_t ldprev, int last, float* out, int64_t ldo,
+                         void* partial, size_t partial_bytes, plagnn_stream_t stream);
+int plagnn_spmm_max_slab(const int32_t* indptr, const int32_t* indices, const void* plan, const int64_t* plan_counts /* host[3] */,
+                         int64_t num_rows, const float* x, int64_t ldx, int64_t feat,
+                         const float* prev_val, const int32_t* prev_arg, int64_t ldprev, int last,
+                         float* out, int32_t* arg, int64_t ldo, void* partial, size_t partial_bytes, plagnn_stream_t stream);
 /* backward companion of the dropout epilogue: grad[r,c] *= keep(r,c)/(1-p) with the same counter-based mask */
 int plagnn_dropout_scale(float* grad, int64_t rows, int64_t feat, int64_t ld, float dropout_p,
                          uint64_t dropout_seed, plagnn_stream_t stream);

@@ -7,6 +7,7 @@ Public surface (mirrors what the reference's train loop touches)
     FusedAdam                  fused optimiser (optim.py)
     TrainStep                  the epoch body (forward, loss, backward, Adam) as one CUDA graph replay (epoch.py)
     protein_loc_correction     on-device label decision (metrics.py)
+    pipeline                   configs[1] end to end: train both states, merge, score, rank (pipeline.py)
     scoring                    alteration scoring after training: scaling / mat_merge / alteration_rank (scoring.py)
     preprocess                 offline stage on the device: edge_clustering_coefficients / modify_network_topology (preprocess.py)
 The kernels live in libplagnn.so (csrc/, C ABI in include/plagnn.h); importing this package does not
@@ -22,6 +23,7 @@ from .epoch import TrainStep
 from .metrics import protein_loc_correction, performances_record
 from .utils import create_graph
 from . import scoring
+from . import pipeline
 from . import preprocess
 
 __all__ = ["GNN32", "SAGEConv", "GraphConvSum", "GCN", "Graph", "Csr", "graph", "add_self_loop", "build_csr",

@@ -64,6 +64,11 @@ PROTOTYPES = {
     "plagnn_spmm_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64, c_void_p, c_void_p,
                                 c_void_p, c_int64, c_int64, c_void_p, c_int, c_float, c_float, c_uint64,
                                 c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "plagnn_spmm_sum_slab": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64, c_void_p, c_void_p,
+                                     c_void_p, c_int64, c_int64, c_void_p, c_int, c_float, c_void_p, c_int64, c_int,
+                                     c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "plagnn_spmm_max_slab": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64, c_void_p, c_int64, c_int64,
+                                     c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "plagnn_spmm_plan_range": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(c_int64), c_void_p]),
     "plagnn_spmm_sum_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_int64,
                                      c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_float,

@@ -36,6 +36,17 @@ struct SpmmEpilogue {
     unsigned long long seed;
 };
 
+// Source-slab passes (L2 blocking of the gather): the in-edges of every row are split by SOURCE range into several CSR
+// structures, one pass per slab, so that the rows a pass gathers from (a slab of the feature matrix) stay L2-resident.
+// A pass continues from the running result of the earlier slabs (`prev_val` / `prev_arg`, may alias the outputs) and only the
+// last one applies the epilogue (sum) or turns "no in-edge at all" into 0 (max).  On value ties the earlier slab wins.
+struct SpmmChain {
+    const float* prev_val;     // nullable: first slab
+    const int32_t* prev_arg;   // max reducer only
+    int64_t ldprev;
+    int last;                  // 1: finalise
+};
+
 __device__ __forceinline__ unsigned hash_u32(unsigned long long seed, unsigned long long idx) {
     unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -288,7 +299,8 @@ spmm_narrow_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict
                    const float* __restrict__ ew, const int32_t* __restrict__ plan_hdr, const int32_t* __restrict__ item_ptr,
                    const int32_t* __restrict__ slot_ptr, const int32_t* __restrict__ item_row, int item_begin, int n_items,
                    const float* __restrict__ x, int64_t ldx, int feat, float* __restrict__ out, int32_t* __restrict__ arg_out,
-                   int64_t ldo, float* __restrict__ part_val, int32_t* __restrict__ part_arg, int part_ld, SpmmEpilogue ep) {
+                   int64_t ldo, float* __restrict__ part_val, int32_t* __restrict__ part_arg, int part_ld, SpmmEpilogue ep,
+                   SpmmChain ch) {
     static_assert(MODE == MODE_MAX || MODE == MODE_SUM, "narrow kernel: max and sum reducers");
     constexpr int S = 32 / G;          // lane groups = in-edges in flight per load instruction
     constexpr int U = 4;               // rounds unrolled: U rows in flight per lane (32 warps x 32 lanes x 4 x 16 B = 64 KB per SM)
@@ -313,6 +325,15 @@ spmm_narrow_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict
     float4 acc = make_float4(init, init, init, init);
     int4 arg = make_int4(-1, -1, -1, -1);
     int4 pos = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
+    // continue from the earlier slabs' result (unsplit rows only: split rows take it in the combine kernel).  Plain loads:
+    // prev may alias the output this kernel writes.  Position -1 makes the earlier slab win value ties.
+    if (ch.prev_val && nch == 1 && cok && (MODE == MODE_MAX || sub == 0)) {
+        acc = *reinterpret_cast<const float4*>(ch.prev_val + (int64_t)row * ch.ldprev + col);
+        if (MODE == MODE_MAX) {
+            arg = *reinterpret_cast<const int4*>(ch.prev_arg + (int64_t)row * ch.ldprev + col);
+            pos = make_int4(-1, -1, -1, -1);
+        }
+    }
 
     for (int base = beg; base < end; base += 32) {
         const int cnt = min(32, end - base);
@@ -372,10 +393,12 @@ spmm_narrow_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict
     if (nch == 1) {
         float4 r = acc;
         if (MODE == MODE_MAX) {
-            r.x = arg.x < 0 ? 0.f : r.x; r.y = arg.y < 0 ? 0.f : r.y;
-            r.z = arg.z < 0 ? 0.f : r.z; r.w = arg.w < 0 ? 0.f : r.w;
+            if (ch.last) {
+                r.x = arg.x < 0 ? 0.f : r.x; r.y = arg.y < 0 ? 0.f : r.y;
+                r.z = arg.z < 0 ? 0.f : r.z; r.w = arg.w < 0 ? 0.f : r.w;
+            }
             *reinterpret_cast<int4*>(arg_out + (int64_t)row * ldo + col) = arg;
-        } else {
+        } else if (ch.last) {
             r = sum_epilogue(r, ep, row, col, feat);
         }
         *reinterpret_cast<float4*>(out + (int64_t)row * ldo + col) = r;
@@ -393,7 +416,7 @@ spmm_combine_kernel(const int32_t* __restrict__ item_ptr, const int32_t* __restr
                     const int32_t* __restrict__ hub_rows, int hub_begin, int n_hubs, int feat,
                     const float* __restrict__ part_val,
                     const int32_t* __restrict__ part_arg, int part_ld, float* __restrict__ out,
-                    int32_t* __restrict__ arg_out, int64_t ldo, SpmmEpilogue ep) {
+                    int32_t* __restrict__ arg_out, int64_t ldo, SpmmEpilogue ep, SpmmChain ch) {
     pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int h = hub_begin + blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
@@ -407,6 +430,10 @@ spmm_combine_kernel(const int32_t* __restrict__ item_ptr, const int32_t* __restr
     const float init = MODE == MODE_MAX ? -INFINITY : 0.f;
     float4 acc = make_float4(init, init, init, init);
     int4 arg = make_int4(-1, -1, -1, -1);
+    if (ch.prev_val) {      // running result of the earlier source slabs (strict > below: it wins value ties)
+        acc = *reinterpret_cast<const float4*>(ch.prev_val + (int64_t)row * ch.ldprev + col);
+        if (MODE == MODE_MAX) arg = *reinterpret_cast<const int4*>(ch.prev_arg + (int64_t)row * ch.ldprev + col);
+    }
     constexpr int CU = 8;   // partials in flight per lane (a hub of 16k edges has > 100 partials)
     for (int k0 = 0; k0 < nch; k0 += CU) {
         float4 v[CU];
@@ -434,10 +461,12 @@ spmm_combine_kernel(const int32_t* __restrict__ item_ptr, const int32_t* __restr
         }
     }
     if (MODE == MODE_MAX) {
-        acc.x = arg.x < 0 ? 0.f : acc.x; acc.y = arg.y < 0 ? 0.f : acc.y;
-        acc.z = arg.z < 0 ? 0.f : acc.z; acc.w = arg.w < 0 ? 0.f : acc.w;
+        if (ch.last) {
+            acc.x = arg.x < 0 ? 0.f : acc.x; acc.y = arg.y < 0 ? 0.f : acc.y;
+            acc.z = arg.z < 0 ? 0.f : acc.z; acc.w = arg.w < 0 ? 0.f : acc.w;
+        }
         *reinterpret_cast<int4*>(arg_out + (int64_t)row * ldo + col) = arg;
-    } else if (MODE == MODE_SUM) {
+    } else if (MODE == MODE_SUM && ch.last) {
         acc = sum_epilogue(acc, ep, row, col, feat);
     }
     *reinterpret_cast<float4*>(out + (int64_t)row * ldo + col) = acc;
@@ -506,6 +535,7 @@ struct SpmmArgs {
     size_t partial_bytes;
     SpmmEpilogue ep;
     const int64_t* range = nullptr;   // optional host[4]: item_begin, item_end, hub_begin, hub_end (row-range launch)
+    SpmmChain chain = SpmmChain{nullptr, nullptr, 0, 1};   // source-slab pass (narrow rows only)
 };
 
 static inline int part_ld_of(int64_t feat) { return (int)((feat + 3) / 4 * 4); }
@@ -531,7 +561,7 @@ static void launch_narrow(const SpmmArgs& a, const int32_t* item_ptr, const int3
     dim3 grid((unsigned)ceil_div(n_items - item_begin, SPMM_WARPS));
     launch_pdl(spmm_narrow_kernel<MODE, G>, grid, dim3(SPMM_WARPS * 32), 0, st,
         a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, item_begin, n_items, a.x, a.ldx,
-        (int)a.feat, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep);
+        (int)a.feat, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep, a.chain);
 }
 
 template <int MODE>
@@ -563,7 +593,10 @@ static int spmm_dispatch(const SpmmArgs& a, const char* name, cudaStream_t st) {
     static const int deep = [] { const char* e = getenv("PLAGNN_SPMM_DEEP"); return e ? atoi(e) : 0; }();
     // rows of <= 64 floats: several in-edges per load instruction (PLAGNN_SPMM_NARROW=0: the wide kernel, for A/B runs)
     static const bool narrow_ok = [] { const char* e = getenv("PLAGNN_SPMM_NARROW"); return !e || e[0] != '0'; }();
-    if (MODE != MODE_MATCH && narrow_ok && groups <= 16) {
+    const bool chained = a.chain.prev_val != nullptr || !a.chain.last;
+    if (chained && (MODE == MODE_MATCH || groups > 16))
+        return fail(PLAGNN_ERR_UNSUPPORTED, name, "source-slab passes are implemented for rows of at most 64 columns");
+    if (MODE != MODE_MATCH && (narrow_ok || chained) && groups <= 16) {
         constexpr int NM = MODE == MODE_MATCH ? MODE_SUM : MODE;     // (MATCH never gets here; keeps the template instantiable)
         if (groups <= 8) launch_narrow<NM, 8>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
         else launch_narrow<NM, 16>(a, item_ptr, slot_ptr, item_row, pv, pa, st);
@@ -584,7 +617,7 @@ static int spmm_dispatch(const SpmmArgs& a, const char* name, cudaStream_t st) {
     if (hub_end > hub_begin) {
         dim3 grid((unsigned)ceil_div(hub_end - hub_begin, SPMM_WARPS), (unsigned)ceil_div(a.feat, 128));
         launch_pdl(spmm_combine_kernel<MODE>, grid, dim3(SPMM_WARPS * 32), 0, st, item_ptr, slot_ptr, hub_rows, (int)hub_begin, (int)hub_end, (int)a.feat,
-                                                                     pv, pa, pld, a.out, a.arg_out, a.ldo, a.ep);
+                                                                     pv, pa, pld, a.out, a.arg_out, a.ldo, a.ep, a.chain);
     }
     return check_launch(name, hub_end > hub_begin ? 2 : 1);
 }
@@ -655,6 +688,35 @@ int plagnn_spmm_sum(const int32_t* indptr, const int32_t* indices, const int32_t
     SpmmArgs a{indptr, indices, eids, w, plan, plan_counts, num_rows, x, ldx, feat, nullptr, 0, nullptr, 0, out, nullptr, ldo,
                partial, partial_bytes, SpmmEpilogue{scale, bias, act, slope, dropout_p, (unsigned long long)dropout_seed}};
     return spmm_dispatch<MODE_SUM>(a, "spmm_sum", (cudaStream_t)stream);
+}
+
+int plagnn_spmm_sum_slab(const int32_t* indptr, const int32_t* indices, const int32_t* eids, const void* plan,
+                         const int64_t* plan_counts, int64_t num_rows, const float* w, const float* scale, const float* x,
+                         int64_t ldx, int64_t feat, const float* bias, int act, float slope, const float* prev, int64_t ldprev,
+                         int last, float* out, int64_t ldo, void* partial, size_t partial_bytes, plagnn_stream_t stream) {
+    ProfileScope prof("spmm_sum", feat, num_rows, w ? 3 : 2, stream);
+    if (act < PLAGNN_ACT_NONE || act > PLAGNN_ACT_SIGMOID) return fail(PLAGNN_ERR_ARG, "spmm_sum_slab", "unknown activation");
+    if (prev && (ldprev < (feat + 3) / 4 * 4 || (ldprev & 3) || !aligned16(prev)))
+        return fail(PLAGNN_ERR_ALIGN, "spmm_sum_slab", "prev needs 16-byte aligned rows");
+    SpmmArgs a{indptr, indices, eids, w, plan, plan_counts, num_rows, x, ldx, feat, nullptr, 0, nullptr, 0, out, nullptr, ldo,
+               partial, partial_bytes, SpmmEpilogue{scale, bias, act, slope, 0.f, 0ull}};
+    a.chain = SpmmChain{prev, nullptr, ldprev, last ? 1 : 0};
+    return spmm_dispatch<MODE_SUM>(a, "spmm_sum_slab", (cudaStream_t)stream);
+}
+
+int plagnn_spmm_max_slab(const int32_t* indptr, const int32_t* indices, const void* plan, const int64_t* plan_counts,
+                         int64_t num_rows, const float* x, int64_t ldx, int64_t feat, const float* prev_val,
+                         const int32_t* prev_arg, int64_t ldprev, int last, float* out, int32_t* arg, int64_t ldo, void* partial,
+                         size_t partial_bytes, plagnn_stream_t stream) {
+    if (!arg) return fail(PLAGNN_ERR_ARG, "spmm_max_slab", "arg output is required");
+    if ((prev_val == nullptr) != (prev_arg == nullptr)) return fail(PLAGNN_ERR_ARG, "spmm_max_slab", "prev_val and prev_arg go together");
+    if (prev_val && (ldprev < (feat + 3) / 4 * 4 || (ldprev & 3) || !aligned16(prev_val) || !aligned16(prev_arg)))
+        return fail(PLAGNN_ERR_ALIGN, "spmm_max_slab", "prev needs 16-byte aligned rows");
+    ProfileScope prof("spmm_max_fwd", feat, num_rows, 2, stream);
+    SpmmArgs a{indptr, indices, nullptr, nullptr, plan, plan_counts, num_rows, x, ldx, feat, nullptr, 0, nullptr, 0,
+               out, arg, ldo, partial, partial_bytes, SpmmEpilogue{nullptr, nullptr, 0, 0.f, 0.f, 0ull}};
+    a.chain = SpmmChain{prev_val, prev_arg, ldprev, last ? 1 : 0};
+    return spmm_dispatch<MODE_MAX>(a, "spmm_max_slab", (cudaStream_t)stream);
 }
 
 int plagnn_spmm_plan_range(const void* plan, int64_t num_rows, int64_t row_begin, int64_t row_end, int64_t* host_range,

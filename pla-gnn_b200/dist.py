@@ -191,10 +191,15 @@ class DistSAGEPool(torch.nn.Module):
 
 class PartitionedGraph:
     """Device structures of one rank.  Row partition: in-edge CSR of the owned rows (gathered source ids) and its
-    transpose.  Feature partition: in-edge and out-edge CSR of the whole graph in the gathered numbering.  Edge weights
-    are stored once per direction in that direction's CSR order (no edge-id indirection in the kernel)."""
+    transpose.  Feature partition: in-edge and out-edge CSR of the whole graph in the gathered numbering; when the column
+    slice of a rank is narrow (feat / world <= 64) each direction is additionally cut by SOURCE range into slabs whose slice of
+    the feature matrix (rows x feat / world floats) is at most `slab_mb` MB, so that one aggregation pass gathers from an
+    L2-resident slab (plagnn_spmm_*_slab).  Edge weights are stored once per structure in its CSR order (no edge-id
+    indirection in the kernel)."""
 
-    def __init__(self, plan, weight_global: torch.Tensor | None, build_csr, device, transposed: bool = True):
+    def __init__(self, plan, weight_global: torch.Tensor | None, build_csr, device, transposed: bool = True, feat: int | None = None,
+                 slab_mb: float | None = None):
+        import os
         self.plan = plan
         self.mode = "cols" if isinstance(plan, FeaturePartitionPlan) else "rows"
         if self.mode == "rows":
@@ -208,6 +213,35 @@ class PartitionedGraph:
             n_dst, w = plan.n_padded, None if weight_global is None else weight_global.to(device)
             self.scale = plan.scale_local.to(device)
             self.scale_full = plan.scale_full.to(device)
+        self.csc_slabs = self.w_csc_slabs = self.csr_t_slabs = self.w_csr_t_slabs = None
+        n_slabs = 1
+        if self.mode == "cols" and feat is not None and feat // plan.world <= 64:
+            slab_mb = float(os.environ.get("PLAGNN_DIST_SLAB_MB", "32")) if slab_mb is None else slab_mb
+            if slab_mb > 0:
+                n_slabs = max(1, math.ceil(plan.n_padded * (feat // plan.world) * 4 / (slab_mb * 2 ** 20)))
+        self.n_slabs = n_slabs
+
+        def slabs_of(key, other, n_key, n_other):
+            """CSR structures with rows = key, entries = other restricted to `n_slabs` consecutive ranges of `other`."""
+            rows_per = (n_other + n_slabs - 1) // n_slabs
+            slab_id = other // rows_per
+            out, ws = [], []
+            for i in range(n_slabs):
+                m = slab_id == i
+                c = build_csr(key[m], other[m], n_key, False, num_other=n_other)
+                out.append(c)
+                ws.append(None if w is None else w[m][c.eids.long()].contiguous())
+            return out, (None if w is None else ws)
+
+        if n_slabs > 1:
+            self.csc_slabs, self.w_csc_slabs = slabs_of(d, s, n_dst, plan.n_padded)
+            if transposed:
+                self.csr_t_slabs, self.w_csr_t_slabs = slabs_of(s, d, plan.n_padded, n_dst)
+            self.csc = self.csc_slabs[0]                       # (identity of the direction for the backend's dispatch)
+            self.csr_t = self.csr_t_slabs[0] if transposed else None
+            self.w_csc = self.w_csr_t = None
+            self.edge_weight = w
+            return
         # rows = destination rows, entries = rows of the gathered matrix
         self.csc = build_csr(d, s, n_dst, False, num_other=plan.n_padded)
         self.w_csc = None if w is None else w[self.csc.eids.long()].contiguous()
@@ -460,6 +494,7 @@ class CudaBackend:
         from . import _lib, ops
         self.ops, self._lib, self.lib = ops, _lib, _lib.load()
         self.comm = comm
+        self.pg = pg
         self.skip_comm = False
         # highest priority: when an SM slot frees up, the exchange kernel's CTAs are placed before the pending CTAs of the
         # aggregation launched ahead of it — otherwise the collective only starts once that whole grid has been scheduled
@@ -529,11 +564,17 @@ class CudaBackend:
                           act=ops.ACT_LEAKY if act else ops.ACT_NONE, w_in_csr_order=True)
 
     def spmm_cols(self, csx, key, x_col, w, scale, bias, act):
-        ops = self.ops
-        return ops.spmm_sum(csx, x_col, w=w, scale=scale, bias=bias, act=ops.ACT_LEAKY if act else ops.ACT_NONE,
-                            w_in_csr_order=True)
+        ops, pg = self.ops, self.pg
+        a = ops.ACT_LEAKY if act else ops.ACT_NONE
+        slabs = pg.csc_slabs if key == "csc" else pg.csr_t_slabs
+        if slabs is not None:                      # narrow column slice: one pass per L2-sized source slab
+            return ops.spmm_sum_slabs(slabs, x_col, ws=pg.w_csc_slabs if key == "csc" else pg.w_csr_t_slabs, scale=scale,
+                                      bias=bias, act=a)
+        return ops.spmm_sum(csx, x_col, w=w, scale=scale, bias=bias, act=a, w_in_csr_order=True)
 
     def spmm_max(self, csc, x):
+        if self.pg.csc_slabs is not None:
+            return self.ops.spmm_max_slabs(self.pg.csc_slabs, x)
         return self.ops.spmm_max_fwd(csc, x)
 
     def max_scatter(self, dneigh, arg, neigh, n_src):

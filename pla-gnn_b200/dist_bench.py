@@ -47,7 +47,8 @@ class Variant:
         else:
             self.plan = RowPartitionPlan(sg.src, sg.dst, n, rank, world, chunks, balance=balance)
         plan = self.plan
-        self.pg = PartitionedGraph(plan, sg.weight if reducer == "sum" else None, P.build_csr, dev, transposed=reducer == "sum")
+        self.pg = PartitionedGraph(plan, sg.weight if reducer == "sum" else None, P.build_csr, dev, transposed=reducer == "sum",
+                                   feat=f)
         dims = [f] * (layers + 1)
         self.model = (DistGCN(dims, seed=7) if reducer == "sum" else DistSAGEPool(dims, seed=7)).to(dev)
         self.params = self.model.grad_order()
@@ -156,7 +157,7 @@ def measure_variant(v: Variant, steps, warmup, rank, world, dev, reference=None)
            "collective_ms_per_step": coll, "aggregation_ms_per_step": agg_ms,
            "aggregation_algorithmic_gbs_per_gpu": alg / (agg_ms * 1e-3) / 1e9 if agg_ms else None,
            "aggregation_frac_of_hbm_peak": alg / (agg_ms * 1e-3) / 1e9 / hbm if agg_ms else None, "hbm_peak": hbm, "peak_source": src,
-           "local_edges_rank0": el, "checksum": csum, "check": check,
+           "local_edges_rank0": el, "source_slabs": v.pg.n_slabs, "checksum": csum, "check": check,
            "kernels": sorted([{"kernel": k, "ms_per_step": round(t, 4)} for k, t in per_step.items()], key=lambda d: -d["ms_per_step"])[:8]}
     return res
 

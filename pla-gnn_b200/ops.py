@@ -338,6 +338,44 @@ def spmm_sum(csx, x: torch.Tensor, w=None, scale=None, bias=None, act=ACT_NONE, 
 
 
 @on_tensor_device
+def spmm_sum_slabs(slabs, x: torch.Tensor, ws=None, scale=None, bias=None, act=ACT_NONE, slope: float = LEAKY_SLOPE) -> torch.Tensor:
+    """The sum reducer as one pass per SOURCE slab (plagnn_spmm_sum_slab): `slabs` = CSR structures of the same rows whose
+    entries are restricted to consecutive source ranges, `ws` = edge weights of each in its CSR order (or None)."""
+    lib = _lib.load()
+    x = aligned(x)
+    n, f = slabs[0].num_rows, x.shape[1]
+    out = alloc(n, f, x.device)
+    nb = max(lib.plagnn_spmm_partial_bytes(c.counts[2], f, REDUCE_SUM) for c in slabs)
+    part = workspace(nb, x.device, "spmm_partial")
+    for i, csx in enumerate(slabs):
+        w = None if ws is None else ws[i]
+        last = i + 1 == len(slabs)
+        check(lib.plagnn_spmm_sum_slab(_p(csx.indptr), _p(csx.indices), None, _p(csx.plan), csx.counts_c, n, _p(w), _p(scale),
+                                       _p(x), x.stride(0), f, _p(bias), act, slope, _p(out) if i else None, out.stride(0),
+                                       int(last), _p(out), out.stride(0), _p(part), nb, _stream()), "spmm_sum_slab")
+    return out
+
+
+@on_tensor_device
+def spmm_max_slabs(slabs, x: torch.Tensor):
+    """The max reducer as one pass per source slab (plagnn_spmm_max_slab).  Returns (out, arg); on equal values the earlier
+    slab wins, inside a slab the first in-edge."""
+    lib = _lib.load()
+    x = aligned(x)
+    n, f = slabs[0].num_rows, x.shape[1]
+    out = alloc(n, f, x.device)
+    arg = alloc(n, f, x.device, dtype=torch.int32)
+    nb = max(lib.plagnn_spmm_partial_bytes(c.counts[2], f, REDUCE_MAX) for c in slabs)
+    part = workspace(nb, x.device, "spmm_partial")
+    for i, csx in enumerate(slabs):
+        last = i + 1 == len(slabs)
+        check(lib.plagnn_spmm_max_slab(_p(csx.indptr), _p(csx.indices), _p(csx.plan), csx.counts_c, n, _p(x), x.stride(0), f,
+                                       _p(out) if i else None, _p(arg) if i else None, out.stride(0), int(last), _p(out), _p(arg),
+                                       out.stride(0), _p(part), nb, _stream()), "spmm_max_slab")
+    return out, arg
+
+
+@on_tensor_device
 def plan_range(csx, row_begin: int, row_end: int):
     """Host handle (ctypes int64[4]) for aggregating only rows [row_begin, row_end) of `csx` (set-up call)."""
     rng = (ctypes.c_int64 * 4)()

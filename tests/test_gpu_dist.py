@@ -168,3 +168,78 @@ def test_two_gpu_nccl_partitions_match_whole_graph_run(cuda, tmp_path):
     mp.start_processes(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True, start_method="spawn")
     block = json.load(open(tmp_path / "block.json"))
     assert len(block["variants"]) == 4 and block["checks_ok"], block
+
+
+@pytest.mark.parametrize("f", [32, 64, 20])
+def test_source_slab_passes_equal_the_single_pass(cuda, f):
+    """plagnn_spmm_sum_slab / _max_slab: the in-edges cut by source range into 3 CSR structures, one pass each, against the
+    single pass over the whole structure (sum within fp32 reordering, max values bit-exact, arg equal wherever the maximum is
+    attained by one source only)."""
+    n, e = 4000, 150000
+    sg = synth.scaled_graph(n, e, seed=9, max_degree=5000)
+    s, d = sg.src.to(cuda).to(torch.int32), sg.dst.to(cuda).to(torch.int32)
+    w = sg.weight.to(cuda)
+    full = P.build_csr(d, s, n, False, chunk=128)                      # chunk 128: some rows are split (combine kernel path)
+    assert full.counts[1] > 0
+    slab_id = s // ((n + 2) // 3)
+    slabs, ws = [], []
+    for i in range(3):
+        m = slab_id == i
+        c = P.build_csr(d[m], s[m], n, False, chunk=128)
+        slabs.append(c)
+        ws.append(w[m][c.eids.long()].contiguous())
+    x = ops.alloc(n, f, cuda)
+    x.copy_(torch.randn(n, f, device=cuda))
+    scale = torch.rand(n, device=cuda) + 0.5
+    bias = torch.randn(f, device=cuda)
+    ref = ops.spmm_sum(full, x, w=w[full.eids.long()].contiguous(), scale=scale, bias=bias, act=ops.ACT_LEAKY, w_in_csr_order=True)
+    got = ops.spmm_sum_slabs(slabs, x, ws=ws, scale=scale, bias=bias, act=ops.ACT_LEAKY)
+    assert rel_err(got, ref) < 2e-6
+    xr = torch.relu(x)                                                  # ties at 0, like the pooled activations
+    ro, ra = ops.spmm_max_fwd(full, ops.aligned(xr))
+    go, ga = ops.spmm_max_slabs(slabs, ops.aligned(xr))
+    assert torch.equal(go, ro)
+    cols = torch.arange(f, device=cuda).expand(n, f)
+    has = ra >= 0
+    assert torch.equal(ga >= 0, has)
+    assert torch.equal(xr[ga.clamp(min=0).long(), cols][has], ro[has])   # the chosen source attains the maximum
+    pos = has & (ro > 0)
+    assert (ga[pos] != ra[pos]).float().mean().item() < 1e-3            # positive maxima are attained by one source (a.s.)
+
+
+def test_feature_partition_with_source_slabs_world1(cuda):
+    """The feature partition with the slab passes forced on (tiny slab budget) at world 1, both reducers, against the oracle."""
+    from plagnn_b200.dist import FeaturePartitionPlan, dist_pool_forward_backward
+    n, e, f = 2000, 60000, 48
+    sg = synth.scaled_graph(n, e, seed=5, max_degree=3000)
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(1))
+    plan = FeaturePartitionPlan(sg.src, sg.dst, n, 0, 1)
+    go = orc.OracleGraph(sg.src.numpy(), sg.dst.numpy(), n)
+    h0 = ops.alloc(plan.per, f, cuda, zero=True)
+    h0[:n].copy_(x)
+    # weighted sum (all widths <= 64 so that every aggregation takes the slab path)
+    pg = PartitionedGraph(plan, sg.weight, P.build_csr, cuda, feat=64, slab_mb=0.1)
+    assert pg.n_slabs > 2
+    model = DistGCN([f, 40, 24], seed=3)
+    ref = orc.GCNSumRef([f, 40, 24])
+    with torch.no_grad():
+        for lin, w_, b_ in zip(ref.lins, model.weights, model.biases):
+            lin.weight.copy_(w_); lin.bias.copy_(b_)
+    model = model.to(cuda)
+    with torch.cuda.device(cuda):
+        out, grads = dist_gcn_forward_backward(model, pg, h0, CudaBackend(pg), None, lambda o: o / n)
+    scale = 1.0 / torch.bincount(sg.dst, minlength=n).clamp(min=1).float()
+    out_ref = ref(go, x, sg.weight, scale)
+    (0.5 * (out_ref ** 2).sum() / n).backward()
+    assert rel_err(out[:n], out_ref) < REL_TOL
+    for g, gr in zip(grads, [t.grad for lin in ref.lins for t in (lin.weight, lin.bias)]):
+        assert rel_err(g, gr) < 2 * REL_TOL
+    # max-pool
+    pgm = PartitionedGraph(plan, None, P.build_csr, cuda, transposed=False, feat=64, slab_mb=0.1)
+    pmodel, pout_ref, pgrads_ref = _pool_reference(sg, x, n, [f, 40, 24])
+    pmodel = pmodel.to(cuda)
+    with torch.cuda.device(cuda):
+        pout, pgrads = dist_pool_forward_backward(pmodel, pgm, h0, CudaBackend(pgm), None, lambda o: o / n)
+    assert rel_err(pout[:n], pout_ref) < REL_TOL
+    for g, gr in zip(pgrads, pgrads_ref):
+        assert rel_err(g, gr) < 2 * REL_TOL

@@ -94,3 +94,13 @@ def test_product_package_never_imports_the_oracle():
                 if any(n == "oracle" or n.startswith("oracle.") for n in names):
                     offenders.append(os.path.relpath(path, root))
     assert not offenders, offenders
+
+
+def test_fold_splits_are_the_reference_kfold():
+    from sklearn.model_selection import KFold
+    label = [5, 9, 11, 20, 21, 30, 41, 57, 63, 70, 88]
+    got = list(__import__("plagnn_b200").pipeline.fold_splits(label, 3, 42))
+    ref = list(KFold(n_splits=3, random_state=42, shuffle=True).split(label))
+    assert len(got) == 3
+    for (tr, va), (rt, rv) in zip(got, ref):
+        assert tr.tolist() == [label[i] for i in rt] and va.tolist() == [label[i] for i in rv]    # train.py:183-188

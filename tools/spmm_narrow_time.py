@@ -18,7 +18,22 @@ sg = synth.scaled_graph(n, e, seed=1234, device=dev)
 csc = P.build_csr(sg.dst.to(torch.int32), sg.src.to(torch.int32), n, False)
 w = sg.weight[csc.eids.long()].contiguous()
 scale = (1.0 / csc.degrees.clamp(min=1).float()).contiguous()
+src32, dst32, wfull = sg.src.to(torch.int32), sg.dst.to(torch.int32), sg.weight
 del sg
+
+
+def slab_structs(n_slabs):
+    rows_per = (n + n_slabs - 1) // n_slabs
+    sid = src32 // rows_per
+    cs, ws = [], []
+    for i in range(n_slabs):
+        m = sid == i
+        c = P.build_csr(dst32[m], src32[m], n, False)
+        cs.append(c)
+        ws.append(wfull[m][c.eids.long()].contiguous())
+    return cs, ws
+
+
 out = {"narrow": os.environ.get("PLAGNN_SPMM_NARROW", "1"), "edges": int(csc.num_edges)}
 for f in (32, 64, 128, 256):
     x = ops.alloc(n, f, dev)
@@ -38,5 +53,21 @@ for f in (32, 64, 128, 256):
         ms = s.elapsed_time(t) / 5
         alg = 4 * f * csc.num_edges + 4 * csc.num_edges * (2 if name == "sum" else 1) + 4 * f * n * (1 if name == "sum" else 2)
         out[f"{name}/{f}"] = {"ms": round(ms, 3), "algorithmic_gb_per_s": round(alg / ms / 1e6, 0)}
+    if f <= 64 and os.environ.get("PLAGNN_SPMM_NARROW", "1") != "0":
+        for n_slabs in ((2, 4, 8) if f == 32 else (4, 8, 16)):
+            cs, ws = slab_structs(n_slabs)
+            for name, fn in (("sum", lambda: ops.spmm_sum_slabs(cs, x, ws=ws, scale=scale, bias=bias, act=ops.ACT_LEAKY)),
+                             ("max", lambda: ops.spmm_max_slabs(cs, x))):
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                for _ in range(5):
+                    fn()
+                t.record()
+                torch.cuda.synchronize()
+                out[f"{name}/{f}/slabs{n_slabs}"] = {"ms": round(s.elapsed_time(t) / 5, 3), "slab_mb": round(n * f * 4 / n_slabs / 2 ** 20, 1)}
+            del cs, ws
     del x
 print(json.dumps(out))
