@@ -387,6 +387,28 @@ int plagnn_nccl_alltoall_blocks(const float* send, float* recv, int64_t block_el
 int plagnn_cols_pack(const float* x, int64_t ldx, int64_t rows, int64_t feat, int world, float* blocks, plagnn_stream_t stream);
 int plagnn_cols_unpack(const float* blocks, int64_t rows, int64_t feat, int world, float* x, int64_t ldx, plagnn_stream_t stream);
 
+/* Peer-memory exchange for the feature partition (one process per GPU, NVLink / NVSwitch): the all-to-all around an aggregation
+ * as one kernel that stores every column block straight into its owner's window, then a flag per peer; no NCCL, no pack /
+ * unpack pass.  Set-up: every rank creates a window (device memory allocated by the library, because it has to be exported
+ * with cudaIpcGetMemHandle), the 64-byte handles are exchanged by any means, plagnn_p2p_attach opens the peers' windows.
+ *   plagnn_p2p_send mode 0: x[rows x feat] (my rows, all columns) -> every peer q gets my rows of ITS columns at
+ *                           window[offset + ((rank * rows + r) * feat/world + j)]   (window = all rows x my columns)
+ *                   mode 1: x_col[world * rows x feat/world] (all rows, my columns) -> peer q gets its rows of MY columns at
+ *                           window[offset + (r * feat + rank * feat/world + j)]     (window = my rows x all columns)
+ *   plagnn_p2p_wait: enqueues a one-warp kernel that returns when every peer has published `seq` (sequence numbers grow by
+ *                    one per exchange, the same on every rank); it gives up after ~1 s and records `seq` (plagnn_p2p_error).
+ * The caller alternates between two window offsets so that a peer's next exchange never lands on data still being read. */
+typedef void* plagnn_p2p_t;
+#define PLAGNN_P2P_HANDLE_BYTES 64
+int plagnn_p2p_create(size_t bytes, int rank, int world, void* handle_out /* host, 64 bytes */, plagnn_p2p_t* out);
+int plagnn_p2p_attach(plagnn_p2p_t p2p, const void* all_handles /* host, world x 64 bytes, rank order */);
+void* plagnn_p2p_window(plagnn_p2p_t p2p);        /* device pointer of the local window's data */
+long long plagnn_p2p_error(plagnn_p2p_t p2p);     /* 0, or the sequence number a wait gave up on (synchronises) */
+int plagnn_p2p_destroy(plagnn_p2p_t p2p);
+int plagnn_p2p_send(plagnn_p2p_t p2p, const float* src, int64_t lds, int64_t rows, int64_t feat, int mode,
+                    size_t dst_offset_bytes, long long seq, plagnn_stream_t stream);
+int plagnn_p2p_wait(plagnn_p2p_t p2p, long long seq, plagnn_stream_t stream);
+
 /* small utilities used by the host layer */
 int plagnn_pad_copy(const float* src, int64_t rows, int64_t cols, int64_t lds, float* dst, int64_t ldd,
                     plagnn_stream_t stream); /* dst[:, :cols] = src; dst[:, cols:ldd] = 0 */

@@ -128,6 +128,13 @@ PROTOTYPES = {
     "plagnn_nccl_alltoall_blocks": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "plagnn_cols_pack": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "plagnn_cols_unpack": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "plagnn_p2p_create": (c_int, [c_size_t, c_int, c_int, c_void_p, POINTER(c_void_p)]),
+    "plagnn_p2p_attach": (c_int, [c_void_p, c_void_p]),
+    "plagnn_p2p_window": (c_void_p, [c_void_p]),
+    "plagnn_p2p_error": (ctypes.c_longlong, [c_void_p]),
+    "plagnn_p2p_destroy": (c_int, [c_void_p]),
+    "plagnn_p2p_send": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_size_t, ctypes.c_longlong, c_void_p]),
+    "plagnn_p2p_wait": (c_int, [c_void_p, ctypes.c_longlong, c_void_p]),
     "plagnn_pad_copy": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "plagnn_transpose": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
 }

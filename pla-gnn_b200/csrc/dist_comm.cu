@@ -238,3 +238,204 @@ int plagnn_cols_unpack(const float* in, int64_t rows, int64_t feat, int world, f
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// Peer-memory exchange for the feature partition: the two all-to-all steps around an aggregation written as ONE kernel each
+// that reads the local matrix and stores every column block straight into its owner's window over NVLink (no pack kernel, no
+// staging buffer, no NCCL), followed by a system-scope flag per peer; the receiver's stream waits on those flags in a
+// one-warp kernel.  Windows are device allocations of the library (they have to be exportable with cudaIpcGetMemHandle),
+// opened by the peers at set-up.
+// =====================================================================================================================
+namespace plagnn {
+
+constexpr int P2P_MAX_WORLD = 16;
+constexpr size_t P2P_FLAG_BYTES = 4096;          // flags[world] (int64) + error word, ahead of the data
+
+struct P2P {
+    int rank, world;
+    size_t bytes;
+    char* local;                                  // flags | data
+    char* peer[P2P_MAX_WORLD];                    // opened windows (peer[rank] == local)
+    char** d_peer;                                // device copy of peer[]
+    unsigned int* d_counter;                      // blocks of the running send kernel that have finished
+};
+
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+    asm volatile("st.release.sys.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+    long long v;
+    asm volatile("ld.acquire.sys.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// mode 0 (rows -> columns): src = x[rows x feat] (pitch lds); block q = columns [q fc, (q+1) fc) goes to peer q at
+//                            data[off + ((rank * rows + r) * fc + j)]: the peer's window is the all-rows matrix [world * rows x fc].
+// mode 1 (columns -> rows): src = x_col[world * rows x fc] (pitch lds); rows [q rows, (q+1) rows) go to peer q at
+//                            data[off + (r * feat + rank * fc + j)]: the peer's window is its [rows x feat] matrix.
+__global__ void __launch_bounds__(256)
+p2p_send_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int feat, int fc, int mode, char* const* __restrict__ peer,
+                size_t off_bytes, int rank, int world, long long seq, unsigned int* __restrict__ counter) {
+    pdl_enter();
+    const int fc4 = fc >> 2;
+    const int64_t total = (int64_t)world * rows * fc4;            // float4 elements of the source in both modes
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int q, j4;
+        int64_t r;
+        float4 v;
+        float* dst;
+        if (mode == 0) {
+            const int f4 = world * fc4;
+            r = i / f4;
+            const int c4 = (int)(i - r * f4);
+            q = c4 / fc4;
+            j4 = c4 - q * fc4;
+            v = ldg_f4(src + r * lds + 4 * c4);
+            dst = reinterpret_cast<float*>(peer[q] + P2P_FLAG_BYTES + off_bytes) + ((int64_t)rank * rows + r) * fc + 4 * j4;
+        } else {
+            const int64_t gr = i / fc4;
+            j4 = (int)(i - gr * fc4);
+            q = (int)(gr / rows);
+            r = gr - (int64_t)q * rows;
+            v = ldg_f4(src + gr * lds + 4 * j4);
+            dst = reinterpret_cast<float*>(peer[q] + P2P_FLAG_BYTES + off_bytes) + r * feat + (int64_t)rank * fc + 4 * j4;
+        }
+        *reinterpret_cast<float4*>(dst) = v;
+    }
+    // the last block to finish publishes the sequence number in every peer's flag array (after everybody's stores)
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(counter, 1u);
+        if (done == gridDim.x - 1) {
+            *counter = 0;
+            __threadfence_system();
+            for (int q = 0; q < world; ++q) st_release_sys(reinterpret_cast<long long*>(peer[q]) + rank, seq);
+        }
+    }
+}
+
+// one warp: lane p waits until peer p has published `seq`; gives up after ~1 s (error word set, later waits return at once)
+__global__ void p2p_wait_kernel(char* local, int world, long long seq) {
+    pdl_enter();
+    long long* flags = reinterpret_cast<long long*>(local);
+    long long* err = flags + P2P_MAX_WORLD;
+    const int p = threadIdx.x;
+    if (p < world && *reinterpret_cast<volatile long long*>(err) == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flags + p) < seq) {
+            if (clock64() - t0 > 2000000000ll) {
+                *reinterpret_cast<volatile long long*>(err) = seq;
+                break;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+}  // namespace plagnn
+
+extern "C" {
+
+int plagnn_p2p_create(size_t bytes, int rank, int world, void* handle_out, plagnn_p2p_t* out) {
+    if (!handle_out || !out || bytes == 0 || world <= 0 || world > P2P_MAX_WORLD || rank < 0 || rank >= world)
+        return fail(PLAGNN_ERR_ARG, "p2p_create", "bad arguments");
+    P2P* p = new P2P();
+    p->rank = rank; p->world = world; p->bytes = bytes;
+    p->local = nullptr; p->d_peer = nullptr; p->d_counter = nullptr;
+    for (int i = 0; i < P2P_MAX_WORLD; ++i) p->peer[i] = nullptr;
+    cudaError_t e = cudaMalloc(&p->local, bytes + P2P_FLAG_BYTES);
+    if (e == cudaSuccess) e = cudaMemset(p->local, 0, P2P_FLAG_BYTES);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_peer, sizeof(char*) * P2P_MAX_WORLD);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_counter, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(p->d_counter, 0, sizeof(unsigned int));
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p->local);
+    if (e != cudaSuccess) {
+        set_error("p2p_create: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        if (p->local) cudaFree(p->local);
+        if (p->d_peer) cudaFree(p->d_peer);
+        if (p->d_counter) cudaFree(p->d_counter);
+        delete p;
+        return PLAGNN_ERR_CUDA;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == PLAGNN_P2P_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    memcpy(handle_out, &h, sizeof(h));
+    p->peer[rank] = p->local;
+    *out = (plagnn_p2p_t)p;
+    return PLAGNN_OK;
+}
+
+int plagnn_p2p_attach(plagnn_p2p_t px, const void* all_handles) {
+    P2P* p = (P2P*)px;
+    if (!p || !all_handles) return fail(PLAGNN_ERR_ARG, "p2p_attach", "bad arguments");
+    for (int q = 0; q < p->world; ++q) {
+        if (q == p->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)all_handles + (size_t)q * PLAGNN_P2P_HANDLE_BYTES, sizeof(h));
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_error("p2p_attach: cudaIpcOpenMemHandle(peer %d): %s", q, cudaGetErrorString(e));
+            cudaGetLastError();
+            return PLAGNN_ERR_CUDA;
+        }
+        p->peer[q] = (char*)ptr;
+    }
+    PLAGNN_CUDA_TRY(cudaMemcpy(p->d_peer, p->peer, sizeof(char*) * P2P_MAX_WORLD, cudaMemcpyHostToDevice));
+    return PLAGNN_OK;
+}
+
+void* plagnn_p2p_window(plagnn_p2p_t px) {
+    P2P* p = (P2P*)px;
+    return p ? (void*)(p->local + P2P_FLAG_BYTES) : nullptr;
+}
+
+long long plagnn_p2p_error(plagnn_p2p_t px) {
+    P2P* p = (P2P*)px;
+    if (!p) return -1;
+    long long v = 0;
+    if (cudaMemcpy(&v, p->local + sizeof(long long) * P2P_MAX_WORLD, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return v;
+}
+
+int plagnn_p2p_destroy(plagnn_p2p_t px) {
+    P2P* p = (P2P*)px;
+    if (!p) return PLAGNN_OK;
+    cudaDeviceSynchronize();
+    for (int q = 0; q < p->world; ++q)
+        if (q != p->rank && p->peer[q]) cudaIpcCloseMemHandle(p->peer[q]);
+    cudaFree(p->local);
+    cudaFree(p->d_peer);
+    cudaFree(p->d_counter);
+    delete p;
+    return PLAGNN_OK;
+}
+
+int plagnn_p2p_send(plagnn_p2p_t px, const float* src, int64_t lds, int64_t rows, int64_t feat, int mode, size_t dst_offset_bytes,
+                    long long seq, plagnn_stream_t stream) {
+    P2P* p = (P2P*)px;
+    if (!p || !src || rows <= 0 || feat <= 0 || (mode != 0 && mode != 1)) return fail(PLAGNN_ERR_ARG, "p2p_send", "bad arguments");
+    if (feat % (4 * (int64_t)p->world)) return fail(PLAGNN_ERR_ARG, "p2p_send", "feat must be a multiple of 4 * world");
+    const int64_t fc = feat / p->world;
+    if ((lds & 3) || lds < (mode == 0 ? feat : fc) || !aligned16(src) || (dst_offset_bytes & 15))
+        return fail(PLAGNN_ERR_ALIGN, "p2p_send", "16-byte aligned rows needed");
+    if (dst_offset_bytes + (size_t)rows * feat * sizeof(float) > p->bytes) return fail(PLAGNN_ERR_WORKSPACE, "p2p_send", "window too small");
+    ProfileScope prof(mode == 0 ? "p2p_send_cols" : "p2p_send_rows", rows, feat, p->world, stream);
+    const int64_t total = rows * (feat / 4);
+    const int grid = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 8 ? ceil_div(total, 256) : (int64_t)sm_count() * 8);
+    launch_pdl(p2p_send_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, src, lds, rows, (int)feat, (int)fc, mode,
+               (char* const*)p->d_peer, dst_offset_bytes, p->rank, p->world, seq, p->d_counter);
+    return check_launch("p2p_send");
+}
+
+int plagnn_p2p_wait(plagnn_p2p_t px, long long seq, plagnn_stream_t stream) {
+    P2P* p = (P2P*)px;
+    if (!p) return fail(PLAGNN_ERR_ARG, "p2p_wait", "bad arguments");
+    ProfileScope prof("p2p_wait", seq, 0, 0, stream);
+    launch_pdl(p2p_wait_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, p->local, p->world, seq);
+    return check_launch("p2p_wait");
+}
+
+}  // extern "C"

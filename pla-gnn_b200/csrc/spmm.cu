@@ -293,6 +293,16 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
 // the same work item: edge e of a batch of 32 goes to group e % S.  Every LDG.128 of the warp then fetches S neighbour rows
 // (512 bytes per request, as in the wide kernel, instead of 128), and the S partial results are folded with shuffles at the
 // end.  The max reducer keeps "first maximum in in-edge order wins" across the groups by carrying the winning edge position.
+//
+// An item of ~100 edges of 128 bytes is short: walked one item per warp, the chain item -> row -> (indptr, plan) -> neighbour
+// ids -> rows -> store is five dependent memory round trips for two or three batches of gathers, and the kernel is bound by
+// that latency, not by bandwidth (measured on the 1 M-node / 100 M-edge graph, F = 32: 2.55 ms per aggregation = 5.4 TB/s
+// algorithmic; cutting the gather into L2-sized source slabs made it slower, 3.7 ms at 4 slabs, because it made the items
+// shorter still).  So a warp takes NARROW_IPW consecutive items: lane l fetches the meta data of item l in one coalesced
+// sweep (two round trips per 32 items), the items are then walked one after the other with their meta data broadcast by
+// shuffles, and the neighbour ids of the next batch — of this item or of the next one — are requested before the current
+// batch is gathered.
+constexpr int NARROW_IPW = 32;
 template <int MODE, int G>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, 4)
 spmm_narrow_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int32_t* __restrict__ eids,
@@ -306,106 +316,135 @@ spmm_narrow_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict
     constexpr int U = 4;               // rounds unrolled: U rows in flight per lane (32 warps x 32 lanes x 4 x 16 B = 64 KB per SM)
     pdl_trigger();
     const int lane = threadIdx.x & 31;
-    const int item = item_begin + blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
-    if (item >= n_items) return;
+    const int item0 = item_begin + (blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5)) * NARROW_IPW;
+    if (item0 >= n_items) return;
     pdl_wait();
+    const int n_mine = min(NARROW_IPW, n_items - item0);
+    // ---- meta data of my items, one per lane -------------------------------------------------------------------------
     const int chunk = __ldg(plan_hdr);
-    const int row = __ldg(item_row + item);
-    const int first = __ldg(item_ptr + row);
-    const int nch = __ldg(item_ptr + row + 1) - first;
-    const int k = item - first;
-    const int rbeg = __ldg(indptr + row), rend = __ldg(indptr + row + 1);
-    const int beg = rbeg + k * chunk;
-    const int end = min(rend, beg + chunk);
+    int m_row = 0, m_beg = 0, m_end = 0, m_nch = 1, m_k = 0;
+    if (lane < n_mine) {
+        m_row = __ldg(item_row + item0 + lane);
+        const int first = __ldg(item_ptr + m_row);
+        m_nch = __ldg(item_ptr + m_row + 1) - first;
+        m_k = item0 + lane - first;
+        const int rbeg = __ldg(indptr + m_row), rend = __ldg(indptr + m_row + 1);
+        m_beg = rbeg + m_k * chunk;
+        m_end = min(rend, m_beg + chunk);
+    }
     const int sub = lane / G, gl = lane % G;
     const int col = 4 * gl;
     const bool cok = col < feat;
     const float* xc = x + (cok ? col : 0);                  // lanes past the last column re-read column 0 (nothing stored)
     const float init = MODE == MODE_MAX ? -INFINITY : 0.f;
-    float4 acc = make_float4(init, init, init, init);
-    int4 arg = make_int4(-1, -1, -1, -1);
-    int4 pos = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
-    // continue from the earlier slabs' result (unsplit rows only: split rows take it in the combine kernel).  Plain loads:
-    // prev may alias the output this kernel writes.  Position -1 makes the earlier slab win value ties.
-    if (ch.prev_val && nch == 1 && cok && (MODE == MODE_MAX || sub == 0)) {
-        acc = *reinterpret_cast<const float4*>(ch.prev_val + (int64_t)row * ch.ldprev + col);
-        if (MODE == MODE_MAX) {
-            arg = *reinterpret_cast<const int4*>(ch.prev_arg + (int64_t)row * ch.ldprev + col);
-            pos = make_int4(-1, -1, -1, -1);
-        }
-    }
 
-    for (int base = beg; base < end; base += 32) {
-        const int cnt = min(32, end - base);
-        int my_u = 0;
-        float my_w = 1.f;
-        if (lane < cnt) {
-            my_u = __ldg(indices + base + lane);
-            if (MODE == MODE_SUM && ew) my_w = __ldg(ew + (eids ? __ldg(eids + base + lane) : base + lane));
-        }
-        for (int t = 0; t * S < cnt; t += U) {
-            int u[U];
-            float w[U];
-            float4 v[U];
-#pragma unroll
-            for (int i = 0; i < U; ++i) {
-                const int e = min((t + i) * S + sub, 31);
-                u[i] = __shfl_sync(0xffffffffu, my_u, e);
-                if (MODE == MODE_SUM) w[i] = __shfl_sync(0xffffffffu, my_w, e);
-                const bool live = (t + i) * S + sub < cnt;
-                v[i] = live ? ldg_f4(xc + (int64_t)u[i] * ldx) : make_float4(init, init, init, init);
+    int cb = __shfl_sync(0xffffffffu, m_beg, 0), ce = __shfl_sync(0xffffffffu, m_end, 0);
+    // neighbour ids (and weights) of the batch about to be processed, requested one batch ahead
+    int pf_u = 0;
+    float pf_w = 1.f;
+    if (cb + lane < ce) {
+        pf_u = __ldg(indices + cb + lane);
+        if (MODE == MODE_SUM && ew) pf_w = __ldg(ew + (eids ? __ldg(eids + cb + lane) : cb + lane));
+    }
+    for (int it = 0; it < n_mine; ++it) {
+        const int row = __shfl_sync(0xffffffffu, m_row, it);
+        const int nch = __shfl_sync(0xffffffffu, m_nch, it);
+        const int k = __shfl_sync(0xffffffffu, m_k, it);
+        const int nb_item = it + 1 < n_mine ? __shfl_sync(0xffffffffu, m_beg, (it + 1) & 31) : 0;
+        const int ne_item = it + 1 < n_mine ? __shfl_sync(0xffffffffu, m_end, (it + 1) & 31) : 0;
+        float4 acc = make_float4(init, init, init, init);
+        int4 arg = make_int4(-1, -1, -1, -1);
+        int4 pos = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
+        // continue from the earlier slabs' result (unsplit rows only: split rows take it in the combine kernel).  Plain loads:
+        // prev may alias the output this kernel writes.  Position -1 makes the earlier slab win value ties.
+        if (ch.prev_val && nch == 1 && cok && (MODE == MODE_MAX || sub == 0)) {
+            acc = *reinterpret_cast<const float4*>(ch.prev_val + (int64_t)row * ch.ldprev + col);
+            if (MODE == MODE_MAX) {
+                arg = *reinterpret_cast<const int4*>(ch.prev_arg + (int64_t)row * ch.ldprev + col);
+                pos = make_int4(-1, -1, -1, -1);
             }
+        }
+        int base = cb;
+        do {                                              // at least once: hands the prefetch on even for an empty item
+            const int cnt = max(0, min(32, ce - base));
+            const int my_u = pf_u;
+            const float my_w = pf_w;
+            // request the next batch: of this item, else the first one of the next item
+            int nbase = base + 32, nend = ce;
+            if (nbase >= ce) { nbase = nb_item; nend = ne_item; }
+            pf_u = 0;
+            pf_w = 1.f;
+            if (nbase + lane < nend) {
+                pf_u = __ldg(indices + nbase + lane);
+                if (MODE == MODE_SUM && ew) pf_w = __ldg(ew + (eids ? __ldg(eids + nbase + lane) : nbase + lane));
+            }
+            for (int t = 0; t * S < cnt; t += U) {
+                int u[U];
+                float w[U];
+                float4 v[U];
 #pragma unroll
-            for (int i = 0; i < U; ++i) {
-                if (MODE == MODE_MAX) {
-                    const int p = base + (t + i) * S + sub;
-                    if (v[i].x > acc.x) { acc.x = v[i].x; arg.x = u[i]; pos.x = p; }
-                    if (v[i].y > acc.y) { acc.y = v[i].y; arg.y = u[i]; pos.y = p; }
-                    if (v[i].z > acc.z) { acc.z = v[i].z; arg.z = u[i]; pos.z = p; }
-                    if (v[i].w > acc.w) { acc.w = v[i].w; arg.w = u[i]; pos.w = p; }
-                } else {
-                    const float ww = ew ? w[i] : 1.f;
-                    acc.x = fmaf(ww, v[i].x, acc.x); acc.y = fmaf(ww, v[i].y, acc.y);
-                    acc.z = fmaf(ww, v[i].z, acc.z); acc.w = fmaf(ww, v[i].w, acc.w);
+                for (int i = 0; i < U; ++i) {
+                    const int e = min((t + i) * S + sub, 31);
+                    u[i] = __shfl_sync(0xffffffffu, my_u, e);
+                    if (MODE == MODE_SUM) w[i] = __shfl_sync(0xffffffffu, my_w, e);
+                    const bool live = (t + i) * S + sub < cnt;
+                    v[i] = live ? ldg_f4(xc + (int64_t)u[i] * ldx) : make_float4(init, init, init, init);
+                }
+#pragma unroll
+                for (int i = 0; i < U; ++i) {
+                    if (MODE == MODE_MAX) {
+                        const int p = base + (t + i) * S + sub;
+                        if (v[i].x > acc.x) { acc.x = v[i].x; arg.x = u[i]; pos.x = p; }
+                        if (v[i].y > acc.y) { acc.y = v[i].y; arg.y = u[i]; pos.y = p; }
+                        if (v[i].z > acc.z) { acc.z = v[i].z; arg.z = u[i]; pos.z = p; }
+                        if (v[i].w > acc.w) { acc.w = v[i].w; arg.w = u[i]; pos.w = p; }
+                    } else {
+                        const float ww = ew ? w[i] : 1.f;
+                        acc.x = fmaf(ww, v[i].x, acc.x); acc.y = fmaf(ww, v[i].y, acc.y);
+                        acc.z = fmaf(ww, v[i].z, acc.z); acc.w = fmaf(ww, v[i].w, acc.w);
+                    }
                 }
             }
-        }
-    }
-    // fold the S lane groups (group 0 ends up with the result)
+            base += 32;
+        } while (base < ce);
+        cb = nb_item;
+        ce = ne_item;
+        // fold the S lane groups (group 0 ends up with the result)
 #pragma unroll
-    for (int off = G; off < 32; off <<= 1) {
-        const float ox = __shfl_xor_sync(0xffffffffu, acc.x, off), oy = __shfl_xor_sync(0xffffffffu, acc.y, off);
-        const float oz = __shfl_xor_sync(0xffffffffu, acc.z, off), ow = __shfl_xor_sync(0xffffffffu, acc.w, off);
-        if (MODE == MODE_MAX) {
-            const int ax = __shfl_xor_sync(0xffffffffu, arg.x, off), ay = __shfl_xor_sync(0xffffffffu, arg.y, off);
-            const int az = __shfl_xor_sync(0xffffffffu, arg.z, off), aw = __shfl_xor_sync(0xffffffffu, arg.w, off);
-            const int px = __shfl_xor_sync(0xffffffffu, pos.x, off), py = __shfl_xor_sync(0xffffffffu, pos.y, off);
-            const int pz = __shfl_xor_sync(0xffffffffu, pos.z, off), pw = __shfl_xor_sync(0xffffffffu, pos.w, off);
-            if (ox > acc.x || (ox == acc.x && px < pos.x)) { acc.x = ox; arg.x = ax; pos.x = px; }
-            if (oy > acc.y || (oy == acc.y && py < pos.y)) { acc.y = oy; arg.y = ay; pos.y = py; }
-            if (oz > acc.z || (oz == acc.z && pz < pos.z)) { acc.z = oz; arg.z = az; pos.z = pz; }
-            if (ow > acc.w || (ow == acc.w && pw < pos.w)) { acc.w = ow; arg.w = aw; pos.w = pw; }
-        } else {
-            acc.x += ox; acc.y += oy; acc.z += oz; acc.w += ow;
-        }
-    }
-    if (sub != 0 || !cok) return;
-    if (nch == 1) {
-        float4 r = acc;
-        if (MODE == MODE_MAX) {
-            if (ch.last) {
-                r.x = arg.x < 0 ? 0.f : r.x; r.y = arg.y < 0 ? 0.f : r.y;
-                r.z = arg.z < 0 ? 0.f : r.z; r.w = arg.w < 0 ? 0.f : r.w;
+        for (int off = G; off < 32; off <<= 1) {
+            const float ox = __shfl_xor_sync(0xffffffffu, acc.x, off), oy = __shfl_xor_sync(0xffffffffu, acc.y, off);
+            const float oz = __shfl_xor_sync(0xffffffffu, acc.z, off), ow = __shfl_xor_sync(0xffffffffu, acc.w, off);
+            if (MODE == MODE_MAX) {
+                const int ax = __shfl_xor_sync(0xffffffffu, arg.x, off), ay = __shfl_xor_sync(0xffffffffu, arg.y, off);
+                const int az = __shfl_xor_sync(0xffffffffu, arg.z, off), aw = __shfl_xor_sync(0xffffffffu, arg.w, off);
+                const int px = __shfl_xor_sync(0xffffffffu, pos.x, off), py = __shfl_xor_sync(0xffffffffu, pos.y, off);
+                const int pz = __shfl_xor_sync(0xffffffffu, pos.z, off), pw = __shfl_xor_sync(0xffffffffu, pos.w, off);
+                if (ox > acc.x || (ox == acc.x && px < pos.x)) { acc.x = ox; arg.x = ax; pos.x = px; }
+                if (oy > acc.y || (oy == acc.y && py < pos.y)) { acc.y = oy; arg.y = ay; pos.y = py; }
+                if (oz > acc.z || (oz == acc.z && pz < pos.z)) { acc.z = oz; arg.z = az; pos.z = pz; }
+                if (ow > acc.w || (ow == acc.w && pw < pos.w)) { acc.w = ow; arg.w = aw; pos.w = pw; }
+            } else {
+                acc.x += ox; acc.y += oy; acc.z += oz; acc.w += ow;
             }
-            *reinterpret_cast<int4*>(arg_out + (int64_t)row * ldo + col) = arg;
-        } else if (ch.last) {
-            r = sum_epilogue(r, ep, row, col, feat);
         }
-        *reinterpret_cast<float4*>(out + (int64_t)row * ldo + col) = r;
-    } else {
-        const int64_t slot = (int64_t)__ldg(slot_ptr + row) + k;
-        *reinterpret_cast<float4*>(part_val + slot * part_ld + col) = acc;
-        if (MODE == MODE_MAX) *reinterpret_cast<int4*>(part_arg + slot * part_ld + col) = arg;
+        if (sub != 0 || !cok) continue;
+        if (nch == 1) {
+            float4 r = acc;
+            if (MODE == MODE_MAX) {
+                if (ch.last) {
+                    r.x = arg.x < 0 ? 0.f : r.x; r.y = arg.y < 0 ? 0.f : r.y;
+                    r.z = arg.z < 0 ? 0.f : r.z; r.w = arg.w < 0 ? 0.f : r.w;
+                }
+                *reinterpret_cast<int4*>(arg_out + (int64_t)row * ldo + col) = arg;
+            } else if (ch.last) {
+                r = sum_epilogue(r, ep, row, col, feat);
+            }
+            *reinterpret_cast<float4*>(out + (int64_t)row * ldo + col) = r;
+        } else {
+            const int64_t slot = (int64_t)__ldg(slot_ptr + row) + k;
+            *reinterpret_cast<float4*>(part_val + slot * part_ld + col) = acc;
+            if (MODE == MODE_MAX) *reinterpret_cast<int4*>(part_arg + slot * part_ld + col) = arg;
+        }
     }
 }
 
@@ -558,7 +597,7 @@ static void launch_narrow(const SpmmArgs& a, const int32_t* item_ptr, const int3
     const int item_begin = a.range ? (int)a.range[0] : 0;
     const int n_items = a.range ? (int)a.range[1] : (int)a.counts[0];
     if (n_items <= item_begin) return;
-    dim3 grid((unsigned)ceil_div(n_items - item_begin, SPMM_WARPS));
+    dim3 grid((unsigned)ceil_div(n_items - item_begin, SPMM_WARPS * NARROW_IPW));
     launch_pdl(spmm_narrow_kernel<MODE, G>, grid, dim3(SPMM_WARPS * 32), 0, st,
         a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, item_begin, n_items, a.x, a.ldx,
         (int)a.feat, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep, a.chain);

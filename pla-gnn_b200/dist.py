@@ -216,7 +216,9 @@ class PartitionedGraph:
         self.csc_slabs = self.w_csc_slabs = self.csr_t_slabs = self.w_csr_t_slabs = None
         n_slabs = 1
         if self.mode == "cols" and feat is not None and feat // plan.world <= 64:
-            slab_mb = float(os.environ.get("PLAGNN_DIST_SLAB_MB", "32")) if slab_mb is None else slab_mb
+            # off by default: measured on the 1 M / 100 M graph at 32 columns, 1 / 2 / 4 / 8 slabs -> 2.56 / 2.85 / 3.72 / 5.92 ms per
+            # aggregation (the items get shorter and the kernel is latency-bound per item, not L2-miss-bound)
+            slab_mb = float(os.environ.get("PLAGNN_DIST_SLAB_MB", "0")) if slab_mb is None else slab_mb
             if slab_mb > 0:
                 n_slabs = max(1, math.ceil(plan.n_padded * (feat // plan.world) * 4 / (slab_mb * 2 ** 20)))
         self.n_slabs = n_slabs
@@ -485,15 +487,91 @@ class NcclComm:
             self.handle = None
 
 
+class _WindowView:
+    """CUDA array interface over a slice of a peer-exchange window, so that torch can view library-owned device memory."""
+
+    def __init__(self, ptr: int, shape, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        self._owner = owner
+
+
+class P2PExchange:
+    """Peer-memory exchange of the feature partition (plagnn_p2p_*): one window per rank, opened by every peer over CUDA IPC;
+    the all-to-all steps become one kernel that stores straight into the owners' windows plus a flag wait.  `region_bytes` =
+    rows_per_rank * feat * 4 (the size of one exchanged matrix); the window holds two regions used alternately."""
+
+    def __init__(self, region_bytes: int, rank: int, world: int, device):
+        from . import _lib
+        self._lib, self.lib = _lib, _lib.load()
+        self.rank, self.world, self.device = rank, world, device
+        self.region_bytes = (int(region_bytes) + 255) // 256 * 256
+        self.handle = ctypes.c_void_p()
+        hbuf = (ctypes.c_ubyte * 64)()
+        # every step is agreed on by all ranks (a rank that failed alone would leave the others waiting in a collective)
+        err = None
+        try:
+            with torch.cuda.device(device):
+                _lib.check(self.lib.plagnn_p2p_create(2 * self.region_bytes, rank, world, hbuf, ctypes.byref(self.handle)), "p2p_create")
+        except Exception as ex:
+            err = repr(ex)
+        got = [None] * world
+        dist.all_gather_object(got, (err, bytes(hbuf)))
+        if any(e is not None for e, _ in got):
+            self._free()
+            raise _lib.PlagnnError("peer-memory window: " + "; ".join(str(e) for e, _ in got if e is not None))
+        allh = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(h for _, h in got))
+        try:
+            with torch.cuda.device(device):
+                _lib.check(self.lib.plagnn_p2p_attach(self.handle, allh), "p2p_attach")
+        except Exception as ex:
+            err = repr(ex)
+        got = [None] * world
+        dist.all_gather_object(got, err)            # also: every window is open everywhere before the first store
+        if any(e is not None for e in got):
+            self._free()
+            raise _lib.PlagnnError("peer-memory window: " + "; ".join(str(e) for e in got if e is not None))
+        self.base = int(self.lib.plagnn_p2p_window(self.handle))
+        self.seq = 0
+
+    def _free(self):
+        if self.handle:
+            self.lib.plagnn_p2p_destroy(self.handle)
+            self.handle = None
+
+    def _region(self, seq):
+        return (seq & 1) * self.region_bytes
+
+    def exchange(self, src: torch.Tensor, rows: int, feat: int, mode: int, stream) -> torch.Tensor:
+        """Sends `src` (mode 0: [rows x feat] -> all rows x my columns; mode 1: [world*rows x feat/world] -> my rows x all
+        columns), waits for the peers' parts and returns a view of the window region that now holds the result."""
+        self.seq += 1
+        off = self._region(self.seq)
+        self._lib.check(self.lib.plagnn_p2p_send(self.handle, src.data_ptr(), src.stride(0), rows, feat, mode, off, self.seq, stream),
+                        "p2p_send")
+        self._lib.check(self.lib.plagnn_p2p_wait(self.handle, self.seq, stream), "p2p_wait")
+        shape = (self.world * rows, feat // self.world) if mode == 0 else (rows, feat)
+        return torch.as_tensor(_WindowView(self.base + off, shape, self), device=self.device)
+
+    def error(self) -> int:
+        return int(self.lib.plagnn_p2p_error(self.handle))
+
+    def destroy(self):
+        if self.handle:
+            torch.cuda.synchronize()
+            dist.barrier()             # nobody is still storing into a window that is about to go away
+            self._free()
+
+
 class CudaBackend:
     """Compute + collectives on the CUDA kernels / NCCL wrappers.  (Tests use a CPU twin with the same method names.)
     comm: NcclComm or None (world 1).  skip_comm = True leaves every collective out (timing of the compute alone: the
     difference to the full step is the exposed exchange time; results are then meaningless)."""
 
-    def __init__(self, pg: PartitionedGraph, comm: NcclComm | None = None):
+    def __init__(self, pg: PartitionedGraph, comm: NcclComm | None = None, p2p: "P2PExchange | None" = None):
         from . import _lib, ops
         self.ops, self._lib, self.lib = ops, _lib, _lib.load()
         self.comm = comm
+        self.p2p = p2p                 # feature partition: peer-memory exchange instead of pack + NCCL all-to-all + unpack
         self.pg = pg
         self.skip_comm = False
         # highest priority: when an SM slot frees up, the exchange kernel's CTAs are placed before the pending CTAs of the
@@ -633,6 +711,8 @@ class CudaBackend:
         rows, feat = x_local.shape
         fc = feat // world
         st = ops._stream()
+        if self.p2p is not None and world > 1 and not self.skip_comm:
+            return self.p2p.exchange(x_local, rows, feat, 0, st)       # a view of the window: consumed by the next kernel
         send = torch.empty((world * rows, fc), device=x_local.device, dtype=torch.float32)
         self._lib.check(self.lib.plagnn_cols_pack(x_local.data_ptr(), x_local.stride(0), rows, feat, world, send.data_ptr(), st),
                         "cols_pack")
@@ -649,6 +729,11 @@ class CudaBackend:
         fc = feat // world
         rows = x_col.shape[0] // world
         st = ops._stream()
+        if self.p2p is not None and world > 1 and not self.skip_comm:
+            if x_col.stride(0) % 4 or x_col.data_ptr() % 16:
+                x_col = x_col.contiguous()
+            # callers keep this matrix (layer input / saved activation), the window region is reused two exchanges later
+            return self.p2p.exchange(x_col, rows, feat, 1, st).clone()
         if x_col.stride(0) != fc:
             x_col = x_col.contiguous()
         recv = x_col

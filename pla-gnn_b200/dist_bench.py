@@ -36,7 +36,7 @@ def _hbm_peak():
 class Variant:
     """One (partition mode, reducer) combination on one rank: plan, device structures, model, step function."""
 
-    def __init__(self, sg, n, f, mode, reducer, rank, world, dev, comm, chunks, balance, h0_global, layers=2):
+    def __init__(self, sg, n, f, mode, reducer, rank, world, dev, comm, chunks, balance, h0_global, layers=2, p2p=None):
         import plagnn_b200 as P
         from .dist import (CudaBackend, DistGCN, DistSAGEPool, FeaturePartitionPlan, PartitionedGraph, RowPartitionPlan,
                            dist_gcn_forward_backward, dist_pool_forward_backward)
@@ -55,7 +55,8 @@ class Variant:
         self.opt = P.FusedAdam(self.params, lr=1e-3)
         self.h0 = ops.alloc(plan.per, f, dev, zero=True)
         self.h0[:plan.n_local].copy_(h0_global[plan.r0:plan.r1])
-        self.backend = CudaBackend(self.pg, comm)
+        self.backend = CudaBackend(self.pg, comm, p2p if mode == "cols" else None)
+        self.exchange = "p2p" if (mode == "cols" and p2p is not None) else ("nccl" if world > 1 else None)
         self.inv = 1.0 / (n * f)
         self._fb = dist_gcn_forward_backward if reducer == "sum" else dist_pool_forward_backward
         self.layers = layers
@@ -152,7 +153,7 @@ def measure_variant(v: Variant, steps, warmup, rank, world, dev, reference=None)
         bwd = 16 * fc * plan.n_padded if v.mode == "cols" else 4 * f * (2 * plan.per + 2 * plan.n_padded)
         alg = v.layers * ((4 * fc * el + 4 * el + 8 * fc * rows_out) + bwd)
     hbm, src = _hbm_peak()
-    res = {"mode": v.mode, "reducer": v.reducer, "ms_per_step": ms, "ms_per_step_with_events": ms_prof,
+    res = {"mode": v.mode, "reducer": v.reducer, "exchange": v.exchange, "ms_per_step": ms, "ms_per_step_with_events": ms_prof,
            "ms_per_step_without_collectives": ms_nocomm, "exposed_exchange_ms": (ms - ms_nocomm) if ms_nocomm else 0.0,
            "collective_ms_per_step": coll, "aggregation_ms_per_step": agg_ms,
            "aggregation_algorithmic_gbs_per_gpu": alg / (agg_ms * 1e-3) / 1e9 if agg_ms else None,
@@ -228,6 +229,17 @@ def run_partitioned(n, e, f, steps, warmup, rank, world, dev, modes=("rows", "co
     max_ctas = int(os.environ.get("PLAGNN_NCCL_MAX_CTAS", "0")) if max_ctas is None else max_ctas
     comm = NcclComm(rank, world, dev, max_ctas=max_ctas) if world > 1 else None
     probe = probe_collectives(comm, n, f, world, dev) if world > 1 else None
+    p2p = None
+    if world > 1 and "cols" in modes and f % (4 * world) == 0 and os.environ.get("PLAGNN_DIST_P2P", "1") != "0":
+        from .dist import P2PExchange, block_bounds_by_edges
+        per = block_bounds_by_edges(torch.bincount(sg.dst, minlength=n), world)[0] if balance == "edges" else (n + world - 1) // world
+        try:
+            p2p = P2PExchange(per * f * 4, rank, world, dev)
+        except Exception as ex:                       # e.g. CUDA IPC not permitted in this container: NCCL all-to-all instead
+            if rank == 0:
+                import sys
+                print(f"[plagnn] peer-memory exchange unavailable ({ex!r}); using the NCCL all-to-all", file=sys.stderr, flush=True)
+            p2p = None
     results = []
     single_ms = {}
     for reducer in reducers:
@@ -255,7 +267,7 @@ def run_partitioned(n, e, f, steps, warmup, rank, world, dev, modes=("rows", "co
         for mode in modes:
             if mode == "cols" and f % (4 * world):
                 continue
-            v = Variant(sg, n, f, mode, reducer, rank, world, dev, comm, chunks, balance, h0_global)
+            v = Variant(sg, n, f, mode, reducer, rank, world, dev, comm, chunks, balance, h0_global, p2p=p2p)
             r = measure_variant(v, steps, warmup, rank, world, dev, reference)
             if r is not None:
                 r["chunks"] = v.plan.chunks
@@ -263,6 +275,11 @@ def run_partitioned(n, e, f, steps, warmup, rank, world, dev, modes=("rows", "co
             del v
             torch.cuda.empty_cache()
         del reference
+    p2p_err = None
+    if p2p is not None:
+        torch.cuda.synchronize()
+        p2p_err = p2p.error()
+        p2p.destroy()
     if comm is not None:
         torch.cuda.synchronize()
         comm.destroy()
@@ -287,6 +304,7 @@ def run_partitioned(n, e, f, steps, warmup, rank, world, dev, modes=("rows", "co
             "variants": results,
             "winner": {k: {"mode": v["mode"], "ms_per_step": v["ms_per_step"], "edges_per_s": v["edges_per_s"],
                            "strong_scaling_efficiency": v.get("strong_scaling_efficiency")} for k, v in best.items()},
+            "p2p_wait_gave_up_at_seq": p2p_err,
             "checks_ok": all(r["check"]["ok"] for r in results if r["check"]) if world > 1 else None}
 
 

@@ -243,3 +243,44 @@ def test_feature_partition_with_source_slabs_world1(cuda):
     assert rel_err(pout[:n], pout_ref) < REL_TOL
     for g, gr in zip(pgrads, pgrads_ref):
         assert rel_err(g, gr) < 2 * REL_TOL
+
+
+def _p2p_worker(rank, world, port, out_dir):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+    from plagnn_b200 import ops
+    from plagnn_b200.dist import P2PExchange
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", device_id=dev)
+    rows, feat = 1000, 64
+    fc = feat // world
+    x = ops.alloc(rows, feat, dev)
+    x.copy_(torch.arange(rows * feat, device=dev, dtype=torch.float32).reshape(rows, feat) + 1e6 * rank)
+    ex = P2PExchange(rows * feat * 4, rank, world, dev)
+    ok = True
+    for it in range(5):                                   # several rounds: the two window regions alternate
+        xc = ex.exchange(x, rows, feat, 0, ops._stream())        # all rows x my columns
+        for q in range(world):
+            ref = torch.arange(rows * feat, device=dev, dtype=torch.float32).reshape(rows, feat)[:, rank * fc:(rank + 1) * fc] + 1e6 * q
+            ok = ok and torch.equal(xc[q * rows:(q + 1) * rows], ref)
+        back = ex.exchange(xc.clone(), rows, feat, 1, ops._stream()).clone()      # my rows x all columns again
+        ok = ok and torch.equal(back, x)
+    ok = ok and ex.error() == 0
+    ex.destroy()
+    with open(os.path.join(out_dir, f"p2p{rank}.txt"), "w") as fh:
+        fh.write("ok" if ok else "mismatch")
+    dist.destroy_process_group()
+
+
+def test_two_gpu_peer_memory_exchange_round_trip(cuda, tmp_path):
+    """plagnn_p2p_*: rows -> columns -> rows between two GPUs over CUDA IPC windows, bit-exact, five rounds."""
+    import os
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    port = 29500 + (os.getpid() * 17) % 2000
+    mp.start_processes(_p2p_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True, start_method="spawn")
+    assert [open(tmp_path / f"p2p{r}.txt").read() for r in range(2)] == ["ok", "ok"]

@@ -104,3 +104,23 @@ def test_fold_splits_are_the_reference_kfold():
     assert len(got) == 3
     for (tr, va), (rt, rv) in zip(got, ref):
         assert tr.tolist() == [label[i] for i in rt] and va.tolist() == [label[i] for i in rv]    # train.py:183-188
+
+
+def test_matplotlib_stand_in_yields_to_a_real_installation(tmp_path):
+    """drop_in/matplotlib must not shadow a real matplotlib that sits later on sys.path."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    drop_in = os.path.join(root, "pla-gnn_b200", "drop_in")
+    real = tmp_path / "site" / "matplotlib"
+    real.mkdir(parents=True)
+    (real / "__init__.py").write_text("REAL = True\n")
+    (real / "pyplot.py").write_text("def plot():\n    return 'real plot'\n")
+    code = ("import sys; sys.path[:0] = [%r, %r]\nimport matplotlib.pyplot as plt\nimport matplotlib\n"
+            "print(getattr(matplotlib, 'REAL', False), plt.plot())" % (drop_in, str(tmp_path / "site")))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.stdout.split() == ["True", "real", "plot"], out.stdout + out.stderr
+    code = "import sys; sys.path.insert(0, %r)\nimport matplotlib.pyplot as plt\nprint('stub ok')" % drop_in
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert "stub ok" in out.stdout, out.stdout + out.stderr

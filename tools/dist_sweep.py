@@ -14,7 +14,7 @@ import torch
 import torch.distributed as dist
 
 from plagnn_b200 import dist_bench, synth
-from plagnn_b200.dist import NcclComm
+from plagnn_b200.dist import NcclComm, P2PExchange, block_bounds_by_edges
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=5)
@@ -22,6 +22,7 @@ ap.add_argument("--ctas", default="0,16")
 ap.add_argument("--chunks", default="2,4")
 ap.add_argument("--modes", default="rows,cols")
 ap.add_argument("--reducers", default="sum,max")
+ap.add_argument("--exchange", default="p2p,nccl", help="feature partition: peer-memory exchange and / or NCCL all-to-all")
 ap.add_argument("--nodes", type=int, default=1_000_000)
 ap.add_argument("--edges", type=int, default=100_000_000)
 ap.add_argument("--feat", type=int, default=256)
@@ -53,6 +54,14 @@ for reducer in args.reducers.split(","):
         del ref, out, grads
         torch.cuda.empty_cache()
     dist.barrier()
+p2p = None
+if "p2p" in args.exchange.split(",") and "cols" in args.modes.split(","):
+    per = block_bounds_by_edges(torch.bincount(sg.dst, minlength=n), world)[0]
+    try:
+        p2p = P2PExchange(per * f * 4, rank, world, dev)
+    except Exception as ex:
+        if rank == 0:
+            print(json.dumps({"p2p_unavailable": repr(ex)[:300]}), flush=True)
 for ctas in [int(c) for c in args.ctas.split(",")]:
     comm = NcclComm(rank, world, dev, max_ctas=ctas)
     probe = dist_bench.probe_collectives(comm, n, f, world, dev)
@@ -60,8 +69,9 @@ for ctas in [int(c) for c in args.ctas.split(",")]:
         print(json.dumps({"nccl_max_ctas": ctas, "nccl_alone": probe}), flush=True)
     for reducer in args.reducers.split(","):
         for mode in args.modes.split(","):
-            for chunks in ([int(c) for c in args.chunks.split(",")] if mode == "rows" else [1]):
-                v = dist_bench.Variant(sg, n, f, mode, reducer, rank, world, dev, comm, chunks, "edges", h0)
+            for chunks, xp in ([(int(c), None) for c in args.chunks.split(",")] if mode == "rows" else
+                               [(1, p2p if x == "p2p" else None) for x in args.exchange.split(",") if x == "nccl" or p2p is not None]):
+                v = dist_bench.Variant(sg, n, f, mode, reducer, rank, world, dev, comm, chunks, "edges", h0, p2p=xp)
                 r = dist_bench.measure_variant(v, args.steps, 3, rank, world, dev, refs.get(reducer))
                 if rank == 0:
                     r.update({"nccl_max_ctas": ctas, "chunks": chunks, "n_gpus": world})
@@ -71,4 +81,9 @@ for ctas in [int(c) for c in args.ctas.split(",")]:
                 torch.cuda.empty_cache()
     torch.cuda.synchronize()
     comm.destroy()
+if p2p is not None:
+    torch.cuda.synchronize()
+    if rank == 0:
+        print(json.dumps({"p2p_wait_gave_up_at_seq": p2p.error()}), flush=True)
+    p2p.destroy()
 dist.destroy_process_group()
