@@ -333,6 +333,12 @@ int plagnn_gnn32_backward(const plagnn_gnn32_shape* shape, const float* x, int64
  *   bit-identical for given thresholds); rowptr[N+1] = CSR row pointer of new_mask, *n_out (device) = its entry count.
  * bitmask_to_coo: the set bits of mask in row-major order (= coo_matrix(dense), code/data_preprocess.py:255).
  * ---------------------------------------------------------------------------------------- */
+/* pearson: out[rows x rows] (float64) = np.corrcoef(expr[rows x samples]) with the diagonal and every NaN (constant rows) set
+ *   to 0 — what code/data_preprocess.py:165-170 (construct_gcn_matrix) leaves in memory before coo_matrix().  numpy's steps in
+ *   numpy's order; the three-term products are FMA chains in sample order (numpy: a BLAS call), test bar 4 ulp. */
+size_t plagnn_pearson_workspace_bytes(int64_t rows, int64_t samples);
+int plagnn_pearson(const double* expr, int64_t ldx, int64_t rows, int64_t samples, double* out, int64_t ldo,
+                   void* workspace, size_t workspace_bytes, plagnn_stream_t stream);
 size_t plagnn_ecc_workspace_bytes(int64_t num_nodes);
 int plagnn_ecc(const int32_t* indptr, const int32_t* indices, int64_t num_nodes, int64_t nnz, double epsilon,
                int32_t* ecc_row, int32_t* ecc_col, double* ecc_data, int64_t capacity, int64_t* n_out /* device */,

@@ -76,3 +76,14 @@ def modify_network_topology(ppi_net, pcc_nor, pcc_inter, thr, l_threshold=None, 
     out[(diff < l_threshold) & (adj == 1)] = 0
     out[(diff > r_threshold) & (adj == 0)] = 1
     return coo_matrix(out)
+
+
+def pearson_matrix(expr_gcn: np.ndarray) -> np.ndarray:
+    """data_preprocess.py:165-170 (the numeric tail of construct_gcn_matrix): np.corrcoef of the protein x sample matrix,
+    diagonal and NaN entries (zero-variance rows) set to 0.  np.corrcoef is the reference's own call; its BLAS product is not
+    bit-stable across builds, so comparisons against it carry a 4-ulp bar (values in [-1, 1])."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        p = np.corrcoef(np.asarray(expr_gcn, dtype=np.float64))
+    np.fill_diagonal(p, 0)
+    p[np.isnan(p)] = 0
+    return p

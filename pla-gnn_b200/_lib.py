@@ -101,6 +101,8 @@ PROTOTYPES = {
     "plagnn_divide_f64": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_double, c_void_p]),
     "plagnn_alteration_rank": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
                                        c_void_p, c_size_t, c_void_p]),
+    "plagnn_pearson_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "plagnn_pearson": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "plagnn_ecc_workspace_bytes": (c_size_t, [c_int64]),
     "plagnn_ecc": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                            c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -265,7 +265,70 @@ static int pp_stream_blocks(int64_t rows) {
 
 using namespace plagnn;
 
+// ---------------------------------------------------------------- Pearson matrix of the expression rows (np.corrcoef)
+// code/data_preprocess.py:165-170: expr_pcc = np.corrcoef(expr_gcn); fill_diagonal(0); NaN -> 0.  numpy's steps, restated:
+// X = x - mean(x, axis 1); c = (X X^T) * (1 / (S - 1)); sd = sqrt(diag(c)); c /= sd[:, None]; c /= sd[None, :]; clip to
+// [-1, 1].  The product X X^T is a BLAS call there (S = 3 samples: three terms per entry, whose rounding depends on the BLAS
+// micro-kernel); here it is a fused-multiply-add chain in sample order, which agrees with numpy to <= 2 ulp on every entry
+// probed, so the test bar is 4 ulp on values in [-1, 1], not bit-exactness.
+__global__ void __launch_bounds__(PP_THREADS)
+pp_center_kernel(const double* __restrict__ x, int64_t ldx, int64_t rows, int samples, double* __restrict__ xc /* rows x samples */,
+                 double* __restrict__ sd /* rows */) {
+    const int64_t r = (int64_t)blockIdx.x * PP_THREADS + threadIdx.x;
+    if (r >= rows) return;
+    double s = 0.0;
+    for (int k = 0; k < samples; ++k) s += x[r * ldx + k];                 // np.add.reduce over < 8 items: left to right
+    const double mean = s / (double)samples;
+    double acc = 0.0;
+    for (int k = 0; k < samples; ++k) {
+        const double v = x[r * ldx + k] - mean;
+        xc[r * samples + k] = v;
+        acc = k ? fma(v, v, acc) : v * v;
+    }
+    sd[r] = sqrt(acc * (1.0 / (double)(samples - 1)));
+}
+
+__global__ void __launch_bounds__(PP_THREADS)
+pp_pearson_kernel(const double* __restrict__ xc, const double* __restrict__ sd, int64_t rows, int samples, double* __restrict__ out,
+                  int64_t ldo) {
+    const int64_t j = (int64_t)blockIdx.x * PP_THREADS + threadIdx.x;      // consecutive threads: consecutive columns
+    const double fact = 1.0 / (double)(samples - 1);
+    for (int64_t i = blockIdx.y; i < rows; i += gridDim.y) {
+        if (j >= rows) continue;
+        double acc = 0.0;
+        for (int k = 0; k < samples; ++k) {
+            const double a = xc[i * samples + k], b = xc[j * samples + k];
+            acc = k ? fma(a, b, acc) : a * b;
+        }
+        double c = ((acc * fact) / sd[i]) / sd[j];
+        c = fmin(fmax(c, -1.0), 1.0);                                      // np.clip (NaN stays NaN: fmin / fmax would drop it)
+        if (i == j || !(c == c) || !(sd[i] == sd[i]) || sd[i] == 0.0 || sd[j] == 0.0) c = 0.0;   // diagonal, NaN -> 0
+        out[i * ldo + j] = c;
+    }
+}
+
 extern "C" {
+
+size_t plagnn_pearson_workspace_bytes(int64_t rows, int64_t samples) {
+    if (rows <= 0 || samples <= 0) return 0;
+    return align_up((size_t)rows * (size_t)(samples + 1) * sizeof(double), 256);
+}
+
+int plagnn_pearson(const double* expr, int64_t ldx, int64_t rows, int64_t samples, double* out, int64_t ldo, void* workspace,
+                   size_t workspace_bytes, plagnn_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfileScope prof("pearson", rows, samples, 0, stream);
+    if (!expr || !out || rows <= 0 || samples < 2 || samples > 4096 || ldx < samples || ldo < rows)
+        return fail(PLAGNN_ERR_ARG, "pearson", "bad arguments (at least two samples)");
+    if (!workspace || workspace_bytes < plagnn_pearson_workspace_bytes(rows, samples))
+        return fail(PLAGNN_ERR_WORKSPACE, "pearson", "workspace too small");
+    double* xc = reinterpret_cast<double*>(workspace);
+    double* sd = xc + rows * samples;
+    pp_center_kernel<<<(unsigned)ceil_div(rows, PP_THREADS), PP_THREADS, 0, st>>>(expr, ldx, rows, (int)samples, xc, sd);
+    const int64_t gy = rows < (int64_t)sm_count() * 8 ? rows : (int64_t)sm_count() * 8;
+    pp_pearson_kernel<<<dim3((unsigned)ceil_div(rows, PP_THREADS), (unsigned)gy), PP_THREADS, 0, st>>>(xc, sd, rows, (int)samples, out, ldo);
+    return check_launch("pearson", 2);
+}
 
 size_t plagnn_ecc_workspace_bytes(int64_t num_nodes) {
     if (num_nodes <= 0) return 0;

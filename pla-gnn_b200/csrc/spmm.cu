@@ -288,35 +288,23 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
     }
 }
 
-// Narrow rows (feat <= 64: the column slice of one GPU in the feature partition, 128 or 256 bytes per row) — the aggregation
-// with SHARED-MEMORY STAGING of the gathered neighbour rows (north_star kernel 2).
+// Narrow rows (feat <= 64: the column slice of one GPU in the feature partition, 128 or 256 bytes per row).  With one
+// float4 per lane a row needs only G = 8 or 16 lanes, so the warp's S = 32 / G lane groups each take a different in-edge of
+// the same work item: edge e of a batch of 32 goes to group e % S.  Every LDG.128 of the warp then fetches S neighbour rows
+// (512 bytes per request, as in the wide kernel, instead of 128), and the S partial results are folded with shuffles at the
+// end.  The max reducer keeps "first maximum in in-edge order wins" across the groups by carrying the winning edge position.
 //
-// With one float4 per lane a row needs only G = 8 or 16 lanes, so the warp's S = 32 / G lane groups each take a different
-// in-edge: edge e of a batch of 32 goes to group e % S and every 16-byte request of the warp fetches S neighbour rows.
-// An item of ~100 edges of 128 bytes is short, and gathered into registers the kernel is bound by latency, not bandwidth:
-// a lane can hold 4 rows in flight, an item is 2-3 dependent batches behind a 3-level chain (item -> row -> indptr ->
-// neighbour ids), and the measured rate on the 1 M-node / 100 M-edge graph at 32 columns was 5.4 TB/s algorithmic = 2.55 ms
-// per aggregation with one item per warp, 3.7 ms with 32 items per warp and register gathers (in-order issue: the next
-// item's loads wait behind the current item's fold), 3.7 ms when the gather was cut into 4 L2-sized source slabs (shorter
-// items).  What it needs is more bytes in flight per warp than registers can hold:
-//   * a warp owns NARROW_IPW consecutive items; lane l fetches the meta data of item l in one coalesced sweep, a prefix sum
-//     over the lanes numbers the items' 32-edge batches, so the warp walks one flat sequence of batches;
-//   * per step it takes D batches: their neighbour ids (and weights) with D independent coalesced loads, then the rows of all
-//     D x 32 edges with cp.async (LDGSTS, 16 bytes per lane, no register held) into its slice of shared memory — D x 32 rows
-//     in flight per warp instead of 16 — and reduces them from shared memory (conflict-free LDS.128) once they have landed;
-//   * results are folded over the S lane groups and written when a batch ends its item.  The max reducer keeps "first maximum
-//     in in-edge order wins" across the groups by carrying the winning edge position.
-constexpr int NARROW_IPW = 32;
-
-__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-
-template <int MODE, int G, int D, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+// Measured on the 1 M-node / 100 M-edge graph, 32 columns (tools/spmm_narrow_time.py): this kernel 2.55 ms per aggregation =
+// 5.4 TB/s algorithmic (the wide kernel with 24 idle lanes: 5.99 ms).  It is bound by latency, not by a bandwidth (L2 -> SM
+// fabric at ~40 %, HBM at ~45 %), and three attempts to put more bytes in flight all LOST: (a) cutting the gather by source
+// range into L2-sized slabs (plagnn_spmm_*_slab, kept as an option): 2.85 / 3.72 / 5.92 ms at 2 / 4 / 8 slabs — the items get
+// shorter; (b) one warp walking 32 consecutive items with prefetched meta data and neighbour ids, rows still gathered into
+// registers: 3.72 ms — in-order issue serialises the items of a warp; (c) the same walk with the rows of three 32-edge
+// batches staged in shared memory by cp.async (96 rows in flight per warp, 16 warps per SM): 4.51 ms (max 5.39) — the extra
+// LDS / STS / shuffle traffic and the three-phase step cost more than the deeper queue gains.  Staging pays when a staged row
+// is reused; a gathered neighbour row is consumed once.
+template <int MODE, int G, int U, int OCC>
+__global__ void __launch_bounds__(SPMM_WARPS * 32, OCC)
 spmm_narrow_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int32_t* __restrict__ eids,
                    const float* __restrict__ ew, const int32_t* __restrict__ plan_hdr, const int32_t* __restrict__ item_ptr,
                    const int32_t* __restrict__ slot_ptr, const int32_t* __restrict__ item_row, int item_begin, int n_items,
@@ -324,168 +312,110 @@ spmm_narrow_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict
                    int64_t ldo, float* __restrict__ part_val, int32_t* __restrict__ part_arg, int part_ld, SpmmEpilogue ep,
                    SpmmChain ch) {
     static_assert(MODE == MODE_MAX || MODE == MODE_SUM, "narrow kernel: max and sum reducers");
-    constexpr int S = 32 / G;          // lane groups = in-edges per 16-byte request of the warp
-    constexpr int ROUNDS = 32 / S;     // requests per batch of 32 edges (= G)
-    extern __shared__ float4 narrow_smem[];
+    constexpr int S = 32 / G;          // lane groups = in-edges in flight per load instruction
+    // U rounds unrolled = U rows in flight per lane (U = 4 at 32 warps per SM: 64 KB in flight per SM)
     pdl_trigger();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int item0 = item_begin + (blockIdx.x * WARPS + warp) * NARROW_IPW;
-    if (item0 >= n_items) return;
+    const int lane = threadIdx.x & 31;
+    const int item = item_begin + blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+    if (item >= n_items) return;
     pdl_wait();
-    const int n_mine = min(NARROW_IPW, n_items - item0);
-    float4* stage = narrow_smem + (size_t)warp * (D * 32 * G);          // [D][32 edges][G float4]
-    const uint32_t stage_u32 = (uint32_t)__cvta_generic_to_shared(stage);
-    // ---- meta data of my items, one per lane ---------------------------------------------------------------------------
     const int chunk = __ldg(plan_hdr);
-    int m_row = 0, m_beg = 0, m_end = 0, m_nch = 1, m_k = 0;
-    if (lane < n_mine) {
-        m_row = __ldg(item_row + item0 + lane);
-        const int first = __ldg(item_ptr + m_row);
-        m_nch = __ldg(item_ptr + m_row + 1) - first;
-        m_k = item0 + lane - first;
-        const int rbeg = __ldg(indptr + m_row), rend = __ldg(indptr + m_row + 1);
-        m_beg = rbeg + m_k * chunk;
-        m_end = max(m_beg, min(rend, m_beg + chunk));
-    }
-    // batches per item (an item without edges still takes one, to write its zeros), inclusive prefix sum over the lanes
-    const int m_nb = lane < n_mine ? max(1, (m_end - m_beg + 31) >> 5) : 0;
-    int pre = m_nb;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, pre, o);
-        if (lane >= o) pre += t;
-    }
-    const int total_batches = __shfl_sync(0xffffffffu, pre, 31);
-    const int m_first = pre - m_nb;                                    // number of the item's first batch
-
+    const int row = __ldg(item_row + item);
+    const int first = __ldg(item_ptr + row);
+    const int nch = __ldg(item_ptr + row + 1) - first;
+    const int k = item - first;
+    const int rbeg = __ldg(indptr + row), rend = __ldg(indptr + row + 1);
+    const int beg = rbeg + k * chunk;
+    const int end = min(rend, beg + chunk);
     const int sub = lane / G, gl = lane % G;
     const int col = 4 * gl;
     const bool cok = col < feat;
-    const float* xc = x + (cok ? col : 0);                  // lanes past the last column copy column 0 (never stored)
+    const float* xc = x + (cok ? col : 0);                  // lanes past the last column re-read column 0 (nothing stored)
     const float init = MODE == MODE_MAX ? -INFINITY : 0.f;
     float4 acc = make_float4(init, init, init, init);
     int4 arg = make_int4(-1, -1, -1, -1);
     int4 pos = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
+    // continue from the earlier slabs' result (unsplit rows only: split rows take it in the combine kernel).  Plain loads:
+    // prev may alias the output this kernel writes.  Position -1 makes the earlier slab win value ties.
+    if (ch.prev_val && nch == 1 && cok && (MODE == MODE_MAX || sub == 0)) {
+        acc = *reinterpret_cast<const float4*>(ch.prev_val + (int64_t)row * ch.ldprev + col);
+        if (MODE == MODE_MAX) {
+            arg = *reinterpret_cast<const int4*>(ch.prev_arg + (int64_t)row * ch.ldprev + col);
+            pos = make_int4(-1, -1, -1, -1);
+        }
+    }
 
-    for (int j0 = 0; j0 < total_batches; j0 += D) {
-        // ---- the D batches of this step: item, first edge, edge count; their neighbour ids and weights ----------------
-        int b_it[D], b_base[D], b_cnt[D], b_u[D];
-        float b_w[D];
-        bool b_first[D], b_last[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const int j = j0 + d;
-            const bool on = j < total_batches;
-            const int it = min(__popc(__ballot_sync(0xffffffffu, lane < n_mine && pre <= j)), n_mine - 1);   // items whose batches all precede j
-            const int first = __shfl_sync(0xffffffffu, m_first, it);
-            const int ibeg = __shfl_sync(0xffffffffu, m_beg, it), iend = __shfl_sync(0xffffffffu, m_end, it);
-            const int nb = __shfl_sync(0xffffffffu, m_nb, it);
-            b_it[d] = it;
-            b_base[d] = ibeg + 32 * (j - first);
-            b_cnt[d] = on ? max(0, min(32, iend - b_base[d])) : 0;
-            b_first[d] = on && j == first;
-            b_last[d] = on && j == first + nb - 1;
-            b_u[d] = 0;
-            b_w[d] = 1.f;
-            if (lane < b_cnt[d]) {
-                b_u[d] = __ldg(indices + b_base[d] + lane);
-                if (MODE == MODE_SUM && ew) b_w[d] = __ldg(ew + (eids ? __ldg(eids + b_base[d] + lane) : b_base[d] + lane));
-            }
+    for (int base = beg; base < end; base += 32) {
+        const int cnt = min(32, end - base);
+        int my_u = 0;
+        float my_w = 1.f;
+        if (lane < cnt) {
+            my_u = __ldg(indices + base + lane);
+            if (MODE == MODE_SUM && ew) my_w = __ldg(ew + (eids ? __ldg(eids + base + lane) : base + lane));
         }
-        // ---- all rows of the D batches into shared memory, asynchronously ----------------------------------------------
+        for (int t = 0; t * S < cnt; t += U) {
+            int u[U];
+            float w[U];
+            float4 v[U];
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-#pragma unroll
-            for (int t = 0; t < ROUNDS; ++t) {
-                const int e = t * S + sub;
-                const int u = __shfl_sync(0xffffffffu, b_u[d], e);
-                if (e < b_cnt[d]) cp_async16(stage_u32 + (uint32_t)(((d * 32 + e) * G + gl) * 16), xc + (int64_t)u * ldx);
+            for (int i = 0; i < U; ++i) {
+                const int e = min((t + i) * S + sub, 31);
+                u[i] = __shfl_sync(0xffffffffu, my_u, e);
+                if (MODE == MODE_SUM) w[i] = __shfl_sync(0xffffffffu, my_w, e);
+                const bool live = (t + i) * S + sub < cnt;
+                v[i] = live ? ldg_f4(xc + (int64_t)u[i] * ldx) : make_float4(init, init, init, init);
             }
-        }
-        cp_async_commit_wait_all();
-        __syncwarp();
-        // ---- reduce from shared memory; fold and write where a batch ends its item -------------------------------------
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            if (j0 + d >= total_batches) break;
-            const int it = b_it[d];
-            const int row = __shfl_sync(0xffffffffu, m_row, it);
-            const int nch = __shfl_sync(0xffffffffu, m_nch, it);
-            const int k = __shfl_sync(0xffffffffu, m_k, it);
-            if (b_first[d]) {
-                acc = make_float4(init, init, init, init);
-                arg = make_int4(-1, -1, -1, -1);
-                pos = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
-                // continue from the earlier slabs' result (unsplit rows only: split rows take it in the combine kernel).
-                // Plain loads: prev may alias the output this kernel writes.  Position -1: the earlier slab wins value ties.
-                if (ch.prev_val && nch == 1 && cok && (MODE == MODE_MAX || sub == 0)) {
-                    acc = *reinterpret_cast<const float4*>(ch.prev_val + (int64_t)row * ch.ldprev + col);
-                    if (MODE == MODE_MAX) {
-                        arg = *reinterpret_cast<const int4*>(ch.prev_arg + (int64_t)row * ch.ldprev + col);
-                        pos = make_int4(-1, -1, -1, -1);
-                    }
-                }
-            }
-            const int cnt = b_cnt[d];
-#pragma unroll
-            for (int t = 0; t < ROUNDS; ++t) {
-                const int e = t * S + sub;
-                const int u = __shfl_sync(0xffffffffu, b_u[d], e);
-                const float w = MODE == MODE_SUM ? __shfl_sync(0xffffffffu, b_w[d], e) : 1.f;
-                if (e < cnt) {
-                    const float4 v = stage[(d * 32 + e) * G + gl];
-                    if (MODE == MODE_MAX) {
-                        const int p = b_base[d] + e;
-                        if (v.x > acc.x) { acc.x = v.x; arg.x = u; pos.x = p; }
-                        if (v.y > acc.y) { acc.y = v.y; arg.y = u; pos.y = p; }
-                        if (v.z > acc.z) { acc.z = v.z; arg.z = u; pos.z = p; }
-                        if (v.w > acc.w) { acc.w = v.w; arg.w = u; pos.w = p; }
-                    } else {
-                        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
-                        acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
-                    }
-                }
-            }
-            if (!b_last[d]) continue;
-            // fold the S lane groups (group 0 ends up with the result)
-            float4 r = acc;
-            int4 ra = arg, rp = pos;
-#pragma unroll
-            for (int off = G; off < 32; off <<= 1) {
-                const float ox = __shfl_xor_sync(0xffffffffu, r.x, off), oy = __shfl_xor_sync(0xffffffffu, r.y, off);
-                const float oz = __shfl_xor_sync(0xffffffffu, r.z, off), ow = __shfl_xor_sync(0xffffffffu, r.w, off);
+            for (int i = 0; i < U; ++i) {
                 if (MODE == MODE_MAX) {
-                    const int ax = __shfl_xor_sync(0xffffffffu, ra.x, off), ay = __shfl_xor_sync(0xffffffffu, ra.y, off);
-                    const int az = __shfl_xor_sync(0xffffffffu, ra.z, off), aw = __shfl_xor_sync(0xffffffffu, ra.w, off);
-                    const int px = __shfl_xor_sync(0xffffffffu, rp.x, off), py = __shfl_xor_sync(0xffffffffu, rp.y, off);
-                    const int pz = __shfl_xor_sync(0xffffffffu, rp.z, off), pw = __shfl_xor_sync(0xffffffffu, rp.w, off);
-                    if (ox > r.x || (ox == r.x && px < rp.x)) { r.x = ox; ra.x = ax; rp.x = px; }
-                    if (oy > r.y || (oy == r.y && py < rp.y)) { r.y = oy; ra.y = ay; rp.y = py; }
-                    if (oz > r.z || (oz == r.z && pz < rp.z)) { r.z = oz; ra.z = az; rp.z = pz; }
-                    if (ow > r.w || (ow == r.w && pw < rp.w)) { r.w = ow; ra.w = aw; rp.w = pw; }
+                    const int p = base + (t + i) * S + sub;
+                    if (v[i].x > acc.x) { acc.x = v[i].x; arg.x = u[i]; pos.x = p; }
+                    if (v[i].y > acc.y) { acc.y = v[i].y; arg.y = u[i]; pos.y = p; }
+                    if (v[i].z > acc.z) { acc.z = v[i].z; arg.z = u[i]; pos.z = p; }
+                    if (v[i].w > acc.w) { acc.w = v[i].w; arg.w = u[i]; pos.w = p; }
                 } else {
-                    r.x += ox; r.y += oy; r.z += oz; r.w += ow;
+                    const float ww = ew ? w[i] : 1.f;
+                    acc.x = fmaf(ww, v[i].x, acc.x); acc.y = fmaf(ww, v[i].y, acc.y);
+                    acc.z = fmaf(ww, v[i].z, acc.z); acc.w = fmaf(ww, v[i].w, acc.w);
                 }
-            }
-            if (sub != 0 || !cok) continue;
-            if (nch == 1) {
-                if (MODE == MODE_MAX) {
-                    if (ch.last) {
-                        r.x = ra.x < 0 ? 0.f : r.x; r.y = ra.y < 0 ? 0.f : r.y;
-                        r.z = ra.z < 0 ? 0.f : r.z; r.w = ra.w < 0 ? 0.f : r.w;
-                    }
-                    *reinterpret_cast<int4*>(arg_out + (int64_t)row * ldo + col) = ra;
-                } else if (ch.last) {
-                    r = sum_epilogue(r, ep, row, col, feat);
-                }
-                *reinterpret_cast<float4*>(out + (int64_t)row * ldo + col) = r;
-            } else {
-                const int64_t slot = (int64_t)__ldg(slot_ptr + row) + k;
-                *reinterpret_cast<float4*>(part_val + slot * part_ld + col) = r;
-                if (MODE == MODE_MAX) *reinterpret_cast<int4*>(part_arg + slot * part_ld + col) = ra;
             }
         }
-        __syncwarp();           // everybody has read this step's rows before the next step's copies overwrite them
+    }
+    // fold the S lane groups (group 0 ends up with the result)
+#pragma unroll
+    for (int off = G; off < 32; off <<= 1) {
+        const float ox = __shfl_xor_sync(0xffffffffu, acc.x, off), oy = __shfl_xor_sync(0xffffffffu, acc.y, off);
+        const float oz = __shfl_xor_sync(0xffffffffu, acc.z, off), ow = __shfl_xor_sync(0xffffffffu, acc.w, off);
+        if (MODE == MODE_MAX) {
+            const int ax = __shfl_xor_sync(0xffffffffu, arg.x, off), ay = __shfl_xor_sync(0xffffffffu, arg.y, off);
+            const int az = __shfl_xor_sync(0xffffffffu, arg.z, off), aw = __shfl_xor_sync(0xffffffffu, arg.w, off);
+            const int px = __shfl_xor_sync(0xffffffffu, pos.x, off), py = __shfl_xor_sync(0xffffffffu, pos.y, off);
+            const int pz = __shfl_xor_sync(0xffffffffu, pos.z, off), pw = __shfl_xor_sync(0xffffffffu, pos.w, off);
+            if (ox > acc.x || (ox == acc.x && px < pos.x)) { acc.x = ox; arg.x = ax; pos.x = px; }
+            if (oy > acc.y || (oy == acc.y && py < pos.y)) { acc.y = oy; arg.y = ay; pos.y = py; }
+            if (oz > acc.z || (oz == acc.z && pz < pos.z)) { acc.z = oz; arg.z = az; pos.z = pz; }
+            if (ow > acc.w || (ow == acc.w && pw < pos.w)) { acc.w = ow; arg.w = aw; pos.w = pw; }
+        } else {
+            acc.x += ox; acc.y += oy; acc.z += oz; acc.w += ow;
+        }
+    }
+    if (sub != 0 || !cok) return;
+    if (nch == 1) {
+        float4 r = acc;
+        if (MODE == MODE_MAX) {
+            if (ch.last) {
+                r.x = arg.x < 0 ? 0.f : r.x; r.y = arg.y < 0 ? 0.f : r.y;
+                r.z = arg.z < 0 ? 0.f : r.z; r.w = arg.w < 0 ? 0.f : r.w;
+            }
+            *reinterpret_cast<int4*>(arg_out + (int64_t)row * ldo + col) = arg;
+        } else if (ch.last) {
+            r = sum_epilogue(r, ep, row, col, feat);
+        }
+        *reinterpret_cast<float4*>(out + (int64_t)row * ldo + col) = r;
+    } else {
+        const int64_t slot = (int64_t)__ldg(slot_ptr + row) + k;
+        *reinterpret_cast<float4*>(part_val + slot * part_ld + col) = acc;
+        if (MODE == MODE_MAX) *reinterpret_cast<int4*>(part_arg + slot * part_ld + col) = arg;
     }
 }
 
@@ -635,25 +565,14 @@ static void launch_main(const SpmmArgs& a, const int32_t* item_ptr, const int32_
 template <int MODE, int G>
 static void launch_narrow(const SpmmArgs& a, const int32_t* item_ptr, const int32_t* slot_ptr, const int32_t* item_row,
                           float* pv, int32_t* pa, cudaStream_t st) {
-    // 3 batches of 32 rows in flight per warp: 12 KB (G = 8, 8 warps per block) or 24 KB (G = 16, 4 warps) -> 96 KB per block,
-    // two blocks per SM
-    constexpr int D = 3, WARPS = G == 8 ? 8 : 4;
-    constexpr size_t smem = (size_t)WARPS * D * 32 * G * sizeof(float4);
     const int item_begin = a.range ? (int)a.range[0] : 0;
     const int n_items = a.range ? (int)a.range[1] : (int)a.counts[0];
     if (n_items <= item_begin) return;
-    static thread_local int attr_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (attr_dev != dev) {
-        cudaFuncSetAttribute(spmm_narrow_kernel<MODE_SUM, 8, D, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * D * 32 * 8 * 16));
-        cudaFuncSetAttribute(spmm_narrow_kernel<MODE_MAX, 8, D, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * D * 32 * 8 * 16));
-        cudaFuncSetAttribute(spmm_narrow_kernel<MODE_SUM, 16, D, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * D * 32 * 16 * 16));
-        cudaFuncSetAttribute(spmm_narrow_kernel<MODE_MAX, 16, D, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * D * 32 * 16 * 16));
-        attr_dev = dev;
-    }
-    dim3 grid((unsigned)ceil_div(n_items - item_begin, WARPS * NARROW_IPW));
-    launch_pdl(spmm_narrow_kernel<MODE, G, D, WARPS>, grid, dim3(WARPS * 32), smem, st,
+    dim3 grid((unsigned)ceil_div(n_items - item_begin, SPMM_WARPS));
+    // PLAGNN_SPMM_NARROW_U=8: eight rows in flight per lane at 24 warps per SM (A/B against the default 4 at 32 warps)
+    static const int deep = [] { const char* e = getenv("PLAGNN_SPMM_NARROW_U"); return e && atoi(e) == 8; }();
+    auto kernel = deep ? spmm_narrow_kernel<MODE, G, 8, 3> : spmm_narrow_kernel<MODE, G, 4, 4>;
+    launch_pdl(kernel, grid, dim3(SPMM_WARPS * 32), 0, st,
         a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, item_begin, n_items, a.x, a.ldx,
         (int)a.feat, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep, a.chain);
 }

@@ -140,7 +140,14 @@ def measure_variant(v: Variant, steps, warmup, rank, world, dev, reference=None)
     per_step = {}
     for k, (c, t) in prof.items():
         per_step[k[0]] = per_step.get(k[0], 0.0) + t / steps
-    coll = {k: round(t, 4) for k, t in per_step.items() if k.startswith("nccl_")}
+    coll = {k: round(t, 4) for k, t in per_step.items() if k.startswith("nccl_") or k.startswith("p2p_")}
+    # aggregation launches by (kernel, rows of the launch): the forward walks few long rows, the transposed backward of the row
+    # partition walks every source row with 1 / world of its out-edges
+    agg_shapes = {}
+    for k, (c, t) in prof.items():
+        if k[0].startswith("spmm"):
+            key = f"{k[0]}/rows={k[2]}"
+            agg_shapes[key] = round(agg_shapes.get(key, 0.0) + t / steps, 4)
     n, f, plan = v.n, v.f, v.plan
     el = plan.num_local_edges
     agg_names = ("spmm_sum", "spmm_max_fwd", "spmm_max_bwd")
@@ -155,7 +162,7 @@ def measure_variant(v: Variant, steps, warmup, rank, world, dev, reference=None)
     hbm, src = _hbm_peak()
     res = {"mode": v.mode, "reducer": v.reducer, "exchange": v.exchange, "ms_per_step": ms, "ms_per_step_with_events": ms_prof,
            "ms_per_step_without_collectives": ms_nocomm, "exposed_exchange_ms": (ms - ms_nocomm) if ms_nocomm else 0.0,
-           "collective_ms_per_step": coll, "aggregation_ms_per_step": agg_ms,
+           "collective_ms_per_step": coll, "aggregation_ms_per_step": agg_ms, "aggregation_by_launch_shape": agg_shapes,
            "aggregation_algorithmic_gbs_per_gpu": alg / (agg_ms * 1e-3) / 1e9 if agg_ms else None,
            "aggregation_frac_of_hbm_peak": alg / (agg_ms * 1e-3) / 1e9 / hbm if agg_ms else None, "hbm_peak": hbm, "peak_source": src,
            "local_edges_rank0": el, "source_slabs": v.pg.n_slabs, "checksum": csum, "check": check,

@@ -82,6 +82,27 @@ def edge_clustering_coefficients(ppi_net, epsilon=0, device="cuda"):
     return coo_matrix((d.cpu().numpy(), (r.cpu().numpy(), c.cpu().numpy())), shape=ppi_net.shape)
 
 
+def pearson_matrix(expr_gcn, device="cuda") -> torch.Tensor:
+    """The numeric tail of ``construct_gcn_matrix`` (code/data_preprocess.py:165-170): ``np.corrcoef(expr_gcn)`` with the
+    diagonal and the NaN entries (proteins without expression: constant rows) set to 0, as a dense float64 CUDA matrix —
+    the form ``modify_network_topology`` consumes (the reference wraps it in a ``coo_matrix`` and densifies it again there)."""
+    x = expr_gcn if isinstance(expr_gcn, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(expr_gcn, dtype=np.float64)))
+    x = x.to(device=device, dtype=torch.float64)
+    if x.dim() != 2 or x.shape[1] < 2:
+        raise _lib.PlagnnError("expected a [proteins x samples] matrix with at least two samples")
+    if not x.is_cuda:
+        raise _lib.PlagnnError("plagnn kernels run on CUDA tensors only (no CPU fallback)")
+    x = x if x.stride(1) == 1 else x.contiguous()
+    lib = _lib.load()
+    n, s = x.shape
+    out = torch.empty((n, n), dtype=torch.float64, device=x.device)
+    nb = lib.plagnn_pearson_workspace_bytes(n, s)
+    ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.plagnn_pearson(_p(x), x.stride(0), n, s, _p(out), out.stride(0), _p(ws), nb, _stream()), "pearson")
+    return out
+
+
 def _dense_f64(m, device) -> torch.Tensor:
     if isinstance(m, torch.Tensor):
         t = m

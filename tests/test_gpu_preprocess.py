@@ -102,3 +102,46 @@ def test_rewiring_bit_exact_vs_oracle(cuda, n, m):
     mean, std = pp.diff_moments(torch.tensor(mats[0], device=cuda), torch.tensor(mats[1], device=cuda))
     rm, rs = po.diff_moments(mats[0], mats[1])
     assert abs(mean - rm) <= 1e-12 * max(abs(rm), rs) and abs(std - rs) <= 1e-12 * rs
+
+
+def test_pearson_matrix_against_the_reference_statements(cuda, golden_dir):
+    """plagnn_pearson (np.corrcoef tail of construct_gcn_matrix, code/data_preprocess.py:165-170) against the fixture made from
+    the reference's own statements: 4 ulp on values in [-1, 1], zero diagonal, zero-variance rows -> 0."""
+    import os
+    from plagnn_b200 import preprocess
+    z = np.load(os.path.join(golden_dir, "pearson.npz"))
+    got = preprocess.pearson_matrix(z["expr"], cuda).cpu().numpy()
+    assert got.shape == z["pcc"].shape and np.isfinite(got).all() and (np.diag(got) == 0).all()
+    assert np.abs(got - z["pcc"]).max() <= 4 * 2.0 ** -53
+    zero_var = z["expr"].std(1) == 0
+    assert (got[zero_var] == 0).all() and (got[:, zero_var] == 0).all()
+    assert np.array_equal(got, got.T)                       # the FMA chain is symmetric in its two rows
+    # and it feeds the rewiring step like the reference's matrix does: same thresholds, same rewired network
+    rng = np.random.default_rng(5)
+    n = got.shape[0]
+    expr2 = z["expr"] + rng.normal(0, 0.5, size=z["expr"].shape) * (z["expr"].std(1, keepdims=True) > 0)
+    pcc2_ref = __import__("oracle.preprocess_oracle", fromlist=["x"]).pearson_matrix(expr2)
+    pcc2 = preprocess.pearson_matrix(expr2, cuda)
+    m_ref = (float(np.mean(pcc2_ref - z["pcc"])), float(np.std(pcc2_ref - z["pcc"])))
+    m_got = preprocess.diff_moments(torch.from_numpy(got).to(cuda), pcc2)
+    assert abs(m_got[0] - m_ref[0]) < 1e-12 and abs(m_got[1] - m_ref[1]) < 1e-12
+
+
+def test_pearson_full_ppi_shape(cuda):
+    """N = 24 041 proteins x 3 samples (BASELINE.json configs[0-1] shape): 4.6 GB matrix, spot rows against numpy."""
+    from plagnn_b200 import preprocess
+    rng = np.random.default_rng(11)
+    n = 24041
+    expr = np.abs(rng.normal(8.0, 2.0, size=(n, 3)))
+    expr[rng.random(n) < 0.1] = 0.0
+    out = preprocess.pearson_matrix(expr, cuda)
+    rows = [0, 1, 777, 12000, n - 1]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for r in rows:
+            x = expr - expr.mean(1, keepdims=True)
+            c = (x @ x[r]) * 0.5
+            sd = np.sqrt((x * x).sum(1) * 0.5)
+            ref = np.clip(c / sd[r] / sd, -1, 1)
+            ref[r] = 0
+            ref[np.isnan(ref)] = 0
+            assert np.abs(out[r].cpu().numpy() - ref).max() <= 8 * 2.0 ** -53

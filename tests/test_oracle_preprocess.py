@@ -126,3 +126,14 @@ def test_workspace_queries():
     assert lib.plagnn_ecc_workspace_bytes(24041) >= 3 * 4 * 24042
     assert lib.plagnn_ecc_workspace_bytes(0) == 0
     assert lib.plagnn_rewire_workspace_bytes(24041) >= 4 * 24041
+
+
+def test_pearson_oracle_against_the_reference_statements(golden_dir):
+    """np.corrcoef tail of construct_gcn_matrix (code/data_preprocess.py:165-170), fixture from the reference's own statements."""
+    import os
+    z = np.load(os.path.join(golden_dir, "pearson.npz"))
+    got = po.pearson_matrix(z["expr"])
+    assert got.shape == z["pcc"].shape and np.isfinite(got).all() and (np.diag(got) == 0).all()
+    assert np.abs(got - z["pcc"]).max() <= 4 * 2.0 ** -53          # 4 ulp at 1.0 (BLAS builds may differ in the last bits)
+    zero_var = z["expr"].std(1) == 0
+    assert zero_var.sum() > 5 and (got[zero_var] == 0).all() and (got[:, zero_var] == 0).all()

@@ -34,8 +34,10 @@ def slab_structs(n_slabs):
     return cs, ws
 
 
-out = {"narrow": os.environ.get("PLAGNN_SPMM_NARROW", "1"), "edges": int(csc.num_edges)}
-for f in (32, 64, 128, 256):
+out = {"narrow": os.environ.get("PLAGNN_SPMM_NARROW", "1"), "narrow_u": os.environ.get("PLAGNN_SPMM_NARROW_U", "4"),
+       "edges": int(csc.num_edges)}
+SLABS = os.environ.get("PLAGNN_TIME_SLABS", "0") == "1"
+for f in ((32, 64) if os.environ.get('PLAGNN_TIME_NARROW_ONLY') == '1' else (32, 64, 128, 256)):
     x = ops.alloc(n, f, dev)
     x.copy_(torch.randn(n, f, device=dev))
     bias = torch.zeros(f, device=dev)
@@ -53,7 +55,7 @@ for f in (32, 64, 128, 256):
         ms = s.elapsed_time(t) / 5
         alg = 4 * f * csc.num_edges + 4 * csc.num_edges * (2 if name == "sum" else 1) + 4 * f * n * (1 if name == "sum" else 2)
         out[f"{name}/{f}"] = {"ms": round(ms, 3), "algorithmic_gb_per_s": round(alg / ms / 1e6, 0)}
-    if f <= 64 and os.environ.get("PLAGNN_SPMM_NARROW", "1") != "0":
+    if SLABS and f <= 64 and os.environ.get("PLAGNN_SPMM_NARROW", "1") != "0":
         for n_slabs in ((2, 4, 8) if f == 32 else (4, 8, 16)):
             cs, ws = slab_structs(n_slabs)
             for name, fn in (("sum", lambda: ops.spmm_sum_slabs(cs, x, ws=ws, scale=scale, bias=bias, act=ops.ACT_LEAKY)),
