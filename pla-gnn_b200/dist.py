@@ -498,20 +498,25 @@ class _WindowView:
 class P2PExchange:
     """Peer-memory exchange of the feature partition (plagnn_p2p_*): one window per rank, opened by every peer over CUDA IPC;
     the all-to-all steps become one kernel that stores straight into the owners' windows plus a flag wait.  `region_bytes` =
-    rows_per_rank * feat * 4 (the size of one exchanged matrix); the window holds two regions used alternately."""
+    rows_per_rank * feat * 4 (the size of one exchanged matrix).  The window is a ring of `regions` such matrices used in turn:
+    a result may be kept (saved activation) for up to regions - 1 further exchanges without a copy — a step of the 2-layer
+    models makes 8 — and a peer can only reach the exchange that overwrites a region after it has seen this rank's flags for all
+    exchanges in between, which this rank publishes in program order after its reads."""
 
-    def __init__(self, region_bytes: int, rank: int, world: int, device):
+    def __init__(self, region_bytes: int, rank: int, world: int, device, regions: int = 16):
         from . import _lib
         self._lib, self.lib = _lib, _lib.load()
         self.rank, self.world, self.device = rank, world, device
         self.region_bytes = (int(region_bytes) + 255) // 256 * 256
+        self.regions = int(regions)
         self.handle = ctypes.c_void_p()
         hbuf = (ctypes.c_ubyte * 64)()
         # every step is agreed on by all ranks (a rank that failed alone would leave the others waiting in a collective)
         err = None
         try:
             with torch.cuda.device(device):
-                _lib.check(self.lib.plagnn_p2p_create(2 * self.region_bytes, rank, world, hbuf, ctypes.byref(self.handle)), "p2p_create")
+                _lib.check(self.lib.plagnn_p2p_create(self.regions * self.region_bytes, rank, world, hbuf, ctypes.byref(self.handle)),
+                           "p2p_create")
         except Exception as ex:
             err = repr(ex)
         got = [None] * world
@@ -539,7 +544,7 @@ class P2PExchange:
             self.handle = None
 
     def _region(self, seq):
-        return (seq & 1) * self.region_bytes
+        return (seq % self.regions) * self.region_bytes
 
     def exchange(self, src: torch.Tensor, rows: int, feat: int, mode: int, stream) -> torch.Tensor:
         """Sends `src` (mode 0: [rows x feat] -> all rows x my columns; mode 1: [world*rows x feat/world] -> my rows x all
@@ -732,8 +737,8 @@ class CudaBackend:
         if self.p2p is not None and world > 1 and not self.skip_comm:
             if x_col.stride(0) % 4 or x_col.data_ptr() % 16:
                 x_col = x_col.contiguous()
-            # callers keep this matrix (layer input / saved activation), the window region is reused two exchanges later
-            return self.p2p.exchange(x_col, rows, feat, 1, st).clone()
+            # callers keep this matrix (layer input / saved activation): it stays valid for regions - 1 further exchanges
+            return self.p2p.exchange(x_col, rows, feat, 1, st)
         if x_col.stride(0) != fc:
             x_col = x_col.contiguous()
         recv = x_col

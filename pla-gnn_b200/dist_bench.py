@@ -17,7 +17,13 @@ import time
 import torch
 import torch.distributed as dist
 
-CHECK_TOL = 1e-5
+CHECK_TOL = 1e-5          # output rows of the first step against the whole-graph run
+# Gradients: the row partition reproduces the whole-graph forward pass bit for bit (measured: output error 0.0, gradients
+# 1.7e-6 .. 3.5e-6 from the different split of the weight-gradient sums).  The feature partition's narrow kernel adds a row's
+# in-edges in another order (output error 4e-7); a handful of pre-activations within that distance of zero then take the other
+# leaky_relu branch, and the bias gradients (column sums over 1 M rows that cancel) move by up to 3.5e-5 — the near-tie effect of
+# DESIGN.md section 3 again, not an exchange error (a wrong block offset shows up as percents, as the first N = 2 run did).
+CHECK_TOL_GRAD = 1e-4
 
 
 def _rel(a, b):
@@ -121,7 +127,9 @@ def measure_variant(v: Variant, steps, warmup, rank, world, dev, reference=None)
         ref_out, ref_grads = reference
         errs = [_rel(full, ref_out)] + [_rel(g, r) for g, r in zip(grads, ref_grads)]
         check = {"against": "the same first step on the whole graph (world 1) on rank 0", "out_rel_err": errs[0],
-                 "grad_rel_err_max": max(errs[1:]), "tol": CHECK_TOL, "ok": bool(max(errs) <= CHECK_TOL)}
+                 "grad_rel_err_max": max(errs[1:]), "grad_rel_err": [float(f"{e:.3g}") for e in errs[1:]],
+                 "tol_out": CHECK_TOL, "tol_grad": CHECK_TOL_GRAD,
+                 "ok": bool(errs[0] <= CHECK_TOL and max(errs[1:]) <= CHECK_TOL_GRAD)}
     del full
     for _ in range(max(warmup, 3)):
         v.step()
