@@ -45,6 +45,8 @@ out["ecc_ms"] = timed(lambda: pp.ecc_device(row, col, a.nodes, 0.0))
 gen = torch.Generator(device=dev).manual_seed(1)
 nor = torch.rand((a.nodes, a.nodes), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
 inter = torch.rand((a.nodes, a.nodes), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+expr = torch.abs(torch.randn((a.nodes, 3), dtype=torch.float64, device=dev, generator=gen) * 2 + 8)
+out["pearson_ms"] = timed(lambda: pp.pearson_matrix(expr, dev))
 out["moments_ms"] = timed(lambda: pp.diff_moments(nor, inter))
 mean, std = pp.diff_moments(nor, inter)
 out["rewire_ms"] = timed(lambda: pp.rewire_device(row, col, a.nodes, nor, inter, mean - 2 * std, mean + 2 * std))
@@ -54,4 +56,5 @@ if a.once:
 gb = 2 * 8 * a.nodes * a.nodes / 1e9
 out["moments_GBps"] = 2 * gb / (out["moments_ms"] * 1e-3)           # two passes over both matrices
 out["rewire_GBps"] = gb / (out["rewire_ms"] * 1e-3)                 # one pass (+ the bit matrices)
+out["pearson_write_GBps"] = 8 * a.nodes * a.nodes / 1e9 / (out["pearson_ms"] * 1e-3)   # the N x N float64 matrix written once
 print(json.dumps(out))

@@ -8,6 +8,7 @@ timeout 300 python tools/kernels_once.py all > gpurun_out/r2_k1.log 2>&1; echo "
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_tma_kernel|spmm_kernel|spmm_max_scatter|narrow_" -c 24 -f -o gpurun_out/prof_r2_ppi python tools/kernels_once.py all > gpurun_out/r2_ncu_ppi.log 2>&1; echo "ncu ppi exit $?"
 timeout 300 python tools/scaled_once.py > gpurun_out/r2_s1.log 2>&1; echo "scaled_once exit $?"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"spmm_kernel|spmm_narrow_kernel|spmm_max_scatter|spmm_combine" -c 12 -f -o gpurun_out/prof_r2_scaled python tools/scaled_once.py > gpurun_out/r2_ncu_scaled.log 2>&1; echo "ncu scaled exit $?"
+timeout 120 python tools/preprocess_time.py > gpurun_out/r2_pp_time.json 2> gpurun_out/r2_pp_time.err; echo "pp timing exit $?"; cat gpurun_out/r2_pp_time.json
 timeout 60 python tools/preprocess_time.py --nodes 8192 --edges 400000 --once > gpurun_out/pp_once.json 2> gpurun_out/pp_once.err; echo "pp once exit $?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"ecc_kernel|pp_moment_kernel|pp_rewire_kernel|pp_emit_kernel|pp_bitmask_kernel" -c 10 -f -o gpurun_out/prof_r2_preprocess python tools/preprocess_time.py --nodes 8192 --edges 400000 --once > gpurun_out/r2_ncu_pp.log 2>&1; echo "ncu preprocess exit $?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"ecc_kernel|pp_moment_kernel|pp_rewire_kernel|pp_emit_kernel|pp_bitmask_kernel|pp_pearson_kernel|pp_center_kernel" -c 14 -f -o gpurun_out/prof_r2_preprocess python tools/preprocess_time.py --nodes 8192 --edges 400000 --once > gpurun_out/r2_ncu_pp.log 2>&1; echo "ncu preprocess exit $?"
 ls -la gpurun_out/*.ncu-rep
