@@ -237,6 +237,10 @@ class GNN32EngineFunction(torch.autograd.Function):
     @ops.on_tensor_device
     def backward(ctx, dprob):
         lib = ops._lib.load()
+        if ctx.arena is None:
+            raise ops._lib.PlagnnError("GNN32: a second backward through the same forward pass — the whole-network engine hands "
+                                       "its arena back after the first one (the reference's loop runs one backward per forward, "
+                                       "code/train.py:204); set model.engine = 'python' for retain_graph use")
         params = ctx.saved_tensors
         p = [t.detach() if t.is_contiguous() else t.detach().contiguous() for t in params]
         dp = dprob if dprob.stride(1) == 1 else dprob.contiguous()

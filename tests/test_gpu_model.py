@@ -342,3 +342,11 @@ def test_model_on_second_gpu_while_device_zero_is_current(cuda):
     assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1] and torch.equal(outs[0][2], outs[1][2])
     for a, b in zip(outs[0][3], outs[1][3]):
         assert rel_err(a, b) < 1e-5                     # the scatter's fp32 reductions are unordered
+
+
+def test_second_backward_through_the_engine_raises(cuda):
+    prob, g, go, m, mo = build_pair(cuda, n=800, e=16000, dims=(3, 20, 20))
+    y = m(g, g.ndata["feat"])
+    y.sum().backward(retain_graph=True)
+    with pytest.raises(P.PlagnnError):
+        y.sum().backward()
