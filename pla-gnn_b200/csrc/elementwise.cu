@@ -137,6 +137,9 @@ adam_kernel(const plagnn_adam_tensor* __restrict__ tensors, float lerp_w, float 
         const float g = T.grad[i];
         float m = T.exp_avg[i];
         float v = T.exp_avg_sq[i];
+        // The update of torch 2.x's single-tensor Adam (lerp form).  torch 1.10, which the reference pins, writes the same
+        // mathematics as exp_avg.mul_(beta1).add_(grad, alpha=1-beta1) and multiplies by reciprocals of the scalar divisors:
+        // the two differ at the ulp level per step; the tests hold this kernel to 1e-6 against torch.optim.Adam over 6 steps.
         m = m + lerp_w * (g - m);                     // exp_avg.lerp_(grad, 1 - beta1)
         v = v * beta2;                                // exp_avg_sq.mul_(beta2)
         v = v + one_minus_beta2 * (g * g);            //   .addcmul_(grad, grad, value=1 - beta2)
