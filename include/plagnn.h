@@ -402,7 +402,7 @@ int plagnn_cols_unpack(const float* blocks, int64_t rows, int64_t feat, int worl
  *                   mode 1: x_col[world * rows x feat/world] (all rows, my columns) -> peer q gets its rows of MY columns at
  *                           window[offset + (r * feat + rank * feat/world + j)]     (window = my rows x all columns)
  *   plagnn_p2p_wait: enqueues a one-warp kernel that returns when every peer has published `seq` (sequence numbers grow by
- *                    one per exchange, the same on every rank); it gives up after ~1 s and records `seq` (plagnn_p2p_error).
+ *                    one per exchange, the same on every rank); it gives up after ~4 s and records `seq` (plagnn_p2p_error).
  * The caller alternates between two window offsets so that a peer's next exchange never lands on data still being read. */
 typedef void* plagnn_p2p_t;
 #define PLAGNN_P2P_HANDLE_BYTES 64

@@ -315,7 +315,7 @@ p2p_send_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int fe
     }
 }
 
-// one warp: lane p waits until peer p has published `seq`; gives up after ~1 s (error word set, later waits return at once)
+// one warp: lane p waits until peer p has published `seq`; gives up after ~4 s (error word set, later waits return at once)
 __global__ void p2p_wait_kernel(char* local, int world, long long seq) {
     pdl_enter();
     long long* flags = reinterpret_cast<long long*>(local);
@@ -324,7 +324,7 @@ __global__ void p2p_wait_kernel(char* local, int world, long long seq) {
     if (p < world && *reinterpret_cast<volatile long long*>(err) == 0) {
         const long long t0 = clock64();
         while (ld_acquire_sys(flags + p) < seq) {
-            if (clock64() - t0 > 2000000000ll) {
+            if (clock64() - t0 > 8000000000ll) {          // ~4 s: a peer is not coming
                 *reinterpret_cast<volatile long long*>(err) = seq;
                 break;
             }

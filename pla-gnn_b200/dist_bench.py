@@ -119,6 +119,7 @@ def measure_variant(v: Variant, steps, warmup, rank, world, dev, reference=None)
         return ms / k
 
     check = None
+    barrier()            # ranks build their structures at different speeds; the peer-memory wait gives up after a few seconds
     out, grads = v.forward_backward()
     full = _gather_rows(out, v.plan, world, dev)
     csum = {"out_sum": float(full.double().sum().item()) if rank == 0 else None,
