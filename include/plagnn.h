@@ -155,6 +155,9 @@ int plagnn_spmm_max_slab(const int32_t* indptr, const int32_t* indices, const vo
                          int64_t num_rows, const float* x, int64_t ldx, int64_t feat,
                          const float* prev_val, const int32_t* prev_arg, int64_t ldprev, int last,
                          float* out, int32_t* arg, int64_t ldo, void* partial, size_t partial_bytes, plagnn_stream_t stream);
+int plagnn_spmm_max_fwd_rows(const int32_t* indptr, const int32_t* indices, const void* plan, const int64_t* plan_counts /* host[3] */,
+                             const int64_t* row_range /* host[4] */, int64_t num_rows, const float* x, int64_t ldx, int64_t feat,
+                             float* out, int32_t* arg, int64_t ldo, void* partial, size_t partial_bytes, plagnn_stream_t stream);
 /* backward companion of the dropout epilogue: grad[r,c] *= keep(r,c)/(1-p) with the same counter-based mask */
 int plagnn_dropout_scale(float* grad, int64_t rows, int64_t feat, int64_t ld, float dropout_p,
                          uint64_t dropout_seed, plagnn_stream_t stream);
@@ -413,6 +416,12 @@ long long plagnn_p2p_error(plagnn_p2p_t p2p);     /* 0, or the sequence number a
 int plagnn_p2p_destroy(plagnn_p2p_t p2p);
 int plagnn_p2p_send(plagnn_p2p_t p2p, const float* src, int64_t lds, int64_t rows, int64_t feat, int mode,
                     size_t dst_offset_bytes, long long seq, plagnn_stream_t stream);
+/* one part of a send: source rows [row_begin, row_end) only (mode 0: a chunk of my rows; mode 1: rows of the all-rows matrix),
+ * so that the producer's next chunk is computed while this one crosses NVLink.  publish: 0 = more parts follow on this stream,
+ * 1 = flag every peer, 2 = flag only the owner of these rows (mode 1, range inside one owner's block). */
+int plagnn_p2p_send_part(plagnn_p2p_t p2p, const float* src, int64_t lds, int64_t rows, int64_t feat, int mode,
+                         int64_t row_begin, int64_t row_end, int publish, size_t dst_offset_bytes, long long seq,
+                         plagnn_stream_t stream);
 int plagnn_p2p_wait(plagnn_p2p_t p2p, long long seq, plagnn_stream_t stream);
 
 /* small utilities used by the host layer */

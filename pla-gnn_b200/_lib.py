@@ -73,6 +73,8 @@ PROTOTYPES = {
     "plagnn_spmm_sum_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_int64,
                                      c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_float,
                                      c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "plagnn_spmm_max_fwd_rows": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_int64, c_void_p, c_int64,
+                                         c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "plagnn_dropout_scale": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_uint64, c_void_p]),
     "plagnn_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "plagnn_gemm": (c_int, [c_int64, c_int64, c_int32, POINTER(GemmPair), c_void_p, c_int, c_float,
@@ -136,6 +138,8 @@ PROTOTYPES = {
     "plagnn_p2p_error": (ctypes.c_longlong, [c_void_p]),
     "plagnn_p2p_destroy": (c_int, [c_void_p]),
     "plagnn_p2p_send": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_size_t, ctypes.c_longlong, c_void_p]),
+    "plagnn_p2p_send_part": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int64, c_int64, c_int, c_size_t,
+                                     ctypes.c_longlong, c_void_p]),
     "plagnn_p2p_wait": (c_int, [c_void_p, ctypes.c_longlong, c_void_p]),
     "plagnn_pad_copy": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "plagnn_transpose": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),

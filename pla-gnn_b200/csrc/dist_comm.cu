@@ -273,12 +273,16 @@ __device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
 //                            data[off + ((rank * rows + r) * fc + j)]: the peer's window is the all-rows matrix [world * rows x fc].
 // mode 1 (columns -> rows): src = x_col[world * rows x fc] (pitch lds); rows [q rows, (q+1) rows) go to peer q at
 //                            data[off + (r * feat + rank * fc + j)]: the peer's window is its [rows x feat] matrix.
+// A send may cover only the source rows [row_begin, row_end) (mode 0: a chunk of my rows, for every peer; mode 1: rows of the
+// all-rows matrix, e.g. the block of one owner), so that the producer's next chunk is computed while this one crosses NVLink.
+// publish: 0 = no flag (more parts follow on the same stream), 1 = flag every peer, 2 = flag the owner of row_begin only.
 __global__ void __launch_bounds__(256)
 p2p_send_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int feat, int fc, int mode, char* const* __restrict__ peer,
-                size_t off_bytes, int rank, int world, long long seq, unsigned int* __restrict__ counter) {
+                size_t off_bytes, int rank, int world, long long seq, unsigned int* __restrict__ counter, int64_t row_begin,
+                int64_t row_end, int publish) {
     pdl_enter();
     const int fc4 = fc >> 2;
-    const int64_t total = (int64_t)world * rows * fc4;            // float4 elements of the source in both modes
+    const int64_t total = (row_end - row_begin) * (mode == 0 ? (int64_t)world * fc4 : (int64_t)fc4);   // float4 elements of the part
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int q, j4;
         int64_t r;
@@ -286,15 +290,15 @@ p2p_send_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int fe
         float* dst;
         if (mode == 0) {
             const int f4 = world * fc4;
-            r = i / f4;
-            const int c4 = (int)(i - r * f4);
+            r = row_begin + i / f4;
+            const int c4 = (int)(i - (i / f4) * f4);
             q = c4 / fc4;
             j4 = c4 - q * fc4;
             v = ldg_f4(src + r * lds + 4 * c4);
             dst = reinterpret_cast<float*>(peer[q] + P2P_FLAG_BYTES + off_bytes) + ((int64_t)rank * rows + r) * fc + 4 * j4;
         } else {
-            const int64_t gr = i / fc4;
-            j4 = (int)(i - gr * fc4);
+            const int64_t gr = row_begin + i / fc4;
+            j4 = (int)(i - (i / fc4) * fc4);
             q = (int)(gr / rows);
             r = gr - (int64_t)q * rows;
             v = ldg_f4(src + gr * lds + 4 * j4);
@@ -310,7 +314,11 @@ p2p_send_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int fe
         if (done == gridDim.x - 1) {
             *counter = 0;
             __threadfence_system();
-            for (int q = 0; q < world; ++q) st_release_sys(reinterpret_cast<long long*>(peer[q]) + rank, seq);
+            if (publish == 1) {
+                for (int q = 0; q < world; ++q) st_release_sys(reinterpret_cast<long long*>(peer[q]) + rank, seq);
+            } else if (publish == 2) {
+                st_release_sys(reinterpret_cast<long long*>(peer[(int)(row_begin / rows)]) + rank, seq);
+            }
         }
     }
 }
@@ -413,20 +421,34 @@ int plagnn_p2p_destroy(plagnn_p2p_t px) {
     return PLAGNN_OK;
 }
 
+int plagnn_p2p_send_part(plagnn_p2p_t px, const float* src, int64_t lds, int64_t rows, int64_t feat, int mode, int64_t row_begin,
+                         int64_t row_end, int publish, size_t dst_offset_bytes, long long seq, plagnn_stream_t stream);
+
 int plagnn_p2p_send(plagnn_p2p_t px, const float* src, int64_t lds, int64_t rows, int64_t feat, int mode, size_t dst_offset_bytes,
                     long long seq, plagnn_stream_t stream) {
     P2P* p = (P2P*)px;
+    if (!p) return fail(PLAGNN_ERR_ARG, "p2p_send", "bad arguments");
+    return plagnn_p2p_send_part(px, src, lds, rows, feat, mode, 0, mode == 0 ? rows : rows * p->world, 1, dst_offset_bytes, seq, stream);
+}
+
+int plagnn_p2p_send_part(plagnn_p2p_t px, const float* src, int64_t lds, int64_t rows, int64_t feat, int mode, int64_t row_begin,
+                         int64_t row_end, int publish, size_t dst_offset_bytes, long long seq, plagnn_stream_t stream) {
+    P2P* p = (P2P*)px;
     if (!p || !src || rows <= 0 || feat <= 0 || (mode != 0 && mode != 1)) return fail(PLAGNN_ERR_ARG, "p2p_send", "bad arguments");
+    const int64_t src_rows = mode == 0 ? rows : rows * p->world;
+    if (row_begin < 0 || row_end <= row_begin || row_end > src_rows || publish < 0 || publish > 2 ||
+        (publish == 2 && (mode != 1 || row_begin / rows != (row_end - 1) / rows)))
+        return fail(PLAGNN_ERR_ARG, "p2p_send", "bad row range (publish = 2: mode 1, rows of one owner)");
     if (feat % (4 * (int64_t)p->world)) return fail(PLAGNN_ERR_ARG, "p2p_send", "feat must be a multiple of 4 * world");
     const int64_t fc = feat / p->world;
     if ((lds & 3) || lds < (mode == 0 ? feat : fc) || !aligned16(src) || (dst_offset_bytes & 15))
         return fail(PLAGNN_ERR_ALIGN, "p2p_send", "16-byte aligned rows needed");
     if (dst_offset_bytes + (size_t)rows * feat * sizeof(float) > p->bytes) return fail(PLAGNN_ERR_WORKSPACE, "p2p_send", "window too small");
     ProfileScope prof(mode == 0 ? "p2p_send_cols" : "p2p_send_rows", rows, feat, p->world, stream);
-    const int64_t total = rows * (feat / 4);
+    const int64_t total = (row_end - row_begin) * (mode == 0 ? feat / 4 : fc / 4);
     const int grid = (int)(ceil_div(total, 256) < (int64_t)sm_count() * 8 ? ceil_div(total, 256) : (int64_t)sm_count() * 8);
     launch_pdl(p2p_send_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, src, lds, rows, (int)feat, (int)fc, mode,
-               (char* const*)p->d_peer, dst_offset_bytes, p->rank, p->world, seq, p->d_counter);
+               (char* const*)p->d_peer, dst_offset_bytes, p->rank, p->world, seq, p->d_counter, row_begin, row_end, publish);
     return check_launch("p2p_send");
 }
 

@@ -764,6 +764,18 @@ int plagnn_spmm_sum_rows(const int32_t* indptr, const int32_t* indices, const in
     return spmm_dispatch<MODE_SUM>(a, "spmm_sum_rows", (cudaStream_t)stream);
 }
 
+int plagnn_spmm_max_fwd_rows(const int32_t* indptr, const int32_t* indices, const void* plan, const int64_t* plan_counts,
+                             const int64_t* row_range, int64_t num_rows, const float* x, int64_t ldx, int64_t feat, float* out,
+                             int32_t* arg, int64_t ldo, void* partial, size_t partial_bytes, plagnn_stream_t stream) {
+    if (!row_range) return fail(PLAGNN_ERR_ARG, "spmm_max_fwd_rows", "row_range is required");
+    if (!arg) return fail(PLAGNN_ERR_ARG, "spmm_max_fwd_rows", "arg output is required");
+    ProfileScope prof("spmm_max_fwd", feat, row_range[1] - row_range[0], 0, stream);
+    SpmmArgs a{indptr, indices, nullptr, nullptr, plan, plan_counts, num_rows, x, ldx, feat, nullptr, 0, nullptr, 0,
+               out, arg, ldo, partial, partial_bytes, SpmmEpilogue{nullptr, nullptr, 0, 0.f, 0.f, 0ull}};
+    a.range = row_range;
+    return spmm_dispatch<MODE_MAX>(a, "spmm_max_fwd_rows", (cudaStream_t)stream);
+}
+
 int plagnn_dropout_scale(float* grad, int64_t rows, int64_t feat, int64_t ld, float dropout_p, uint64_t dropout_seed,
                          plagnn_stream_t stream) {
     if (!grad || rows <= 0 || feat <= 0 || dropout_p < 0.f || dropout_p >= 1.f) return fail(PLAGNN_ERR_ARG, "dropout_scale", "bad arguments");

@@ -36,6 +36,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -357,8 +358,12 @@ def dist_pool_forward_backward(model: DistSAGEPool, pg, h0_local, backend, group
             m_local = backend.alloc(plan.per, f)
             backend.gemm_nt_bias_relu_into(h, wp, bp, m_local)
             m_col = backend.to_cols(m_local, world, group)
-            neigh_col, arg = backend.spmm_max(pg.csc, m_col)
-            neigh = backend.to_rows(neigh_col, f, world, group)
+            fused = getattr(backend, "spmm_max_to_rows", None)
+            if fused is not None:
+                neigh, neigh_col, arg = fused(pg.csc, m_col, f, world, group)
+            else:
+                neigh_col, arg = backend.spmm_max(pg.csc, m_col)
+                neigh = backend.to_rows(neigh_col, f, world, group)
             ctx = (neigh_col, arg)
         else:
             m_local = backend.alloc(plan.per, f)
@@ -418,6 +423,15 @@ def dist_pool_forward_backward(model: DistSAGEPool, pg, h0_local, backend, group
 # ======================================================================================================================
 # feature partition, weighted sum
 # ======================================================================================================================
+def _spmm_cols_to_rows(backend, csx, key, x_col, w, scale, bias, act, feat, world, group):
+    """Aggregate all rows of my columns, hand every owner its rows: fused block by block when the backend can (CUDA backend
+    with the peer-memory exchange), else aggregation followed by the exchange."""
+    fused = getattr(backend, "spmm_cols_to_rows", None)
+    if fused is not None:
+        return fused(csx, key, x_col, w, scale, bias, act, feat, world, group)
+    return backend.to_rows(backend.spmm_cols(csx, key, x_col, w, scale, bias, act), feat, world, group)
+
+
 def _gcn_cols_forward_backward(model: DistGCN, pg, h0_local, backend, group, loss_grad_fn, act_leaky):
     plan = pg.plan
     world = plan.world
@@ -432,9 +446,8 @@ def _gcn_cols_forward_backward(model: DistGCN, pg, h0_local, backend, group, los
         backend.gemm_nt_into(h, model.weights[li].detach(), t_local)
         t_col = backend.to_cols(t_local, world, group)
         c0, c1 = plan.col_range(o)
-        out_col = backend.spmm_cols(pg.csc, "csc", t_col, pg.w_csc, pg.scale_full, model.biases[li].detach()[c0:c1],
-                                    act=act_leaky and not last)
-        h = backend.to_rows(out_col, o, world, group)
+        h = _spmm_cols_to_rows(backend, pg.csc, "csc", t_col, pg.w_csc, pg.scale_full, model.biases[li].detach()[c0:c1],
+                               act_leaky and not last, o, world, group)
         outs.append(h)
         if not last:
             hs.append(h)
@@ -449,8 +462,7 @@ def _gcn_cols_forward_backward(model: DistGCN, pg, h0_local, backend, group, los
         grads[2 * li + 1] = backend.colsum(dzb)
         dzs = backend.act_backward(dzb, None, pg.scale)
         dzs_col = backend.to_cols(dzs, world, group)
-        dt_col = backend.spmm_cols(pg.csr_t, "csr_t", dzs_col, pg.w_csr_t, None, None, act=False)
-        dt_local = backend.to_rows(dt_col, o, world, group)
+        dt_local = _spmm_cols_to_rows(backend, pg.csr_t, "csr_t", dzs_col, pg.w_csr_t, None, None, False, o, world, group)
         grads[2 * li] = backend.gemm_tn(dt_local, hs[li])
         if li > 0:
             dz = backend.gemm_nn(dt_local, model.weights[li].detach())
@@ -557,6 +569,20 @@ class P2PExchange:
         shape = (self.world * rows, feat // self.world) if mode == 0 else (rows, feat)
         return torch.as_tensor(_WindowView(self.base + off, shape, self), device=self.device)
 
+    def begin(self):
+        """A new exchange made of several parts: returns (seq, window offset)."""
+        self.seq += 1
+        return self.seq, self._region(self.seq)
+
+    def send_part(self, src, rows, feat, mode, row_begin, row_end, publish, seq, off, stream):
+        self._lib.check(self.lib.plagnn_p2p_send_part(self.handle, src.data_ptr(), src.stride(0), rows, feat, mode, row_begin, row_end,
+                                                      publish, off, seq, stream), "p2p_send_part")
+
+    def finish(self, seq, off, rows, feat, mode, stream) -> torch.Tensor:
+        self._lib.check(self.lib.plagnn_p2p_wait(self.handle, seq, stream), "p2p_wait")
+        shape = (self.world * rows, feat // self.world) if mode == 0 else (rows, feat)
+        return torch.as_tensor(_WindowView(self.base + off, shape, self), device=self.device)
+
     def error(self) -> int:
         return int(self.lib.plagnn_p2p_error(self.handle))
 
@@ -579,9 +605,10 @@ class CudaBackend:
         self.p2p = p2p                 # feature partition: peer-memory exchange instead of pack + NCCL all-to-all + unpack
         self.pg = pg
         self.skip_comm = False
+        self.overlap = False           # feature partition: aggregation and exchange fused block by block (set below)
         # highest priority: when an SM slot frees up, the exchange kernel's CTAs are placed before the pending CTAs of the
         # aggregation launched ahead of it — otherwise the collective only starts once that whole grid has been scheduled
-        self.comm_stream = torch.cuda.Stream(priority=-1) if comm is not None else None
+        self.comm_stream = torch.cuda.Stream(priority=-1) if (comm is not None or p2p is not None) else None
         plan = pg.plan
         self.ranges = {}
         if pg.mode == "rows":
@@ -590,6 +617,14 @@ class CudaBackend:
                 if pg.csr_t is not None:
                     self.ranges[("csr_t", c)] = ops.plan_range(pg.csr_t, *plan.slab_rows(c))
             self.ranges[("csc", -1)] = ops.plan_range(pg.csc, 0, plan.per)
+        elif p2p is not None and plan.world > 1 and pg.csc_slabs is None:
+            # feature partition: the aggregation is launched per owner's row block, so that each block can leave for its owner
+            # while the next one is aggregated
+            for q in range(plan.world):
+                self.ranges[("csc", q)] = ops.plan_range(pg.csc, q * plan.per, (q + 1) * plan.per)
+                if pg.csr_t is not None:
+                    self.ranges[("csr_t", q)] = ops.plan_range(pg.csr_t, q * plan.per, (q + 1) * plan.per)
+            self.overlap = os.environ.get("PLAGNN_DIST_OVERLAP", "1") != "0"
 
     def alloc(self, rows, cols):
         return self.ops.alloc(rows, cols, torch.cuda.current_device())
@@ -659,6 +694,51 @@ class CudaBackend:
         if self.pg.csc_slabs is not None:
             return self.ops.spmm_max_slabs(self.pg.csc_slabs, x)
         return self.ops.spmm_max_fwd(csc, x)
+
+    def _blocks_to_rows(self, launch_block, out_col, feat, world):
+        """Feature partition, aggregation + exchange fused block by block: `launch_block(q)` aggregates the rows owned by rank
+        q into `out_col`; as soon as a block is done its rows leave for their owner on the exchange stream (peer-memory
+        store, flag for that owner only) while the next block is aggregated.  Returns my rows x all columns."""
+        ops, p2p = self.ops, self.p2p
+        rows = out_col.shape[0] // world
+        cur = torch.cuda.current_stream()
+        seq, off = p2p.begin()
+        cst = ctypes.c_void_p(self.comm_stream.cuda_stream)
+        last = None
+        for q in range(world):
+            launch_block(q)
+            done = torch.cuda.Event()
+            done.record(cur)
+            self.comm_stream.wait_event(done)
+            p2p.send_part(out_col, rows, feat, 1, q * rows, (q + 1) * rows, 2, seq, off, cst)
+            last = torch.cuda.Event()
+            last.record(self.comm_stream)
+        res = p2p.finish(seq, off, rows, feat, 1, ops._stream())
+        cur.wait_event(last)          # my own stores are finished before out_col can be reused (and before the next send kernel)
+        return res
+
+    def spmm_cols_to_rows(self, csx, key, x_col, w, scale, bias, act, feat, world, group):
+        ops, pg = self.ops, self.pg
+        if not (self.overlap and self.p2p is not None and world > 1 and not self.skip_comm):
+            return self.to_rows(self.spmm_cols(csx, key, x_col, w, scale, bias, act), feat, world, group)
+        a = ops.ACT_LEAKY if act else ops.ACT_NONE
+        x_col = ops.aligned(x_col)
+        out_col = ops.alloc(csx.num_rows, x_col.shape[1], x_col.device)
+        return self._blocks_to_rows(lambda q: ops.spmm_sum_rows(csx, self.ranges[(key, q)], x_col, out_col, w=w, scale=scale, bias=bias,
+                                                                act=a, w_in_csr_order=True), out_col, feat, world)
+
+    def spmm_max_to_rows(self, csc, x_col, feat, world, group):
+        """Returns (neigh my rows x all columns, neigh all rows x my columns, arg all rows x my columns)."""
+        ops = self.ops
+        if not (self.overlap and self.p2p is not None and world > 1 and not self.skip_comm):
+            neigh_col, arg = self.spmm_max(csc, x_col)
+            return self.to_rows(neigh_col, feat, world, group), neigh_col, arg
+        x_col = ops.aligned(x_col)
+        f = x_col.shape[1]
+        neigh_col = ops.alloc(csc.num_rows, f, x_col.device)
+        arg = ops.alloc(csc.num_rows, f, x_col.device, dtype=torch.int32)
+        neigh = self._blocks_to_rows(lambda q: ops.spmm_max_fwd_rows(csc, self.ranges[("csc", q)], x_col, neigh_col, arg), neigh_col, feat, world)
+        return neigh, neigh_col, arg
 
     def max_scatter(self, dneigh, arg, neigh, n_src):
         return self.ops.spmm_max_bwd(dneigh, arg, neigh, n_src)

@@ -169,11 +169,26 @@ def measure_variant(v: Variant, steps, warmup, rank, world, dev, reference=None)
         bwd = 16 * fc * plan.n_padded if v.mode == "cols" else 4 * f * (2 * plan.per + 2 * plan.n_padded)
         alg = v.layers * ((4 * fc * el + 4 * el + 8 * fc * rows_out) + bwd)
     hbm, src = _hbm_peak()
+    # ncu DRAM bytes per launch of the forward aggregation kernel of this very shape (one GPU, 1 M / 100 M / 256), from the
+    # committed capture; the live launch time comes from this run's events
+    dram = None
+    tpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r2_ncu_traffic.json")
+    if world == 1 and n == 1_000_000 and f == 256 and plan.num_local_edges == 100_000_000 and os.path.exists(tpath):
+        tj = json.load(open(tpath)).get("spmm_kernel<1, 2, 4>/grid133678" if v.reducer == "sum" else "spmm_kernel<0, 2, 4>/grid133678")
+        fwd_name = "spmm_sum" if v.reducer == "sum" else "spmm_max_fwd"
+        launches = v.layers * (2 if v.reducer == "sum" else 1)
+        if tj and per_step.get(fwd_name):
+            ms_launch = per_step[fwd_name] / launches
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            dram = {"kernel": "spmm_kernel<%s, 2, 4> (F = 256, 100 M edges)" % ("sum" if v.reducer == "sum" else "max"),
+                    "traffic": traffic, "avg_ms": ms_launch, "frac_dram": traffic / (ms_launch * 1e-3) / 1e9 / hbm,
+                    "traffic_source": "ncu --set full capture committed under profiles/r2_ncu.md (per launch)"}
     res = {"mode": v.mode, "reducer": v.reducer, "exchange": v.exchange, "ms_per_step": ms, "ms_per_step_with_events": ms_prof,
            "ms_per_step_without_collectives": ms_nocomm, "exposed_exchange_ms": (ms - ms_nocomm) if ms_nocomm else 0.0,
            "collective_ms_per_step": coll, "aggregation_ms_per_step": agg_ms, "aggregation_by_launch_shape": agg_shapes,
            "aggregation_algorithmic_gbs_per_gpu": alg / (agg_ms * 1e-3) / 1e9 if agg_ms else None,
            "aggregation_frac_of_hbm_peak": alg / (agg_ms * 1e-3) / 1e9 / hbm if agg_ms else None, "hbm_peak": hbm, "peak_source": src,
+           "aggregation_dram": dram,
            "local_edges_rank0": el, "source_slabs": v.pg.n_slabs, "checksum": csum, "check": check,
            "kernels": sorted([{"kernel": k, "ms_per_step": round(t, 4)} for k, t in per_step.items()], key=lambda d: -d["ms_per_step"])[:8]}
     return res

@@ -398,6 +398,18 @@ def spmm_sum_rows(csx, rng, x: torch.Tensor, out: torch.Tensor, w=None, scale=No
 
 
 @on_tensor_device
+def spmm_max_fwd_rows(csc, rng, x: torch.Tensor, out: torch.Tensor, arg: torch.Tensor):
+    """Row-range max aggregation into the rows of preallocated `out` / `arg` (other rows untouched)."""
+    lib = _lib.load()
+    f = x.shape[1]
+    nb = lib.plagnn_spmm_partial_bytes(csc.counts[2], f, REDUCE_MAX)
+    part = workspace(nb, x.device, "spmm_partial")
+    check(lib.plagnn_spmm_max_fwd_rows(_p(csc.indptr), _p(csc.indices), _p(csc.plan), csc.counts_c, rng, csc.num_rows, _p(x),
+                                       x.stride(0), f, _p(out), _p(arg), out.stride(0), _p(part), nb, _stream()), "spmm_max_fwd_rows")
+    return out, arg
+
+
+@on_tensor_device
 def dropout_scale_(grad: torch.Tensor, p: float, seed: int) -> torch.Tensor:
     check(_lib.load().plagnn_dropout_scale(_p(grad), grad.shape[0], grad.shape[1], grad.stride(0), float(p), int(seed),
                                            _stream()), "dropout_scale")
