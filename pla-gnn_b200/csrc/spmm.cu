@@ -113,7 +113,7 @@ __device__ __forceinline__ void reduce_one(float4& acc, int4& arg, const float4 
 // The max reducer runs at the L2 -> SM bandwidth cap once enough warps are resident (measured: 24 warps/SM at 80
 // registers 0.198 ms, 16 warps at 110 registers 0.322 ms for F = 503), so its default variants are held to 3 blocks per SM;
 // the sum reducer (no arg registers) to 4 blocks = 32 warps (weighted 100 M-edge graph: 55.7 ms at 64 registers, 71.3 at 72).
-template <int MODE, int VEC, int NB>
+template <int MODE, int VEC, int NB, bool SUM_LEAN = false>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, NB * VEC > 8 ? 1 : MODE == MODE_MAX ? 3 : MODE == MODE_SUM ? 4 : 1)
 spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int32_t* __restrict__ eids,
             const float* __restrict__ ew, const int32_t* __restrict__ plan_hdr, const int32_t* __restrict__ item_ptr,
@@ -197,6 +197,49 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
                     for (int q = 0; q < VEC; ++q) reduce_one<MODE>(acc[q], arg[q], v[t][q], u[t], one, nzero);
 #pragma unroll
                 for (int t = 0; t < NB; ++t) u[t] = un[t];
+            }
+        }
+    } else if (MODE == MODE_SUM && SUM_LEAN) {
+        // The sum reducer with the max reducer's loop shape (round 2): neighbour ids and weights are broadcast loads issued one
+        // step ahead, a slot past the end re-reads the chunk's last neighbour with weight 0, a lane whose column group lies
+        // past the row reads column group 0 (never stored), and the row address is one 32-bit multiply-add — no shuffles, no
+        // load predicates, no 64-bit address arithmetic in the loop.  (ncu on the 1 M / 100 M graph, F = 256: the shuffle form
+        // moved 61.8 GB through DRAM in 12.8 ms = 0.74 of the HBM peak, the max reducer's loop 0.87.)
+        const float* xq[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) xq[q] = x + (cok[q] ? col[q] : col0);
+        const unsigned ldx_bytes = (unsigned)ldx * 4u;      // host checks ldx < 2^30
+        if (beg < end) {
+            const int last = end - 1;
+            int u[NB];
+            float w[NB];
+#pragma unroll
+            for (int t = 0; t < NB; ++t) {
+                const int idx = min(beg + t, last);
+                u[t] = __ldg(indices + idx);
+                w[t] = beg + t <= last ? (ew ? __ldg(ew + (eids ? __ldg(eids + idx) : idx)) : 1.f) : 0.f;
+            }
+            for (int j = beg; j < end; j += NB) {
+                int un[NB];
+                float wn[NB];
+                float4 v[NB][VEC];
+#pragma unroll
+                for (int t = 0; t < NB; ++t) {
+                    const int idx = min(j + NB + t, last);
+                    un[t] = __ldg(indices + idx);
+                    wn[t] = j + NB + t <= last ? (ew ? __ldg(ew + (eids ? __ldg(eids + idx) : idx)) : 1.f) : 0.f;
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) v[t][q] = ldg_f4(row_ptr(xq[q], u[t], ldx_bytes));
+                }
+#pragma unroll
+                for (int t = 0; t < NB; ++t)
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        acc[q].x = fmaf(w[t], v[t][q].x, acc[q].x); acc[q].y = fmaf(w[t], v[t][q].y, acc[q].y);
+                        acc[q].z = fmaf(w[t], v[t][q].z, acc[q].z); acc[q].w = fmaf(w[t], v[t][q].w, acc[q].w);
+                    }
+#pragma unroll
+                for (int t = 0; t < NB; ++t) { u[t] = un[t]; w[t] = wn[t]; }
             }
         }
     } else {
@@ -556,7 +599,10 @@ static void launch_main(const SpmmArgs& a, const int32_t* item_ptr, const int32_
     const int n_items = a.range ? (int)a.range[1] : (int)a.counts[0];
     if (n_items <= item_begin) return;
     dim3 grid((unsigned)ceil_div(n_items - item_begin, SPMM_WARPS), (unsigned)ceil_div((a.feat + 3) / 4, 32 * VEC));
-    launch_pdl(spmm_kernel<MODE, VEC, NB>, grid, dim3(SPMM_WARPS * 32), 0, st,
+    // PLAGNN_SPMM_SUM_LEAN=0: the shuffle form of the sum reducer (A/B runs)
+    static const bool lean = [] { const char* e = getenv("PLAGNN_SPMM_SUM_LEAN"); return !e || e[0] != '0'; }();
+    auto kernel = (MODE == MODE_SUM && lean) ? spmm_kernel<MODE, VEC, NB, true> : spmm_kernel<MODE, VEC, NB, false>;
+    launch_pdl(kernel, grid, dim3(SPMM_WARPS * 32), 0, st,
         a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, item_begin, n_items, a.x, a.ldx,
         (int)a.feat, a.argm, a.ldarg, a.zfwd, a.ldzf, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep, 1.0f, -0.0f);
 }
