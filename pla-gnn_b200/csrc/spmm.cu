@@ -203,8 +203,7 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
         // The sum reducer with the max reducer's loop shape (round 2): neighbour ids and weights are broadcast loads issued one
         // step ahead, a slot past the end re-reads the chunk's last neighbour with weight 0, a lane whose column group lies
         // past the row reads column group 0 (never stored), and the row address is one 32-bit multiply-add — no shuffles, no
-        // load predicates, no 64-bit address arithmetic in the loop.  (ncu on the 1 M / 100 M graph, F = 256: the shuffle form
-        // moved 61.8 GB through DRAM in 12.8 ms = 0.74 of the HBM peak, the max reducer's loop 0.87.)
+        // load predicates, no 64-bit address arithmetic in the loop.  An experiment that lost (see launch_main): opt-in only.
         const float* xq[VEC];
 #pragma unroll
         for (int q = 0; q < VEC; ++q) xq[q] = x + (cok[q] ? col[q] : col0);
@@ -337,9 +336,11 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
 // (512 bytes per request, as in the wide kernel, instead of 128), and the S partial results are folded with shuffles at the
 // end.  The max reducer keeps "first maximum in in-edge order wins" across the groups by carrying the winning edge position.
 //
-// Measured on the 1 M-node / 100 M-edge graph, 32 columns (tools/spmm_narrow_time.py): this kernel 2.55 ms per aggregation =
-// 5.4 TB/s algorithmic (the wide kernel with 24 idle lanes: 5.99 ms).  It is bound by latency, not by a bandwidth (L2 -> SM
-// fabric at ~40 %, HBM at ~45 %), and three attempts to put more bytes in flight all LOST: (a) cutting the gather by source
+// Measured on the 1 M-node / 100 M-edge graph, 32 columns (tools/spmm_narrow_time.py): the wide kernel with 24 idle lanes
+// 5.99 ms per aggregation, the first version of this kernel 2.55 ms, this one **1.99 ms** (6.9 TB/s algorithmic; 64 columns:
+// 4.0 -> 2.94 ms).  What paid was fewer instructions per edge (ncu: 11 warp instructions per edge in the first version, mostly
+// 64-bit address arithmetic and "live ? load : init" selects; the loop below has ~3), as in round 1's max reducer.  What did
+// NOT pay, all measured against the 2.55 ms version, were three attempts to put more bytes in flight: (a) cutting the gather by source
 // range into L2-sized slabs (plagnn_spmm_*_slab, kept as an option): 2.85 / 3.72 / 5.92 ms at 2 / 4 / 8 slabs — the items get
 // shorter; (b) one warp walking 32 consecutive items with prefetched meta data and neighbour ids, rows still gathered into
 // registers: 3.72 ms — in-order issue serialises the items of a warp; (c) the same walk with the rows of three 32-edge
@@ -599,8 +600,10 @@ static void launch_main(const SpmmArgs& a, const int32_t* item_ptr, const int32_
     const int n_items = a.range ? (int)a.range[1] : (int)a.counts[0];
     if (n_items <= item_begin) return;
     dim3 grid((unsigned)ceil_div(n_items - item_begin, SPMM_WARPS), (unsigned)ceil_div((a.feat + 3) / 4, 32 * VEC));
-    // PLAGNN_SPMM_SUM_LEAN=0: the shuffle form of the sum reducer (A/B runs)
-    static const bool lean = [] { const char* e = getenv("PLAGNN_SPMM_SUM_LEAN"); return !e || e[0] != '0'; }();
+    // PLAGNN_SPMM_SUM_LEAN=1: the max reducer's loop shape for the sum reducer.  Off by default — measured on the 1 M / 100 M
+    // graph it LOSES to the shuffle form: F = 256 15.3 vs 12.8 ms, F = 128 9.7 vs 7.4 ms (two broadcast loads per neighbour, id
+    // and weight, issued by every lane, against two coalesced loads and two shuffles per 32 neighbours).
+    static const bool lean = [] { const char* e = getenv("PLAGNN_SPMM_SUM_LEAN"); return e && e[0] == '1'; }();
     auto kernel = (MODE == MODE_SUM && lean) ? spmm_kernel<MODE, VEC, NB, true> : spmm_kernel<MODE, VEC, NB, false>;
     launch_pdl(kernel, grid, dim3(SPMM_WARPS * 32), 0, st,
         a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, item_begin, n_items, a.x, a.ldx,
