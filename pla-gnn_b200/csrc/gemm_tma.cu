@@ -52,7 +52,10 @@ constexpr int TM_RAW_BYTES = 2 * TM_PART_BYTES;          // one ring stage: the 
 constexpr int TM_RAW_STAGES = 4, TM_LO_STAGES = 3;       // raw fp32 tiles (TMA) / derived lo tiles
 constexpr int TM_SMEM_BYTES = (TM_RAW_STAGES + TM_LO_STAGES) * TM_RAW_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TM_EPI_WARPS = 8;
-constexpr int TM_THREADS = (2 + TM_EPI_WARPS) * 32;
+// one more warp per CTA executes the read-out code ONCE, dry (no barriers, no stores), while the first tiles are in flight:
+// the read-out path is ~5-10 KB of straight-line code that every launch otherwise fetches for the first time on its critical
+// path (measured in round 1: ~5 000 cycles of instruction-cache misses in the first read-out of a launch).  P.warm = 0: it idles.
+constexpr int TM_THREADS = (2 + TM_EPI_WARPS + 1) * 32;
 constexpr int TM_MAX_CHAIN = 40;    // k-blocks per TMEM accumulation chain (see gemm_tc.cu: truncating accumulate)
 // Long contractions (the weight gradients: K = number of nodes) can be cut into shorter chains (PLAGNN_TMA_LONG_CHAIN).  The
 // tensor core truncates when it adds into the fp32 accumulator, so one chain's error grows with its length.  Measured at
@@ -75,6 +78,7 @@ struct alignas(64) TmParams {
     float* ones_out;                              // where the reduction writes that column (length m)
     int tiles_m, tiles_n, total_tiles;            // tile t = (split * tiles_m + row block) * tiles_n + column block
     int persistent;                               // fewer CTA pairs than tiles: each pair walks several tiles
+    int warm;                                     // 1: the extra warp pre-executes the read-out code (instruction-cache warm-up)
     int transpose_out;                            // split-K only: the reduction writes C^T (operands were swapped by the launcher)
     int64_t m, n;
     int npairs;
@@ -493,11 +497,13 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
         // Tensor-core operand reads do not compete with LDS/STS for bandwidth (tools/mma_probe.cu, "contend").
         // The raw ring is 4 deep (TMA latency ~2.5 us), the lo ring 3 deep: the chain "MMAs done -> commit -> split warps
         // -> STS -> proxy fence -> (remote) arrive -> issuer" is longer than one k-block of MMAs (1536 cycles).
-        const int ct = t - 64;                                  // 0..255
+        const bool dry = warp >= 2 + TM_EPI_WARPS;              // the warm-up warp: read-out code once, nothing waited for or stored
+        if (!dry || P.warm) {
+        const int ct = t - 64;                                  // 0..255 (splitting warps)
         const uint32_t lo_full0 = CG == 2 ? mapa(bar_lo_full, 0) : bar_lo_full;   // the leader's barriers count both CTAs
         const uint32_t tmem_empty0 = CG == 2 ? mapa(bar_tmem_empty, 0) : bar_tmem_empty;
         const int lg = warp & 3;                        // TMEM lane group this warp may read (warp % 4)
-        const int chalf = (warp - 2) >> 2;              // column half of the tile
+        const int chalf = dry ? 0 : (warp - 2) >> 2;    // column half of the tile
         const bool direct = P.splits == 1;
         constexpr int CHUNKS = TILE_N / 32 / 2;
         // staging images of the read-out: in the raw ring for a single tile per CTA (everything is free by then); with
@@ -525,7 +531,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     if (c >= cbase && c < cbase + 4) { ones_piece = (int)(lc >> 5); ones_elem = c - cbase; }
                 }
             }
-            for (int it = 0; it < T.nkb; ++it, ++g) {
+            const int nkb_run = dry ? 0 : T.nkb;
+            for (int it = 0; it < nkb_run; ++it, ++g) {
                 const int s = g % TM_RAW_STAGES, l = g % TM_LO_STAGES;
                 const uint32_t phr = (uint32_t)((g / TM_RAW_STAGES) & 1), phl = (uint32_t)((g / TM_LO_STAGES) & 1);
                 const long long w0 = (tr && t == 64) ? clock64() : 0;
@@ -570,7 +577,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             }
 
             // ---------------- read-out: TMEM -> registers -> swizzled image -> TMA store ----------------
-            mbar_wait(bar_acc, (uint32_t)(tile_iter & 1));
+            if (!dry) mbar_wait(bar_acc, (uint32_t)(tile_iter & 1));
             tc_fence_after();
             if (tr && t == 64 && tile_iter == 0) tr[4] = clock64();
             const int64_t r = m0 + rank * 128 + lg * 32 + lane;
@@ -584,7 +591,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             // gate tiles (saved activations of the backward epilogues) come in by TMA as 32 x 32 SWIZZLE_128B images, all
             // chunks of this warp at once, while the first accumulator chunk is read
             const bool gate_img_on = direct && P.gate && P.gate_tma;
-            if (gate_img_on && lane == 0) {
+            if (gate_img_on && !dry && lane == 0) {
                 int nch = 0;
                 for (int ch = 0; ch < CHUNKS; ++ch) {
                     const int cb = (chalf * CHUNKS + ch) * 32;
@@ -640,7 +647,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                         for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
                     }
                     if (gate_img_on) {
-                        if (ch == 0) mbar_wait(gbar, (uint32_t)(tile_iter & 1));
+                        if (ch == 0 && !dry) mbar_wait(gbar, (uint32_t)(tile_iter & 1));
                         float gt[32];
 #pragma unroll
                         for (int q = 0; q < 8; ++q)
@@ -677,20 +684,28 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 if (TM_DEBUG(P) == 3) continue;
                 if (P.tma_store) {
                     const long long e1 = (tr && t == 64) ? clock64() : 0;
-                    if (lane == 0) bulk_wait_read<1>();      // the image written two chunks ago has been read
+                    if (lane == 0 && !dry) bulk_wait_read<1>();      // the image written two chunks ago has been read
                     __syncwarp();
                     if (tr && t == 64 && tile_iter == 0) tr[14] += clock64() - e1;
                     const uint32_t img = stg + (uint32_t)buf * 4096u;
+                    if (!dry) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t off = row_off + (uint32_t)((q ^ (lane & 7)) << 4);
-                        sts_v4(img + off, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        for (int q = 0; q < 8; ++q) {
+                            const uint32_t off = row_off + (uint32_t)((q ^ (lane & 7)) << 4);
+                            sts_v4(img + off, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        }
+                    } else {
+                        // keep the dry values alive (the math above must be executed, not removed)
+                        float keep = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) keep += v[j];
+                        asm volatile("" ::"f"(keep));
                     }
                     const long long e2 = (tr && t == 64) ? clock64() : 0;
                     fence_proxy_async_smem();
                     __syncwarp();
                     const long long e3 = (tr && t == 64) ? clock64() : 0;
-                    if (TM_DEBUG(P) != 4 && lane == 0) {     // (bulk groups belong to the issuing thread: always lane 0)
+                    if (TM_DEBUG(P) != 4 && lane == 0 && !dry) {     // (bulk groups belong to the issuing thread: always lane 0)
                         tma_store_3d(&P.map_out, img, (int)c0, row0, direct ? 0 : split);
                         bulk_commit();
                     }
@@ -699,7 +714,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                         tr[15] += e4 - e1; tr[26] += e2 - e1; tr[27] += e3 - e2; tr[28] += e4 - e3;
                     }
                     buf ^= 1;
-                } else if (r < P.m) {
+                } else if (r < P.m && !dry) {
                     // unaligned destination (row pitch % 4 != 0): plain scalar stores
                     float* drow = dst + r * ldd + c0;
 #pragma unroll
@@ -708,6 +723,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 }
             }
             if (tr && t == 64 && tile_iter == 0) tr[5] = clock64();
+            if (dry) break;
             // the accumulators of this tile are in registers / on their way out: the next tile may overwrite TMEM
             tc_fence_before();
             __syncwarp();
@@ -723,9 +739,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             }
             if (tr && t == 64 && tile_iter == 0) tr[6] = clock64();
         }
-        if (P.tma_store) {
+        if (P.tma_store && !dry) {
             if (lane == 0) bulk_wait_all();
             __syncwarp();
+        }
         }
     }
     tc_fence_before();
@@ -1066,6 +1083,8 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
     static const bool allow_persistent = [] { const char* e = getenv("PLAGNN_TMA_PERSISTENT"); return !e || e[0] != '0'; }();
     const int64_t units = sm_count() / cg;
     P.persistent = (allow_persistent && !gate && total_tiles > units) ? 1 : 0;
+    // PLAGNN_TMA_WARM=0: the warm-up warp idles (A/B runs)
+    { const char* e = getenv("PLAGNN_TMA_WARM"); P.warm = (!e || e[0] != '0') ? 1 : 0; }
     const int64_t launched = P.persistent ? units : total_tiles;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(launched * cg), 1u, 1u);
