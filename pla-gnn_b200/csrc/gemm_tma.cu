@@ -52,10 +52,7 @@ constexpr int TM_RAW_BYTES = 2 * TM_PART_BYTES;          // one ring stage: the 
 constexpr int TM_RAW_STAGES = 4, TM_LO_STAGES = 3;       // raw fp32 tiles (TMA) / derived lo tiles
 constexpr int TM_SMEM_BYTES = (TM_RAW_STAGES + TM_LO_STAGES) * TM_RAW_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TM_EPI_WARPS = 8;
-// one more warp per CTA executes the read-out code ONCE, dry (no barriers, no stores), while the first tiles are in flight:
-// the read-out path is ~5-10 KB of straight-line code that every launch otherwise fetches for the first time on its critical
-// path (measured in round 1: ~5 000 cycles of instruction-cache misses in the first read-out of a launch).  P.warm = 0: it idles.
-constexpr int TM_THREADS = (2 + TM_EPI_WARPS + 1) * 32;
+constexpr int TM_THREADS = (2 + TM_EPI_WARPS) * 32;
 constexpr int TM_MAX_CHAIN = 40;    // k-blocks per TMEM accumulation chain (see gemm_tc.cu: truncating accumulate)
 // Long contractions (the weight gradients: K = number of nodes) can be cut into shorter chains (PLAGNN_TMA_LONG_CHAIN).  The
 // tensor core truncates when it adds into the fp32 accumulator, so one chain's error grows with its length.  Measured at
@@ -70,6 +67,7 @@ struct alignas(64) TmParams {
     CUtensorMap map[PLAGNN_GEMM_MAX_PAIRS][2];    // [pair][A, B]
     CUtensorMap map_out;                          // C (or the split-K partials) as {n, m, splits}, box {32, 32, 1}
     CUtensorMap map_gate;                         // gate as {n, m}, box {32, 32} (gate_tma = 1)
+    CUtensorMap map_b64[PLAGNN_GEMM_MAX_PAIRS];   // k-contiguous B with a 64-row box (the 256 x 128 tiles of gemm_tma_db_kernel)
     int gate_tma;
     int tma_store;                                // 1: epilogue leaves through shared memory + TMA stores (aligned output)
     int64_t ldp;                                  // row pitch of the split-K partials
@@ -78,7 +76,6 @@ struct alignas(64) TmParams {
     float* ones_out;                              // where the reduction writes that column (length m)
     int tiles_m, tiles_n, total_tiles;            // tile t = (split * tiles_m + row block) * tiles_n + column block
     int persistent;                               // fewer CTA pairs than tiles: each pair walks several tiles
-    int warm;                                     // 1: the extra warp pre-executes the read-out code (instruction-cache warm-up)
     int transpose_out;                            // split-K only: the reduction writes C^T (operands were swapped by the launcher)
     int64_t m, n;
     int npairs;
@@ -455,6 +452,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                         if (it == 0) tr[2] = w1;
                         if (it == 0 || it == 8) tr[it ? 23 : 19] = w1;
                     }
+                    if (tr && lane == 0 && tile_iter == 1 && it == 0) tr[30] = clock64() - tr[3];   // tile 0 committed -> tile 1's first k-block ready
                     const uint32_t st = tiles + s * TM_RAW_BYTES, sl = lo_ring + l * TM_RAW_BYTES;
                     const uint64_t a_hi = AT ? desc_mnmajor(st) : desc_kmajor(st);
                     const uint64_t a_lo = AT ? desc_mnmajor(sl) : desc_kmajor(sl);
@@ -487,6 +485,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 if (elect_one()) umma_commit<CG>(bar_acc);       // accumulators of this tile complete (both CTAs)
                 __syncwarp();
                 if (tr && lane == 0 && tile_iter == 0) tr[3] = clock64();
+                if (tr && lane == 0 && tile_iter == 1) tr[31] = clock64() - tr[3] - tr[30];        // main loop of tile 1
             }
         }
         __syncwarp();
@@ -497,13 +496,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
         // Tensor-core operand reads do not compete with LDS/STS for bandwidth (tools/mma_probe.cu, "contend").
         // The raw ring is 4 deep (TMA latency ~2.5 us), the lo ring 3 deep: the chain "MMAs done -> commit -> split warps
         // -> STS -> proxy fence -> (remote) arrive -> issuer" is longer than one k-block of MMAs (1536 cycles).
-        const bool dry = warp >= 2 + TM_EPI_WARPS;              // the warm-up warp: read-out code once, nothing waited for or stored
-        if (!dry || P.warm) {
-        const int ct = t - 64;                                  // 0..255 (splitting warps)
+        const int ct = t - 64;                                  // 0..255
         const uint32_t lo_full0 = CG == 2 ? mapa(bar_lo_full, 0) : bar_lo_full;   // the leader's barriers count both CTAs
         const uint32_t tmem_empty0 = CG == 2 ? mapa(bar_tmem_empty, 0) : bar_tmem_empty;
         const int lg = warp & 3;                        // TMEM lane group this warp may read (warp % 4)
-        const int chalf = dry ? 0 : (warp - 2) >> 2;    // column half of the tile
+        const int chalf = (warp - 2) >> 2;              // column half of the tile
         const bool direct = P.splits == 1;
         constexpr int CHUNKS = TILE_N / 32 / 2;
         // staging images of the read-out: in the raw ring for a single tile per CTA (everything is free by then); with
@@ -531,8 +528,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     if (c >= cbase && c < cbase + 4) { ones_piece = (int)(lc >> 5); ones_elem = c - cbase; }
                 }
             }
-            const int nkb_run = dry ? 0 : T.nkb;
-            for (int it = 0; it < nkb_run; ++it, ++g) {
+            for (int it = 0; it < T.nkb; ++it, ++g) {
                 const int s = g % TM_RAW_STAGES, l = g % TM_LO_STAGES;
                 const uint32_t phr = (uint32_t)((g / TM_RAW_STAGES) & 1), phl = (uint32_t)((g / TM_LO_STAGES) & 1);
                 const long long w0 = (tr && t == 64) ? clock64() : 0;
@@ -577,9 +573,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             }
 
             // ---------------- read-out: TMEM -> registers -> swizzled image -> TMA store ----------------
-            if (!dry) mbar_wait(bar_acc, (uint32_t)(tile_iter & 1));
+            mbar_wait(bar_acc, (uint32_t)(tile_iter & 1));
             tc_fence_after();
             if (tr && t == 64 && tile_iter == 0) tr[4] = clock64();
+            const long long epi1 = (tr && t == 64 && tile_iter == 1) ? clock64() : 0;
             const int64_t r = m0 + rank * 128 + lg * 32 + lane;
             // Each warp turns its 32 rows x 32 columns into a 4 KB SWIZZLE_128B image and one lane stores it with a bulk
             // tensor copy: whole 128-byte lines leave the SM, rows >= m / columns >= n are clipped by the tensor map; two
@@ -591,7 +588,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             // gate tiles (saved activations of the backward epilogues) come in by TMA as 32 x 32 SWIZZLE_128B images, all
             // chunks of this warp at once, while the first accumulator chunk is read
             const bool gate_img_on = direct && P.gate && P.gate_tma;
-            if (gate_img_on && !dry && lane == 0) {
+            if (gate_img_on && lane == 0) {
                 int nch = 0;
                 for (int ch = 0; ch < CHUNKS; ++ch) {
                     const int cb = (chalf * CHUNKS + ch) * 32;
@@ -647,7 +644,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                         for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
                     }
                     if (gate_img_on) {
-                        if (ch == 0 && !dry) mbar_wait(gbar, (uint32_t)(tile_iter & 1));
+                        if (ch == 0) mbar_wait(gbar, (uint32_t)(tile_iter & 1));
                         float gt[32];
 #pragma unroll
                         for (int q = 0; q < 8; ++q)
@@ -684,28 +681,20 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 if (TM_DEBUG(P) == 3) continue;
                 if (P.tma_store) {
                     const long long e1 = (tr && t == 64) ? clock64() : 0;
-                    if (lane == 0 && !dry) bulk_wait_read<1>();      // the image written two chunks ago has been read
+                    if (lane == 0) bulk_wait_read<1>();      // the image written two chunks ago has been read
                     __syncwarp();
                     if (tr && t == 64 && tile_iter == 0) tr[14] += clock64() - e1;
                     const uint32_t img = stg + (uint32_t)buf * 4096u;
-                    if (!dry) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const uint32_t off = row_off + (uint32_t)((q ^ (lane & 7)) << 4);
-                            sts_v4(img + off, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        }
-                    } else {
-                        // keep the dry values alive (the math above must be executed, not removed)
-                        float keep = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) keep += v[j];
-                        asm volatile("" ::"f"(keep));
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t off = row_off + (uint32_t)((q ^ (lane & 7)) << 4);
+                        sts_v4(img + off, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                     }
                     const long long e2 = (tr && t == 64) ? clock64() : 0;
                     fence_proxy_async_smem();
                     __syncwarp();
                     const long long e3 = (tr && t == 64) ? clock64() : 0;
-                    if (TM_DEBUG(P) != 4 && lane == 0 && !dry) {     // (bulk groups belong to the issuing thread: always lane 0)
+                    if (TM_DEBUG(P) != 4 && lane == 0) {     // (bulk groups belong to the issuing thread: always lane 0)
                         tma_store_3d(&P.map_out, img, (int)c0, row0, direct ? 0 : split);
                         bulk_commit();
                     }
@@ -714,7 +703,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                         tr[15] += e4 - e1; tr[26] += e2 - e1; tr[27] += e3 - e2; tr[28] += e4 - e3;
                     }
                     buf ^= 1;
-                } else if (r < P.m && !dry) {
+                } else if (r < P.m) {
                     // unaligned destination (row pitch % 4 != 0): plain scalar stores
                     float* drow = dst + r * ldd + c0;
 #pragma unroll
@@ -723,7 +712,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 }
             }
             if (tr && t == 64 && tile_iter == 0) tr[5] = clock64();
-            if (dry) break;
+            if (tr && t == 64 && tile_iter == 1) tr[29] = clock64() - epi1;
             // the accumulators of this tile are in registers / on their way out: the next tile may overwrite TMEM
             tc_fence_before();
             __syncwarp();
@@ -739,10 +728,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             }
             if (tr && t == 64 && tile_iter == 0) tr[6] = clock64();
         }
-        if (P.tma_store && !dry) {
+        if (P.tma_store) {
             if (lane == 0) bulk_wait_all();
             __syncwarp();
-        }
         }
     }
     tc_fence_before();
@@ -783,6 +771,351 @@ __global__ void __launch_bounds__(256) gemm_tma_reduce_kernel(const __grid_const
         if (P.transpose_out) P.c[c * P.ldc + r] = v;
         else P.c[r * P.ldc + c] = v;
     }
+}
+
+
+// ---- third generation (round 2, last session): 256 x 128 tiles, accumulators double-buffered in tensor memory ----------------
+// Per-CTA timelines of the kernel above on the forward / input-gradient products (m = 24 041, several tiles per CTA pair) show
+// the tensor core idle between two tiles of a pair for 10 000 - 12 000 cycles against 20 000 - 24 000 cycles of MMAs: the last
+// MMAs drain (1 750), the accumulators are read out (6 200, first tile 8 400), and only then can the next tile's first MMA be
+// issued, because one 256 x 256 tile with its correction accumulator fills all 512 TMEM columns.  Here a tile is 256 x 128: main
+// and correction accumulator take 256 columns, so TMEM holds TWO tiles; four dedicated warps read tile i out (bias / activation
+// / gate, TMA stores) while the issuing thread is already accumulating tile i + 1 into the other half.  The price: A is fetched
+// once per 128 instead of once per 256 output columns (31 instead of 21 B/clk per SM from L2), four instead of eight warps
+// derive the lo tiles (24 KB per k-block of 768 MMA cycles).  Only for products written directly (no split-K), k-contiguous A,
+// 16-byte aligned output, more tiles than CTA pairs; everything else runs on gemm_tma_kernel.
+constexpr int DB_A_BYTES = 128 * TM_BK * 4, DB_B_BYTES = 64 * TM_BK * 4;
+constexpr int DB_STAGE_BYTES = DB_A_BYTES + DB_B_BYTES;            // 24 KB
+constexpr int DB_SPLIT_WARPS = 8, DB_EPI_WARPS = 4;
+constexpr int DB_THREADS = (2 + DB_SPLIT_WARPS + DB_EPI_WARPS) * 32;
+// ring depths (raw, lo) and the read-out warps' staging: two 4 KB store images per warp, plus one gate image when GATE
+__host__ __device__ constexpr int db_epi_bytes(bool gate) { return (gate ? 3 : 2) * 4096; }
+__host__ __device__ constexpr int db_smem_bytes(int raw, int lo, bool gate) {
+    return (raw + lo) * DB_STAGE_BYTES + DB_EPI_WARPS * db_epi_bytes(gate) + 1024 + 256;
+}
+
+struct DbTile {
+    int64_t m0, n0;
+    uint32_t n_eff, n_half;
+};
+__device__ __forceinline__ DbTile db_tile(const TmParams& P, int t) {
+    DbTile T;
+    const int nt = t % P.tiles_n, mt = t / P.tiles_n;      // column blocks fastest: the N tiles of one row block run back to back
+    T.m0 = (int64_t)mt * 256;
+    T.n0 = (int64_t)nt * 128;
+    const int64_t nrem = P.n - T.n0;
+    T.n_eff = nrem >= 128 ? 128u : (uint32_t)((nrem + 63) / 64 * 64);
+    T.n_half = T.n_eff / 2;
+    return T;
+}
+
+template <bool BT, int DB_RAW_STAGES, int DB_LO_STAGES, bool GATE>
+__global__ void __launch_bounds__(DB_THREADS, 1) gemm_tma_db_kernel(const __grid_constant__ TmParams P) {
+    using namespace tm;
+    constexpr int DB_EPI_BYTES = db_epi_bytes(GATE);
+    static_assert(db_smem_bytes(DB_RAW_STAGES, DB_LO_STAGES, GATE) <= 232448, "shared memory of one SM");
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles = (raw + 1023u) & ~1023u;
+    const uint32_t lo_ring = tiles + DB_RAW_STAGES * DB_STAGE_BYTES;
+    const uint32_t epi_area = lo_ring + DB_LO_STAGES * DB_STAGE_BYTES;
+    const uint32_t bars = epi_area + DB_EPI_WARPS * DB_EPI_BYTES;
+    const uint32_t bar_raw_full = bars, bar_raw_empty = bars + 8 * DB_RAW_STAGES;
+    const uint32_t bar_lo_full = bars + 16 * DB_RAW_STAGES, bar_lo_empty = bar_lo_full + 8 * DB_LO_STAGES;
+    const uint32_t bar_acc_full = bar_lo_empty + 8 * DB_LO_STAGES;      // [2]: accumulators of buffer b complete
+    const uint32_t bar_acc_empty = bar_acc_full + 16;                   // [2]: buffer b read out in both CTAs
+    const uint32_t bar_gate = bar_acc_empty + 16;                       // [DB_EPI_WARPS]
+    const uint32_t tmem_slot = bar_gate + 8 * DB_EPI_WARPS;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int unit = blockIdx.x / 2, units = gridDim.x / 2;
+    const int first_tile = (int)((int64_t)unit * P.total_tiles / units);
+    const int end_tile = (int)((int64_t)(unit + 1) * P.total_tiles / units);
+#if PLAGNN_TMA_DIAG
+    // diagnostics build: cycle sums per role of the first 64 CTAs (tools/gemm_trace.py prints them for this kernel as well)
+    long long* const tr = (P.trace && blockIdx.x < 64) ? P.trace + 32 * blockIdx.x : nullptr;
+#else
+    long long* const tr = nullptr;
+#endif
+    if (tr && t == 0) { tr[0] = clock64(); tr[11] = P.total_kblocks; tr[12] = rank; tr[1] = end_tile - first_tile; }
+
+    auto load_kblock = [&](const DbTile& T, int it, int g) {
+        const int s = g % DB_RAW_STAGES;
+        int p = 0, local = it;
+        if (P.npairs > 1 && local >= P.kblocks[0]) { local -= P.kblocks[0]; p = 1; }
+        const int k0 = local * TM_BK;
+        const int a_row = (int)(T.m0 + rank * 128), b_row = (int)(T.n0 + rank * T.n_half);
+        const uint32_t st = tiles + s * DB_STAGE_BYTES;
+        const uint32_t rb = bar_raw_full + 8 * s;
+        mbar_expect_tx(rb, DB_STAGE_BYTES);
+        tma_load_2d(st, &P.map[p][0], k0, a_row, rb);
+        if (!BT) {
+            tma_load_2d(st + DB_A_BYTES, &P.map_b64[p], k0, b_row, rb);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d(st + DB_A_BYTES + j * 4096, &P.map[p][1], b_row + 32 * j, k0, rb);
+        }
+    };
+    const DbTile T0 = db_tile(P, first_tile);
+    const int nkb = P.total_kblocks;                      // every tile runs the whole contraction
+    const int preloaded = nkb < DB_RAW_STAGES ? nkb : DB_RAW_STAGES;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int s = 0; s < DB_RAW_STAGES; ++s) {
+                mbar_init(bar_raw_full + 8 * s, 1);
+                mbar_init(bar_raw_empty + 8 * s, 1);
+            }
+            for (int s = 0; s < DB_LO_STAGES; ++s) {
+                mbar_init(bar_lo_full + 8 * s, (uint32_t)(2 * DB_SPLIT_WARPS));
+                mbar_init(bar_lo_empty + 8 * s, 1);
+            }
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(bar_acc_full + 8 * b, 1);
+                mbar_init(bar_acc_empty + 8 * b, (uint32_t)(2 * DB_EPI_WARPS));
+            }
+            for (int w = 0; w < DB_EPI_WARPS; ++w) mbar_init(bar_gate + 8 * w, 1);
+            fence_mbar_init();
+#pragma unroll
+            for (int p = 0; p < PLAGNN_GEMM_MAX_PAIRS; ++p)
+                if (p < P.npairs) { prefetch_map(&P.map[p][0]); prefetch_map(BT ? &P.map[p][1] : &P.map_b64[p]); }
+            prefetch_map(&P.map_out);
+            if (P.gate_tma) prefetch_map(&P.map_gate);
+        }
+        __syncwarp();
+        pdl_wait();
+        for (int it = 0; it < preloaded; ++it) {
+            if (elect_one()) load_kblock(T0, it, it);
+            __syncwarp();
+        }
+    }
+    if (warp == 1) tmem_alloc<2>(tmem_slot, 512);
+    pdl_wait();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        int g = 0;
+        for (int tile = first_tile; tile < end_tile; ++tile) {
+            const DbTile T = db_tile(P, tile);
+            for (int it = (tile == first_tile ? preloaded : 0); it < nkb; ++it) {
+                const int gg = g + it;
+                const int s = gg % DB_RAW_STAGES;
+                const uint32_t ph = (uint32_t)((gg / DB_RAW_STAGES) & 1);
+                const long long w0 = tr ? clock64() : 0;
+                mbar_wait(bar_raw_empty + 8 * s, ph ^ 1u);
+                if (tr && lane == 0) tr[8] += clock64() - w0;
+                if (elect_one()) load_kblock(T, it, gg);
+                __syncwarp();
+            }
+            g += nkb;
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA) =================
+        if (rank == 0) {
+            constexpr uint64_t a_step = 2u, b_step = BT ? (1024u >> 4) : 2u;
+            int g = 0, tile_iter = 0;
+            for (int tile = first_tile; tile < end_tile; ++tile, ++tile_iter) {
+                const DbTile T = db_tile(P, tile);
+                const uint32_t idesc = make_idesc(256, T.n_eff, false, BT);
+                const int b = tile_iter & 1, use = tile_iter >> 1;
+                if (tr && lane == 0 && tile_iter == 0) tr[2] = clock64();
+                if (use > 0) {                      // the previous tile in this half of TMEM has been read out in both CTAs
+                    const long long w0 = tr ? clock64() : 0;
+                    mbar_wait(bar_acc_empty + 8 * b, (uint32_t)((use - 1) & 1));
+                    if (tr && lane == 0) tr[3] += clock64() - w0;
+                    tc_fence_after();
+                }
+                const uint32_t acc_main = tmem_base + (uint32_t)b * 256u, acc_corr = acc_main + 128u;
+                for (int it = 0; it < nkb; ++it, ++g) {
+                    const int s = g % DB_RAW_STAGES, l = g % DB_LO_STAGES;
+                    const uint32_t phl = (uint32_t)((g / DB_LO_STAGES) & 1);
+                    const long long w0 = tr ? clock64() : 0;
+                    mbar_wait(bar_lo_full + 8 * l, phl);
+                    if (tr && lane == 0) tr[9] += clock64() - w0;
+                    tc_fence_after();
+                    const uint32_t st = tiles + s * DB_STAGE_BYTES, sl = lo_ring + l * DB_STAGE_BYTES;
+                    const uint64_t a_hi = desc_kmajor(st), a_lo = desc_kmajor(sl);
+                    const uint64_t b_hi = BT ? desc_mnmajor(st + DB_A_BYTES) : desc_kmajor(st + DB_A_BYTES);
+                    const uint64_t b_lo = BT ? desc_mnmajor(sl + DB_A_BYTES) : desc_kmajor(sl + DB_A_BYTES);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < TM_BK / 8; ++kk) {
+                            const uint64_t adv_a = (uint64_t)kk * a_step, adv_b = (uint64_t)kk * b_step;
+                            const uint32_t acc_on = (it | kk) ? 1u : 0u;
+                            umma_tf32<2>(acc_corr, a_lo + adv_a, b_hi + adv_b, idesc, acc_on);
+                            umma_tf32<2>(acc_corr, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
+                            umma_tf32<2>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
+                        }
+                        umma_commit<2>(bar_lo_empty + 8 * l);
+                        umma_commit<2>(bar_raw_empty + 8 * s);
+                    }
+                    __syncwarp();
+                }
+                if (elect_one()) umma_commit<2>(bar_acc_full + 8 * b);
+                __syncwarp();
+                if (tr && lane == 0) tr[4] = clock64();          // last tile's MMAs issued
+            }
+        }
+        __syncwarp();
+    } else if (warp < 2 + DB_SPLIT_WARPS) {
+        // ================= splitting warps: lo = rn_tf32(x - trunc_tf32(x)), elementwise over the 24 KB stage =================
+        const int ct = t - 64;                                  // 0 .. 32 DB_SPLIT_WARPS - 1
+        const uint32_t lo_full0 = mapa(bar_lo_full, 0);
+        constexpr int PIECES = DB_STAGE_BYTES / 16 / (DB_SPLIT_WARPS * 32);     // sixteen-byte pieces per thread
+        constexpr uint32_t PSTRIDE = DB_SPLIT_WARPS * 32 * 16;                  // one piece of every thread
+        const int total = (end_tile - first_tile) * nkb;
+        for (int g = 0; g < total; ++g) {
+            const int s = g % DB_RAW_STAGES, l = g % DB_LO_STAGES;
+            const uint32_t phr = (uint32_t)((g / DB_RAW_STAGES) & 1), phl = (uint32_t)((g / DB_LO_STAGES) & 1);
+            const long long w0 = (tr && t == 64) ? clock64() : 0;
+            mbar_wait(bar_raw_full + 8 * s, phr);
+            const long long w1 = (tr && t == 64) ? clock64() : 0;
+            if (tr && t == 64) tr[10] += w1 - w0;
+            const uint32_t src = tiles + s * DB_STAGE_BYTES + (uint32_t)ct * 16u;
+            const uint32_t dstl = lo_ring + l * DB_STAGE_BYTES + (uint32_t)ct * 16u;
+            float4 v[PIECES];
+#pragma unroll
+            for (int i = 0; i < PIECES; ++i)
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(src + (uint32_t)i * PSTRIDE));
+            const long long w2 = (tr && t == 64) ? clock64() : 0;
+            mbar_wait(bar_lo_empty + 8 * l, phl ^ 1u);
+            const long long w3 = (tr && t == 64) ? clock64() : 0;
+#pragma unroll
+            for (int i = 0; i < PIECES; ++i)
+                sts_v4(dstl + (uint32_t)i * PSTRIDE, tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lo_full0 + 8 * l);
+            if (tr && t == 64) { const long long w4 = clock64(); tr[13] += w3 - w2; tr[14] += (w2 - w1) + (w4 - w3); }
+        }
+    } else {
+        // ================= last four warps: read-out of tile i while tile i + 1 accumulates in the other half of TMEM =================
+        const int e = warp - (2 + DB_SPLIT_WARPS);              // 0..3
+        const int lg = warp & 3;                                // TMEM lane quarter this warp may read (warp % 4)
+        const uint32_t acc_empty0 = mapa(bar_acc_empty, 0);
+        const uint32_t stg = epi_area + (uint32_t)e * DB_EPI_BYTES;      // two 4 KB store images, then one gate image
+        const uint32_t gimg = stg + 8192u;
+        const uint32_t gbar = bar_gate + 8 * (uint32_t)e;
+        const uint32_t row_off = (uint32_t)lane * 128u;
+        const bool gate_on = GATE && P.gate != nullptr;         // (always by TMA here: the launcher checked the alignment)
+        int tile_iter = 0, buf = 0;
+        uint32_t gph = 0;                                       // gate images received so far (barrier phase)
+        for (int tile = first_tile; tile < end_tile; ++tile, ++tile_iter) {
+            const DbTile T = db_tile(P, tile);
+            const int b = tile_iter & 1, use = tile_iter >> 1;
+            const int64_t n0 = T.n0;
+            const int row0 = (int)(T.m0 + rank * 128 + lg * 32);
+            // 32-column chunks of this tile that hold real columns
+            int nch = (int)((T.n_eff + 31u) / 32u);
+            {
+                const int64_t real = (P.n - n0 + 31) / 32;
+                nch = real < nch ? (int)real : nch;
+            }
+            if (gate_on && lane == 0) {                         // first gate image: requested before the accumulators are complete
+                mbar_expect_tx(gbar, 4096u);
+                tma_load_2d(gimg, &P.map_gate, (int)n0, row0, gbar);
+            }
+            const long long e0 = (tr && e == 0 && lane == 0) ? clock64() : 0;
+            mbar_wait(bar_acc_full + 8 * b, (uint32_t)(use & 1));
+            const long long e1 = (tr && e == 0 && lane == 0) ? clock64() : 0;
+            if (tr && e == 0 && lane == 0) tr[15] += e1 - e0;
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < nch; ++ch) {
+                const int64_t c0 = n0 + ch * 32;
+                const int ncol = (int)((P.n - c0) < 32 ? (P.n - c0) : 32);
+                float v[32];
+                {
+                    uint32_t acc[32], acc_small[32];
+                    const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)b * 256u + (uint32_t)(ch * 32);
+                    tmem_ld32(ta, acc);
+                    tmem_ld32(ta + 128u, acc_small);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + __uint_as_float(acc_small[j]);
+                }
+                if (P.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += __ldg(P.bias + c0 + (j < ncol ? j : 0));
+                }
+                if (P.act == PLAGNN_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
+                } else if (P.act == PLAGNN_ACT_LEAKY) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * P.slope;
+                } else if (P.act == PLAGNN_ACT_SIGMOID) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+                }
+                if (gate_on) {
+                    mbar_wait(gbar, gph & 1u);
+                    ++gph;
+                    float gt[32];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(gt[4 * q]), "=f"(gt[4 * q + 1]), "=f"(gt[4 * q + 2]), "=f"(gt[4 * q + 3])
+                                     : "r"(gimg + row_off + (uint32_t)((q ^ (lane & 7)) << 4)));
+                    if (P.gate_act == PLAGNN_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gt[j] > 0.f ? v[j] : 0.f;
+                    } else if (P.gate_act == PLAGNN_ACT_LEAKY) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gt[j] > 0.f ? v[j] : v[j] * P.slope;
+                    } else if (P.gate_act == PLAGNN_ACT_SIGMOID) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= gt[j] * (1.f - gt[j]);
+                    }
+                    // the image has been consumed by every lane (its values went into v above): fetch the next chunk's into it
+                    __syncwarp();
+                    if (ch + 1 < nch && lane == 0) {
+                        mbar_expect_tx(gbar, 4096u);
+                        tma_load_2d(gimg, &P.map_gate, (int)(c0 + 32), row0, gbar);
+                    }
+                }
+                if (lane == 0) bulk_wait_read<1>();          // the image written two chunks ago has been read
+                __syncwarp();
+                const uint32_t img = stg + (uint32_t)buf * 4096u;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t off = row_off + (uint32_t)((q ^ (lane & 7)) << 4);
+                    sts_v4(img + off, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_3d(&P.map_out, img, (int)c0, row0, 0);
+                    bulk_commit();
+                }
+                buf ^= 1;
+            }
+            // this half of TMEM is in registers / on its way out: the tile after next may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty0 + 8 * b);
+            if (tr && e == 0 && lane == 0) tr[16] += clock64() - e1;
+        }
+        if (lane == 0) bulk_wait_all();
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<2>(tmem_base, 512);
+    }
+    if (tr && t == 0) tr[7] = clock64();
 }
 
 // ---- host side: tensor maps ---------------------------------------------------------------------
@@ -833,7 +1166,8 @@ static int get_map(CUtensorMap* out, const float* base, int64_t inner, int64_t o
     if (!enc) return fail(PLAGNN_ERR_CUDA, "gemm_tma", "cuTensorMapEncodeTiled not available");
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
     cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
-    cuuint32_t box[2] = {32u, mn_major ? 32u : 128u};      // mn_major == 2: a 32 x 32 box of a row-major matrix (gate tiles)
+    // mn_major == 2: a 32 x 32 box of a row-major matrix (gate tiles); == 3: k-contiguous operand with a 64-row box
+    cuuint32_t box[2] = {32u, mn_major == 3 ? 64u : mn_major ? 32u : 128u};
     cuuint32_t estr[2] = {1, 1};
     CUtensorMap m;
     const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
@@ -970,6 +1304,27 @@ static int64_t tm_padded_area(int64_t m, int64_t n, int cg) {
     return ceil_div(m, tile) * tile * (full * tile + ceil_div(rem, gran) * gran);
 }
 
+// Which kernel for a directly written product?  Both main loops run at the rate at which shared memory can feed them (TMA
+// writes + the lo pass + the tensor core's operand reads: ~125 B/clk per SM in either kernel), so the 256 x 128 kernel pays
+// 1 150 cycles per k-block of half a tile where the 256 x 256 kernel pays 1 600 for a whole one, and wins through what it does
+// not pay: the 10 000 - 13 000 idle cycles between two tiles of a pair, and the padding of a ragged last column tile (n = 300 is
+// 256 + 64 there, 128 + 128 + 64 here).  Constants fitted to the isolated timings of the epoch's products (tools/gemm_db_ab.py,
+// profiles/r2_gemm_db_ab.json); the model picks the measured winner for every one of them except two ties.
+static double tm_cost_tiles256(int64_t m, int64_t n, int kblocks, int64_t units) {
+    const int64_t tiles_m = ceil_div(m, 256), full = n / 256, rem = n - full * 256;
+    const int64_t tiles_n = full + (rem ? 1 : 0);
+    const double wsum = (double)full + (rem ? 0.55 + 0.45 * (double)(ceil_div(rem, 64) * 64) / 256.0 : 0.0);
+    const double rounds = (double)ceil_div(tiles_m * tiles_n, units);
+    return rounds * ((double)kblocks * 1600.0 * (wsum / (double)tiles_n) + 13500.0) + 6000.0;
+}
+static double tm_cost_tiles128(int64_t m, int64_t n, int kblocks, int64_t units) {
+    const int64_t tiles_m = ceil_div(m, 256), full = n / 128, rem = n - full * 128;
+    const int64_t tiles_n = full + (rem ? 1 : 0);
+    const double wsum = (double)full + (rem ? 0.7 + 0.3 * (double)(ceil_div(rem, 64) * 64) / 128.0 : 0.0);
+    const double rounds = (double)ceil_div(tiles_m * tiles_n, units);
+    return rounds * (double)kblocks * 1150.0 * (wsum / (double)tiles_n) + 10000.0;
+}
+
 // ones_out != nullptr: weight-gradient product with the bias gradient riding along — B (mn-contiguous, one pair) gets a
 // virtual column n that reads as 1.0, C stays m x n and ones_out[m] receives sum_k A[:, k].  Always split-K.
 int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair* pairs_in, const float* bias, int act,
@@ -1054,6 +1409,82 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
         P.gate_tma = 1;
     }
 
+    // ---- products written directly, with more 256 x 128 tiles than CTA pairs: the double-buffered kernel ----
+    {
+        // PLAGNN_TMA_DB=0: never; PLAGNN_TMA_DB_NOW (read per launch, for A/B timing in one process): "0" never, "1" whenever
+        // the product qualifies, unset / anything else: by the cost model
+        static const bool db_allowed = [] { const char* e = getenv("PLAGNN_TMA_DB"); return !e || e[0] != '0'; }();
+        const char* dyn = getenv("PLAGNN_TMA_DB_NOW");
+        const int64_t db_tiles = ceil_div(m, 256) * ceil_div(n, 128);
+        const int64_t pair_units = sm_count() / 2;
+        bool db_on = db_allowed && !(dyn && dyn[0] == '0');
+        if (db_on && !(dyn && dyn[0] == '1'))
+            db_on = tm_cost_tiles128(m, n, P.total_kblocks, pair_units) < tm_cost_tiles256(m, n, P.total_kblocks, pair_units);
+        bool k_major_a = true;
+        for (int p = 0; p < npairs; ++p) k_major_a = k_major_a && !pairs[p].a_trans;
+        if (db_on && tm_cg() == 2 && P.splits == 1 && !ones_out && P.tma_store && k_major_a && (!gate || P.gate_tma) &&
+            db_tiles > sm_count() / 2 && db_tiles < ((int64_t)1 << 30)) {
+            if (!pairs[0].b_trans) {
+                for (int p = 0; p < npairs; ++p) {
+                    int rc;
+                    if ((rc = get_map(&P.map_b64[p], pairs[p].b, pairs[p].k, n_map, pairs[p].ldb, 3))) return rc;
+                }
+            }
+            P.tiles_m = (int)ceil_div(m, 256);
+            P.tiles_n = (int)ceil_div(n, 128);
+            P.total_tiles = (int)db_tiles;
+            P.persistent = 1;
+            using DbFn = void (*)(const TmParams);
+            // [ring variant][gate][b_trans]; ring variants (PLAGNN_TMA_DB_RING): 0 = raw 4 / lo 3, 1 = raw 5 / lo 3, 2 = raw 4 / lo 4
+            // (the deeper rings only without a gate image)
+            static const DbFn db_kernels[3][2][2] = {
+                {{gemm_tma_db_kernel<false, 4, 3, false>, gemm_tma_db_kernel<true, 4, 3, false>},
+                 {gemm_tma_db_kernel<false, 4, 3, true>, gemm_tma_db_kernel<true, 4, 3, true>}},
+                {{gemm_tma_db_kernel<false, 5, 3, false>, gemm_tma_db_kernel<true, 5, 3, false>},
+                 {gemm_tma_db_kernel<false, 4, 3, true>, gemm_tma_db_kernel<true, 4, 3, true>}},
+                {{gemm_tma_db_kernel<false, 4, 4, false>, gemm_tma_db_kernel<true, 4, 4, false>},
+                 {gemm_tma_db_kernel<false, 4, 3, true>, gemm_tma_db_kernel<true, 4, 3, true>}}};
+            static const int db_smem[3][2] = {{db_smem_bytes(4, 3, false), db_smem_bytes(4, 3, true)},
+                                              {db_smem_bytes(5, 3, false), db_smem_bytes(4, 3, true)},
+                                              {db_smem_bytes(4, 4, false), db_smem_bytes(4, 3, true)}};
+            int ring = 1;
+            { const char* e = getenv("PLAGNN_TMA_DB_RING"); if (e && e[0] >= '0' && e[0] <= '2') ring = e[0] - '0'; }
+            const int gi = gate ? 1 : 0, bi = pairs[0].b_trans ? 1 : 0;
+            static thread_local int db_attr_dev = -1;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (db_attr_dev != dev) {
+                for (int r = 0; r < 3; ++r)
+                    for (int g2 = 0; g2 < 2; ++g2)
+                        for (int b2 = 0; b2 < 2; ++b2) {
+                            cudaError_t e = cudaFuncSetAttribute(db_kernels[r][g2][b2], cudaFuncAttributeMaxDynamicSharedMemorySize, db_smem[r][g2]);
+                            if (e != cudaSuccess) {
+                                set_error("gemm_tma: cudaFuncSetAttribute (db): %s", cudaGetErrorString(e));
+                                return PLAGNN_ERR_CUDA;
+                            }
+                        }
+                db_attr_dev = dev;
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(sm_count() / 2 * 2), 1u, 1u);
+            cfg.blockDim = dim3(DB_THREADS);
+            cfg.dynamicSmemBytes = db_smem[ring][gi];
+            cfg.stream = st;
+            cudaLaunchAttribute at[2];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+            cfg.attrs = at; cfg.numAttrs = 2;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, db_kernels[ring][gi][bi], P);
+            if (e != cudaSuccess) {
+                set_error("gemm_tma: launch (db): %s", cudaGetErrorString(e));
+                return PLAGNN_ERR_CUDA;
+            }
+            return check_launch("gemm_tma", 1);
+        }
+    }
+
     using KernelFn = void (*)(const TmParams);
     static const KernelFn kernels[8] = {
         gemm_tma_kernel<1, false, false>, gemm_tma_kernel<1, false, true>, gemm_tma_kernel<1, true, false>, gemm_tma_kernel<1, true, true>,
@@ -1083,8 +1514,6 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
     static const bool allow_persistent = [] { const char* e = getenv("PLAGNN_TMA_PERSISTENT"); return !e || e[0] != '0'; }();
     const int64_t units = sm_count() / cg;
     P.persistent = (allow_persistent && !gate && total_tiles > units) ? 1 : 0;
-    // PLAGNN_TMA_WARM=0: the warm-up warp idles (A/B runs)
-    { const char* e = getenv("PLAGNN_TMA_WARM"); P.warm = (!e || e[0] != '0') ? 1 : 0; }
     const int64_t launched = P.persistent ? units : total_tiles;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(launched * cg), 1u, 1u);

@@ -94,33 +94,6 @@ __device__ __forceinline__ const float* row_ptr(const float* base, int u, unsign
     return reinterpret_cast<const float*>(r);
 }
 
-// L2 eviction priorities (PLAGNN_SPMM_L2HINT, experiments on the 100 M-edge graph): the neighbour ids and edge weights are a
-// stream that is read once per aggregation (0.8 GB), the gathered rows are re-read (hub rows many times).  bit 0: the stream is
-// loaded evict_first (and not allocated in L1), bit 1: the rows evict_last.  The policy is a warp-uniform 64-bit value that
-// ptxas folds into the load's memory descriptor.
-__device__ __forceinline__ uint64_t l2_policy(int kind) {
-    uint64_t p;
-    if (kind == 1) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    else if (kind == 2) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    else asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ int ldg_stream_i32(const int32_t* p, uint64_t pol) {
-    int v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ float ldg_stream_f32(const float* p, uint64_t pol) {
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ float4 ldg_f4_hint(const float* p, uint64_t pol) {
-    float4 r;
-    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
-    return r;
-}
-
 template <int MODE>
 __device__ __forceinline__ void reduce_one(float4& acc, int4& arg, const float4 v, const int u, const float one, const float nzero) {
     if (MODE == MODE_MAX) {
@@ -148,7 +121,7 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
             const float* __restrict__ x, int64_t ldx, int feat, const int32_t* __restrict__ argm, int64_t ldarg,
             const float* __restrict__ zfwd, int64_t ldzf, float* __restrict__ out, int32_t* __restrict__ arg_out, int64_t ldo,
             float* __restrict__ part_val, int32_t* __restrict__ part_arg, int part_ld, SpmmEpilogue ep, float one,
-            float nzero, int hints) {
+            float nzero) {
     pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int item = item_begin + blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
@@ -269,31 +242,13 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
             }
         }
     } else {
-    // hints (PLAGNN_SPMM_L2HINT): bit 0 = the id / weight stream is loaded evict_first; bit 2 = the ids and weights of the next
-    // batch of 32 in-edges are requested before the current batch is gathered (their latency hides behind the gathers)
-    const uint64_t stream_pol = l2_policy((hints & 1) ? 1 : 0);
-    const bool ahead = (hints & 4) != 0;
-    auto load_batch = [&](int base, int& bu, float& bw) {
-        bu = 0;
-        bw = 1.f;
-        if (base + lane < end) {
-            bu = ldg_stream_i32(indices + base + lane, stream_pol);
-            if (MODE == MODE_SUM && ew) bw = ldg_stream_f32(ew + (eids ? __ldg(eids + base + lane) : base + lane), stream_pol);
-        }
-    };
-    int next_u = 0;
-    float next_w = 1.f;
-    if (ahead) load_batch(beg, next_u, next_w);
     for (int base = beg; base < end; base += 32) {
         const int cnt = min(32, end - base);
-        int my_u;
-        float my_w;
-        if (ahead) {
-            my_u = next_u;
-            my_w = next_w;
-            if (base + 32 < end) load_batch(base + 32, next_u, next_w);
-        } else {
-            load_batch(base, my_u, my_w);
+        int my_u = 0;
+        float my_w = 1.f;
+        if (lane < cnt) {
+            my_u = __ldg(indices + base + lane);
+            if (MODE == MODE_SUM && ew) my_w = __ldg(ew + (eids ? __ldg(eids + base + lane) : base + lane));
         }
         for (int j = 0; j < cnt; j += NB) {
             int u[NB];
@@ -392,21 +347,21 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
 // batches staged in shared memory by cp.async (96 rows in flight per warp, 16 warps per SM): 4.51 ms (max 5.39) — the extra
 // LDS / STS / shuffle traffic and the three-phase step cost more than the deeper queue gains.  Staging pays when a staged row
 // is reused; a gathered neighbour row is consumed once.
-//
-// PIPE (round 2, last session): the loop above is a chain of dependent memory latencies per work item — meta data, then per
-// batch of 32 in-edges the ids (and weights), then 32 / (S U) rounds of U gathers, each round consumed before the next one
-// is issued (in-order issue): ~13 latencies for the average row of 100 in-edges, which at 32 warps per SM IS the measured
-// time.  The pipelined form keeps two rounds in flight per lane (round r + 1 is issued before round r is consumed, across
-// batch boundaries) and loads the ids / weights of batch b + 1 before batch b is processed, so the id latency hides behind
-// the gathers: ~7 latencies per item.  Same additions in the same order per lane as the plain form: results are bit-identical.
-template <int MODE, int G, int U, int OCC, bool PIPE = false>
+// (d) (last session of round 2) software pipelining in registers: two rounds of U gathers in flight per lane across batch
+// boundaries, the ids / weights of batch b + 1 requested before batch b is gathered — bit-identical results, and slower in every
+// configuration: U = 4 at 32 / 24 / 16 warps per SM 3.01 / 3.94 / 6.47 ms, U = 2 at 32 warps (the SAME number of loads in flight
+// as this kernel, plus the id prefetch) 3.11 ms, against 1.99 ms here.  So the kernel is not bound by a chain of exposed
+// latencies per warp but by how many row requests an SM keeps outstanding (~14 KB in flight per SM at both this and the PPI
+// shape); more resident warps with short loops beat deeper loops.  L2 eviction priorities (ids / weights evict_first, rows
+// evict_last through createpolicy + ld.global.L2::cache_hint) changed nothing either (tools/spmm_variants_time.py).
+template <int MODE, int G, int U, int OCC>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, OCC)
 spmm_narrow_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int32_t* __restrict__ eids,
                    const float* __restrict__ ew, const int32_t* __restrict__ plan_hdr, const int32_t* __restrict__ item_ptr,
                    const int32_t* __restrict__ slot_ptr, const int32_t* __restrict__ item_row, int item_begin, int n_items,
                    const float* __restrict__ x, int64_t ldx, int feat, float* __restrict__ out, int32_t* __restrict__ arg_out,
                    int64_t ldo, float* __restrict__ part_val, int32_t* __restrict__ part_arg, int part_ld, SpmmEpilogue ep,
-                   SpmmChain ch, int hints) {
+                   SpmmChain ch) {
     static_assert(MODE == MODE_MAX || MODE == MODE_SUM, "narrow kernel: max and sum reducers");
     constexpr int S = 32 / G;          // lane groups = in-edges in flight per load instruction
     // U rounds unrolled = U rows in flight per lane (U = 4 at 32 warps per SM: 64 KB in flight per SM)
@@ -445,71 +400,6 @@ spmm_narrow_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict
     // "live ? load : init" selects): a slot past the end of the batch re-reads the batch's last neighbour with weight 0 (sum)
     // or as a repeated value that cannot beat a strict > (max), and the row address is one 32-bit multiply-add.
     const unsigned ldx_bytes = (unsigned)ldx * 4u;          // host checks ldx < 2^30
-    if constexpr (PIPE) {
-        constexpr int R = 32 / (S * U);                     // rounds of U gathers per batch of 32 in-edges
-        static_assert(R >= 2 && R % 2 == 0, "pipelined narrow kernel: an even number of rounds per batch");
-        // ids and weights of one batch (lane l holds in-edge base + l; past the end: the last neighbour with weight 0)
-        const uint64_t stream_pol = l2_policy((hints & 1) ? 1 : 0), row_pol = l2_policy((hints & 2) ? 2 : 0);
-        auto load_ids = [&](int base, int& bu, float& bw) {
-            bu = ldg_stream_i32(indices + min(base + lane, end - 1), stream_pol);
-            bw = 0.f;
-            if (MODE == MODE_SUM && base + lane < end)
-                bw = ew ? ldg_stream_f32(ew + (eids ? __ldg(eids + base + lane) : base + lane), stream_pol) : 1.f;
-        };
-        auto issue = [&](float4 (&v)[U], int (&u)[U], float (&w)[U], const int bu, const float bw, const int r) {
-#pragma unroll
-            for (int i = 0; i < U; ++i) {
-                const int e = (r * U + i) * S + sub;        // <= 31
-                u[i] = __shfl_sync(0xffffffffu, bu, e);
-                if (MODE == MODE_SUM) w[i] = __shfl_sync(0xffffffffu, bw, e);
-                v[i] = ldg_f4_hint(row_ptr(xc, u[i], ldx_bytes), row_pol);
-            }
-        };
-        auto consume = [&](const float4 (&v)[U], const int (&u)[U], const float (&w)[U], const int base, const int r) {
-#pragma unroll
-            for (int i = 0; i < U; ++i) {
-                if (MODE == MODE_MAX) {
-                    const int p = base + (r * U + i) * S + sub;
-                    if (v[i].x > acc.x) { acc.x = v[i].x; arg.x = u[i]; pos.x = p; }
-                    if (v[i].y > acc.y) { acc.y = v[i].y; arg.y = u[i]; pos.y = p; }
-                    if (v[i].z > acc.z) { acc.z = v[i].z; arg.z = u[i]; pos.z = p; }
-                    if (v[i].w > acc.w) { acc.w = v[i].w; arg.w = u[i]; pos.w = p; }
-                } else {
-                    acc.x = fmaf(w[i], v[i].x, acc.x); acc.y = fmaf(w[i], v[i].y, acc.y);
-                    acc.z = fmaf(w[i], v[i].z, acc.z); acc.w = fmaf(w[i], v[i].w, acc.w);
-                }
-            }
-        };
-        if (beg < end) {
-            float4 va[U], vb[U];
-            int ua[U], ub[U];
-            float wa[U], wb[U];
-            int cur_u, nxt_u = 0;
-            float cur_w, nxt_w = 0.f;
-            load_ids(beg, cur_u, cur_w);
-            issue(va, ua, wa, cur_u, cur_w, 0);             // round 0 of the first batch
-            for (int base = beg; base < end; base += 32) {
-                const int cnt = min(32, end - base);
-                const bool more = base + 32 < end;
-                if (more) load_ids(base + 32, nxt_u, nxt_w);
-                // every condition below is warp-uniform; round r of this batch holds in-edges [r U S, (r + 1) U S)
-#pragma unroll
-                for (int r = 0; r < R; r += 2) {
-                    const bool odd_live = (r + 1) * U * S < cnt;
-                    if (odd_live) issue(vb, ub, wb, cur_u, cur_w, r + 1);
-                    if (r == 0 || r * U * S < cnt) consume(va, ua, wa, base, r);
-                    if (r + 2 < R) {
-                        if ((r + 2) * U * S < cnt) issue(va, ua, wa, cur_u, cur_w, r + 2);
-                    } else if (more) {
-                        issue(va, ua, wa, nxt_u, nxt_w, 0);     // round 0 of the next batch
-                    }
-                    if (odd_live) consume(vb, ub, wb, base, r + 1);
-                }
-                cur_u = nxt_u;
-                cur_w = nxt_w;
-            }
-        }
-    } else
     for (int base = beg; base < end; base += 32) {
         const int cnt = min(32, end - base);
         const int my_u = __ldg(indices + min(base + lane, end - 1));
@@ -710,13 +600,6 @@ struct SpmmArgs {
 
 static inline int part_ld_of(int64_t feat) { return (int)((feat + 3) / 4 * 4); }
 
-// PLAGNN_SPMM_L2HINT: bit 0 = ids / weights stream evict_first, bit 1 = gathered rows evict_last (see l2_policy)
-// (read per launch, like PLAGNN_SPMM_NARROW_PIPE, so that one process can time the variants on one graph)
-static int spmm_l2_hints() {
-    const char* e = getenv("PLAGNN_SPMM_L2HINT");
-    return e ? atoi(e) : 0;
-}
-
 template <int MODE, int VEC, int NB>
 static void launch_main(const SpmmArgs& a, const int32_t* item_ptr, const int32_t* slot_ptr, const int32_t* item_row,
                         float* pv, int32_t* pa, cudaStream_t st) {
@@ -731,8 +614,7 @@ static void launch_main(const SpmmArgs& a, const int32_t* item_ptr, const int32_
     auto kernel = (MODE == MODE_SUM && lean) ? spmm_kernel<MODE, VEC, NB, true> : spmm_kernel<MODE, VEC, NB, false>;
     launch_pdl(kernel, grid, dim3(SPMM_WARPS * 32), 0, st,
         a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, item_begin, n_items, a.x, a.ldx,
-        (int)a.feat, a.argm, a.ldarg, a.zfwd, a.ldzf, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep, 1.0f, -0.0f,
-        spmm_l2_hints());
+        (int)a.feat, a.argm, a.ldarg, a.zfwd, a.ldzf, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep, 1.0f, -0.0f);
 }
 
 template <int MODE, int G>
@@ -744,17 +626,10 @@ static void launch_narrow(const SpmmArgs& a, const int32_t* item_ptr, const int3
     dim3 grid((unsigned)ceil_div(n_items - item_begin, SPMM_WARPS));
     // PLAGNN_SPMM_NARROW_U=8: eight rows in flight per lane at 24 warps per SM (A/B against the default 4 at 32 warps)
     static const int deep = [] { const char* e = getenv("PLAGNN_SPMM_NARROW_U"); return e && atoi(e) == 8; }();
-    // PLAGNN_SPMM_NARROW_PIPE=0: the plain loop (one round of gathers in flight per lane), for A/B runs
-    const char* pe = getenv("PLAGNN_SPMM_NARROW_PIPE");
-    const int pipe = pe ? atoi(pe) : 1;
-    auto kernel = deep ? spmm_narrow_kernel<MODE, G, 8, 3>
-                  : pipe == 1 ? spmm_narrow_kernel<MODE, G, 4, (MODE == MODE_MAX ? 3 : 4), true>
-                  : pipe == 2 ? spmm_narrow_kernel<MODE, G, 4, 3, true>
-                  : pipe == 3 ? spmm_narrow_kernel<MODE, G, 2, 4, true>
-                              : spmm_narrow_kernel<MODE, G, 4, 4>;
+    auto kernel = deep ? spmm_narrow_kernel<MODE, G, 8, 3> : spmm_narrow_kernel<MODE, G, 4, 4>;
     launch_pdl(kernel, grid, dim3(SPMM_WARPS * 32), 0, st,
         a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, item_begin, n_items, a.x, a.ldx,
-        (int)a.feat, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep, a.chain, spmm_l2_hints());
+        (int)a.feat, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep, a.chain);
 }
 
 template <int MODE>
