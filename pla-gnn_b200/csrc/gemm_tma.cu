@@ -948,8 +948,13 @@ __global__ void __launch_bounds__(DB_THREADS, 1) gemm_tma_db_kernel(const __grid
                     if (elect_one()) {
 #pragma unroll
                         for (int kk = 0; kk < TM_BK / 8; ++kk) {
+                            if (TM_DEBUG(P) == 2) break;
                             const uint64_t adv_a = (uint64_t)kk * a_step, adv_b = (uint64_t)kk * b_step;
                             const uint32_t acc_on = (it | kk) ? 1u : 0u;
+                            if (TM_DEBUG(P) == 7) {          // main product only (a third of the operand reads)
+                                umma_tf32<2>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
+                                continue;
+                            }
                             umma_tf32<2>(acc_corr, a_lo + adv_a, b_hi + adv_b, idesc, acc_on);
                             umma_tf32<2>(acc_corr, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
                             umma_tf32<2>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
@@ -982,16 +987,28 @@ __global__ void __launch_bounds__(DB_THREADS, 1) gemm_tma_db_kernel(const __grid
             const uint32_t src = tiles + s * DB_STAGE_BYTES + (uint32_t)ct * 16u;
             const uint32_t dstl = lo_ring + l * DB_STAGE_BYTES + (uint32_t)ct * 16u;
             float4 v[PIECES];
+            if (TM_DEBUG(P) != 5) {
 #pragma unroll
             for (int i = 0; i < PIECES; ++i)
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                              : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(src + (uint32_t)i * PSTRIDE));
+            } else {
+#pragma unroll
+                for (int i = 0; i < PIECES; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             const long long w2 = (tr && t == 64) ? clock64() : 0;
             mbar_wait(bar_lo_empty + 8 * l, phl ^ 1u);
             const long long w3 = (tr && t == 64) ? clock64() : 0;
+            if (TM_DEBUG(P) != 5 && TM_DEBUG(P) != 6) {
 #pragma unroll
             for (int i = 0; i < PIECES; ++i)
                 sts_v4(dstl + (uint32_t)i * PSTRIDE, tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
+            } else {
+                float keep = 0.f;
+#pragma unroll
+                for (int i = 0; i < PIECES; ++i) keep += tf32_lo(v[i].x) + tf32_lo(v[i].y) + tf32_lo(v[i].z) + tf32_lo(v[i].w);
+                asm volatile("" ::"f"(keep));
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(lo_full0 + 8 * l);

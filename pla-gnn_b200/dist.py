@@ -270,6 +270,8 @@ def dist_gcn_forward_backward(model: DistGCN, pg, h0_local, backend, group=None,
     """One forward + backward of the row-partitioned weighted-sum GCN.  h0_local: [per, F0] (rows past n_local are zero).
     Returns (out_local, grads) with grads = [W0, b0, W1, b1, ...] already summed over ranks."""
     if getattr(pg, "mode", "rows") == "cols":
+        if len(model.weights) >= 2 and os.environ.get("PLAGNN_DIST_COLS_ALT", "1") != "0":
+            return _gcn_cols_alt_forward_backward(model, pg, h0_local, backend, group, loss_grad_fn, act_leaky)
         return _gcn_cols_forward_backward(model, pg, h0_local, backend, group, loss_grad_fn, act_leaky)
     plan = pg.plan
     world, chunks = plan.world, plan.chunks
@@ -469,6 +471,86 @@ def _gcn_cols_forward_backward(model: DistGCN, pg, h0_local, backend, group, los
     return out_last, backend.all_reduce_grads(grads, world, group)
 
 
+def _gcn_cols_alt_forward_backward(model: DistGCN, pg, h0_local, backend, group, loss_grad_fn, act_leaky):
+    """Feature partition with the layers taken in pairs: layer 2j transforms first (X W, then aggregate), layer 2j + 1 aggregates
+    first (aggregate, then multiply by W) — the order DGL's GraphConv itself picks when in_feats <= out_feats.  The two
+    aggregations of a pair then follow each other in the column layout (bias and activation are per column / elementwise and
+    need no exchange), so a pair costs two exchanges per direction instead of four: rows -> columns before the first
+    aggregation, columns -> rows after the second.  Same function as `_gcn_cols_forward_backward` up to fp32 rounding
+    ((A h) W against A (h W))."""
+    plan = pg.plan
+    world = plan.world
+    n_layers = len(model.weights)
+    dims = model.dims
+    W = [w.detach() for w in model.weights]
+    B = [b.detach() for b in model.biases]
+    saved = [None] * n_layers
+    h = h0_local
+    li = 0
+    while li < n_layers:
+        last = li + 1 == n_layers
+        o = dims[li + 1]
+        c0, c1 = plan.col_range(o)
+        t_local = backend.alloc(plan.per, o)
+        backend.gemm_nt_into(h, W[li], t_local)
+        t_col = backend.to_cols(t_local, world, group)
+        if last:                                   # an odd layer count: the last layer stands alone
+            out = _spmm_cols_to_rows(backend, pg.csc, "csc", t_col, pg.w_csc, pg.scale_full, B[li][c0:c1], False, o, world, group)
+            saved[li] = ("single", h, None)
+            h = out
+            li += 1
+            continue
+        z_col = backend.spmm_cols(pg.csc, "csc", t_col, pg.w_csc, pg.scale_full, B[li][c0:c1], act_leaky)      # all rows x my columns
+        saved[li] = ("first", h, z_col)
+        last2 = li + 2 == n_layers
+        a_col = backend.spmm_cols(pg.csc, "csc", z_col, pg.w_csc, pg.scale_full, None, False)
+        a_rows = backend.to_rows(a_col, o, world, group)
+        out = backend.gemm_nt_bias_act(a_rows, W[li + 1], B[li + 1], act_leaky and not last2)
+        saved[li + 1] = ("second", a_rows, out)
+        h = out
+        li += 2
+    out_last = h
+    d_out = loss_grad_fn(out_last) if loss_grad_fn is not None else torch.ones_like(out_last)
+    d = _mask_padded_rows(plan, d_out)
+    grads = [None] * (2 * n_layers)
+    li = n_layers - 1
+    while li >= 0:
+        kind, x_in, y = saved[li]
+        last = li + 1 == n_layers
+        if kind == "single":
+            grads[2 * li + 1] = backend.colsum(d)
+            dzs_col = backend.to_cols(backend.act_backward(d, None, pg.scale), world, group)
+            dt_local = _spmm_cols_to_rows(backend, pg.csr_t, "csr_t", dzs_col, pg.w_csr_t, None, None, False, dims[li + 1], world, group)
+            grads[2 * li] = backend.gemm_tn(dt_local, x_in)
+            if li > 0:
+                d = backend.gemm_nn(dt_local, W[li])
+            li -= 1
+            continue
+        # the pair (li - 1, li): out = act(a_rows W_li^T + b_li), a = A z, z = act(A (h W_{li-1}^T) + b_{li-1})
+        dzb = backend.act_backward(d, y if (not last and act_leaky) else None, None)
+        grads[2 * li + 1] = backend.colsum(dzb)
+        grads[2 * li] = backend.gemm_tn(dzb, x_in)
+        da = backend.gemm_nn(dzb, W[li])                                       # my rows x dims[li]
+        das_col = backend.to_cols(backend.act_backward(da, None, pg.scale), world, group)
+        dz_col = backend.spmm_cols(pg.csr_t, "csr_t", das_col, pg.w_csr_t, None, None, False)      # all rows x my columns
+        lp = li - 1
+        _, h_in, z_col = saved[lp]
+        o = dims[lp + 1]
+        c0, c1 = plan.col_range(o)
+        dzb_col = backend.act_backward(dz_col, z_col if act_leaky else None, None)
+        gb = torch.zeros(o, device=dzb_col.device, dtype=dzb_col.dtype)
+        gb[c0:c1] = backend.colsum(dzb_col)                                     # complete for my columns, zero elsewhere: the sum
+        grads[2 * lp + 1] = gb                                                  # over ranks assembles the vector
+        dzs_col = backend.act_backward(dzb_col, None, pg.scale_full)
+        dt_col = backend.spmm_cols(pg.csr_t, "csr_t", dzs_col, pg.w_csr_t, None, None, False)
+        dt_local = backend.to_rows(dt_col, o, world, group)
+        grads[2 * lp] = backend.gemm_tn(dt_local, h_in)
+        if lp > 0:
+            d = backend.gemm_nn(dt_local, W[lp])
+        li -= 2
+    return out_last, backend.all_reduce_grads(grads, world, group)
+
+
 # ======================================================================================================================
 # CUDA backend: the library's kernels + its NCCL wrappers
 # ======================================================================================================================
@@ -645,6 +727,12 @@ class CudaBackend:
         ops = self.ops
         a = ops.aligned(a)
         ops.gemm(a.shape[0], w.shape[0], [(a, 0, ops.aligned(w), 0, a.shape[1])], bias=bias, act=ops.ACT_RELU, out=out)
+
+    def gemm_nt_bias_act(self, a, w, bias, leaky):
+        ops = self.ops
+        a = ops.aligned(a)
+        return ops.gemm(a.shape[0], w.shape[0], [(a, 0, ops.aligned(w), 0, a.shape[1])], bias=bias,
+                        act=ops.ACT_LEAKY if leaky else ops.ACT_NONE)
 
     def gemm2_nt(self, h, ws, neigh, wn, bias, leaky):
         ops = self.ops

@@ -34,6 +34,10 @@ class CpuBackend:
     def gemm_nt_bias_relu_into(self, a, w, bias, out): out.copy_(torch.relu(a @ w.t() + bias))
     def gemm_nn2(self, a0, w0, a1, w1): return a0 @ w0 + a1 @ w1
 
+    def gemm_nt_bias_act(self, a, w, bias, leaky):
+        y = a @ w.t() + bias
+        return torch.where(y > 0, y, 0.01 * y) if leaky else y
+
     def gemm2_nt(self, h, ws, neigh, wn, bias, leaky):
         r = h @ ws.t() + neigh @ wn.t() + bias
         return torch.nn.functional.leaky_relu(r) if leaky else r
@@ -130,7 +134,8 @@ def _problem(n=403, e=6000, f=24):
     return sg, x
 
 
-DIMS = [24, 24, 12]            # every width a multiple of 4 * world for world in (2, 3)
+# every width a multiple of 4 * world for world in (2, 3); PLAGNN_TEST_DIMS (inherited by the spawned ranks) overrides
+DIMS = [int(v) for v in os.environ["PLAGNN_TEST_DIMS"].split(",")] if os.environ.get("PLAGNN_TEST_DIMS") else [24, 24, 12]
 
 
 def _make_plan(sg, n, rank, world, mode, balance):
@@ -313,6 +318,17 @@ def test_row_partition_edge_balanced_three_ranks(tmp_path):
 def test_feature_partition_weighted_sum_two_and_three_ranks(tmp_path):
     _run_world(2, tmp_path, mode="cols")
     _run_world(3, tmp_path, mode="cols", balance="edges")
+
+
+def test_feature_partition_three_layers_pair_plus_single(tmp_path, monkeypatch):
+    """Three layers in the feature partition: layers 0 / 1 run as a pair (transform-first, then aggregate-first: two exchanges
+    per direction), layer 2 alone; also the plain order (every layer transform-first) on the same problem."""
+    import tests.test_dist_gloo as me
+    monkeypatch.setenv("PLAGNN_TEST_DIMS", "24,24,24,12")
+    monkeypatch.setattr(me, "DIMS", [24, 24, 24, 12])
+    _run_world(2, tmp_path, mode="cols")
+    monkeypatch.setenv("PLAGNN_DIST_COLS_ALT", "0")
+    _run_world(2, tmp_path, mode="cols")
 
 
 def test_feature_partition_max_pool_three_ranks(tmp_path):
