@@ -127,8 +127,11 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
     const int item = item_begin + blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
     pdl_wait();
+    // item_row holds one int4 record per work item, {row, first in-edge, end in-edge, partial slot or -1} (graph_build.cu): the
+    // narrow kernel below starts from that one load; here, with rows of >= 512 bytes and items that live for thousands of
+    // cycles, the three-step walk costs nothing measurable and keeps the register allocation the tuned loops were measured with
     const int chunk = __ldg(plan_hdr);
-    const int row = __ldg(item_row + item);
+    const int row = __ldg(item_row + 4 * item);
     const int first = __ldg(item_ptr + row);
     const int nch = __ldg(item_ptr + row + 1) - first;
     const int k = item - first;
@@ -370,14 +373,9 @@ spmm_narrow_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict
     const int item = item_begin + blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
     pdl_wait();
-    const int chunk = __ldg(plan_hdr);
-    const int row = __ldg(item_row + item);
-    const int first = __ldg(item_ptr + row);
-    const int nch = __ldg(item_ptr + row + 1) - first;
-    const int k = item - first;
-    const int rbeg = __ldg(indptr + row), rend = __ldg(indptr + row + 1);
-    const int beg = rbeg + k * chunk;
-    const int end = min(rend, beg + chunk);
+    const int4 rec = __ldg(reinterpret_cast<const int4*>(item_row) + item);       // {row, first in-edge, end in-edge, slot or -1}
+    const int row = rec.x, beg = rec.y, end = rec.z;
+    const int nch = rec.w < 0 ? 1 : 2;
     const int sub = lane / G, gl = lane % G;
     const int col = 4 * gl;
     const bool cok = col < feat;
@@ -463,7 +461,7 @@ spmm_narrow_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict
         }
         *reinterpret_cast<float4*>(out + (int64_t)row * ldo + col) = r;
     } else {
-        const int64_t slot = (int64_t)__ldg(slot_ptr + row) + k;
+        const int64_t slot = rec.w;
         *reinterpret_cast<float4*>(part_val + slot * part_ld + col) = acc;
         if (MODE == MODE_MAX) *reinterpret_cast<int4*>(part_arg + slot * part_ld + col) = arg;
     }
