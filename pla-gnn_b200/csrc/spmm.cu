@@ -113,8 +113,8 @@ __device__ __forceinline__ void reduce_one(float4& acc, int4& arg, const float4 
 // The max reducer runs at the L2 -> SM bandwidth cap once enough warps are resident (measured: 24 warps/SM at 80
 // registers 0.198 ms, 16 warps at 110 registers 0.322 ms for F = 503), so its default variants are held to 3 blocks per SM;
 // the sum reducer (no arg registers) to 4 blocks = 32 warps (weighted 100 M-edge graph: 55.7 ms at 64 registers, 71.3 at 72).
-template <int MODE, int VEC, int NB, bool SUM_LEAN = false>
-__global__ void __launch_bounds__(SPMM_WARPS * 32, NB * VEC > 8 ? 1 : MODE == MODE_MAX ? 3 : MODE == MODE_SUM ? 4 : 1)
+template <int MODE, int VEC, int NB, bool SUM_LEAN = false, int WARPS = SPMM_WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (NB * VEC > 8 ? 1 : MODE == MODE_MAX ? 3 : MODE == MODE_SUM ? 4 : 1) * (SPMM_WARPS / WARPS))
 spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int32_t* __restrict__ eids,
             const float* __restrict__ ew, const int32_t* __restrict__ plan_hdr, const int32_t* __restrict__ item_ptr,
             const int32_t* __restrict__ slot_ptr, const int32_t* __restrict__ item_row, int item_begin, int n_items,
@@ -124,7 +124,7 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
             float nzero) {
     pdl_trigger();
     const int lane = threadIdx.x & 31;
-    const int item = item_begin + blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+    const int item = item_begin + blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
     pdl_wait();
     // item_row holds one int4 record per work item, {row, first in-edge, end in-edge, partial slot or -1} (graph_build.cu): the
@@ -357,8 +357,8 @@ spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indi
 // latencies per warp but by how many row requests an SM keeps outstanding (~14 KB in flight per SM at both this and the PPI
 // shape); more resident warps with short loops beat deeper loops.  L2 eviction priorities (ids / weights evict_first, rows
 // evict_last through createpolicy + ld.global.L2::cache_hint) changed nothing either (tools/spmm_variants_time.py).
-template <int MODE, int G, int U, int OCC>
-__global__ void __launch_bounds__(SPMM_WARPS * 32, OCC)
+template <int MODE, int G, int U, int OCC, int WARPS = SPMM_WARPS>
+__global__ void __launch_bounds__(WARPS * 32, OCC * SPMM_WARPS / WARPS)
 spmm_narrow_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int32_t* __restrict__ eids,
                    const float* __restrict__ ew, const int32_t* __restrict__ plan_hdr, const int32_t* __restrict__ item_ptr,
                    const int32_t* __restrict__ slot_ptr, const int32_t* __restrict__ item_row, int item_begin, int n_items,
@@ -370,7 +370,7 @@ spmm_narrow_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict
     // U rounds unrolled = U rows in flight per lane (U = 4 at 32 warps per SM: 64 KB in flight per SM)
     pdl_trigger();
     const int lane = threadIdx.x & 31;
-    const int item = item_begin + blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+    const int item = item_begin + blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
     pdl_wait();
     const int4 rec = __ldg(reinterpret_cast<const int4*>(item_row) + item);       // {row, first in-edge, end in-edge, slot or -1}
@@ -604,13 +604,25 @@ static void launch_main(const SpmmArgs& a, const int32_t* item_ptr, const int32_
     const int item_begin = a.range ? (int)a.range[0] : 0;
     const int n_items = a.range ? (int)a.range[1] : (int)a.counts[0];
     if (n_items <= item_begin) return;
-    dim3 grid((unsigned)ceil_div(n_items - item_begin, SPMM_WARPS), (unsigned)ceil_div((a.feat + 3) / 4, 32 * VEC));
+    // PLAGNN_SPMM_WARPS (read per launch): work items per block, 8 / 4 / 2 (default).  A block keeps its SM slot until its
+    // longest item is done, and the rows of a power-law graph differ by orders of magnitude.  Measured, 8 / 4 / 2 warps per
+    // block: 1 M / 100 M graph, 256 columns 12.85 / 11.96 / 11.87 ms (weighted sum), 11.29 / 10.45 / 10.32 (max); 128 columns
+    // 7.40 / 6.66 / 6.47; PPI shape (24 041 rows, F = 503, max) 0.1916 / 0.1899 / 0.1903 ms.
+    const char* we = getenv("PLAGNN_SPMM_WARPS");
+    static const bool lean_env = [] { const char* e = getenv("PLAGNN_SPMM_SUM_LEAN"); return e && e[0] == '1'; }();
+    const int want = we ? atoi(we) : 2;
+    const int bw = ((want == 4 || want == 2) && MODE != MODE_MATCH && !(MODE == MODE_SUM && lean_env)) ? want : SPMM_WARPS;
+    dim3 grid((unsigned)ceil_div(n_items - item_begin, bw), (unsigned)ceil_div((a.feat + 3) / 4, 32 * VEC));
     // PLAGNN_SPMM_SUM_LEAN=1: the max reducer's loop shape for the sum reducer.  Off by default — measured on the 1 M / 100 M
     // graph it LOSES to the shuffle form: F = 256 15.3 vs 12.8 ms, F = 128 9.7 vs 7.4 ms (two broadcast loads per neighbour, id
     // and weight, issued by every lane, against two coalesced loads and two shuffles per 32 neighbours).
     static const bool lean = [] { const char* e = getenv("PLAGNN_SPMM_SUM_LEAN"); return e && e[0] == '1'; }();
-    auto kernel = (MODE == MODE_SUM && lean) ? spmm_kernel<MODE, VEC, NB, true> : spmm_kernel<MODE, VEC, NB, false>;
-    launch_pdl(kernel, grid, dim3(SPMM_WARPS * 32), 0, st,
+    constexpr int M2 = MODE == MODE_MATCH ? MODE_SUM : MODE;      // (MATCH never takes the small blocks; keeps the table instantiable)
+    auto kernel = (MODE == MODE_SUM && lean) ? spmm_kernel<MODE, VEC, NB, true>
+                  : bw == 4 ? spmm_kernel<M2, VEC, NB, false, 4>
+                  : bw == 2 ? spmm_kernel<M2, VEC, NB, false, 2>
+                            : spmm_kernel<MODE, VEC, NB, false>;
+    launch_pdl(kernel, grid, dim3(bw * 32), 0, st,
         a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, item_begin, n_items, a.x, a.ldx,
         (int)a.feat, a.argm, a.ldarg, a.zfwd, a.ldzf, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep, 1.0f, -0.0f);
 }
@@ -621,11 +633,20 @@ static void launch_narrow(const SpmmArgs& a, const int32_t* item_ptr, const int3
     const int item_begin = a.range ? (int)a.range[0] : 0;
     const int n_items = a.range ? (int)a.range[1] : (int)a.counts[0];
     if (n_items <= item_begin) return;
-    dim3 grid((unsigned)ceil_div(n_items - item_begin, SPMM_WARPS));
     // PLAGNN_SPMM_NARROW_U=8: eight rows in flight per lane at 24 warps per SM (A/B against the default 4 at 32 warps)
     static const int deep = [] { const char* e = getenv("PLAGNN_SPMM_NARROW_U"); return e && atoi(e) == 8; }();
-    auto kernel = deep ? spmm_narrow_kernel<MODE, G, 8, 3> : spmm_narrow_kernel<MODE, G, 4, 4>;
-    launch_pdl(kernel, grid, dim3(SPMM_WARPS * 32), 0, st,
+    // PLAGNN_SPMM_NARROW_WARPS (read per launch): warps = work items per block.  A block keeps its SM slot until its longest
+    // item is done; the rows of a power-law graph differ by orders of magnitude, so smaller blocks waste fewer warp slots.
+    const char* we = getenv("PLAGNN_SPMM_NARROW_WARPS");
+    const int warps = we ? atoi(we) : 2;      // measured at 32 columns, 8 / 4 / 2 / 1 warps per block: 1.95 / 1.78 / 1.75 / 1.83 ms (sum)
+    auto kernel = deep ? spmm_narrow_kernel<MODE, G, 8, 3>
+                  : warps == 4 ? spmm_narrow_kernel<MODE, G, 4, 4, 4>
+                  : warps == 2 ? spmm_narrow_kernel<MODE, G, 4, 4, 2>
+                  : warps == 1 ? spmm_narrow_kernel<MODE, G, 4, 4, 1>
+                               : spmm_narrow_kernel<MODE, G, 4, 4>;
+    const int bw = deep ? SPMM_WARPS : (warps == 4 || warps == 2 || warps == 1) ? warps : SPMM_WARPS;
+    dim3 grid((unsigned)ceil_div(n_items - item_begin, bw));
+    launch_pdl(kernel, grid, dim3(bw * 32), 0, st,
         a.indptr, a.indices, a.eids, a.ew, (const int32_t*)a.plan, item_ptr, slot_ptr, item_row, item_begin, n_items, a.x, a.ldx,
         (int)a.feat, a.out, a.arg_out, a.ldo, pv, pa, part_ld_of(a.feat), a.ep, a.chain);
 }

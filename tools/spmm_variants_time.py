@@ -37,16 +37,16 @@ def timed(fn, reps=5):
 
 
 out = {"edges": int(csc.num_edges)}
-narrow_variants = [(0, 0), (1, 0), (2, 0), (3, 0), (4, 0)]
-wide_variants = [0]
-for f in (32, 64, 128, 256):
+narrow_variants = [(8, 0), (4, 0), (2, 0), (1, 0)]
+wide_variants = []
+for f in (32, 64):
     x = ops.alloc(n, f, dev)
     x.copy_(torch.randn(n, f, device=dev))
     bias = torch.zeros(f, device=dev)
     ref = {}
     variants = narrow_variants if f <= 64 else [(1, h) for h in wide_variants]
     for pipe, hint in variants:
-        os.environ["PLAGNN_SPMM_NARROW_PIPE"] = str(pipe)
+        os.environ["PLAGNN_SPMM_NARROW_WARPS"] = str(pipe)
         os.environ["PLAGNN_SPMM_L2HINT"] = str(hint)
         for name, fn in (("sum", lambda: ops.spmm_sum(csc, x, w=w, scale=scale, bias=bias, act=ops.ACT_LEAKY, w_in_csr_order=True)),
                          ("max", lambda: ops.spmm_max_fwd(csc, x))):
@@ -62,10 +62,10 @@ for f in (32, 64, 128, 256):
             else:
                 same = bool(torch.equal(ref[key], r))
             alg = 4 * f * csc.num_edges + 4 * csc.num_edges * (2 if name == "sum" else 1) + 4 * f * n * (1 if name == "sum" else 2)
-            out[f"{key}/pipe{pipe}/hint{hint}"] = {"ms": round(ms, 3), "algorithmic_gb_per_s": round(alg / ms / 1e6, 0),
+            out[f"{key}/warps{pipe}"] = {"ms": round(ms, 3), "algorithmic_gb_per_s": round(alg / ms / 1e6, 0),
                                                     "bit_identical_to_first": same}
-            print(f"{key} pipe={pipe} hint={hint}: {ms:.3f} ms same={same}", file=sys.stderr, flush=True)
+            print(f"{key} warps={pipe} hint={hint}: {ms:.3f} ms same={same}", file=sys.stderr, flush=True)
     del x, ref
-os.environ.pop("PLAGNN_SPMM_NARROW_PIPE", None)
+os.environ.pop("PLAGNN_SPMM_NARROW_WARPS", None)
 os.environ.pop("PLAGNN_SPMM_L2HINT", None)
 print(json.dumps(out))
