@@ -480,7 +480,7 @@ def run_ours(args):
     sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
     l2_cap = 6300.0 * sm_mhz * 1e6 / 1e9 if sm_mhz else None
     traffic = lts = None
-    tpath = os.path.join(ROOT, "profiles", "r1_spmm_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_spmm_traffic_ppi.json")
     if n == 24041 and os.path.exists(tpath):          # dram__bytes_read + write of this kernel from the committed ncu capture
         tj = json.load(open(tpath))
         traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]

@@ -172,9 +172,9 @@ def measure_variant(v: Variant, steps, warmup, rank, world, dev, reference=None)
     # ncu DRAM bytes per launch of the forward aggregation kernel of this very shape (one GPU, 1 M / 100 M / 256), from the
     # committed capture; the live launch time comes from this run's events
     dram = None
-    tpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r2_ncu_traffic.json")
+    tpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r2_ncu_traffic_final.json")
     if world == 1 and n == 1_000_000 and f == 256 and plan.num_local_edges == 100_000_000 and os.path.exists(tpath):
-        tj = json.load(open(tpath)).get("spmm_kernel<1, 2, 4>/grid133678" if v.reducer == "sum" else "spmm_kernel<0, 2, 4>/grid133678")
+        tj = json.load(open(tpath)).get("spmm_kernel<1, 2, 4, 0, 2>/grid534712" if v.reducer == "sum" else "spmm_kernel<0, 2, 4, 0, 2>/grid534712")
         fwd_name = "spmm_sum" if v.reducer == "sum" else "spmm_max_fwd"
         launches = v.layers * (2 if v.reducer == "sum" else 1)
         if tj and per_step.get(fwd_name):
@@ -182,7 +182,7 @@ def measure_variant(v: Variant, steps, warmup, rank, world, dev, reference=None)
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
             dram = {"kernel": "spmm_kernel<%s, 2, 4> (F = 256, 100 M edges)" % ("sum" if v.reducer == "sum" else "max"),
                     "traffic": traffic, "avg_ms": ms_launch, "frac_dram": traffic / (ms_launch * 1e-3) / 1e9 / hbm,
-                    "traffic_source": "ncu --set full capture committed under profiles/r2_ncu.md (per launch)"}
+                    "traffic_source": "ncu --set full capture committed under profiles/r2_ncu_final.md (per launch)"}
     res = {"mode": v.mode, "reducer": v.reducer, "exchange": v.exchange, "ms_per_step": ms, "ms_per_step_with_events": ms_prof,
            "ms_per_step_without_collectives": ms_nocomm, "exposed_exchange_ms": (ms - ms_nocomm) if ms_nocomm else 0.0,
            "collective_ms_per_step": coll, "aggregation_ms_per_step": agg_ms, "aggregation_by_launch_shape": agg_shapes,

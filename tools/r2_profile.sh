@@ -12,7 +12,7 @@ timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-partitio
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 900 --csv --log-file gpurun_out/launches_r2.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-partitioned --no-pipeline > gpurun_out/r2_ncu_launches.log 2>&1; echo "ncu launches exit $?"
 python tools/summarize_ncu.py launches gpurun_out/launches_r2.csv > gpurun_out/launches_r2.md 2>&1
 timeout 300 python tools/kernels_once.py all > gpurun_out/r2_k1.log 2>&1; echo "kernels_once exit $?"
-timeout 900 ncu --set full --clock-control none -k regex:"gemm_tma_kernel|spmm_kernel|spmm_max_scatter|narrow_" -c 24 -f -o gpurun_out/prof_r2_ppi python tools/kernels_once.py all > gpurun_out/r2_ncu_ppi.log 2>&1; echo "ncu ppi exit $?"
+timeout 900 ncu --set full --clock-control none -k regex:"gemm_tma|spmm_kernel|spmm_max_scatter|narrow_" -c 32 -f -o gpurun_out/prof_r2_ppi python tools/kernels_once.py all > gpurun_out/r2_ncu_ppi.log 2>&1; echo "ncu ppi exit $?"
 summ prof_r2_ppi
 timeout 300 python tools/scaled_once.py > gpurun_out/r2_s1.log 2>&1; echo "scaled_once exit $?"
 timeout 1200 ncu --set full --clock-control none -k regex:"spmm_kernel|spmm_narrow_kernel|spmm_max_scatter|spmm_combine" -c 12 -f -o gpurun_out/prof_r2_scaled python tools/scaled_once.py > gpurun_out/r2_ncu_scaled.log 2>&1; echo "ncu scaled exit $?"
