@@ -559,7 +559,7 @@ def roofline_gemm(prof, steps, flops_epoch, gemm_ms, bf16_peak, peak_src):
         if best is None or tf > best[1]:
             best = ("gemm/%d/%d/%d" % (k[1], k[2], k[3]), tf, t / c)
     all_tf = 3.0 * flops_epoch / (gemm_ms * 1e-3) / 1e12
-    return {"kernel": "gemm_tma_kernel (all 23 products of the epoch)", "bound": "tensor", "achieved": all_tf, "peak": peak,
+    return {"kernel": "gemm_tma_kernel / gemm_tma_db_kernel (all 23 products of the epoch)", "bound": "tensor", "achieved": all_tf, "peak": peak,
             "unit": "TFLOP/s", "frac": all_tf / peak, "traffic": None,
             "peak_source": peak_src + ": sustained dense bf16 / 2 (tf32 rate)",
             "note": "achieved = 3 tf32 MMAs per fp32 product x algorithmic flops / event time (second, fully instrumented pass)",

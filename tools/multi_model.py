@@ -52,3 +52,35 @@ for r in range(1, maxr + 1):
     e.record(); torch.cuda.synchronize()
     ms = s.elapsed_time(e)
     print(f"{r} concurrent models: {r * steps / (ms * 1e-3):.1f} epochs/s aggregate ({ms / steps:.3f} ms per round of {r} epochs), host wall {time.perf_counter() - t0:.3f} s")
+
+# ---- the same with every model's epoch as one CUDA-graph replay (epoch.TrainStep) on its own stream: no host work per kernel ----
+from plagnn_b200.epoch import TrainStep
+steps_g = []
+for i in range(maxr):
+    torch.manual_seed(170 + i)
+    model = P.GNN32(503, 400, 300, 200, 100, 12).to(dev)
+    lab_rows = prob.labelled.copy(); rng.shuffle(lab_rows)
+    idx = torch.as_tensor(np.sort(lab_rows[: len(lab_rows) * 9 // 10]), device=dev)
+    steps_g.append((TrainStep(model, g, feat, lab, idx, w, lr=5e-5), torch.cuda.Stream(device=dev)))
+for r in (1, 2, 4, 6, 8):
+    if r > maxr:
+        break
+    ms_ = steps_g[:r]
+    for _ in range(5):
+        for ts, st in ms_:
+            with torch.cuda.stream(st):
+                ts.step()
+    torch.cuda.synchronize()
+    steps = 40
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _, st in ms_: st.wait_stream(torch.cuda.current_stream())
+    s.record()
+    for _, st in ms_: st.wait_stream(torch.cuda.current_stream())
+    for _ in range(steps):
+        for ts, st in ms_:
+            with torch.cuda.stream(st):
+                ts.step()
+    for _, st in ms_: torch.cuda.current_stream().wait_stream(st)
+    e.record(); torch.cuda.synchronize()
+    ms = s.elapsed_time(e)
+    print(f"{r} concurrent models as graph replays: {r * steps / (ms * 1e-3):.1f} epochs/s aggregate ({ms / steps:.3f} ms per round of {r} epochs)")
