@@ -177,7 +177,13 @@ int plagnn_dropout_scale(float* grad, int64_t rows, int64_t feat, int64_t ld, fl
  *   backend: AUTO picks PLAGNN_GEMM_TMA (TMA-fed tcgen05 on CTA pairs, 3xTF32 split, fp32-level accuracy) when the
  *   operands have 16-byte aligned rows, else TCGEN05 (first-generation kernel) / SIMT (exact fp32 FFMA); products with
  *   n <= 16 or a contraction of at most 32 (the 12-class head, code/model.py:17,28) go to PLAGNN_GEMM_NARROW, streaming
- *   FFMA kernels without tile padding.
+ *   FFMA kernels without tile padding.  Within the TMA backend a directly written product (no split-K) with more 256 x 128
+ *   tiles than CTA pairs may run on the double-buffered kernel (accumulators of two tiles in tensor memory, read-out of one
+ *   overlapping the MMAs of the next); the choice is made per product by a cost model and does not change the result (the
+ *   two kernels are bit-identical).
+ *   Output rows that are 16-byte aligned (ldc % 4 == 0, c 16-byte aligned) leave through TMA stores, which clip at the
+ *   output's extent in 16-byte units: when n % 4 != 0 (and then necessarily ldc > n) the columns [n, roundup4(n)) of each row
+ *   — padding inside the row pitch — may be overwritten with unspecified values.
  * ---------------------------------------------------------------------------------------- */
 #define PLAGNN_GEMM_MAX_PAIRS 2
 typedef struct {

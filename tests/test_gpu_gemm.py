@@ -273,3 +273,61 @@ def test_gemm_tma_many_tiles_per_cta_pair(cuda, monkeypatch, persistent):
     assert rel(got4, ref_gemm(pairs4, None, 0, None, 0)) < TOL
     got5 = ops.gemm(24041, 300, pairs4, gate=gate, gate_act=ops.ACT_LEAKY, backend=ops.GEMM_TMA)
     assert rel(got5, ref_gemm(pairs4, None, 0, gate, ops.ACT_LEAKY)) < TOL
+
+
+# ---- third-generation kernel: 256 x 128 tiles, accumulators double-buffered in tensor memory (gemm_tma_db_kernel) ----------
+# Taken by the cost model only for tall products (more tiles than CTA pairs); PLAGNN_TMA_DB_NOW (read per launch) forces it
+# on ("1") or off ("0") so that both kernels can be compared on the same operands.
+DB_CASES = [  # n, k, pairs, bt, gate, act, bias
+    (503, 503, 1, 0, False, "relu", True),      # conv1 fc_pool forward: four full / ragged 128-column tiles
+    (400, 503, 2, 0, False, "leaky", True),     # two (A, B) pairs in one accumulation chain; last column tile 16 -> 64 wide
+    (300, 200, 1, 1, False, "none", False),     # input gradient: B stored [k x n] (mn-major boxes), column tiles 128 + 128 + 64
+    (300, 250, 2, 1, True, "none", False),      # gated input gradient of a SAGE layer: gate images by TMA, one per chunk
+    (100, 200, 1, 0, False, "leaky", True),     # one column tile (n_eff = 128)
+    (72, 40, 1, 0, False, "sigmoid", True),     # narrow output (n_eff = 128 with 72 real columns), short contraction (2 k-blocks)
+    (129, 33, 1, 1, True, "none", False),       # ragged everything: 129 columns (second tile holds one), k = 33
+]
+
+
+@pytest.mark.parametrize("n,k,pairs,bt,gated,act,with_bias", DB_CASES)
+@pytest.mark.parametrize("m", [19201, 24041])
+def test_gemm_double_buffered_tiles(cuda, monkeypatch, m, n, k, pairs, bt, gated, act, with_bias):
+    act_id = {"none": ops.ACT_NONE, "relu": ops.ACT_RELU, "leaky": ops.ACT_LEAKY, "sigmoid": ops.ACT_SIGMOID}[act]
+    ps = []
+    for p in range(pairs):
+        a = operand(m, k, 0, cuda, 11 + p, pad=True)
+        b = operand(n, k, bt, cuda, 21 + p, pad=True)
+        ps.append((a, 0, b, bt, k))
+    bias = torch.randn(n, generator=torch.Generator().manual_seed(5)).to(cuda) if with_bias else None
+    gate = ops.aligned(torch.randn(m, n, generator=torch.Generator().manual_seed(6)).to(cuda)) if gated else None
+    gate_act = ops.ACT_LEAKY if gated else ops.ACT_NONE
+    ref = ref_gemm(ps, bias, act_id, gate, gate_act)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PLAGNN_TMA_DB_NOW", mode)
+        out = ops.alloc(m, n, cuda, zero=True)
+        ops.gemm(m, n, ps, bias=bias, act=act_id, gate=gate, gate_act=gate_act, out=out, backend=ops.GEMM_TMA)
+        res[mode] = out.clone()
+        assert rel(out, ref) < TOL, mode
+    # same MMAs in the same order into the same kind of accumulators: the two kernels agree to the bit
+    assert torch.equal(res["0"], res["1"])
+    # nothing written past the row's last 16-byte group (the output is a view of a row-padded buffer; TMA stores clip at the
+    # tensor map's extent in 16-byte units, so columns [n, roundup4(n)) of the padding may be written — include/plagnn.h)
+    monkeypatch.setenv("PLAGNN_TMA_DB_NOW", "1")
+    buf = torch.full((m, ops.pitch_of(n)), 7.0, device=cuda)
+    out = buf[:, :n]
+    ops.gemm(m, n, ps, bias=bias, act=act_id, gate=gate, gate_act=gate_act, out=out, backend=ops.GEMM_TMA)
+    assert torch.equal(out, res["1"]) and bool((buf[:, (n + 3) // 4 * 4:] == 7.0).all())
+
+
+def test_gemm_double_buffered_ring_variants(cuda, monkeypatch):
+    """The ring depths of the double-buffered kernel (raw 4 / lo 3, raw 5 / lo 3, raw 4 / lo 4) give identical results."""
+    m, n, k = 19201, 300, 400
+    a, b = operand(m, k, 0, cuda, 31, pad=True), operand(n, k, 0, cuda, 32, pad=True)
+    monkeypatch.setenv("PLAGNN_TMA_DB_NOW", "1")
+    outs = []
+    for ring in ("0", "1", "2"):
+        monkeypatch.setenv("PLAGNN_TMA_DB_RING", ring)
+        outs.append(ops.gemm(m, n, [(a, 0, b, 0, k)], backend=ops.GEMM_TMA).clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert rel(outs[0], ref_gemm([(a, 0, b, 0, k)], None, 0, None, 0)) < TOL
