@@ -503,8 +503,8 @@ def _gcn_cols_alt_forward_backward(model: DistGCN, pg, h0_local, backend, group,
         z_col = backend.spmm_cols(pg.csc, "csc", t_col, pg.w_csc, pg.scale_full, B[li][c0:c1], act_leaky)      # all rows x my columns
         saved[li] = ("first", h, z_col)
         last2 = li + 2 == n_layers
-        a_col = backend.spmm_cols(pg.csc, "csc", z_col, pg.w_csc, pg.scale_full, None, False)
-        a_rows = backend.to_rows(a_col, o, world, group)
+        # (aggregation + exchange fused block by block when the backend can: PLAGNN_DIST_OVERLAP)
+        a_rows = _spmm_cols_to_rows(backend, pg.csc, "csc", z_col, pg.w_csc, pg.scale_full, None, False, o, world, group)
         out = backend.gemm_nt_bias_act(a_rows, W[li + 1], B[li + 1], act_leaky and not last2)
         saved[li + 1] = ("second", a_rows, out)
         h = out
@@ -542,8 +542,7 @@ def _gcn_cols_alt_forward_backward(model: DistGCN, pg, h0_local, backend, group,
         gb[c0:c1] = backend.colsum(dzb_col)                                     # complete for my columns, zero elsewhere: the sum
         grads[2 * lp + 1] = gb                                                  # over ranks assembles the vector
         dzs_col = backend.act_backward(dzb_col, None, pg.scale_full)
-        dt_col = backend.spmm_cols(pg.csr_t, "csr_t", dzs_col, pg.w_csr_t, None, None, False)
-        dt_local = backend.to_rows(dt_col, o, world, group)
+        dt_local = _spmm_cols_to_rows(backend, pg.csr_t, "csr_t", dzs_col, pg.w_csr_t, None, None, False, o, world, group)
         grads[2 * lp] = backend.gemm_tn(dt_local, h_in)
         if lp > 0:
             d = backend.gemm_nn(dt_local, W[lp])
