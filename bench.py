@@ -441,6 +441,24 @@ def run_ours(args):
             ms = tt.item()
         return ms
 
+    # ---- the same epoch on the single-chain GEMM kernels (PLAGNN_GEMM_PARITY=0, read per launch by the library): the fastest
+    # mode, whose gradients sit at 1.5e-5 instead of <= 1e-5 of the fp32 oracle at this size.  Reported beside
+    # `value`; `value` and `e2e` are the default (parity) mode.
+    prev_parity = os.environ.get("PLAGNN_GEMM_PARITY")
+    os.environ["PLAGNN_GEMM_PARITY"] = "0"
+    try:
+        for _ in range(3):
+            epoch()
+        ms_fast = timed(epoch, args.steps)
+    finally:
+        if prev_parity is None:
+            os.environ.pop("PLAGNN_GEMM_PARITY", None)
+        else:
+            os.environ["PLAGNN_GEMM_PARITY"] = prev_parity
+    fast_gemm = {"value": world * args.steps / (ms_fast * 1e-3), "unit": UNIT, "ms_per_step": ms_fast / args.steps,
+                 "note": "PLAGNN_GEMM_PARITY=0: one accumulation chain per GEMM tile (double-buffered read-out where the cost model "
+                         "prefers it), weight-gradient chains of 40 k-blocks; full-size gradients within 1.5e-5 instead of 1e-5"}
+
     ms_e2e = timed_e2e(args.steps)
 
     # ---- device-resident timed region (value): the LAST leg of the process, W warm-up steps right before it --------------
@@ -527,6 +545,9 @@ def run_ours(args):
                                  "note": "the >= 70 % of HBM target is judged on the graph that is NOT L2-resident: "
                                          "`partitioned` (configs[3]) -> aggregation_frac_of_hbm_peak, ncu DRAM bytes for that kernel in "
                                          "profiles/"},
+        "gemm_mode": {"default": os.environ.get("PLAGNN_GEMM_PARITY", "2 (parity: two accumulation chains per tile, weight-gradient "
+                                                 "chains of 24 k-blocks; all 19 gradient tensors <= 1e-5 at N = 24 041)"),
+                      "fast": fast_gemm},
         "gemm": {"ms_per_step": gemm_ms, "tflops_fp32_equiv": flops_epoch / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
                  "flops_per_step": flops_epoch, "backend": os.environ.get("PLAGNN_GEMM", "auto (TMA-fed tcgen05, CTA pairs, 3xTF32)"),
                  "measured_in": "second pass with per-call events (ms_per_step_profiled)"},

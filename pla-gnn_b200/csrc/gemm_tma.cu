@@ -809,7 +809,12 @@ __device__ __forceinline__ DbTile db_tile(const TmParams& P, int t) {
     return T;
 }
 
-template <bool BT, int DB_RAW_STAGES, int DB_LO_STAGES, bool GATE>
+// TWO (parity mode, PLAGNN_GEMM_PARITY=1): the two halves of TMEM are not two tiles but two accumulation chains of ONE tile —
+// even k-blocks accumulate into the first (main + correction) pair, odd k-blocks into the second, the read-out adds the four
+// accumulators in fp32 round-to-nearest.  The tensor core truncates when it adds into an accumulator, so a chain's bias grows
+// with its length; halving the chains of the forward / input-gradient products halves the bias the gradient sums over 24 041
+// rows amplify.  No overlap of read-out and MMAs in this mode (the tile owns all 512 columns again).
+template <bool BT, int DB_RAW_STAGES, int DB_LO_STAGES, bool GATE, bool TWO = false>
 __global__ void __launch_bounds__(DB_THREADS, 1) gemm_tma_db_kernel(const __grid_constant__ TmParams P) {
     using namespace tm;
     constexpr int DB_EPI_BYTES = db_epi_bytes(GATE);
@@ -925,7 +930,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) gemm_tma_db_kernel(const __grid
             for (int tile = first_tile; tile < end_tile; ++tile, ++tile_iter) {
                 const DbTile T = db_tile(P, tile);
                 const uint32_t idesc = make_idesc(256, T.n_eff, false, BT);
-                const int b = tile_iter & 1, use = tile_iter >> 1;
+                const int b = TWO ? 0 : (tile_iter & 1), use = TWO ? tile_iter : (tile_iter >> 1);
                 if (tr && lane == 0 && tile_iter == 0) tr[2] = clock64();
                 if (use > 0) {                      // the previous tile in this half of TMEM has been read out in both CTAs
                     const long long w0 = tr ? clock64() : 0;
@@ -933,8 +938,9 @@ __global__ void __launch_bounds__(DB_THREADS, 1) gemm_tma_db_kernel(const __grid
                     if (tr && lane == 0) tr[3] += clock64() - w0;
                     tc_fence_after();
                 }
-                const uint32_t acc_main = tmem_base + (uint32_t)b * 256u, acc_corr = acc_main + 128u;
                 for (int it = 0; it < nkb; ++it, ++g) {
+                    // TWO: k-block `it` accumulates into chain it & 1; the first k-block of a chain starts it (acc_on = 0)
+                    const uint32_t acc_main = tmem_base + (uint32_t)(TWO ? (it & 1) : b) * 256u, acc_corr = acc_main + 128u;
                     const int s = g % DB_RAW_STAGES, l = g % DB_LO_STAGES;
                     const uint32_t phl = (uint32_t)((g / DB_LO_STAGES) & 1);
                     const long long w0 = tr ? clock64() : 0;
@@ -950,7 +956,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) gemm_tma_db_kernel(const __grid
                         for (int kk = 0; kk < TM_BK / 8; ++kk) {
                             if (TM_DEBUG(P) == 2) break;
                             const uint64_t adv_a = (uint64_t)kk * a_step, adv_b = (uint64_t)kk * b_step;
-                            const uint32_t acc_on = (it | kk) ? 1u : 0u;
+                            const uint32_t acc_on = TWO ? ((it >= 2 || kk) ? 1u : 0u) : ((it | kk) ? 1u : 0u);
                             if (TM_DEBUG(P) == 7) {          // main product only (a third of the operand reads)
                                 umma_tf32<2>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
                                 continue;
@@ -1028,7 +1034,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) gemm_tma_db_kernel(const __grid
         uint32_t gph = 0;                                       // gate images received so far (barrier phase)
         for (int tile = first_tile; tile < end_tile; ++tile, ++tile_iter) {
             const DbTile T = db_tile(P, tile);
-            const int b = tile_iter & 1, use = tile_iter >> 1;
+            const int b = TWO ? 0 : (tile_iter & 1), use = TWO ? tile_iter : (tile_iter >> 1);
             const int64_t n0 = T.n0;
             const int row0 = (int)(T.m0 + rank * 128 + lg * 32);
             // 32-column chunks of this tile that hold real columns
@@ -1054,11 +1060,26 @@ __global__ void __launch_bounds__(DB_THREADS, 1) gemm_tma_db_kernel(const __grid
                 {
                     uint32_t acc[32], acc_small[32];
                     const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)b * 256u + (uint32_t)(ch * 32);
-                    tmem_ld32(ta, acc);
-                    tmem_ld32(ta + 128u, acc_small);
-                    tmem_ld_wait();
+                    if (!TWO) {
+                        tmem_ld32(ta, acc);
+                        tmem_ld32(ta + 128u, acc_small);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + __uint_as_float(acc_small[j]);
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + __uint_as_float(acc_small[j]);
+                    } else {
+                        // (main chain 0 + main chain 1) + (correction 0 + correction 1); a contraction of one k-block has no chain 1
+                        const bool two = nkb >= 2;
+                        tmem_ld32(ta, acc);
+                        if (two) tmem_ld32(ta + 256u, acc_small);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + (two ? __uint_as_float(acc_small[j]) : 0.f);
+                        tmem_ld32(ta + 128u, acc);
+                        if (two) tmem_ld32(ta + 384u, acc_small);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(acc[j]) + (two ? __uint_as_float(acc_small[j]) : 0.f);
+                    }
                 }
                 if (P.bias) {
 #pragma unroll
@@ -1253,10 +1274,22 @@ static int tm_cg() {
     return (e && e[0] == '1') ? 1 : 2;
 }
 
+// Parity mode (DEFAULT; PLAGNN_GEMM_PARITY, read per call: "0" off = the fastest kernels, "1" only the products with a bias /
+// activation epilogue, i.e. the forward pass, "2" / unset all).  Tall directly written products run the 256 x 128 kernel with its
+// two TMEM halves as two accumulation chains of one tile (half the truncation bias of the tensor core's accumulate), the long-K
+// weight-gradient products are cut into chains of 24 k-blocks.  Measured at the full PPI size (N = 24 041), worst of the 19
+// gradient tensors against the fp32 oracle on shared decisions / epoch time: off 1.49e-5 / 2.15 ms; level 1 9.6e-6 / 2.23 ms;
+// level 2 8.6e-6 / 2.29 ms (chains of 40 in the weight gradients: 1.10e-5, of 16: 8.1e-6 / 2.37 ms).  DESIGN.md 3.
+static int tm_parity_level() {
+    const char* e = getenv("PLAGNN_GEMM_PARITY");
+    return e ? (e[0] == '0' ? 0 : e[0] == '1' ? 1 : 2) : 2;
+}
+static bool tm_parity() { return tm_parity_level() > 0; }
+
 // PLAGNN_TMA_LONG_CHAIN overrides TM_LONG_CHAIN (accuracy / speed experiments); read once
 static int tm_long_chain() {
-    static const int v = [] { const char* e = getenv("PLAGNN_TMA_LONG_CHAIN"); const int x = e ? atoi(e) : 0; return x >= 4 && x <= 64 ? x : TM_LONG_CHAIN; }();
-    return v;
+    static const int v = [] { const char* e = getenv("PLAGNN_TMA_LONG_CHAIN"); const int x = e ? atoi(e) : 0; return x >= 4 && x <= 64 ? x : 0; }();
+    return v ? v : tm_parity() ? 24 : TM_LONG_CHAIN;
 }
 
 static int tm_choose_splits(int64_t m, int64_t n, int total_kblocks, int cg) {
@@ -1434,8 +1467,9 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
         const char* dyn = getenv("PLAGNN_TMA_DB_NOW");
         const int64_t db_tiles = ceil_div(m, 256) * ceil_div(n, 128);
         const int64_t pair_units = sm_count() / 2;
-        bool db_on = db_allowed && !(dyn && dyn[0] == '0');
-        if (db_on && !(dyn && dyn[0] == '1'))
+        const bool parity = tm_parity_level() == 2 || (tm_parity_level() == 1 && (bias != nullptr || act != PLAGNN_ACT_NONE));
+        bool db_on = parity || (db_allowed && !(dyn && dyn[0] == '0'));
+        if (db_on && !parity && !(dyn && dyn[0] == '1'))
             db_on = tm_cost_tiles128(m, n, P.total_kblocks, pair_units) < tm_cost_tiles256(m, n, P.total_kblocks, pair_units);
         bool k_major_a = true;
         for (int p = 0; p < npairs; ++p) k_major_a = k_major_a && !pairs[p].a_trans;
@@ -1464,8 +1498,13 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
             static const int db_smem[3][2] = {{db_smem_bytes(4, 3, false), db_smem_bytes(4, 3, true)},
                                               {db_smem_bytes(5, 3, false), db_smem_bytes(4, 3, true)},
                                               {db_smem_bytes(4, 4, false), db_smem_bytes(4, 3, true)}};
+            // parity mode: the same kernel with its TMEM halves as two accumulation chains of one tile; [gate][b_trans]
+            static const DbFn db_two[2][2] = {
+                {gemm_tma_db_kernel<false, 5, 3, false, true>, gemm_tma_db_kernel<true, 5, 3, false, true>},
+                {gemm_tma_db_kernel<false, 4, 3, true, true>, gemm_tma_db_kernel<true, 4, 3, true, true>}};
             int ring = 1;
             { const char* e = getenv("PLAGNN_TMA_DB_RING"); if (e && e[0] >= '0' && e[0] <= '2') ring = e[0] - '0'; }
+            if (parity) ring = 1;
             const int gi = gate ? 1 : 0, bi = pairs[0].b_trans ? 1 : 0;
             static thread_local int db_attr_dev = -1;
             int dev = 0;
@@ -1480,6 +1519,14 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
                                 return PLAGNN_ERR_CUDA;
                             }
                         }
+                for (int g2 = 0; g2 < 2; ++g2)
+                    for (int b2 = 0; b2 < 2; ++b2) {
+                        cudaError_t e = cudaFuncSetAttribute(db_two[g2][b2], cudaFuncAttributeMaxDynamicSharedMemorySize, db_smem[1][g2]);
+                        if (e != cudaSuccess) {
+                            set_error("gemm_tma: cudaFuncSetAttribute (db, two chains): %s", cudaGetErrorString(e));
+                            return PLAGNN_ERR_CUDA;
+                        }
+                    }
                 db_attr_dev = dev;
             }
             cudaLaunchConfig_t cfg = {};
@@ -1493,7 +1540,7 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
             at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
             cfg.attrs = at; cfg.numAttrs = 2;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, db_kernels[ring][gi][bi], P);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, parity ? db_two[gi][bi] : db_kernels[ring][gi][bi], P);
             if (e != cudaSuccess) {
                 set_error("gemm_tma: launch (db): %s", cudaGetErrorString(e));
                 return PLAGNN_ERR_CUDA;

@@ -303,6 +303,14 @@ def test_gemm_double_buffered_tiles(cuda, monkeypatch, m, n, k, pairs, bt, gated
     gate_act = ops.ACT_LEAKY if gated else ops.ACT_NONE
     ref = ref_gemm(ps, bias, act_id, gate, gate_act)
     res = {}
+    # parity mode (the default): the 256 x 128 kernel with two accumulation chains per tile, whatever the cost model says
+    monkeypatch.delenv("PLAGNN_GEMM_PARITY", raising=False)
+    out = ops.alloc(m, n, cuda, zero=True)
+    ops.gemm(m, n, ps, bias=bias, act=act_id, gate=gate, gate_act=gate_act, out=out, backend=ops.GEMM_TMA)
+    assert rel(out, ref) < TOL
+    two_chain = out.clone()
+    # the single-chain kernels (PLAGNN_GEMM_PARITY=0): 256 x 256 tiles and the double-buffered 256 x 128 tiles
+    monkeypatch.setenv("PLAGNN_GEMM_PARITY", "0")
     for mode in ("0", "1"):
         monkeypatch.setenv("PLAGNN_TMA_DB_NOW", mode)
         out = ops.alloc(m, n, cuda, zero=True)
@@ -311,6 +319,8 @@ def test_gemm_double_buffered_tiles(cuda, monkeypatch, m, n, k, pairs, bt, gated
         assert rel(out, ref) < TOL, mode
     # same MMAs in the same order into the same kind of accumulators: the two kernels agree to the bit
     assert torch.equal(res["0"], res["1"])
+    # two chains: a different (shorter) accumulation order, so not bit-identical, but the same product
+    assert rel(two_chain, res["0"].double().cpu()) < 1e-5
     # nothing written past the row's last 16-byte group (the output is a view of a row-padded buffer; TMA stores clip at the
     # tensor map's extent in 16-byte units, so columns [n, roundup4(n)) of the padding may be written — include/plagnn.h)
     monkeypatch.setenv("PLAGNN_TMA_DB_NOW", "1")
@@ -324,6 +334,7 @@ def test_gemm_double_buffered_ring_variants(cuda, monkeypatch):
     """The ring depths of the double-buffered kernel (raw 4 / lo 3, raw 5 / lo 3, raw 4 / lo 4) give identical results."""
     m, n, k = 19201, 300, 400
     a, b = operand(m, k, 0, cuda, 31, pad=True), operand(n, k, 0, cuda, 32, pad=True)
+    monkeypatch.setenv("PLAGNN_GEMM_PARITY", "0")
     monkeypatch.setenv("PLAGNN_TMA_DB_NOW", "1")
     outs = []
     for ring in ("0", "1", "2"):
