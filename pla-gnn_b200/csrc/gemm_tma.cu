@@ -1156,6 +1156,349 @@ __global__ void __launch_bounds__(DB_THREADS, 1) gemm_tma_db_kernel(const __grid
     if (tr && t == 0) tr[7] = clock64();
 }
 
+
+// ---- parity mode with the read-out overlap back: half-chain ping-pong (last session of round 2) ------------------------------
+// gemm_tma_db_kernel<..., TWO> gives a tile two accumulation chains but all 512 TMEM columns, so the tensor core idles during
+// the read-out again.  Here the two chains of a tile are the two HALVES of its contraction in time: k-blocks [0, nkb/2) go to
+// TMEM set h & 1, k-blocks [nkb/2, nkb) to the other set (h = running half-chain count), and the read-out warps fetch a half
+// chain as soon as it is complete — the first half of tile i is read (into registers, main + correction summed) while its
+// second half accumulates, the second half is read, added, finished (bias / activation / gate) and stored while the first
+// half of tile i + 1 accumulates.  Same two chains per output as the TWO kernel (so the same halved truncation bias), summed as
+// (main0 + corr0) + (main1 + corr1).  16 warps: TMA producer, MMA issuer, 6 warps for the lo pass, 8 read-out warps (two per
+// TMEM lane quarter, 64 columns each: 64 partial sums per thread); one 4 KB staging buffer per read-out warp (a gate image
+// and the store image take turns in it).
+constexpr int DB2_SPLIT_WARPS = 6, DB2_EPI_WARPS = 8;
+constexpr int DB2_THREADS = (2 + DB2_SPLIT_WARPS + DB2_EPI_WARPS) * 32;
+constexpr int DB2_RAW = 5, DB2_LO = 3;
+constexpr int DB2_SMEM_BYTES = (DB2_RAW + DB2_LO) * DB_STAGE_BYTES + DB2_EPI_WARPS * 4096 + 1024 + 256;
+static_assert(DB2_SMEM_BYTES <= 232448, "shared memory of one SM");
+
+namespace tm {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+}  // namespace tm
+
+template <bool BT, bool GATE>
+__global__ void __launch_bounds__(DB2_THREADS, 1) gemm_tma_db2_kernel(const __grid_constant__ TmParams P) {
+    using namespace tm;
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles = (raw + 1023u) & ~1023u;
+    const uint32_t lo_ring = tiles + DB2_RAW * DB_STAGE_BYTES;
+    const uint32_t epi_area = lo_ring + DB2_LO * DB_STAGE_BYTES;
+    const uint32_t bars = epi_area + DB2_EPI_WARPS * 4096;
+    const uint32_t bar_raw_full = bars, bar_raw_empty = bars + 8 * DB2_RAW;
+    const uint32_t bar_lo_full = bars + 16 * DB2_RAW, bar_lo_empty = bar_lo_full + 8 * DB2_LO;
+    const uint32_t bar_acc_full = bar_lo_empty + 8 * DB2_LO;            // [2]: the half chain in TMEM set s is complete
+    const uint32_t bar_acc_empty = bar_acc_full + 16;                   // [2]: set s has been read in both CTAs
+    const uint32_t bar_gate = bar_acc_empty + 16;                       // [DB2_EPI_WARPS]
+    const uint32_t tmem_slot = bar_gate + 8 * DB2_EPI_WARPS;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int unit = blockIdx.x / 2, units = gridDim.x / 2;
+    const int first_tile = (int)((int64_t)unit * P.total_tiles / units);
+    const int end_tile = (int)((int64_t)(unit + 1) * P.total_tiles / units);
+    const int nkb = P.total_kblocks;
+    const int nkb0 = (nkb + 1) >> 1;                      // k-blocks of the first half chain (the second has nkb - nkb0, maybe 0)
+
+    auto load_kblock = [&](const DbTile& T, int it, int g) {
+        const int s = g % DB2_RAW;
+        int p = 0, local = it;
+        if (P.npairs > 1 && local >= P.kblocks[0]) { local -= P.kblocks[0]; p = 1; }
+        const int k0 = local * TM_BK;
+        const int a_row = (int)(T.m0 + rank * 128), b_row = (int)(T.n0 + rank * T.n_half);
+        const uint32_t st = tiles + s * DB_STAGE_BYTES;
+        const uint32_t rb = bar_raw_full + 8 * s;
+        mbar_expect_tx(rb, DB_STAGE_BYTES);
+        tma_load_2d(st, &P.map[p][0], k0, a_row, rb);
+        if (!BT) {
+            tma_load_2d(st + DB_A_BYTES, &P.map_b64[p], k0, b_row, rb);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d(st + DB_A_BYTES + j * 4096, &P.map[p][1], b_row + 32 * j, k0, rb);
+        }
+    };
+    const DbTile T0 = db_tile(P, first_tile);
+    const int preloaded = nkb < DB2_RAW ? nkb : DB2_RAW;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int s = 0; s < DB2_RAW; ++s) {
+                mbar_init(bar_raw_full + 8 * s, 1);
+                mbar_init(bar_raw_empty + 8 * s, 1);
+            }
+            for (int s = 0; s < DB2_LO; ++s) {
+                mbar_init(bar_lo_full + 8 * s, (uint32_t)(2 * DB2_SPLIT_WARPS));
+                mbar_init(bar_lo_empty + 8 * s, 1);
+            }
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(bar_acc_full + 8 * b, 1);
+                mbar_init(bar_acc_empty + 8 * b, (uint32_t)(2 * DB2_EPI_WARPS));
+            }
+            for (int w = 0; w < DB2_EPI_WARPS; ++w) mbar_init(bar_gate + 8 * w, 1);
+            fence_mbar_init();
+#pragma unroll
+            for (int p = 0; p < PLAGNN_GEMM_MAX_PAIRS; ++p)
+                if (p < P.npairs) { prefetch_map(&P.map[p][0]); prefetch_map(BT ? &P.map[p][1] : &P.map_b64[p]); }
+            prefetch_map(&P.map_out);
+            if (GATE && P.gate_tma) prefetch_map(&P.map_gate);
+        }
+        __syncwarp();
+        pdl_wait();
+        for (int it = 0; it < preloaded; ++it) {
+            if (elect_one()) load_kblock(T0, it, it);
+            __syncwarp();
+        }
+    }
+    if (warp == 1) tmem_alloc<2>(tmem_slot, 512);
+    pdl_wait();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        int g = 0;
+        for (int tile = first_tile; tile < end_tile; ++tile) {
+            const DbTile T = db_tile(P, tile);
+            for (int it = (tile == first_tile ? preloaded : 0); it < nkb; ++it) {
+                const int gg = g + it;
+                const int s = gg % DB2_RAW;
+                const uint32_t ph = (uint32_t)((gg / DB2_RAW) & 1);
+                mbar_wait(bar_raw_empty + 8 * s, ph ^ 1u);
+                if (elect_one()) load_kblock(T, it, gg);
+                __syncwarp();
+            }
+            g += nkb;
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA): one half chain after the other, TMEM sets alternating =================
+        if (rank == 0) {
+            constexpr uint64_t a_step = 2u, b_step = BT ? (1024u >> 4) : 2u;
+            int g = 0, hc = 0;
+            for (int tile = first_tile; tile < end_tile; ++tile) {
+                const DbTile T = db_tile(P, tile);
+                const uint32_t idesc = make_idesc(256, T.n_eff, false, BT);
+                for (int part = 0; part < 2; ++part) {
+                    const int kb_lo = part ? nkb0 : 0, kb_hi = part ? nkb : nkb0;
+                    if (kb_lo >= kb_hi) continue;                    // a contraction of one k-block has no second half
+                    const int set = hc & 1, use = hc >> 1;
+                    if (use > 0) {                                   // the half chain that used this set before has been read out
+                        mbar_wait(bar_acc_empty + 8 * set, (uint32_t)((use - 1) & 1));
+                        tc_fence_after();
+                    }
+                    const uint32_t acc_main = tmem_base + (uint32_t)set * 256u, acc_corr = acc_main + 128u;
+                    for (int it = kb_lo; it < kb_hi; ++it, ++g) {
+                        const int s = g % DB2_RAW, l = g % DB2_LO;
+                        const uint32_t phl = (uint32_t)((g / DB2_LO) & 1);
+                        mbar_wait(bar_lo_full + 8 * l, phl);
+                        tc_fence_after();
+                        const uint32_t st = tiles + s * DB_STAGE_BYTES, sl = lo_ring + l * DB_STAGE_BYTES;
+                        const uint64_t a_hi = desc_kmajor(st), a_lo = desc_kmajor(sl);
+                        const uint64_t b_hi = BT ? desc_mnmajor(st + DB_A_BYTES) : desc_kmajor(st + DB_A_BYTES);
+                        const uint64_t b_lo = BT ? desc_mnmajor(sl + DB_A_BYTES) : desc_kmajor(sl + DB_A_BYTES);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int kk = 0; kk < TM_BK / 8; ++kk) {
+                                const uint64_t adv_a = (uint64_t)kk * a_step, adv_b = (uint64_t)kk * b_step;
+                                const uint32_t acc_on = (it > kb_lo || kk) ? 1u : 0u;
+                                umma_tf32<2>(acc_corr, a_lo + adv_a, b_hi + adv_b, idesc, acc_on);
+                                umma_tf32<2>(acc_corr, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
+                                umma_tf32<2>(acc_main, a_hi + adv_a, b_hi + adv_b, idesc, acc_on);
+                            }
+                            umma_commit<2>(bar_lo_empty + 8 * l);
+                            umma_commit<2>(bar_raw_empty + 8 * s);
+                        }
+                        __syncwarp();
+                    }
+                    if (elect_one()) umma_commit<2>(bar_acc_full + 8 * set);
+                    __syncwarp();
+                    ++hc;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp < 2 + DB2_SPLIT_WARPS) {
+        // ================= lo pass: lo = rn_tf32(x - trunc_tf32(x)), elementwise over the 24 KB stage =================
+        const int ct = t - 64;                                  // 0 .. 191
+        const uint32_t lo_full0 = mapa(bar_lo_full, 0);
+        constexpr int PIECES = DB_STAGE_BYTES / 16 / (DB2_SPLIT_WARPS * 32);     // 8 sixteen-byte pieces per thread
+        constexpr uint32_t PSTRIDE = DB2_SPLIT_WARPS * 32 * 16;
+        static_assert(PIECES * DB2_SPLIT_WARPS * 32 * 16 == DB_STAGE_BYTES, "the lo pass covers the stage exactly");
+        const int total = (end_tile - first_tile) * nkb;
+        for (int g = 0; g < total; ++g) {
+            const int s = g % DB2_RAW, l = g % DB2_LO;
+            const uint32_t phr = (uint32_t)((g / DB2_RAW) & 1), phl = (uint32_t)((g / DB2_LO) & 1);
+            mbar_wait(bar_raw_full + 8 * s, phr);
+            const uint32_t src = tiles + s * DB_STAGE_BYTES + (uint32_t)ct * 16u;
+            const uint32_t dstl = lo_ring + l * DB_STAGE_BYTES + (uint32_t)ct * 16u;
+            float4 v[PIECES];
+#pragma unroll
+            for (int i = 0; i < PIECES; ++i)
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(src + (uint32_t)i * PSTRIDE));
+            mbar_wait(bar_lo_empty + 8 * l, phl ^ 1u);
+#pragma unroll
+            for (int i = 0; i < PIECES; ++i)
+                sts_v4(dstl + (uint32_t)i * PSTRIDE, tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lo_full0 + 8 * l);
+        }
+    } else {
+        // ================= read-out warps: two per TMEM lane quarter, 64 columns (two chunks of 32) each =================
+        const int e = warp - (2 + DB2_SPLIT_WARPS);             // 0..7
+        const int lg = warp & 3;                                // TMEM lane quarter this warp may read (warp % 4)
+        const int chalf = e >> 2;                               // columns [64 chalf, 64 chalf + 64) of the tile
+        const uint32_t acc_empty0 = mapa(bar_acc_empty, 0);
+        const uint32_t stg = epi_area + (uint32_t)e * 4096u;    // one 4 KB buffer: gate image, then store image
+        const uint32_t gbar = bar_gate + 8 * (uint32_t)e;
+        const uint32_t row_off = (uint32_t)lane * 128u;
+        const bool gate_on = GATE && P.gate != nullptr;
+        const bool two = nkb > nkb0;
+        int hc = 0;
+        uint32_t gph = 0;
+        for (int tile = first_tile; tile < end_tile; ++tile) {
+            const DbTile T = db_tile(P, tile);
+            const int64_t n0 = T.n0;
+            const int row0 = (int)(T.m0 + rank * 128 + lg * 32);
+            int nch_tile = (int)((T.n_eff + 31u) / 32u);        // 32-column chunks of the tile that hold real columns
+            {
+                const int64_t real = (P.n - n0 + 31) / 32;
+                nch_tile = real < nch_tile ? (int)real : nch_tile;
+            }
+            int mych = nch_tile - 2 * chalf;                    // of which this warp reads 0, 1 or 2
+            mych = mych < 0 ? 0 : mych > 2 ? 2 : mych;
+            float v[64];
+            // ---- first half chain: partial sums into registers, then the set is free for the next tile's first half ----
+            {
+                const int set = hc & 1, use = hc >> 1;
+                mbar_wait(bar_acc_full + 8 * set, (uint32_t)(use & 1));
+                tc_fence_after();
+                const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)set * 256u + (uint32_t)(chalf * 64);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q * 16 < mych * 32) {                   // warp-uniform
+                        uint32_t a[16], c[16];
+                        tmem_ld16(ta + (uint32_t)(q * 16), a);
+                        tmem_ld16(ta + 128u + (uint32_t)(q * 16), c);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[q * 16 + j] = __uint_as_float(a[j]) + __uint_as_float(c[j]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty0 + 8 * set);
+                ++hc;
+            }
+            // ---- second half chain: added to the partial sums ----
+            if (two) {
+                const int set = hc & 1, use = hc >> 1;
+                mbar_wait(bar_acc_full + 8 * set, (uint32_t)(use & 1));
+                tc_fence_after();
+                const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)set * 256u + (uint32_t)(chalf * 64);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q * 16 < mych * 32) {
+                        uint32_t a[16], c[16];
+                        tmem_ld16(ta + (uint32_t)(q * 16), a);
+                        tmem_ld16(ta + 128u + (uint32_t)(q * 16), c);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[q * 16 + j] += __uint_as_float(a[j]) + __uint_as_float(c[j]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty0 + 8 * set);
+                ++hc;
+            }
+            // ---- finish and store the warp's chunks (everything is in registers: TMEM is already released) ----
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                if (cc < mych) {                                // warp-uniform
+                    const int64_t c0 = n0 + (chalf * 2 + cc) * 32;
+                    const int ncol = (int)((P.n - c0) < 32 ? (P.n - c0) : 32);
+                    float* w = v + cc * 32;
+                    if (P.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) w[j] += __ldg(P.bias + c0 + (j < ncol ? j : 0));
+                    }
+                    if (P.act == PLAGNN_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) w[j] = w[j] > 0.f ? w[j] : 0.f;
+                    } else if (P.act == PLAGNN_ACT_LEAKY) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) w[j] = w[j] > 0.f ? w[j] : w[j] * P.slope;
+                    } else if (P.act == PLAGNN_ACT_SIGMOID) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) w[j] = 1.f / (1.f + expf(-w[j]));
+                    }
+                    // the staging buffer is free when the previous store has read it
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                    if (gate_on) {
+                        if (lane == 0) {
+                            mbar_expect_tx(gbar, 4096u);
+                            tma_load_2d(stg, &P.map_gate, (int)c0, row0, gbar);
+                        }
+                        mbar_wait(gbar, gph & 1u);
+                        ++gph;
+                        float gt[32];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                         : "=f"(gt[4 * q]), "=f"(gt[4 * q + 1]), "=f"(gt[4 * q + 2]), "=f"(gt[4 * q + 3])
+                                         : "r"(stg + row_off + (uint32_t)((q ^ (lane & 7)) << 4)));
+                        if (P.gate_act == PLAGNN_ACT_RELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) w[j] = gt[j] > 0.f ? w[j] : 0.f;
+                        } else if (P.gate_act == PLAGNN_ACT_LEAKY) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) w[j] = gt[j] > 0.f ? w[j] : w[j] * P.slope;
+                        } else if (P.gate_act == PLAGNN_ACT_SIGMOID) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) w[j] *= gt[j] * (1.f - gt[j]);
+                        }
+                        __syncwarp();                           // every lane has consumed the gate image: the buffer takes the output
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t off = row_off + (uint32_t)((q ^ (lane & 7)) << 4);
+                        sts_v4(stg + off, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&P.map_out, stg, (int)c0, row0, 0);
+                        bulk_commit();
+                    }
+                }
+            }
+        }
+        if (lane == 0) bulk_wait_all();
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<2>(tmem_base, 512);
+    }
+}
+
 // ---- host side: tensor maps ---------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1502,6 +1845,12 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
             static const DbFn db_two[2][2] = {
                 {gemm_tma_db_kernel<false, 5, 3, false, true>, gemm_tma_db_kernel<true, 5, 3, false, true>},
                 {gemm_tma_db_kernel<false, 4, 3, true, true>, gemm_tma_db_kernel<true, 4, 3, true, true>}};
+            // ... and with the read-out overlap back: the two chains as the two halves of the contraction in time
+            // (gemm_tma_db2_kernel; PLAGNN_TMA_DB2=0, read per launch, falls back to the kernel above)
+            static const DbFn db2[2][2] = {{gemm_tma_db2_kernel<false, false>, gemm_tma_db2_kernel<true, false>},
+                                           {gemm_tma_db2_kernel<false, true>, gemm_tma_db2_kernel<true, true>}};
+            bool use_db2 = parity;
+            { const char* e = getenv("PLAGNN_TMA_DB2"); if (e && e[0] == '0') use_db2 = false; }
             int ring = 1;
             { const char* e = getenv("PLAGNN_TMA_DB_RING"); if (e && e[0] >= '0' && e[0] <= '2') ring = e[0] - '0'; }
             if (parity) ring = 1;
@@ -1521,6 +1870,11 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
                         }
                 for (int g2 = 0; g2 < 2; ++g2)
                     for (int b2 = 0; b2 < 2; ++b2) {
+                        cudaError_t e2 = cudaFuncSetAttribute(db2[g2][b2], cudaFuncAttributeMaxDynamicSharedMemorySize, DB2_SMEM_BYTES);
+                        if (e2 != cudaSuccess) {
+                            set_error("gemm_tma: cudaFuncSetAttribute (db2): %s", cudaGetErrorString(e2));
+                            return PLAGNN_ERR_CUDA;
+                        }
                         cudaError_t e = cudaFuncSetAttribute(db_two[g2][b2], cudaFuncAttributeMaxDynamicSharedMemorySize, db_smem[1][g2]);
                         if (e != cudaSuccess) {
                             set_error("gemm_tma: cudaFuncSetAttribute (db, two chains): %s", cudaGetErrorString(e));
@@ -1531,8 +1885,8 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
             }
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)(sm_count() / 2 * 2), 1u, 1u);
-            cfg.blockDim = dim3(DB_THREADS);
-            cfg.dynamicSmemBytes = db_smem[ring][gi];
+            cfg.blockDim = dim3(use_db2 ? DB2_THREADS : DB_THREADS);
+            cfg.dynamicSmemBytes = use_db2 ? DB2_SMEM_BYTES : db_smem[ring][gi];
             cfg.stream = st;
             cudaLaunchAttribute at[2];
             at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1540,7 +1894,7 @@ int gemm_tma_launch(int64_t m, int64_t n, int32_t npairs, const plagnn_gemm_pair
             at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
             cfg.attrs = at; cfg.numAttrs = 2;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, parity ? db_two[gi][bi] : db_kernels[ring][gi][bi], P);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, use_db2 ? db2[gi][bi] : parity ? db_two[gi][bi] : db_kernels[ring][gi][bi], P);
             if (e != cudaSuccess) {
                 set_error("gemm_tma: launch (db): %s", cudaGetErrorString(e));
                 return PLAGNN_ERR_CUDA;

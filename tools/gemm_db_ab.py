@@ -78,13 +78,15 @@ def timed(fn, reps=30):
 
 
 out = {}
-VARIANTS = ("0", "1", "auto")
+VARIANTS = ("0", "auto", "two", "db2")
 tot = {v: 0.0 for v in VARIANTS}
 for name, (run, ref, o) in products:
     rec = {}
     r64 = ref()
     res = {}
     for db in VARIANTS:
+        os.environ["PLAGNN_GEMM_PARITY"] = "2" if db in ("two", "db2") else "0"
+        os.environ["PLAGNN_TMA_DB2"] = "0" if db == "two" else "1"
         os.environ["PLAGNN_TMA_DB_NOW"] = {"0": "0", "auto": "auto"}.get(db, "1")
         os.environ["PLAGNN_TMA_DB_RING"] = {"r43": "0", "r44": "2"}.get(db, "1")
         o.zero_()
@@ -95,9 +97,10 @@ for name, (run, ref, o) in products:
         rec[f"db{db}_ms"] = round(min(timed(run), timed(run)), 5)
         tot[db] += rec[f"db{db}_ms"]
     rec["max_diff_vs_db0"] = max(float((res[v] - res["0"]).abs().max() / res["0"].abs().max()) for v in VARIANTS)
+    rec["db2_vs_two"] = float((res["db2"] - res["two"]).abs().max() / res["two"].abs().max())
     out[name] = rec
-    print(name, {k: (round(v, 9) if isinstance(v, float) and v < 1e-3 else v) for k, v in rec.items() if k.endswith("_ms") or k == "max_diff_vs_db0"}, file=sys.stderr, flush=True)
-os.environ.pop("PLAGNN_TMA_DB_NOW", None); os.environ.pop("PLAGNN_TMA_DB_RING", None)
+    print(name, {k: (round(v, 9) if isinstance(v, float) and v < 1e-3 else v) for k, v in rec.items() if k.endswith("_ms") or k in ("max_diff_vs_db0", "db2_vs_two", "dbdb2_err_vs_f64", "dbtwo_err_vs_f64")}, file=sys.stderr, flush=True)
+os.environ.pop("PLAGNN_TMA_DB_NOW", None); os.environ.pop("PLAGNN_TMA_DB_RING", None); os.environ.pop("PLAGNN_GEMM_PARITY", None); os.environ.pop("PLAGNN_TMA_DB2", None)
 out["sum_ms"] = {k: round(v, 5) for k, v in tot.items()}
 print("sum", out["sum_ms"], file=sys.stderr)
 print(json.dumps(out))
