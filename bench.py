@@ -456,8 +456,8 @@ def run_ours(args):
         else:
             os.environ["PLAGNN_GEMM_PARITY"] = prev_parity
     fast_gemm = {"value": world * args.steps / (ms_fast * 1e-3), "unit": UNIT, "ms_per_step": ms_fast / args.steps,
-                 "note": "PLAGNN_GEMM_PARITY=0: one accumulation chain per GEMM tile (double-buffered read-out where the cost model "
-                         "prefers it), weight-gradient chains of 40 k-blocks; full-size gradients within 1.5e-5 instead of 1e-5"}
+                 "note": "PLAGNN_GEMM_PARITY=0: one accumulation chain per GEMM tile (256 x 256 or double-buffered 256 x 128 tiles by the cost model), "
+                         "weight-gradient chains of 40 k-blocks; full-size gradients within 1.5e-5 instead of 1e-5"}
 
     ms_e2e = timed_e2e(args.steps)
 
@@ -545,7 +545,7 @@ def run_ours(args):
                                  "note": "the >= 70 % of HBM target is judged on the graph that is NOT L2-resident: "
                                          "`partitioned` (configs[3]) -> aggregation_frac_of_hbm_peak, ncu DRAM bytes for that kernel in "
                                          "profiles/"},
-        "gemm_mode": {"default": os.environ.get("PLAGNN_GEMM_PARITY", "2 (parity: two accumulation chains per tile, weight-gradient "
+        "gemm_mode": {"default": os.environ.get("PLAGNN_GEMM_PARITY", "2 (parity: two accumulation chains per tile as the two halves of its contraction, weight-gradient "
                                                  "chains of 24 k-blocks; all 19 gradient tensors <= 1e-5 at N = 24 041)"),
                       "fast": fast_gemm},
         "gemm": {"ms_per_step": gemm_ms, "tflops_fp32_equiv": flops_epoch / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
