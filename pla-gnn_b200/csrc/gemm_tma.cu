@@ -1621,8 +1621,10 @@ static int tm_cg() {
 // activation epilogue, i.e. the forward pass, "2" / unset all).  Tall directly written products run the 256 x 128 kernel with its
 // two TMEM halves as two accumulation chains of one tile (half the truncation bias of the tensor core's accumulate), the long-K
 // weight-gradient products are cut into chains of 24 k-blocks.  Measured at the full PPI size (N = 24 041), worst of the 19
-// gradient tensors against the fp32 oracle on shared decisions / epoch time: off 1.49e-5 / 2.15 ms; level 1 9.6e-6 / 2.23 ms;
-// level 2 8.6e-6 / 2.29 ms (chains of 40 in the weight gradients: 1.10e-5, of 16: 8.1e-6 / 2.37 ms).  DESIGN.md 3.
+// gradient tensors against the fp32 oracle on shared decisions / epoch time: off 1.49e-5 / 2.15 ms; with the two chains side by
+// side in TMEM (gemm_tma_db_kernel<..., TWO>, no read-out overlap): level 1 9.6e-6 / 2.23 ms, level 2 8.6e-6 / 2.29 ms (chains
+// of 40 in the weight gradients: 1.10e-5, of 16: 8.1e-6 / 2.37 ms); with the two chains as the two halves of the contraction in
+// time (gemm_tma_db2_kernel, the default): level 2 8.8e-6 / 2.19 ms.  DESIGN.md 3.
 static int tm_parity_level() {
     const char* e = getenv("PLAGNN_GEMM_PARITY");
     return e ? (e[0] == '0' ? 0 : e[0] == '1' ? 1 : 2) : 2;
