@@ -286,6 +286,8 @@ DB_CASES = [  # n, k, pairs, bt, gate, act, bias
     (100, 200, 1, 0, False, "leaky", True),     # one column tile (n_eff = 128)
     (72, 40, 1, 0, False, "sigmoid", True),     # narrow output (n_eff = 128 with 72 real columns), short contraction (2 k-blocks)
     (129, 33, 1, 1, True, "none", False),       # ragged everything: 129 columns (second tile holds one), k = 33
+    (96, 24, 1, 0, False, "relu", True),        # one k-block: the two-chain kernel has no second half chain
+    (256, 72, 2, 0, True, "leaky", False),      # two pairs of three k-blocks each: the pair switch falls inside a half chain
 ]
 
 
