@@ -515,7 +515,8 @@ def run_ours(args):
                    "l2": "no explicit flush: one step touches >1 GB of distinct activations/gradients (> 126 MB L2); the "
                          "aggregation input is produced by the preceding GEMM, as in the real loop",
                    "legs": "in process order: concurrent models (3 warm-up + K), per-kernel breakdown (3 + K), graph replay (3 + K), partitioned "
-                           "configs[3] block, end-to-end (3 + K), then W warm-up + K timed steps = `value`",
+                           "configs[3] block, single-chain GEMM mode (3 + K, `gemm_mode.fast`), end-to-end (3 + K), then W warm-up + K timed steps = "
+                           "`value` (default GEMM mode: two accumulation chains per tile)",
                    "train_rows": int(len(train_index)), "lr": LR},
         "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": int(feat_h.numel() * 4 + loc_h.numel() * 4 + idx_h.numel() * 8),
