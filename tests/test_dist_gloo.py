@@ -128,7 +128,8 @@ class _PG:
         self.scale = plan.scale_local
 
 
-def _problem(n=403, e=6000, f=24):
+def _problem(n=403, e=6000, f=None):
+    f = DIMS[0] if f is None else f
     sg = synth.scaled_graph(n, e, seed=5, max_degree=200)
     x = torch.randn(n, f, generator=torch.Generator().manual_seed(1))
     return sg, x
@@ -329,6 +330,15 @@ def test_feature_partition_three_layers_pair_plus_single(tmp_path, monkeypatch):
     _run_world(2, tmp_path, mode="cols")
     monkeypatch.setenv("PLAGNN_DIST_COLS_ALT", "0")
     _run_world(2, tmp_path, mode="cols")
+
+
+def test_feature_partition_four_ranks(tmp_path, monkeypatch):
+    """World 4 (the one GPU count of the driver's 1 / 2 / 4 / 8 run that the other tests do not cover): feature partition with
+    the layers in pairs, widths that are multiples of 4 * world."""
+    import tests.test_dist_gloo as me
+    monkeypatch.setenv("PLAGNN_TEST_DIMS", "32,32,16")
+    monkeypatch.setattr(me, "DIMS", [32, 32, 16])
+    _run_world(4, tmp_path, mode="cols", balance="edges")
 
 
 def test_feature_partition_max_pool_three_ranks(tmp_path):
